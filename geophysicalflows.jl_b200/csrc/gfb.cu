@@ -1,0 +1,755 @@
+// gfb.cu -- context and the extern "C" ABI declared in include/gfb.h.
+//
+// Nothing here allocates on the step path: all tables, work arrays and stage states are created in
+// gfb_create and live in the context.  Every entry point only enqueues kernels on the caller's
+// stream (gfb_diag additionally copies a few doubles back and synchronises that stream).
+#include "../../include/gfb.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "launch.h"
+
+using namespace gfb;
+
+static thread_local std::string g_create_error;
+
+struct gfb_ctx {
+  gfb_config cfg;  // host pointers inside are NOT retained (nulled after create)
+  GridDesc g;
+  int nlayers = 1, kind = 0, stepper = 0;
+  bool filtered = false, cplxL = false;
+  double dt = 0, t = 0;
+  long long step = 0;
+  std::string err;
+  long long bytes = 0;
+  std::vector<void*> allocs;
+  // tables
+  cplx *tw_x = nullptr, *tw_y = nullptr;
+  double* G = nullptr;
+  double *Sinv = nullptr, *S = nullptr;
+  double *eta = nullptr, *U = nullptr, *Qx = nullptr, *Qy = nullptr;
+  cplx* Nconst = nullptr;
+  void* L = nullptr;
+  double* filter = nullptr;
+  void *E = nullptr, *Eh = nullptr, *zeta = nullptr, *alpha = nullptr, *beta = nullptr, *Gamma = nullptr;
+  // work
+  cplx *W = nullptr, *P = nullptr;
+  int ldw = 0, ldp = 0, ldi = 0;
+  long long wfs = 0, pfs = 0, ils = 0;  // field / layer strides
+  cplx* st[4] = {nullptr, nullptr, nullptr, nullptr};  // stage states / accumulators / histories
+  double *dpart = nullptr, *dout = nullptr;
+  int dblocks = 0;
+};
+
+static int fail(gfb_ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define GFB_CUDA(c, call)                                                                  \
+  do {                                                                                     \
+    cudaError_t e__ = (call);                                                              \
+    if (e__ != cudaSuccess) return fail((c), GFB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__)); \
+  } while (0)
+
+static int check_launch(gfb_ctx* c, int rc, const char* what) {
+  if (rc == -1) return fail(c, GFB_ERR_UNSUPPORTED, "%s: unsupported size/layer count", what);
+  if (rc != 0) return fail(c, GFB_ERR_CUDA, "%s: cudaFuncSetAttribute failed", what);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(c, GFB_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  return 0;
+}
+
+template <class T>
+static int dev_alloc(gfb_ctx* c, T** p, size_t n) {
+  void* q = nullptr;
+  if (cudaMalloc(&q, n * sizeof(T)) != cudaSuccess) return fail(c, GFB_ERR_ALLOC, "cudaMalloc of %zu bytes failed", n * sizeof(T));
+  c->allocs.push_back(q);
+  c->bytes += (long long)(n * sizeof(T));
+  *p = (T*)q;
+  return 0;
+}
+
+template <class T>
+static int dev_upload(gfb_ctx* c, T** p, const void* host, size_t n) {
+  int rc = dev_alloc(c, p, n);
+  if (rc) return rc;
+  GFB_CUDA(c, cudaMemcpy(*p, host, n * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// upload a dense host table [nlayers][nl][nkr] (double or cplx) into the padded internal layout (ld = ldi)
+static int upload_padded(gfb_ctx* c, void** out, const void* host, int nlay, bool is_cplx) {
+  const int nl = c->g.ny, nkr = c->g.nkr, ldi = c->ldi;
+  const size_t es = is_cplx ? sizeof(cplx) : sizeof(double);
+  std::vector<char> tmp((size_t)nlay * nl * ldi * es, 0);
+  for (int a = 0; a < nlay; ++a)
+    for (int l = 0; l < nl; ++l)
+      std::memcpy(&tmp[((size_t)(a * nl + l) * ldi) * es], (const char*)host + ((size_t)(a * nl + l) * nkr) * es, nkr * es);
+  char* d = nullptr;
+  int rc = dev_alloc(c, &d, tmp.size());
+  if (rc) return rc;
+  GFB_CUDA(c, cudaMemcpy(d, tmp.data(), tmp.size(), cudaMemcpyHostToDevice));
+  *out = d;
+  return 0;
+}
+
+static bool pow2_ok(int n) { return n >= 16 && n <= 8192 && (n & (n - 1)) == 0; }
+
+static int make_twiddles(gfb_ctx* c, cplx** out, int N) {
+  std::vector<cplx> h(N);
+  for (int i = 0; i < N; ++i) {
+    // exact octant symmetries keep |w| = 1 to the last bit where it matters
+    const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)i / (long double)N;
+    h[i] = make_double2((double)cosl(a), (double)sinl(a));
+  }
+  return dev_upload(c, out, h.data(), (size_t)N);
+}
+
+namespace gfb {
+int launch_col_inv(int NY, const ColInvLaunch& L) {
+  switch (NY) {
+#define GFB_CASE(N) case N: return launch_col_inv_##N(L);
+    GFB_CASE(16) GFB_CASE(32) GFB_CASE(64) GFB_CASE(128) GFB_CASE(256) GFB_CASE(512) GFB_CASE(1024) GFB_CASE(2048) GFB_CASE(4096) GFB_CASE(8192)
+#undef GFB_CASE
+  }
+  return -1;
+}
+int launch_row(int NX, const RowLaunch& L) {
+  switch (NX) {
+#define GFB_CASE(N) case N: return launch_row_##N(L);
+    GFB_CASE(16) GFB_CASE(32) GFB_CASE(64) GFB_CASE(128) GFB_CASE(256) GFB_CASE(512) GFB_CASE(1024) GFB_CASE(2048) GFB_CASE(4096) GFB_CASE(8192)
+#undef GFB_CASE
+  }
+  return -1;
+}
+int launch_col_fwd(int NY, const ColFwdLaunch& L) {
+  switch (NY) {
+#define GFB_CASE(N) case N: return launch_col_fwd_##N(L);
+    GFB_CASE(16) GFB_CASE(32) GFB_CASE(64) GFB_CASE(128) GFB_CASE(256) GFB_CASE(512) GFB_CASE(1024) GFB_CASE(2048) GFB_CASE(4096) GFB_CASE(8192)
+#undef GFB_CASE
+  }
+  return -1;
+}
+}  // namespace gfb
+
+extern "C" {
+
+const char* gfb_version(void) { return "gfb 0.1 (sm_100a)"; }
+
+const char* gfb_last_error(const gfb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+long long gfb_device_bytes(const gfb_ctx* ctx) { return ctx ? ctx->bytes : 0; }
+
+int gfb_destroy(gfb_ctx* c) {
+  if (!c) return GFB_OK;
+  for (void* p : c->allocs) cudaFree(p);
+  delete c;
+  return GFB_OK;
+}
+
+int gfb_create(gfb_ctx** out, const gfb_config* cfg) {
+  if (!out || !cfg) return fail(nullptr, GFB_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (!pow2_ok(cfg->nx) || !pow2_ok(cfg->ny))
+    return fail(nullptr, GFB_ERR_UNSUPPORTED, "nx=%d, ny=%d: sizes must be powers of two in [16, 8192]", cfg->nx, cfg->ny);
+  if (cfg->nlayers < 1 || cfg->nlayers > MAX_LAYERS) return fail(nullptr, GFB_ERR_UNSUPPORTED, "nlayers=%d not in [1, %d]", cfg->nlayers, MAX_LAYERS);
+  if (cfg->kind == GFB_KIND_SINGLE && cfg->nlayers != 1) return fail(nullptr, GFB_ERR_INVALID, "GFB_KIND_SINGLE needs nlayers == 1");
+  if (cfg->kind != GFB_KIND_SINGLE && cfg->kind != GFB_KIND_LAYERED) return fail(nullptr, GFB_ERR_INVALID, "unknown kind %d", cfg->kind);
+  if (cfg->stepper < GFB_FORWARD_EULER || cfg->stepper > GFB_FILTERED_AB3) return fail(nullptr, GFB_ERR_INVALID, "unknown stepper %d", cfg->stepper);
+  if (cfg->no_dealias_in_calcN) return fail(nullptr, GFB_ERR_UNSUPPORTED, "calcNlinear! (no dealias) is not supported");
+  if (!cfg->L) return fail(nullptr, GFB_ERR_INVALID, "config.L is null");
+  const int nkr = cfg->nx / 2 + 1;
+  if (cfg->kr_alias0 < 1 || cfg->kr_alias0 > nkr || cfg->l_alias0 < 0 || cfg->l_alias1 > cfg->ny || cfg->l_alias0 > cfg->l_alias1)
+    return fail(nullptr, GFB_ERR_INVALID, "bad alias ranges");
+  gfb_ctx* c = new gfb_ctx();
+  c->cfg = *cfg;
+  c->nlayers = cfg->nlayers;
+  c->kind = cfg->kind;
+  c->stepper = cfg->stepper;
+  c->filtered = (cfg->stepper & 1) != 0;
+  c->cplxL = cfg->L_is_complex != 0;
+  c->dt = cfg->dt;
+  GridDesc& g = c->g;
+  g.nx = cfg->nx;
+  g.ny = cfg->ny;
+  g.nkr = nkr;
+  g.kcut = cfg->kr_alias0;
+  g.la0 = cfg->l_alias0;
+  g.la1 = cfg->l_alias1;
+  // wavenumber multipliers exactly as FourierFlows forms them: (2pi/L*n)/n
+  g.dkx = (2.0 * M_PI / cfg->Lx * cfg->nx) / cfg->nx;
+  g.dky = (2.0 * M_PI / cfg->Ly * cfg->ny) / cfg->ny;
+  g.invN = 1.0 / ((double)cfg->nx * (double)cfg->ny);
+  const int n = c->nlayers, nl = g.ny;
+  c->ldw = c->ldp = c->ldi = (nkr + 1) & ~1;
+  c->wfs = c->pfs = (long long)nl * c->ldw;
+  c->ils = (long long)nl * c->ldi;
+  int rc = 0;
+#define TRY(x)             \
+  do {                     \
+    rc = (x);              \
+    if (rc) {              \
+      g_create_error = c->err; \
+      gfb_destroy(c);      \
+      return rc;           \
+    }                      \
+  } while (0)
+  TRY(make_twiddles(c, &c->tw_x, g.nx));
+  TRY(make_twiddles(c, &c->tw_y, g.ny));
+  const size_t nspec = (size_t)nl * nkr, nphys = (size_t)g.ny * g.nx;
+  if (c->kind == GFB_KIND_SINGLE) {
+    if (!cfg->G) { fail(c, GFB_ERR_INVALID, "GFB_KIND_SINGLE needs config.G"); TRY(GFB_ERR_INVALID); }
+    TRY(dev_upload(c, &c->G, cfg->G, nspec));
+    if (cfg->eta) TRY(dev_upload(c, &c->eta, cfg->eta, nphys));
+  } else {
+    if (!cfg->Sinv || !cfg->Qx || !cfg->Qy) { fail(c, GFB_ERR_INVALID, "GFB_KIND_LAYERED needs config.Sinv, Qx, Qy"); TRY(GFB_ERR_INVALID); }
+    TRY(dev_upload(c, &c->Sinv, cfg->Sinv, nspec * n * n));
+    if (cfg->G) TRY(dev_upload(c, &c->G, cfg->G, nspec));  // optional: only the G-weighted diagnostics use it
+    if (cfg->S) TRY(dev_upload(c, &c->S, cfg->S, nspec * n * n));
+    if (cfg->U) TRY(dev_upload(c, &c->U, cfg->U, (size_t)n * g.ny));
+    TRY(dev_upload(c, &c->Qx, cfg->Qx, nphys * n));
+    TRY(dev_upload(c, &c->Qy, cfg->Qy, nphys * n));
+  }
+  if (cfg->Nconst) TRY(dev_upload(c, &c->Nconst, cfg->Nconst, nspec * n));
+  TRY(upload_padded(c, &c->L, cfg->L, n, c->cplxL));
+  if (c->filtered) {
+    if (!cfg->filter) { fail(c, GFB_ERR_INVALID, "filtered stepper needs config.filter"); TRY(GFB_ERR_INVALID); }
+    void* f = nullptr;
+    TRY(upload_padded(c, &f, cfg->filter, 1, false));
+    c->filter = (double*)f;
+  }
+  const bool etd = cfg->stepper == GFB_ETDRK4 || cfg->stepper == GFB_FILTERED_ETDRK4;
+  if (etd) {
+    if (!cfg->expLdt || !cfg->exphalfLdt || !cfg->zeta || !cfg->alpha || !cfg->beta || !cfg->Gamma) {
+      fail(c, GFB_ERR_INVALID, "ETDRK4 needs expLdt, exphalfLdt, zeta, alpha, beta, Gamma");
+      TRY(GFB_ERR_INVALID);
+    }
+    TRY(upload_padded(c, &c->E, cfg->expLdt, n, c->cplxL));
+    TRY(upload_padded(c, &c->Eh, cfg->exphalfLdt, n, c->cplxL));
+    TRY(upload_padded(c, &c->zeta, cfg->zeta, n, c->cplxL));
+    TRY(upload_padded(c, &c->alpha, cfg->alpha, n, c->cplxL));
+    TRY(upload_padded(c, &c->beta, cfg->beta, n, c->cplxL));
+    TRY(upload_padded(c, &c->Gamma, cfg->Gamma, n, c->cplxL));
+  }
+  TRY(dev_alloc(c, &c->W, (size_t)4 * n * c->wfs));
+  TRY(dev_alloc(c, &c->P, (size_t)2 * n * c->pfs));
+  int nstate = 0;
+  switch (cfg->stepper) {
+    case GFB_FORWARD_EULER: case GFB_FILTERED_FORWARD_EULER: nstate = 0; break;
+    case GFB_RK4: case GFB_FILTERED_RK4: nstate = 3; break;     // s1, s2 (ping-pong), acc
+    case GFB_ETDRK4: case GFB_FILTERED_ETDRK4: nstate = 4; break;  // s1, s2 / s3 reuse, acc, N1
+    default: nstate = 3; break;                                  // AB3: rhs, rhs-1, rhs-2
+  }
+  for (int i = 0; i < nstate; ++i) {
+    TRY(dev_alloc(c, &c->st[i], (size_t)n * c->ils));
+    GFB_CUDA(c, cudaMemset(c->st[i], 0, (size_t)n * c->ils * sizeof(cplx)));
+  }
+  if (cfg->stepper == GFB_ETDRK4 || cfg->stepper == GFB_FILTERED_ETDRK4) {
+    // ETDRK4 needs s1, s2, s3, acc, N1: the fifth array aliases W's fourth field block (unused on the step path)
+  }
+  c->dblocks = 592;
+  TRY(dev_alloc(c, &c->dpart, (size_t)c->dblocks * DIAG_MAXOUT));
+  TRY(dev_alloc(c, &c->dout, (size_t)DIAG_MAXOUT));
+#undef TRY
+  // host pointers are not retained
+  c->cfg.L = c->cfg.filter = nullptr;
+  *out = c;
+  return GFB_OK;
+}
+
+int gfb_get_clock(const gfb_ctx* c, double* t, long long* step) {
+  if (!c) return GFB_ERR_INVALID;
+  if (t) *t = c->t;
+  if (step) *step = c->step;
+  return GFB_OK;
+}
+int gfb_set_clock(gfb_ctx* c, double t, long long step) {
+  if (!c) return GFB_ERR_INVALID;
+  c->t = t;
+  c->step = step;
+  return GFB_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// internal building blocks
+// ---------------------------------------------------------------------------------------------
+static Spec user_spec(const gfb_ctx* c, const void* p) {
+  Spec s;
+  s.p = (cplx*)p;
+  s.ld = c->g.nkr;
+  s.ls = (long long)c->g.ny * c->g.nkr;
+  return s;
+}
+static Spec int_spec(const gfb_ctx* c, cplx* p) {
+  Spec s;
+  s.p = p;
+  s.ld = c->ldi;
+  s.ls = c->ils;
+  return s;
+}
+static Spec null_spec() {
+  Spec s;
+  s.p = nullptr;
+  s.ld = 0;
+  s.ls = 0;
+  return s;
+}
+static Coef coef(const gfb_ctx* c, const void* p) {
+  Coef k;
+  k.r = c->cplxL ? nullptr : (const double*)p;
+  k.c = c->cplxL ? (const cplx*)p : nullptr;
+  k.ld = c->ldi;
+  k.ls = c->ils;
+  return k;
+}
+
+// K1 on a stage input (hot path): fields u, v, q (+psi if nf == 4) for every layer -> W
+static int run_col_inv_state(gfb_ctx* c, const Spec& sin, int nf, cudaStream_t st) {
+  ColInvLaunch L;
+  std::memset(&L, 0, sizeof L);
+  L.g = c->g;
+  L.W = c->W;
+  L.ldw = c->ldw;
+  L.wfs = c->wfs;
+  L.ncols = c->g.kcut;
+  L.tw = c->tw_y;
+  L.st = st;
+  L.nl = c->nlayers;
+  if (c->kind == GFB_KIND_SINGLE) {
+    L.prep = PREP_SINGLE;
+    L.ps.sol = sin.p;
+    L.ps.ld = sin.ld;
+    L.ps.G.p = c->G;
+    L.ps.G.ld = c->g.nkr;
+    L.ps.G.ls = 0;
+    L.nfields = nf;
+  } else {
+    L.prep = PREP_MULTI;
+    L.pm.sol = sin.p;
+    L.pm.ld = sin.ld;
+    L.pm.ls = sin.ls;
+    L.pm.Sinv = c->Sinv;
+    L.pm.ldS = c->g.nkr;
+    L.pm.nf = nf;
+    L.nfields = nf * c->nlayers;
+  }
+  return check_launch(c, launch_col_inv(c->g.ny, L), "k_col_inv");
+}
+
+static int run_row_product(gfb_ctx* c, cudaStream_t st) {
+  RowLaunch R;
+  std::memset(&R, 0, sizeof R);
+  R.mode = (c->kind == GFB_KIND_LAYERED) ? ROW_PRODUCT_Q : ROW_PRODUCT;
+  R.a.W = c->W;
+  R.a.ldw = c->ldw;
+  R.a.wfs = c->wfs;
+  R.a.kc = c->g.kcut;
+  R.a.P = c->P;
+  R.a.ldp = c->ldp;
+  R.a.pfs = c->pfs;
+  R.a.kout = c->g.nkr;
+  R.a.eta = c->eta;
+  R.a.U = c->U;
+  R.a.Qx = c->Qx;
+  R.a.Qy = c->Qy;
+  R.a.dkx = c->g.dkx;
+  R.a.ny = c->g.ny;
+  R.nlayers = c->nlayers;
+  R.tw = c->tw_x;
+  R.st = st;
+  return check_launch(c, launch_row(c->g.nx, R), "k_row");
+}
+
+static int run_col_fwd(gfb_ctx* c, const EpiArgs& e, cudaStream_t st) {
+  ColFwdLaunch F;
+  std::memset(&F, 0, sizeof F);
+  F.g = c->g;
+  F.P = c->P;
+  F.ldp = c->ldp;
+  F.pfs = c->pfs;
+  F.e = e;
+  F.ncols = c->g.nkr;
+  F.nlayers = c->nlayers;
+  F.nl = c->nlayers;
+  F.two = true;
+  F.tw = c->tw_y;
+  F.st = st;
+  return check_launch(c, launch_col_fwd(c->g.ny, F), "k_col_fwd");
+}
+
+static EpiArgs base_epi(const gfb_ctx* c, const void* Fh) {
+  EpiArgs e;
+  std::memset(&e, 0, sizeof e);
+  e.nlayers = c->nlayers;
+  e.F = Fh ? user_spec(c, Fh) : null_spec();
+  e.Nconst = c->Nconst ? user_spec(c, c->Nconst) : null_spec();
+  e.L = coef(c, c->L);
+  e.mu = (c->kind == GFB_KIND_LAYERED) ? c->cfg.mu : 0.0;
+  e.Sinv = c->Sinv;
+  e.ldS = c->g.nkr;
+  e.filter.p = nullptr;
+  return e;
+}
+
+// one full calcN + epilogue on stage input `sin`
+static int run_stage_kernels(gfb_ctx* c, const Spec& sin, EpiArgs& e, cudaStream_t st) {
+  int rc = run_col_inv_state(c, sin, 3, st);
+  if (rc) return rc;
+  rc = run_row_product(c, st);
+  if (rc) return rc;
+  e.sin = sin;
+  return run_col_fwd(c, e, st);
+}
+
+template <int NL>
+static void launch_matvec(const gfb_ctx* c, cplx* y, const cplx* x, const double* M, cudaStream_t st) {
+  GFB_LAUNCH((k_matvec<NL>), dim3(592), dim3(256), 0, st, c->g.ny, c->g.nkr, y, x, M);
+}
+
+static int matvec(gfb_ctx* c, void* y, const void* x, const double* M, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (c->nlayers) {
+    case 1: launch_matvec<1>(c, (cplx*)y, (const cplx*)x, M, st); break;
+    case 2: launch_matvec<2>(c, (cplx*)y, (const cplx*)x, M, st); break;
+    case 3: launch_matvec<3>(c, (cplx*)y, (const cplx*)x, M, st); break;
+    case 4: launch_matvec<4>(c, (cplx*)y, (const cplx*)x, M, st); break;
+    case 5: launch_matvec<5>(c, (cplx*)y, (const cplx*)x, M, st); break;
+    default: return fail(c, GFB_ERR_UNSUPPORTED, "matvec: nlayers");
+  }
+  return check_launch(c, 0, "k_matvec");
+}
+
+static __global__ void k_scale_by_table(const long long n, cplx* __restrict__ y, const cplx* __restrict__ x,
+                                 const double* __restrict__ G, const double sign) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = cscale(x[i], sign * G[i]);
+}
+
+template <int NL>
+static void launch_diag(const gfb_ctx* c, const DiagArgs& d, cudaStream_t st) {
+  GFB_LAUNCH((k_diag_partial<NL>), dim3(c->dblocks), dim3(256), 0, st, c->g, d, c->dpart);
+}
+
+extern "C" {
+
+int gfb_dealias(gfb_ctx* c, void* sol, void* stream) {
+  if (!c || !sol) return fail(c, GFB_ERR_INVALID, "gfb_dealias: null argument");
+  const Spec s = user_spec(c, sol);
+  GFB_LAUNCH(k_dealias, dim3(592), dim3(256), 0, (cudaStream_t)stream, c->g, s.p, s.ld, s.ls, c->nlayers);
+  return check_launch(c, 0, "k_dealias");
+}
+
+int gfb_calcN(gfb_ctx* c, void* N, void* sol, const void* Fh, void* stream) {
+  if (!c || !N || !sol) return fail(c, GFB_ERR_INVALID, "gfb_calcN: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = gfb_dealias(c, sol, stream);
+  if (rc) return rc;
+  EpiArgs e = base_epi(c, Fh);
+  e.kind = EPI_STORE;
+  e.out = user_spec(c, N);
+  return run_stage_kernels(c, user_spec(c, sol), e, st);
+}
+
+int gfb_nstages(const gfb_ctx* c) {
+  if (!c) return GFB_ERR_INVALID;
+  switch (c->stepper) {
+    case GFB_RK4: case GFB_FILTERED_RK4: case GFB_ETDRK4: case GFB_FILTERED_ETDRK4: return 4;
+    default: return 1;
+  }
+}
+
+int gfb_stage(gfb_ctx* c, void* sol, int istage, const void* Fh, void* prevsol, void* stream) {
+  if (!c || !sol) return fail(c, GFB_ERR_INVALID, "gfb_stage: null argument");
+  const int ns = gfb_nstages(c);
+  if (istage < 0 || istage >= ns) return fail(c, GFB_ERR_INVALID, "gfb_stage: stage %d out of range", istage);
+  cudaStream_t st = (cudaStream_t)stream;
+  EpiArgs e = base_epi(c, Fh);
+  const Spec S0 = user_spec(c, sol);
+  const double dt = c->dt;
+  if (c->filtered) {
+    e.filter.p = c->filter;
+    e.filter.ld = c->ldi;
+    e.filter.ls = 0;
+  }
+  Spec sin = S0;
+  e.sol = S0;
+  int rc = 0;
+  switch (c->stepper) {
+    case GFB_FORWARD_EULER: case GFB_FILTERED_FORWARD_EULER:
+      e.kind = EPI_RK_ONLY;
+      e.b = dt;
+      e.out = S0;
+      e.prevsol = prevsol ? user_spec(c, prevsol) : null_spec();
+      break;
+    case GFB_RK4: case GFB_FILTERED_RK4: {
+      const Spec s1 = int_spec(c, c->st[0]), s2 = int_spec(c, c->st[1]), acc = int_spec(c, c->st[2]);
+      e.acc = acc;
+      if (istage == 0) {
+        e.kind = EPI_RK_FIRST; e.a = dt / 2; e.b = dt / 6; sin = S0; e.out = s1;
+        e.prevsol = prevsol ? user_spec(c, prevsol) : null_spec();
+      } else if (istage == 1) {
+        e.kind = EPI_RK_MID; e.a = dt / 2; e.b = dt / 3; sin = s1; e.out = s2;
+      } else if (istage == 2) {
+        e.kind = EPI_RK_MID; e.a = dt; e.b = dt / 3; sin = s2; e.out = s1;
+      } else {
+        e.kind = EPI_RK_LAST; e.b = dt / 6; sin = s1; e.out = S0;
+      }
+    } break;
+    case GFB_ETDRK4: case GFB_FILTERED_ETDRK4: {
+      const Spec s1 = int_spec(c, c->st[0]), s2 = int_spec(c, c->st[1]), acc = int_spec(c, c->st[2]), n1 = int_spec(c, c->st[3]);
+      // third stage state lives in the unused 4th field block of W (only updatevars! uses it)
+      Spec s3;
+      s3.p = c->W + (long long)3 * c->nlayers * c->wfs;
+      s3.ld = c->ldw;
+      s3.ls = c->wfs;
+      e.acc = acc;
+      e.n1 = n1;
+      e.c1 = coef(c, c->Eh);
+      e.c2 = coef(c, c->zeta);
+      if (istage == 0) {
+        e.kind = EPI_ETD_1; sin = S0; e.out = s1; e.c3 = coef(c, c->E); e.c4 = coef(c, c->alpha);
+        e.prevsol = prevsol ? user_spec(c, prevsol) : null_spec();
+      } else if (istage == 1) {
+        e.kind = EPI_ETD_2; sin = s1; e.out = s2; e.c4 = coef(c, c->beta);
+      } else if (istage == 2) {
+        e.kind = EPI_ETD_3; sin = s2; e.sol = s1; e.out = s3; e.c4 = coef(c, c->beta);
+      } else {
+        e.kind = EPI_ETD_4; sin = s3; e.out = S0; e.c4 = coef(c, c->Gamma);
+      }
+    } break;
+    default: {  // AB3
+      const long long k = c->step;
+      cplx* cur = c->st[k % 3];
+      cplx* m1 = c->st[(k + 2) % 3];
+      cplx* m2 = c->st[(k + 1) % 3];
+      e.kind = EPI_AB3;
+      if (k < 3) { e.a = dt; e.b = 0; e.d = 0; }
+      else { e.a = dt * 23.0 / 12.0; e.b = -dt * 16.0 / 12.0; e.d = dt * 5.0 / 12.0; }
+      e.out = S0;
+      e.acc = int_spec(c, m1);
+      e.n1 = int_spec(c, m2);
+      e.prevsol = prevsol ? user_spec(c, prevsol) : null_spec();
+      // the epilogue stores rhs through e.sin, so run the kernels by hand
+      rc = run_col_inv_state(c, S0, 3, st);
+      if (rc) return rc;
+      rc = run_row_product(c, st);
+      if (rc) return rc;
+      e.sin = int_spec(c, cur);
+      rc = run_col_fwd(c, e, st);
+      if (rc) return rc;
+      c->t += c->dt;
+      c->step += 1;
+      return GFB_OK;
+    }
+  }
+  rc = run_stage_kernels(c, sin, e, st);
+  if (rc) return rc;
+  if (istage == ns - 1) {
+    c->t += c->dt;
+    c->step += 1;
+  }
+  return GFB_OK;
+}
+
+int gfb_step(gfb_ctx* c, void* sol, int nsteps, const void* Fh, void* prevsol, void* stream) {
+  if (!c || !sol || nsteps < 0) return fail(c, GFB_ERR_INVALID, "gfb_step: bad argument");
+  const int ns = gfb_nstages(c);
+  for (int s = 0; s < nsteps; ++s)
+    for (int i = 0; i < ns; ++i) {
+      int rc = gfb_stage(c, sol, i, Fh, (s == nsteps - 1) ? prevsol : nullptr, stream);
+      if (rc) return rc;
+    }
+  return GFB_OK;
+}
+
+int gfb_irfft(gfb_ctx* c, double* out_phys, const void* in_spec, int batch, void* stream) {
+  if (!c || !out_phys || !in_spec || batch < 1) return fail(c, GFB_ERR_INVALID, "gfb_irfft: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int maxb = 4 * c->nlayers;
+  for (int b0 = 0; b0 < batch; b0 += maxb) {
+    const int nb = (batch - b0 < maxb) ? batch - b0 : maxb;
+    ColInvLaunch L;
+    std::memset(&L, 0, sizeof L);
+    L.g = c->g;
+    L.prep = PREP_PLAIN;
+    L.pp.in = (const cplx*)in_spec + (long long)b0 * c->g.ny * c->g.nkr;
+    L.pp.ld = c->g.nkr;
+    L.pp.ls = (long long)c->g.ny * c->g.nkr;
+    L.pp.scale = c->g.invN;
+    L.W = c->W;
+    L.ldw = c->ldw;
+    L.wfs = c->wfs;
+    L.ncols = c->g.nkr;
+    L.nfields = nb;
+    L.tw = c->tw_y;
+    L.st = st;
+    L.nl = 1;
+    int rc = check_launch(c, launch_col_inv(c->g.ny, L), "k_col_inv(plain)");
+    if (rc) return rc;
+    RowLaunch R;
+    std::memset(&R, 0, sizeof R);
+    R.mode = ROW_C2R;
+    R.a.W = c->W;
+    R.a.ldw = c->ldw;
+    R.a.wfs = c->wfs;
+    R.a.kc = c->g.nkr;
+    R.a.phys = out_phys + (long long)b0 * c->g.ny * c->g.nx;
+    R.a.ny = c->g.ny;
+    R.nlayers = nb;
+    R.tw = c->tw_x;
+    R.st = st;
+    rc = check_launch(c, launch_row(c->g.nx, R), "k_row(c2r)");
+    if (rc) return rc;
+  }
+  return GFB_OK;
+}
+
+int gfb_rfft(gfb_ctx* c, void* out_spec, const double* in_phys, int batch, void* stream) {
+  if (!c || !out_spec || !in_phys || batch < 1) return fail(c, GFB_ERR_INVALID, "gfb_rfft: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int maxb = 2 * c->nlayers;
+  for (int b0 = 0; b0 < batch; b0 += maxb) {
+    const int nb = (batch - b0 < maxb) ? batch - b0 : maxb;
+    RowLaunch R;
+    std::memset(&R, 0, sizeof R);
+    R.mode = ROW_R2C;
+    R.a.P = c->P;
+    R.a.ldp = c->ldp;
+    R.a.pfs = c->pfs;
+    R.a.kout = c->g.nkr;
+    R.a.phys = const_cast<double*>(in_phys) + (long long)b0 * c->g.ny * c->g.nx;
+    R.a.ny = c->g.ny;
+    R.nlayers = nb;
+    R.tw = c->tw_x;
+    R.st = st;
+    int rc = check_launch(c, launch_row(c->g.nx, R), "k_row(r2c)");
+    if (rc) return rc;
+    ColFwdLaunch F;
+    std::memset(&F, 0, sizeof F);
+    F.g = c->g;
+    F.P = c->P;
+    F.ldp = c->ldp;
+    F.pfs = c->pfs;
+    F.e.kind = EPI_PLAIN;
+    F.e.out.p = (cplx*)out_spec + (long long)b0 * c->g.ny * c->g.nkr;
+    F.e.out.ld = c->g.nkr;
+    F.e.out.ls = (long long)c->g.ny * c->g.nkr;
+    F.ncols = c->g.nkr;
+    F.nlayers = nb;
+    F.nl = 1;
+    F.two = false;
+    F.tw = c->tw_y;
+    F.st = st;
+    rc = check_launch(c, launch_col_fwd(c->g.ny, F), "k_col_fwd(plain)");
+    if (rc) return rc;
+  }
+  return GFB_OK;
+}
+
+int gfb_updatevars(gfb_ctx* c, void* sol, double* q, double* psi, double* u, double* v, void* stream) {
+  if (!c || !sol) return fail(c, GFB_ERR_INVALID, "gfb_updatevars: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = gfb_dealias(c, sol, stream);
+  if (rc) return rc;
+  const int nf = 4;
+  rc = run_col_inv_state(c, user_spec(c, sol), nf, st);
+  if (rc) return rc;
+  double* outs[4] = {u, v, q, psi};
+  for (int f = 0; f < 4; ++f) {
+    if (!outs[f]) continue;
+    RowLaunch R;
+    std::memset(&R, 0, sizeof R);
+    R.mode = ROW_C2R;
+    R.a.W = c->W + (long long)f * c->wfs;
+    R.a.ldw = c->ldw;
+    R.a.wfs = (long long)nf * c->wfs;  // consecutive layers of the same field
+    R.a.kc = c->g.kcut;
+    R.a.phys = outs[f];
+    R.a.ny = c->g.ny;
+    R.nlayers = c->nlayers;
+    R.tw = c->tw_x;
+    R.st = st;
+    rc = check_launch(c, launch_row(c->g.nx, R), "k_row(c2r,updatevars)");
+    if (rc) return rc;
+  }
+  return GFB_OK;
+}
+
+int gfb_streamfunction_from_pv(gfb_ctx* c, void* psih, const void* qh, void* stream) {
+  if (!c || !psih || !qh) return fail(c, GFB_ERR_INVALID, "gfb_streamfunction_from_pv: null argument");
+  if (c->kind == GFB_KIND_SINGLE) {
+    GFB_LAUNCH(k_scale_by_table, dim3(592), dim3(256), 0, (cudaStream_t)stream, (long long)c->g.ny * c->g.nkr,
+               (cplx*)psih, (const cplx*)qh, (const double*)c->G, -1.0);
+    return check_launch(c, 0, "k_scale_by_table");
+  }
+  return matvec(c, psih, qh, c->Sinv, stream);
+}
+
+int gfb_pv_from_streamfunction(gfb_ctx* c, void* qh, const void* psih, void* stream) {
+  if (!c || !qh || !psih) return fail(c, GFB_ERR_INVALID, "gfb_pv_from_streamfunction: null argument");
+  if (c->kind == GFB_KIND_SINGLE || !c->S) return fail(c, GFB_ERR_UNSUPPORTED, "gfb_pv_from_streamfunction needs GFB_KIND_LAYERED with config.S");
+  return matvec(c, qh, psih, c->S, stream);
+}
+
+int gfb_diag(gfb_ctx* c, int kind, const void* sol, const void* aux, const void* aux2, double p,
+             double* out_host, int nout, void* stream) {
+  if (!c || !sol || !out_host || nout < 1 || nout > DIAG_MAXOUT) return fail(c, GFB_ERR_INVALID, "gfb_diag: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  DiagArgs d;
+  std::memset(&d, 0, sizeof d);
+  d.kind = kind;
+  d.s = (const cplx*)sol;
+  d.aux = (const cplx*)aux;
+  d.aux2 = (const cplx*)aux2;
+  d.G = c->G;
+  d.Sinv = c->Sinv;
+  d.p = p;
+  d.scale = 1.0;
+  int need = 1;
+  if (kind == GFB_DIAG_LAYERED_ENERGIES) {
+    if (c->kind != GFB_KIND_LAYERED) return fail(c, GFB_ERR_INVALID, "gfb_diag: layered energies need GFB_KIND_LAYERED");
+    need = 2 * c->nlayers - 1;
+  } else if (c->nlayers != 1 && kind != GFB_DIAG_ABS2) {
+    // single-array kinds act on one layer: the caller passes a pointer to that layer
+  }
+  if ((kind == GFB_DIAG_G_ABS2 || kind == GFB_DIAG_G2_ABS2 || kind == GFB_DIAG_KG2_ABS2) && !c->G)
+    return fail(c, GFB_ERR_INVALID, "gfb_diag: kind %d needs the G table (GFB_KIND_SINGLE)", kind);
+  if ((kind == GFB_DIAG_ABS2_PLUS || kind == GFB_DIAG_WORK || kind == GFB_DIAG_WORK_INVK) && !aux)
+    return fail(c, GFB_ERR_INVALID, "gfb_diag: kind %d needs aux", kind);
+  if (kind < 0 || kind > GFB_DIAG_LAYERED_ENERGIES) return fail(c, GFB_ERR_INVALID, "gfb_diag: unknown kind %d", kind);
+  if (nout < need) return fail(c, GFB_ERR_INVALID, "gfb_diag: nout=%d < %d", nout, need);
+  if (kind == GFB_DIAG_LAYERED_ENERGIES) {
+    switch (c->nlayers) {
+      case 1: launch_diag<1>(c, d, st); break;
+      case 2: launch_diag<2>(c, d, st); break;
+      case 3: launch_diag<3>(c, d, st); break;
+      case 4: launch_diag<4>(c, d, st); break;
+      case 5: launch_diag<5>(c, d, st); break;
+    }
+  } else {
+    launch_diag<1>(c, d, st);
+  }
+  int rc = check_launch(c, 0, "k_diag_partial");
+  if (rc) return rc;
+  GFB_LAUNCH(k_diag_final, dim3(1), dim3(256), 0, st, (const double*)c->dpart, c->dblocks, need, c->dout);
+  rc = check_launch(c, 0, "k_diag_final");
+  if (rc) return rc;
+  GFB_CUDA(c, cudaMemcpyAsync(out_host, c->dout, need * sizeof(double), cudaMemcpyDeviceToHost, st));
+  GFB_CUDA(c, cudaStreamSynchronize(st));
+  return GFB_OK;
+}
+
+}  // extern "C"

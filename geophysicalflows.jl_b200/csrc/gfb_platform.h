@@ -1,0 +1,34 @@
+// gfb_platform.h -- the one place that knows whether we are compiled by nvcc (product) or by g++
+// through the test-only emulation layer (tests/emu/cuda_emu.h, -DGFB_EMULATE).
+#pragma once
+
+#ifdef GFB_EMULATE
+#include "cuda_emu.h"  // found via -I tests/emu (test builds only)
+#define GFB_HD
+#else
+#include <cuda_runtime.h>
+#define GFB_HD __host__ __device__
+#define GFB_DYN_SMEM(type, name)                           \
+  extern __shared__ __align__(16) unsigned char gfb_smem_raw[]; \
+  type* name = reinterpret_cast<type*>(gfb_smem_raw)
+#define GFB_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+
+#include <cstdint>
+
+namespace gfb {
+
+typedef double2 cplx;
+
+__device__ __forceinline__ cplx cmake(double x, double y) { return make_double2(x, y); }
+__device__ __forceinline__ cplx cadd(cplx a, cplx b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ cplx csub(cplx a, cplx b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ cplx cmul(cplx a, cplx b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ cplx cscale(cplx a, double s) { return make_double2(a.x * s, a.y * s); }
+__device__ __forceinline__ cplx cconj(cplx a) { return make_double2(a.x, -a.y); }
+__device__ __forceinline__ cplx cmul_i(cplx a) { return make_double2(-a.y, a.x); }    //  i * a
+__device__ __forceinline__ cplx cmul_mi(cplx a) { return make_double2(a.y, -a.x); }   // -i * a
+__device__ __forceinline__ cplx cfma(cplx a, cplx b, cplx c) { return cadd(cmul(a, b), c); }
+__device__ __forceinline__ double cabs2(cplx a) { return a.x * a.x + a.y * a.y; }
+
+}  // namespace gfb

@@ -1,0 +1,834 @@
+// kernels.cuh -- the three fused passes of one calcN! + stage update, and the plain 2-D transforms.
+//
+//   K1  k_col_inv   : spectral pre-pass (dealias mask on load, psi inversion / S^-1 matvec, i*k
+//                     derivatives, 1/(nx*ny)) fused with the inverse FFT along y (columns)
+//   K2  k_row       : Hermitian c2r along x of (u, v) and q, physical products, r2c along x --
+//                     physical fields never touch HBM
+//   K3  k_col_fwd   : forward FFT along y of the two product fields fused with the divergence
+//                     (-i kr, -i l), forcing and the time-stepper stage update
+//
+// Reference sequence being replaced: calcN_advection! /root/reference/src/twodnavierstokes.jl:253-275,
+// src/surfaceqg.jl:257-278, src/singlelayerqg.jl:356-432, src/multilayerqg.jl:695-731; dealias!
+// (FourierFlows) called at src/twodnavierstokes.jl:287; stage updates of FourierFlows' RK4/ETDRK4/...
+// steppers.
+//
+// Layouts: spectral `cplx a[layer][l][kr]` (kr contiguous), physical
+// `double a[layer][y][x]`.  Work arrays between the passes: W[field][y][kr] (ld = ldw) and
+// P[field][y][kr] (ld = ldp), ctx-owned.
+#pragma once
+#include "fft_core.cuh"
+
+namespace gfb {
+
+struct GridDesc {
+  int nx, ny, nkr;
+  int kcut;        // dealias!: kr columns [kcut, nkr) are zeroed
+  int la0, la1;    // dealias!: l rows [la0, la1) are zeroed
+  double dkx, dky; // kr = m*dkx ; l = (n < ny/2 ? n : n - ny)*dky   (FourierFlows TwoDGrid)
+  double invN;     // 1/(nx*ny): ldiv!(., rfftplan, .) normalisation
+};
+
+__device__ __forceinline__ double wav_l(const GridDesc& g, int n) { return (n < g.ny / 2 ? n : n - g.ny) * g.dky; }
+__device__ __forceinline__ double wav_kr(const GridDesc& g, int m) { return m * g.dkx; }
+__device__ __forceinline__ bool l_aliased(const GridDesc& g, int n) { return n >= g.la0 && n < g.la1; }
+
+// a spectral array view: element (layer, l, kr) = p[layer*ls + l*ld + kr]
+struct Spec {
+  cplx* p;
+  int ld;
+  long long ls;
+  __device__ __forceinline__ cplx& at(int layer, int l, int kr) const { return p[layer * ls + (long long)l * ld + kr]; }
+};
+struct SpecR {  // real-valued table with the same indexing
+  const double* p;
+  int ld;
+  long long ls;
+  __device__ __forceinline__ double at(int layer, int l, int kr) const { return p[layer * ls + (long long)l * ld + kr]; }
+};
+
+// threads per CTA for a column kernel of length NY and columns per CTA
+template <int NY>
+struct ColCfg {
+  static constexpr int T = NY / PT;
+  static constexpr int THREADS = (T >= 256) ? 512 : 256;
+  static constexpr int C = THREADS / T;  // adjacent kr columns per CTA (2 at 4096)
+  // group stride of the exchange buffers (in elements) so that the C interleaved lanes of a
+  // quarter-warp land in different banks
+  static constexpr int want = (C >= 8) ? 1 : (C == 1 ? 0 : 8 / C);
+  static constexpr int GS = xbuf_elems(NY) + ((want - xbuf_elems(NY) % 8) + 8) % 8;
+};
+
+// ------------------------------------------------------------------------------------------------
+// K1 pre-pass functors: value of `field` at (l, col) ready for the inverse y-FFT
+// ------------------------------------------------------------------------------------------------
+struct PrepPlain {  // irfft of arbitrary spectra: field = batch index
+  const cplx* in;
+  int ld;
+  long long ls;
+  double scale;
+  __device__ __forceinline__ cplx load(const GridDesc&, int field, int l, int col) const {
+    return cscale(in[field * ls + (long long)l * ld + col], scale);
+  }
+};
+
+struct PrepSingle {  // single-layer modules: psi_h = -G*sol ; uh = i l G sol ; vh = -i kr G sol ; qh = sol
+  const cplx* sol;
+  int ld;
+  SpecR G;
+  __device__ __forceinline__ cplx load(const GridDesc& g, int field, int l, int col) const {
+    if (l_aliased(g, l)) return cmake(0.0, 0.0);
+    cplx s = cscale(sol[(long long)l * ld + col], g.invN);
+    if (field == 2) return s;
+    const double gg = G.at(0, l, col);
+    if (field == 0) return cscale(cmul_i(s), wav_l(g, l) * gg);
+    if (field == 1) return cscale(cmul_mi(s), wav_kr(g, col) * gg);
+    return cscale(s, -gg);  // field 3: psi_h (updatevars! only)
+  }
+};
+
+template <int NL>
+struct PrepMulti {  // MultiLayerQG: psi_h = S^-1 q_h ; uh = -i l psi_h ; vh = i kr psi_h ; field = 3*layer + {u,v,q}
+  const cplx* sol;
+  int ld;
+  long long ls;
+  const double* Sinv;  // [l][kr][row][col] row-major NLxNL, ld = nkr
+  int ldS;
+  int nf;              // fields per layer: 3 (u, v, q) on the hot path, 4 (+psi) for updatevars!
+  __device__ __forceinline__ cplx load(const GridDesc& g, int field, int l, int col) const {
+    if (l_aliased(g, l)) return cmake(0.0, 0.0);
+    const int layer = field / nf, what = field - nf * layer;
+    if (what == 2) return cscale(sol[layer * ls + (long long)l * ld + col], g.invN);
+    const double* M = Sinv + ((long long)l * ldS + col) * (NL * NL) + layer * NL;
+    cplx psi = cmake(0.0, 0.0);
+#pragma unroll
+    for (int m = 0; m < NL; ++m) {
+      const cplx q = sol[m * ls + (long long)l * ld + col];
+      const double a = __ldg(&M[m]);
+      psi.x += a * q.x;
+      psi.y += a * q.y;
+    }
+    psi = cscale(psi, g.invN);
+    if (what == 0) return cscale(cmul_mi(psi), wav_l(g, l));
+    if (what == 1) return cscale(cmul_i(psi), wav_kr(g, col));
+    return psi;
+  }
+};
+
+template <int NY, class Prep>
+__global__ void __launch_bounds__(ColCfg<NY>::THREADS, ColCfg<NY>::THREADS == 512 ? 1 : 2)
+    k_col_inv(const GridDesc g, const Prep prep, cplx* __restrict__ W, const int ldw, const long long wfs,
+              const int ncols, const cplx* __restrict__ tw) {
+  using CC = ColCfg<NY>;
+  constexpr int T = CC::T, C = CC::C;
+  GFB_DYN_SMEM(cplx, sm);
+  const int c = threadIdx.x % C, j = threadIdx.x / C;
+  const int col = blockIdx.x * C + c;
+  const int field = blockIdx.y;
+  const bool live = col < ncols;
+  cplx* xb = sm + c * CC::GS;
+  cplx v[PT];
+#pragma unroll
+  for (int r = 0; r < PT; ++r) v[r] = live ? prep.load(g, field, j + r * T, col) : cmake(0.0, 0.0);
+  block_fft<NY, INV>(v, j, xb, tw);
+  if (live) {
+    cplx* out = W + field * wfs + col;
+#pragma unroll
+    for (int r = 0; r < PT; ++r) out[(long long)(j + r * T) * ldw] = v[r];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 row pass
+// ------------------------------------------------------------------------------------------------
+template <int NX>
+struct RowCfg {
+  static constexpr int T = NX / PT;
+  static constexpr int THREADS = (T >= 256) ? T : 256;  // 8192 -> 512 threads
+  static constexpr int G = THREADS / T;                 // row pairs per CTA
+  static constexpr int GS = xbuf_elems(NX) + ((T < 8 ? 4 : 0) + 8 - xbuf_elems(NX) % 8) % 8;
+};
+
+// Z[k] = A[k] + i B[k] with Hermitian extension, A/B half-spectra rows known for k < kc (else 0).
+// c2r semantics of FFTW/cuFFT/pocketfft: imaginary parts of the k = 0 and k = N/2 entries are ignored.
+template <int N>
+__device__ __forceinline__ void load_hermitian(cplx (&v)[PT], const int j, const cplx* __restrict__ A,
+                                               const cplx* __restrict__ B, const int kc) {
+  constexpr int T = N / PT;
+#pragma unroll
+  for (int r = 0; r < PT; ++r) {
+    const int k = j + r * T;
+    const int kk = (k <= N / 2) ? k : N - k;
+    cplx a = cmake(0.0, 0.0), b = cmake(0.0, 0.0);
+    if (kk < kc) {
+      a = A[kk];
+      b = B[kk];
+    }
+    if (k == 0 || k == N / 2) {
+      v[r] = cmake(a.x, b.x);
+    } else if (k < N / 2) {
+      v[r] = cmake(a.x - b.y, a.y + b.x);
+    } else {
+      v[r] = cmake(a.x + b.y, b.x - a.y);
+    }
+  }
+}
+
+// After a forward FFT of z = a + i b (a, b real rows): thread holds Z[k], k = j + r*T.  Exchanges
+// through shared memory to fetch Z[N-k] and returns A[k], B[k] for r = 0..8 (r = 8 only valid
+// for j == 0, k = N/2).
+template <int N>
+__device__ __forceinline__ void unpack_pair(const cplx (&v)[PT], const int j, cplx* __restrict__ xb,
+                                            cplx (&A)[9], cplx (&B)[9]) {
+  constexpr int T = N / PT;
+#pragma unroll
+  for (int r = 0; r < PT; ++r) xb[xpad(j + r * T)] = v[r];
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 9; ++r) {
+    const int k = j + r * T;
+    const int m = (N - k) & (N - 1);
+    cplx o = v[r];
+    cplx w = (r < 8 || j == 0) ? xb[xpad(m)] : o;
+    A[r] = cmake(0.5 * (o.x + w.x), 0.5 * (o.y - w.y));
+    B[r] = cmake(0.5 * (o.y + w.y), -0.5 * (o.x - w.x));
+  }
+  __syncthreads();
+}
+
+enum RowMode { ROW_PRODUCT = 0, ROW_C2R = 1, ROW_R2C = 2, ROW_PRODUCT_Q = 3 };
+
+struct RowArgs {
+  // inputs: per-field arrays [.][y][kr] with ld = ldw and field stride wfs; field = 3*layer + {u,v,q}
+  const cplx* W;
+  int ldw;
+  long long wfs;
+  int kc;  // live input columns (kcut, or nkr for plain transforms)
+  // outputs of the forward part: field = 2*layer + {d, v}
+  cplx* P;
+  int ldp;
+  long long pfs;
+  int kout;  // columns to write (nkr)
+  // physical-space operands
+  const double* eta;  // [y][x] or null              (SingleLayerQG: q + eta)
+  const double* U;    // [layer][y] or null          (imposed zonal flow added to u)
+  const double* Qx;   // [layer][y][x] or null
+  const double* Qy;   // [layer][y][x] or null
+  double* phys;       // ROW_C2R output / ROW_R2C input, [batch][y][x]
+  double dkx;
+  int ny;
+};
+
+template <int NX, int MODE>
+__global__ void __launch_bounds__(RowCfg<NX>::THREADS, RowCfg<NX>::THREADS == 256 ? 2 : 1)
+    k_row(const RowArgs a, const cplx* __restrict__ tw) {
+  using RC = RowCfg<NX>;
+  constexpr int T = RC::T, THREADS = RC::THREADS;
+  GFB_DYN_SMEM(cplx, sm);
+  const int gi = threadIdx.x / T, j = threadIdx.x % T;
+  const int unit = blockIdx.x * RC::G + gi;  // row pair
+  const int layer = blockIdx.y;
+  const int ya = 2 * unit, yb = ya + 1;
+  const bool live = yb < a.ny;
+  cplx* xb = sm + gi * RC::GS;
+  cplx* stash = sm + RC::G * RC::GS;  // thread-private: stash[r*THREADS + tid]
+  const int tid = threadIdx.x;
+  cplx v[PT];
+  cplx A[9], B[9];
+
+  if (MODE == ROW_C2R) {
+    const cplx* Wa = a.W + layer * a.wfs + (long long)ya * a.ldw;
+    const cplx* Wb = Wa + a.ldw;
+    if (live) load_hermitian<NX>(v, j, Wa, Wb, a.kc);
+    else {
+#pragma unroll
+      for (int r = 0; r < PT; ++r) v[r] = cmake(0.0, 0.0);
+    }
+    block_fft<NX, INV>(v, j, xb, tw);
+    if (live) {
+      double* oa = a.phys + ((long long)layer * a.ny + ya) * NX;
+      double* ob = oa + NX;
+#pragma unroll
+      for (int r = 0; r < PT; ++r) {
+        oa[j + r * T] = v[r].x;
+        ob[j + r * T] = v[r].y;
+      }
+    }
+    return;
+  }
+  if (MODE == ROW_R2C) {
+    if (live) {
+      const double* ia = a.phys + ((long long)layer * a.ny + ya) * NX;
+      const double* ib = ia + NX;
+#pragma unroll
+      for (int r = 0; r < PT; ++r) v[r] = cmake(ia[j + r * T], ib[j + r * T]);
+    } else {
+#pragma unroll
+      for (int r = 0; r < PT; ++r) v[r] = cmake(0.0, 0.0);
+    }
+    block_fft<NX, FWD>(v, j, xb, tw);
+    unpack_pair<NX>(v, j, xb, A, B);
+    if (live) {
+      cplx* pa = a.P + layer * a.pfs + (long long)ya * a.ldp;
+      cplx* pb = pa + a.ldp;
+#pragma unroll
+      for (int r = 0; r < 9; ++r) {
+        const int k = j + r * T;
+        if ((r < 8 || j == 0) && k < a.kout) {
+          pa[k] = A[r];
+          pb[k] = B[r];
+        }
+      }
+    }
+    return;
+  }
+
+  // ---- ROW_PRODUCT (+_Q: extra (u+U)*Qx + v*Qy term, MultiLayerQG / SingleLayerQG with U(y)) ----
+  const bool withQ = (MODE == ROW_PRODUCT_Q);
+  const cplx* Wu = a.W + (3 * layer + 0) * a.wfs;
+  const cplx* Wv = a.W + (3 * layer + 1) * a.wfs;
+  const cplx* Wq = a.W + (3 * layer + 2) * a.wfs;
+  // 1. q of both rows: one complex transform gives q_a + i q_b
+  if (live) load_hermitian<NX>(v, j, Wq + (long long)ya * a.ldw, Wq + (long long)yb * a.ldw, a.kc);
+  else {
+#pragma unroll
+    for (int r = 0; r < PT; ++r) v[r] = cmake(0.0, 0.0);
+  }
+  block_fft<NX, INV>(v, j, xb, tw);
+  if (a.eta != nullptr && live) {
+    const double* ea = a.eta + (long long)ya * NX;
+    const double* eb = ea + NX;
+#pragma unroll
+    for (int r = 0; r < PT; ++r) {
+      v[r].x += ea[j + r * T];
+      v[r].y += eb[j + r * T];
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < PT; ++r) stash[r * THREADS + tid] = v[r];
+  cplx* gst = stash + PT * THREADS;  // second thread-private stash (ROW_PRODUCT_Q only)
+
+  // 2. per row: (u + i v) -> times q -> forward -> split into uq_h, vq_h
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {
+    const int y = ya + h;
+    if (live) load_hermitian<NX>(v, j, Wu + (long long)y * a.ldw, Wv + (long long)y * a.ldw, a.kc);
+    else {
+#pragma unroll
+      for (int r = 0; r < PT; ++r) v[r] = cmake(0.0, 0.0);
+    }
+    block_fft<NX, INV>(v, j, xb, tw);
+    if (withQ && live) {
+      const double Uy = a.U ? a.U[(long long)layer * a.ny + y] : 0.0;
+      const double* qx = a.Qx + ((long long)layer * a.ny + y) * NX;
+      const double* qy = a.Qy + ((long long)layer * a.ny + y) * NX;
+#pragma unroll
+      for (int r = 0; r < PT; ++r) {
+        v[r].x += Uy;
+        const double gq = v[r].x * qx[j + r * T] + v[r].y * qy[j + r * T];
+        cplx& gs = gst[r * THREADS + tid];
+        if (h == 0) gs.x = gq; else gs.y = gq;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < PT; ++r) {
+      const cplx q2 = stash[r * THREADS + tid];
+      const double q = (h == 0) ? q2.x : q2.y;
+      v[r].x *= q;
+      v[r].y *= q;
+    }
+    block_fft<NX, FWD>(v, j, xb, tw);
+    unpack_pair<NX>(v, j, xb, A, B);  // A = (uq)_h, B = (vq)_h
+    if (live) {
+      cplx* pd = a.P + (2 * layer + 0) * a.pfs + (long long)y * a.ldp;
+      cplx* pv = a.P + (2 * layer + 1) * a.pfs + (long long)y * a.ldp;
+#pragma unroll
+      for (int r = 0; r < 9; ++r) {
+        const int k = j + r * T;
+        if ((r < 8 || j == 0) && k < a.kout) {
+          const double kr = k * a.dkx;
+          pd[k] = cmake(kr * A[r].y, -kr * A[r].x);  // -i kr (uq)_h
+          pv[k] = B[r];
+        }
+      }
+    }
+  }
+  // 3. the Q-gradient term of both rows with one more transform: d -= ((u+U) Qx + v Qy)_h
+  if (withQ) {
+#pragma unroll
+    for (int r = 0; r < PT; ++r) v[r] = live ? gst[r * THREADS + tid] : cmake(0.0, 0.0);
+    block_fft<NX, FWD>(v, j, xb, tw);
+    unpack_pair<NX>(v, j, xb, A, B);
+    if (live) {
+      cplx* pa = a.P + (2 * layer + 0) * a.pfs + (long long)ya * a.ldp;
+      cplx* pb = pa + a.ldp;
+#pragma unroll
+      for (int r = 0; r < 9; ++r) {
+        const int k = j + r * T;
+        if ((r < 8 || j == 0) && k < a.kout) {
+          pa[k] = csub(pa[k], A[r]);  // same thread wrote pa[k] in step 2
+          pb[k] = csub(pb[k], B[r]);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3 epilogues: what happens to N(l, kr) = FFTy(d) - i l FFTy(v)
+// ------------------------------------------------------------------------------------------------
+enum EpiKind {
+  EPI_STORE = 0,   // N (+F +Nconst + drag) -> out                (calcN! seam)
+  EPI_RK_FIRST,    // RK4 stage 1 / first stage of any explicit RK
+  EPI_RK_MID,
+  EPI_RK_LAST,
+  EPI_RK_ONLY,     // ForwardEuler
+  EPI_ETD_1,
+  EPI_ETD_2,
+  EPI_ETD_3,
+  EPI_ETD_4,
+  EPI_AB3,
+  EPI_PLAIN        // plain forward transform: single field, store
+};
+
+struct Coef {  // real or complex coefficient table [layer][l][kr]
+  const double* r;
+  const cplx* c;
+  int ld;
+  long long ls;
+  __device__ __forceinline__ cplx mul(int layer, int l, int kr, cplx x) const {
+    const long long i = layer * ls + (long long)l * ld + kr;
+    if (c != nullptr) return cmul(c[i], x);
+    return cscale(x, r[i]);
+  }
+};
+
+struct EpiArgs {
+  int kind;
+  int nlayers;
+  Spec out;        // EPI_STORE / EPI_PLAIN: destination of N ; stage kinds: the state written this stage
+  Spec sol;        // s0 source (the problem state `sol`), masked on load
+  Spec sin;        // stage input (== sol for stage 1), masked on load
+  Spec acc;        // accumulator
+  Spec n1;         // saved N1 (ETDRK4) / RHS history (AB3: rhs, rhs-1, rhs-2 via out/acc/n1)
+  Spec F;          // forcing or null
+  Spec Nconst;     // constant addition to N or null (SingleLayerQG: -i kr U eta_h)
+  Spec prevsol;    // if non-null at a first stage: receives the dealiased state
+  Coef L;          // linear operator
+  Coef c1, c2, c3, c4;  // ETD: exp(L dt/2), zeta, exp(L dt) / alpha, 2*beta or Gamma  (see gfb.cu)
+  SpecR filter;    // null p -> no filter (layer stride 0: shared by layers)
+  double a, b, d;  // RK: a = c_i*dt (sub-step), b = weight*dt ; AB3: a, b, d = dt*(23/12, -16/12, 5/12)
+  // MultiLayerQG bottom drag: N[nlayers-1] += mu * Krsq * psi_h[nlayers-1], psi = S^-1 q recomputed
+  double mu;
+  const double* Sinv;
+  int ldS;
+};
+
+template <int NL>
+__device__ __forceinline__ cplx masked(const GridDesc& g, const Spec& s, int layer, int l, int col) {
+  if (col >= g.kcut || l_aliased(g, l)) return cmake(0.0, 0.0);
+  return s.at(layer, l, col);
+}
+
+template <int NL>
+__device__ __forceinline__ void epilogue(const GridDesc& g, const EpiArgs& e, int layer, int l, int col, cplx N) {
+  if (e.kind == EPI_PLAIN) {
+    e.out.at(layer, l, col) = N;
+    return;
+  }
+  if (e.Nconst.p) N = cadd(N, e.Nconst.at(layer, l, col));
+  if (e.mu != 0.0 && layer == NL - 1) {
+    // bottom drag on the stage input (dealiased): psi_n = sum_m Sinv[n-1][m] q_m
+    cplx psi = cmake(0.0, 0.0);
+    const double* M = e.Sinv + ((long long)l * e.ldS + col) * (NL * NL) + (NL - 1) * NL;
+#pragma unroll
+    for (int m = 0; m < NL; ++m) {
+      const cplx q = masked<NL>(g, e.sin, m, l, col);
+      psi.x += M[m] * q.x;
+      psi.y += M[m] * q.y;
+    }
+    const double kr = wav_kr(g, col), ll = wav_l(g, l);
+    const double K2 = kr * kr + ll * ll;
+    N.x += e.mu * K2 * psi.x;
+    N.y += e.mu * K2 * psi.y;
+  }
+  if (e.F.p) N = cadd(N, e.F.at(layer, l, col));
+  const double filt = e.filter.p ? e.filter.at(0, l, col) : 1.0;
+  switch (e.kind) {
+    case EPI_STORE:
+      e.out.at(layer, l, col) = N;
+      break;
+    case EPI_RK_FIRST: {
+      const cplx s0 = masked<NL>(g, e.sol, layer, l, col);
+      const cplx rhs = cadd(N, e.L.mul(layer, l, col, s0));
+      e.out.at(layer, l, col) = cmake(s0.x + e.a * rhs.x, s0.y + e.a * rhs.y);
+      e.acc.at(layer, l, col) = cmake(s0.x + e.b * rhs.x, s0.y + e.b * rhs.y);
+      if (e.prevsol.p) e.prevsol.at(layer, l, col) = s0;
+    } break;
+    case EPI_RK_MID: {
+      const cplx s0 = masked<NL>(g, e.sol, layer, l, col);
+      const cplx si = masked<NL>(g, e.sin, layer, l, col);
+      const cplx rhs = cadd(N, e.L.mul(layer, l, col, si));
+      cplx ac = e.acc.at(layer, l, col);
+      e.out.at(layer, l, col) = cmake(s0.x + e.a * rhs.x, s0.y + e.a * rhs.y);
+      e.acc.at(layer, l, col) = cmake(ac.x + e.b * rhs.x, ac.y + e.b * rhs.y);
+    } break;
+    case EPI_RK_LAST: {
+      const cplx si = masked<NL>(g, e.sin, layer, l, col);
+      const cplx rhs = cadd(N, e.L.mul(layer, l, col, si));
+      const cplx ac = e.acc.at(layer, l, col);
+      e.out.at(layer, l, col) = cmake((ac.x + e.b * rhs.x) * filt, (ac.y + e.b * rhs.y) * filt);
+    } break;
+    case EPI_RK_ONLY: {
+      const cplx s0 = masked<NL>(g, e.sol, layer, l, col);
+      const cplx rhs = cadd(N, e.L.mul(layer, l, col, s0));
+      if (e.prevsol.p) e.prevsol.at(layer, l, col) = s0;
+      e.out.at(layer, l, col) = cmake((s0.x + e.b * rhs.x) * filt, (s0.y + e.b * rhs.y) * filt);
+    } break;
+    case EPI_ETD_1: {  // c1 = exp(L dt/2), c2 = zeta, c3 = exp(L dt), c4 = alpha
+      const cplx s0 = masked<NL>(g, e.sol, layer, l, col);
+      e.out.at(layer, l, col) = cadd(e.c1.mul(layer, l, col, s0), e.c2.mul(layer, l, col, N));
+      e.acc.at(layer, l, col) = cadd(e.c3.mul(layer, l, col, s0), e.c4.mul(layer, l, col, N));
+      e.n1.at(layer, l, col) = N;
+      if (e.prevsol.p) e.prevsol.at(layer, l, col) = s0;
+    } break;
+    case EPI_ETD_2: {  // c1 = exp(L dt/2), c2 = zeta, c4 = beta (2*beta applied here)
+      const cplx s0 = masked<NL>(g, e.sol, layer, l, col);
+      e.out.at(layer, l, col) = cadd(e.c1.mul(layer, l, col, s0), e.c2.mul(layer, l, col, N));
+      const cplx ac = e.acc.at(layer, l, col);
+      e.acc.at(layer, l, col) = cadd(ac, e.c4.mul(layer, l, col, cscale(N, 2.0)));
+    } break;
+    case EPI_ETD_3: {  // sin = sol2 (input of N3); sol here = sol1 (dealiased on load); out = sol2
+      const cplx s1 = masked<NL>(g, e.sol, layer, l, col);
+      const cplx n1 = e.n1.at(layer, l, col);
+      const cplx t = cmake(2.0 * N.x - n1.x, 2.0 * N.y - n1.y);
+      e.out.at(layer, l, col) = cadd(e.c1.mul(layer, l, col, s1), e.c2.mul(layer, l, col, t));
+      const cplx ac = e.acc.at(layer, l, col);
+      e.acc.at(layer, l, col) = cadd(ac, e.c4.mul(layer, l, col, cscale(N, 2.0)));
+    } break;
+    case EPI_ETD_4: {  // c4 = Gamma
+      const cplx ac = e.acc.at(layer, l, col);
+      const cplx r = cadd(ac, e.c4.mul(layer, l, col, N));
+      e.out.at(layer, l, col) = cscale(r, filt);
+    } break;
+    case EPI_AB3: {  // out = sol (in place); acc = rhs-1 ; n1 = rhs-2 ; sin = where rhs is stored
+      const cplx s0 = masked<NL>(g, e.sol, layer, l, col);
+      const cplx rhs = cadd(N, e.L.mul(layer, l, col, s0));
+      cplx upd = cscale(rhs, e.a);
+      if (e.b != 0.0 || e.d != 0.0) {
+        const cplx r1 = e.acc.at(layer, l, col), r2 = e.n1.at(layer, l, col);
+        upd.x += e.b * r1.x + e.d * r2.x;
+        upd.y += e.b * r1.y + e.d * r2.y;
+      }
+      if (e.prevsol.p) e.prevsol.at(layer, l, col) = s0;
+      e.sin.at(layer, l, col) = rhs;
+      e.out.at(layer, l, col) = cmake((s0.x + upd.x) * filt, (s0.y + upd.y) * filt);
+    } break;
+    default:
+      break;
+  }
+}
+
+// Split (re / im) exchange variant of the FFT for kernels that also need a large stash.
+template <int N, int DIR, int R, int Ns, bool LAST>
+__device__ __forceinline__ void fft_pass_split(cplx (&v)[PT], const int j, double* __restrict__ xb,
+                                               const cplx* __restrict__ tw) {
+  constexpr int T = N / PT;
+  constexpr int M = PT / R;
+  int base[M];
+#pragma unroll
+  for (int i = 0; i < M; ++i) {
+    const int b = j + i * T;
+    cplx x[R];
+#pragma unroll
+    for (int s = 0; s < R; ++s) x[s] = v[i + s * M];
+    if (Ns > 1) {
+      const int k = b & (Ns - 1);
+      cplx w1 = __ldg(&tw[k * (N / (Ns * R))]);
+      if (DIR == INV) w1.y = -w1.y;
+      cplx w[R];
+      w[1] = w1;
+#pragma unroll
+      for (int s = 2; s < R; ++s) {
+        if ((s & 1) == 0) {
+          const cplx h = w[s / 2];
+          w[s] = cmake(h.x * h.x - h.y * h.y, 2.0 * h.x * h.y);
+        } else {
+          w[s] = cmul(w[s - 1], w1);
+        }
+      }
+#pragma unroll
+      for (int s = 1; s < R; ++s) x[s] = cmul(x[s], w[s]);
+    }
+    Dft<DIR, R>::run(x);
+#pragma unroll
+    for (int s = 0; s < R; ++s) v[i + s * M] = x[s];
+    const int k = b & (Ns - 1);
+    base[i] = (b - k) * R + k;
+  }
+  if (!LAST) {
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+#pragma unroll
+      for (int s = 0; s < R; ++s) xb[xpad(base[i] + s * Ns)] = v[i + s * M].x;
+    __syncthreads();
+    double re[PT];
+#pragma unroll
+    for (int r = 0; r < PT; ++r) re[r] = xb[xpad(j + r * T)];
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+#pragma unroll
+      for (int s = 0; s < R; ++s) xb[xpad(base[i] + s * Ns)] = v[i + s * M].y;
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < PT; ++r) v[r] = cmake(re[r], xb[xpad(j + r * T)]);
+    __syncthreads();
+  }
+}
+
+template <int N, int DIR>
+__device__ __forceinline__ void block_fft_split(cplx (&v)[PT], const int j, double* __restrict__ xb,
+                                                const cplx* __restrict__ tw) {
+  using P = Plan<N>;
+  constexpr int rem = P::rem;
+  constexpr int RR = rem > 1 ? rem : 2;
+  if constexpr (P::n16 == 1) {
+    if constexpr (rem == 1) {
+      fft_pass_split<N, DIR, 16, 1, true>(v, j, xb, tw);
+    } else {
+      fft_pass_split<N, DIR, 16, 1, false>(v, j, xb, tw);
+      fft_pass_split<N, DIR, RR, 16, true>(v, j, xb, tw);
+    }
+  } else if constexpr (P::n16 == 2) {
+    fft_pass_split<N, DIR, 16, 1, false>(v, j, xb, tw);
+    if constexpr (rem == 1) {
+      fft_pass_split<N, DIR, 16, 16, true>(v, j, xb, tw);
+    } else {
+      fft_pass_split<N, DIR, 16, 16, false>(v, j, xb, tw);
+      fft_pass_split<N, DIR, RR, 256, true>(v, j, xb, tw);
+    }
+  } else {
+    fft_pass_split<N, DIR, 16, 1, false>(v, j, xb, tw);
+    fft_pass_split<N, DIR, 16, 16, false>(v, j, xb, tw);
+    if constexpr (rem == 1) {
+      fft_pass_split<N, DIR, 16, 256, true>(v, j, xb, tw);
+    } else {
+      fft_pass_split<N, DIR, 16, 256, false>(v, j, xb, tw);
+      fft_pass_split<N, DIR, RR, 4096, true>(v, j, xb, tw);
+    }
+  }
+}
+
+template <int NY>
+struct ColSplitCfg {
+  using CC = ColCfg<NY>;
+  // doubles; half-warp (16 lanes) of 8-byte accesses: C interleaved lanes -> offsets of 16/C doubles
+  static constexpr int want = (CC::C >= 16) ? 1 : (CC::C == 1 ? 0 : 16 / CC::C);
+  static constexpr int GS = xbuf_elems(NY) + ((want - xbuf_elems(NY) % 16) + 16) % 16;
+};
+
+// K3.  TWO = true: N = FFTy(Pd) - i l FFTy(Pv) ; TWO = false: plain forward transform of one field.
+template <int NY, int NL, bool TWO>
+__global__ void __launch_bounds__(ColCfg<NY>::THREADS, ColCfg<NY>::THREADS == 512 ? 1 : 2)
+    k_col_fwd(const GridDesc g, const cplx* __restrict__ P, const int ldp, const long long pfs,
+              const EpiArgs e, const int ncols, const cplx* __restrict__ tw) {
+  using CC = ColCfg<NY>;
+  constexpr int T = CC::T, C = CC::C, THREADS = CC::THREADS;
+  GFB_DYN_SMEM(double, smd);
+  const int tid = threadIdx.x;
+  const int c = tid % C, j = tid / C;
+  const int col = blockIdx.x * C + c;
+  const int layer = blockIdx.y;
+  const bool live = col < ncols;
+  double* xb = smd + c * ColSplitCfg<NY>::GS;
+  cplx* stash = reinterpret_cast<cplx*>(smd + ((C * ColSplitCfg<NY>::GS + 1) & ~1));
+  cplx v[PT];
+  if (TWO) {
+    const cplx* pv = P + (2 * layer + 1) * pfs + col;
+#pragma unroll
+    for (int r = 0; r < PT; ++r) v[r] = live ? pv[(long long)(j + r * T) * ldp] : cmake(0.0, 0.0);
+    block_fft_split<NY, FWD>(v, j, xb, tw);
+#pragma unroll
+    for (int r = 0; r < PT; ++r) {
+      const double ll = wav_l(g, j + r * T);
+      stash[r * THREADS + tid] = cmake(ll * v[r].y, -ll * v[r].x);  // -i l (vq)_h
+    }
+  }
+  const cplx* pd = P + (TWO ? 2 * layer : layer) * pfs + col;
+#pragma unroll
+  for (int r = 0; r < PT; ++r) v[r] = live ? pd[(long long)(j + r * T) * ldp] : cmake(0.0, 0.0);
+  block_fft_split<NY, FWD>(v, j, xb, tw);
+  if (live) {
+#pragma unroll
+    for (int r = 0; r < PT; ++r) {
+      cplx N = v[r];
+      if (TWO) N = cadd(N, stash[r * THREADS + tid]);
+      epilogue<NL>(g, e, layer, j + r * T, col, N);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// small elementwise kernels
+// ------------------------------------------------------------------------------------------------
+static __global__ void k_dealias(const GridDesc g, cplx* __restrict__ a, const int ld, const long long ls, const int nlayers) {
+  const long long n = (long long)g.ny * g.nkr;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n * nlayers; i += (long long)gridDim.x * blockDim.x) {
+    const int layer = (int)(i / n);
+    const long long rr = i - layer * n;
+    const int l = (int)(rr / g.nkr), k = (int)(rr - (long long)l * g.nkr);
+    if (k >= g.kcut || l_aliased(g, l)) a[layer * ls + (long long)l * ld + k] = cmake(0.0, 0.0);
+  }
+}
+
+// y[:, l, k] = M[l, k] (NL x NL, row-major) * x[:, l, k]   -- pv_streamfunction_kernel!,
+// /root/reference/src/multilayerqg.jl:495-509.  One thread per wavenumber, vectors and the matrix row
+// live in registers (register-blocked small matvec); consecutive threads = consecutive kr.
+template <int NL>
+__global__ void k_matvec(const int nl, const int nkr, cplx* __restrict__ y, const cplx* __restrict__ x,
+                         const double* __restrict__ M) {
+  const long long n = (long long)nl * nkr;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    cplx xv[NL];
+#pragma unroll
+    for (int m = 0; m < NL; ++m) xv[m] = x[m * n + i];
+    const double* Mi = M + i * (NL * NL);
+#pragma unroll
+    for (int r = 0; r < NL; ++r) {
+      cplx acc = cmake(0.0, 0.0);
+#pragma unroll
+      for (int m = 0; m < NL; ++m) {
+        const double a = __ldg(&Mi[r * NL + m]);
+        acc.x += a * xv[m].x;
+        acc.y += a * xv[m].y;
+      }
+      y[r * n + i] = acc;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// diagnostics: weighted Parseval sums (parsevalsum / parsevalsum2 of FourierFlows; call sites
+// /root/reference/src/twodnavierstokes.jl:374-393, src/surfaceqg.jl:390-416,
+// src/singlelayerqg.jl:548-599, src/multilayerqg.jl:918-951)
+// ------------------------------------------------------------------------------------------------
+enum DiagKind {
+  DIAG_ABS2 = 0,        // sum w |s|^2
+  DIAG_INVK_ABS2,       // sum w invKrsq |s|^2          ([0,0] -> 0)
+  DIAG_K_ABS2,          // sum w Krsq |s|^2
+  DIAG_KP_ABS2,         // sum w Krsq^p |s|^2 with [0,0] excluded
+  DIAG_G_ABS2,          // sum w G |s|^2
+  DIAG_G2_ABS2,         // sum w G^2 |s|^2              (|psi_h|^2)
+  DIAG_KG2_ABS2,        // sum w Krsq G^2 |s|^2         (|k|^2 |psi_h|^2)
+  DIAG_ABS2_PLUS,       // sum w |s + aux|^2            (enstrophy with eta_h)
+  DIAG_WORK,            // Re sum w s conj(F)           ; aux2 = prevsol -> (prevsol + s)/2
+  DIAG_WORK_INVK,       // Re sum w invKrsq s conj(F)
+  DIAG_MLQG_ENERGIES    // per layer: sum w Krsq |psi_j|^2 (NL values) then sum w |psi_j - psi_j+1|^2 (NL-1)
+};
+
+struct DiagArgs {
+  int kind;
+  const cplx* s;
+  const cplx* aux;   // eta_h or F
+  const cplx* aux2;  // prevsol
+  const double* G;   // [l][kr]
+  const double* Sinv;
+  double p;
+  double scale;      // multiplies every term (e.g. 0.5)
+};
+
+constexpr int DIAG_MAXOUT = 16;
+
+template <int NL>
+__global__ void __launch_bounds__(256) k_diag_partial(const GridDesc g, const DiagArgs d, double* __restrict__ partial) {
+  const long long n = (long long)g.ny * g.nkr;
+  constexpr int NOUT = (2 * NL - 1) > 1 ? (2 * NL - 1) : 1;
+  double acc[NOUT];
+#pragma unroll
+  for (int q = 0; q < NOUT; ++q) acc[q] = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int l = (int)(i / g.nkr), k = (int)(i - (long long)l * g.nkr);
+    const double w = (k == 0 || k == g.nkr - 1) ? 1.0 : 2.0;
+    const double kr = wav_kr(g, k), ll = wav_l(g, l);
+    const double K2 = kr * kr + ll * ll;
+    if (d.kind == DIAG_MLQG_ENERGIES) {
+      cplx psi[NL];
+      const double* Mi = d.Sinv + i * (NL * NL);
+#pragma unroll
+      for (int r = 0; r < NL; ++r) {
+        psi[r] = cmake(0.0, 0.0);
+#pragma unroll
+        for (int m = 0; m < NL; ++m) {
+          const cplx q = d.s[m * n + i];
+          psi[r].x += Mi[r * NL + m] * q.x;
+          psi[r].y += Mi[r * NL + m] * q.y;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < NL; ++r) acc[r] += w * K2 * cabs2(psi[r]);
+#pragma unroll
+      for (int r = 0; r + 1 < NL; ++r) acc[NL + r] += w * cabs2(csub(psi[r], psi[r + 1]));
+      continue;
+    }
+    const cplx s = d.s[i];
+    double t = 0.0;
+    switch (d.kind) {
+      case DIAG_ABS2: t = cabs2(s); break;
+      case DIAG_INVK_ABS2: t = (i == 0) ? 0.0 : cabs2(s) / K2; break;
+      case DIAG_K_ABS2: t = K2 * cabs2(s); break;
+      case DIAG_KP_ABS2: t = (i == 0) ? 0.0 : pow(K2, d.p) * cabs2(s); break;
+      case DIAG_G_ABS2: t = d.G[i] * cabs2(s); break;
+      case DIAG_G2_ABS2: t = d.G[i] * d.G[i] * cabs2(s); break;
+      case DIAG_KG2_ABS2: t = K2 * d.G[i] * d.G[i] * cabs2(s); break;
+      case DIAG_ABS2_PLUS: t = cabs2(cadd(s, d.aux[i])); break;
+      case DIAG_WORK:
+      case DIAG_WORK_INVK: {
+        cplx ss = s;
+        if (d.aux2) ss = cscale(cadd(ss, d.aux2[i]), 0.5);
+        const cplx f = d.aux[i];
+        t = ss.x * f.x + ss.y * f.y;  // Re(s conj f)
+        if (d.kind == DIAG_WORK_INVK) t = (i == 0) ? 0.0 : t / K2;
+      } break;
+      default: break;
+    }
+    acc[0] += w * t * d.scale;
+  }
+  // warp-shuffle tree, then one partial per warp through shared memory
+  __shared__ double red[8][DIAG_MAXOUT];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < NOUT; ++q) {
+    double x = acc[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    if (lane == 0) red[warp][q] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < NOUT) {
+    double x = 0.0;
+    for (int wv = 0; wv < 8; ++wv) x += red[wv][threadIdx.x];
+    partial[(long long)blockIdx.x * DIAG_MAXOUT + threadIdx.x] = x;
+  }
+}
+
+// deterministic second stage: one block sums the per-block partials in a fixed order
+static __global__ void __launch_bounds__(256) k_diag_final(const double* __restrict__ partial, const int nblocks, const int nout,
+                                                    double* __restrict__ out) {
+  __shared__ double red[8];
+  for (int q = 0; q < nout; ++q) {
+    double x = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += blockDim.x) x += partial[(long long)b * DIAG_MAXOUT + q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int wv = 0; wv < 8; ++wv) t += red[wv];
+      out[q] = t;
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace gfb

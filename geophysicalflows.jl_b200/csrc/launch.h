@@ -1,0 +1,79 @@
+// launch.h -- size-dispatched launchers.  Each supported FFT length has its own translation unit
+// (launchers.cu compiled with -DGFB_N=<length>) so the library builds in parallel.
+#pragma once
+#include "kernels.cuh"
+
+namespace gfb {
+
+struct PrepMultiArgs {
+  const cplx* sol;
+  int ld;
+  long long ls;
+  const double* Sinv;
+  int ldS;
+  int nf;
+};
+
+enum PrepKind { PREP_PLAIN = 0, PREP_SINGLE = 1, PREP_MULTI = 2 };
+
+struct ColInvLaunch {
+  GridDesc g;
+  int prep;            // PrepKind
+  PrepPlain pp;
+  PrepSingle ps;
+  PrepMultiArgs pm;
+  int nl;              // layers (PREP_MULTI template argument)
+  cplx* W;
+  int ldw;
+  long long wfs;
+  int ncols;
+  int nfields;         // grid.y
+  const cplx* tw;
+  cudaStream_t st;
+};
+
+struct RowLaunch {
+  int mode;            // RowMode
+  RowArgs a;
+  int nlayers;         // grid.y
+  const cplx* tw;
+  cudaStream_t st;
+};
+
+struct ColFwdLaunch {
+  GridDesc g;
+  const cplx* P;
+  int ldp;
+  long long pfs;
+  EpiArgs e;
+  int ncols;
+  int nlayers;         // grid.y
+  int nl;              // template NL (layers coupled in the epilogue)
+  bool two;
+  const cplx* tw;
+  cudaStream_t st;
+};
+
+constexpr int MAX_LAYERS = 5;
+
+#define GFB_DECL_SIZE(N)                            \
+  int launch_col_inv_##N(const ColInvLaunch& L);    \
+  int launch_row_##N(const RowLaunch& L);           \
+  int launch_col_fwd_##N(const ColFwdLaunch& L);
+GFB_DECL_SIZE(16)
+GFB_DECL_SIZE(32)
+GFB_DECL_SIZE(64)
+GFB_DECL_SIZE(128)
+GFB_DECL_SIZE(256)
+GFB_DECL_SIZE(512)
+GFB_DECL_SIZE(1024)
+GFB_DECL_SIZE(2048)
+GFB_DECL_SIZE(4096)
+GFB_DECL_SIZE(8192)
+#undef GFB_DECL_SIZE
+
+int launch_col_inv(int NY, const ColInvLaunch& L);
+int launch_row(int NX, const RowLaunch& L);
+int launch_col_fwd(int NY, const ColFwdLaunch& L);
+
+}  // namespace gfb

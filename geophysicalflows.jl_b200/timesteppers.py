@@ -1,0 +1,245 @@
+"""Host-side mirror of FourierFlows' `Problem`, `Clock`, `Equation`, time-stepper construction and
+`stepforward!` ([FF-upstream]; call sites /root/reference/src/twodnavierstokes.jl:99,153,
+test/test_twodnavierstokes.jl:251, examples/twodnavierstokes_decaying.jl:65).
+
+Construction computes the same tables the reference's time-stepper constructors compute on the host
+(`filter`, `expLdt`, `exp½Ldt`, `ζ`, `α`, `β`, `Γ`) and hands them to gfb_create; stepping is one
+`gfb_step` (or per-stage `gfb_stage`) call into the CUDA library."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class Clock:
+    def __init__(self, dt):
+        self.dt, self.t, self.step = float(dt), 0.0, 0
+
+
+class Equation:
+    def __init__(self, L, calcN, grid, dims):
+        self.L, self.calcN, self.grid, self.dims = L, calcN, grid, tuple(dims)
+
+
+def makefilter(grid, order=4, innerK=2 / 3, outerK=1, tol=1e-15):
+    """exp(-decay (K - innerK)^order) above innerK, 1 below; K = |(kr dx, l dy)| / pi."""
+    K = np.hypot(grid.kr * grid.dx / np.pi, grid.l * grid.dy / np.pi)
+    decay = -np.log(tol) / (outerK - innerK) ** order
+    return np.where(K < innerK, 1.0, np.exp(-decay * (K - innerK) ** order))
+
+
+def getetdcoeffs(dt, L, ncirc=32, rcirc=1):
+    """ETDRK4 coefficients by the 32-point contour mean (Kassam & Trefethen)."""
+    pts = rcirc * np.exp(2j * np.pi * (np.arange(ncirc) + 0.5) / ncirc)
+    z = dt * L[..., None] + pts
+    ez, ezh = np.exp(z), np.exp(z / 2)
+    out = [dt * np.mean((ezh - 1) / z, axis=-1),
+           dt * np.mean((-4 - z + ez * (4 - 3 * z + z**2)) / z**3, axis=-1),
+           dt * np.mean((2 + z + ez * (z - 2)) / z**3, axis=-1),
+           dt * np.mean((-4 - 3 * z - z**2 + ez * (4 - z)) / z**3, axis=-1)]
+    if not np.iscomplexobj(L):
+        out = [o.real for o in out]
+    return out
+
+
+class TimeStepper:
+    """Field names follow the reference's steppers where the library exposes them."""
+
+    def __init__(self, name, eqn, dt):
+        if name not in _lib.STEPPERS:
+            raise ValueError("unknown stepper %r" % name)
+        self.name = name
+        self.filtered = name.startswith("Filtered")
+        self.etd = "ETDRK4" in name
+        grid = eqn.grid
+        self.filter = makefilter(grid) if self.filtered else None
+        if self.etd:
+            L = eqn.L
+            self.expLdt = np.exp(dt * L)
+            self.exphalfLdt = np.exp(dt * L / 2)
+            self.zeta, self.alpha, self.beta, self.Gamma = getetdcoeffs(dt, L)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Problem:
+    """FourierFlows.Problem(equation, stepper, dt, grid, vars, params) on the B200 library."""
+
+    def __init__(self, eqn, stepper, dt, grid, vars, params, kind, tables):
+        self.eqn, self.grid, self.vars, self.params = eqn, grid, vars, params
+        self.clock = Clock(dt)
+        self.timestepper = TimeStepper(stepper, eqn, dt)
+        self.dev = grid.device
+        self.lib = self.dev.lib
+        self.nlayers = eqn.dims[0] if len(eqn.dims) == 3 else 1
+        self.sol = self.dev.zeros(eqn.dims, torch.complex128)
+        self._keep = []  # host arrays referenced by the config during gfb_create
+        cfg = _lib.GfbConfig()
+        cfg.kind = kind
+        cfg.nx, cfg.ny, cfg.nlayers = grid.nx, grid.ny, self.nlayers
+        cfg.Lx, cfg.Ly = grid.Lx, grid.Ly
+        cfg.kr_alias0 = grid.kr_alias0
+        cfg.l_alias0, cfg.l_alias1 = grid.l_alias
+        cfg.stepper = _lib.STEPPERS[stepper]
+        cfg.dt = float(dt)
+        L = eqn.L
+        cfg.L_is_complex = int(np.iscomplexobj(L))
+        ldt = np.complex128 if cfg.L_is_complex else np.float64
+        full = (self.nlayers, grid.nl, grid.nkr)
+
+        def table(a, dtype=ldt, shape=full):
+            if a is None:
+                return None
+            b = np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=dtype).reshape(
+                shape if np.ndim(a) == len(shape) else np.shape(a)), shape), dtype=dtype)
+            self._keep.append(b)
+            return b
+        cfg.L = _ptr(table(L))
+        ts = self.timestepper
+        cfg.filter = _ptr(table(ts.filter, np.float64, (grid.nl, grid.nkr)))
+        if ts.etd:
+            cfg.expLdt = _ptr(table(ts.expLdt))
+            cfg.exphalfLdt = _ptr(table(ts.exphalfLdt))
+            cfg.zeta = _ptr(table(ts.zeta))
+            cfg.alpha = _ptr(table(ts.alpha))
+            cfg.beta = _ptr(table(ts.beta))
+            cfg.Gamma = _ptr(table(ts.Gamma))
+        for key, (arr, dtype, shape) in tables.items():
+            if key == "mu":
+                cfg.mu = float(arr)
+            else:
+                setattr(cfg, key, _ptr(table(arr, dtype, shape)))
+        ctx = C.c_void_p()
+        rc = self.lib.gfb_create(C.byref(ctx), C.byref(cfg))
+        if rc != 0:
+            raise _lib.GfbError("gfb_create failed (%d): %s" % (rc, self.lib.gfb_last_error(None).decode()))
+        self.ctx = ctx
+        self._keep = []
+        if params is not None:
+            params._prob = self
+        grid._prob = self
+
+    def __del__(self):
+        try:
+            if getattr(self, "ctx", None):
+                self.lib.gfb_destroy(self.ctx)
+                self.ctx = None
+        except Exception:
+            pass
+
+    # -- thin checked wrappers over the C ABI ------------------------------------------------
+    def _check(self, rc, what):
+        if rc != 0:
+            raise _lib.GfbError("%s failed (%d): %s" % (what, rc, self.lib.gfb_last_error(self.ctx).decode()))
+
+    def _p(self, t):
+        if t is None:
+            return None
+        assert t.is_contiguous() and t.device == self.sol.device
+        return t.data_ptr()
+
+    def step_lib(self, nsteps, Fh=None, prevsol=None):
+        self._check(self.lib.gfb_step(self.ctx, self._p(self.sol), int(nsteps), self._p(Fh), self._p(prevsol),
+                                      self.dev.stream_ptr()), "gfb_step")
+
+    def stage_lib(self, istage, Fh=None, prevsol=None):
+        self._check(self.lib.gfb_stage(self.ctx, self._p(self.sol), int(istage), self._p(Fh), self._p(prevsol),
+                                       self.dev.stream_ptr()), "gfb_stage")
+
+    def calcN_lib(self, N, sol, Fh=None):
+        self._check(self.lib.gfb_calcN(self.ctx, self._p(N), self._p(sol), self._p(Fh), self.dev.stream_ptr()), "gfb_calcN")
+
+    def dealias_lib(self, a):
+        self._check(self.lib.gfb_dealias(self.ctx, self._p(a), self.dev.stream_ptr()), "gfb_dealias")
+
+    def rfft(self, a, out=None):
+        """mul!(out, grid.rfftplan, a) for a [.., ny, nx] real tensor."""
+        a = a.contiguous()
+        batch = int(a.numel() // (self.grid.ny * self.grid.nx))
+        if out is None:
+            out = self.dev.zeros(tuple(a.shape[:-2]) + (self.grid.nl, self.grid.nkr), torch.complex128)
+        self._check(self.lib.gfb_rfft(self.ctx, self._p(out), self._p(a), batch, self.dev.stream_ptr()), "gfb_rfft")
+        return out
+
+    def irfft(self, ah, out=None):
+        """ldiv!(out, grid.rfftplan, ah); `ah` is left intact."""
+        ah = ah.contiguous()
+        batch = int(ah.numel() // (self.grid.nl * self.grid.nkr))
+        if out is None:
+            out = self.dev.zeros(tuple(ah.shape[:-2]) + (self.grid.ny, self.grid.nx), torch.float64)
+        self._check(self.lib.gfb_irfft(self.ctx, self._p(out), self._p(ah), batch, self.dev.stream_ptr()), "gfb_irfft")
+        return out
+
+    def updatevars_lib(self, q=None, psi=None, u=None, v=None):
+        self._check(self.lib.gfb_updatevars(self.ctx, self._p(self.sol), self._p(q), self._p(psi), self._p(u),
+                                            self._p(v), self.dev.stream_ptr()), "gfb_updatevars")
+
+    def diag(self, kind, sol=None, aux=None, aux2=None, p=0.0, nout=1):
+        out = (C.c_double * 16)()
+        sol = self.sol if sol is None else sol
+        self._check(self.lib.gfb_diag(self.ctx, kind, self._p(sol), self._p(aux), self._p(aux2), float(p), out, 16,
+                                      self.dev.stream_ptr()), "gfb_diag")
+        return [out[i] for i in range(nout)]
+
+    def parseval_factor(self):
+        g = self.grid
+        return g.Lx * g.Ly / (g.nx**2 * g.ny**2)
+
+
+_STAGE_C = {4: (0.0, 0.5, 0.5, 1.0), 1: (0.0,)}
+
+
+def stepforward_(prob, nsteps=1, diags=()):
+    """stepforward!(prob[, diags], nsteps)."""
+    v, p, c = prob.vars, prob.params, prob.clock
+    calcF = getattr(p, "calcF", None)
+    Fh = getattr(v, "Fh", None)
+    nst = prob.lib.gfb_nstages(prob.ctx)
+
+    def advance(n):
+        for _ in range(n):
+            c.t += c.dt
+            c.step += 1
+            for d in diags:
+                d.increment(prob)
+    if calcF is None:
+        if diags:
+            for _ in range(nsteps):
+                prob.step_lib(1)
+                advance(1)
+        else:
+            prob.step_lib(nsteps)
+            advance(nsteps)
+        return
+    if v.stochastic:
+        # addforcing!: forcing drawn once per step at t == clock.t on the dealiased state, prevsol kept
+        for _ in range(nsteps):
+            prob.dealias_lib(prob.sol)
+            calcF(Fh, prob.sol, c.t, c, v, p, prob.grid)
+            prob.step_lib(1, Fh, v.prevsol)
+            advance(1)
+        return
+    # deterministic forcing: re-evaluated at every stage time (src/twodnavierstokes.jl:304-310)
+    for _ in range(nsteps):
+        for i in range(nst):
+            calcF(Fh, prob.sol, c.t + _STAGE_C[nst][i] * c.dt, c, v, p, prob.grid)
+            prob.stage_lib(i, Fh)
+        advance(1)
+
+
+class Diagnostic:
+    """Diagnostic(calc, prob; freq): (t, step, value) series."""
+
+    def __init__(self, calc, prob, freq=1):
+        self.calc, self.freq = calc, freq
+        self.t, self.steps, self.data = [prob.clock.t], [prob.clock.step], [calc(prob)]
+
+    def increment(self, prob):
+        if prob.clock.step % self.freq == 0:
+            self.t.append(prob.clock.t)
+            self.steps.append(prob.clock.step)
+            self.data.append(self.calc(prob))
