@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the pseudospectral timestep hot path.
+
+  python bench.py --gpus N --steps K --warmup W            our arm (CUDA library through the C ABI)
+  python bench.py --impl reference --gpus N --steps K ...  reference arm: the CPU restatement of the
+                                                           reference path (oracle/), all host threads
+
+Metric (BASELINE.json): grid-point-steps/s = nx*ny*steps / seconds.  Workload at N = 1: configs[3],
+"SurfaceQG decaying 4096^2 ETDRK4 Float64 on 1 B200 (HBM-roofline headline)", synthetic random-phase
+initial buoyancy.  One "step" = one ETDRK4 step = 4 x (calcN! + stage update).
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "grid-point-steps/sec"
+UNIT = "grid-point-steps/s"
+ALGO_BYTES_PER_POINT_STEP = 480.0  # 60 field passes x 8 B (Float64), RK4/ETDRK4 families
+
+
+def workload(name):
+    n = {"sqg4096": 4096, "sqg2048": 2048, "sqg1024": 1024, "sqg512": 512}[name]
+    return dict(module="SurfaceQG", nx=n, ny=n, Lx=2 * np.pi, nu=1e-19 * (256 / n) ** 8, nnu=4, H=np.inf,
+                dt=0.03 * 256 / n, stepper="ETDRK4")
+
+
+def initial_bh(n, seed=0):
+    """Random-phase half-spectrum b_h = A(|k|) e^{i theta}, A ~ |k| (1 + (|k|/6)^4)^-1/2, rms b = 1, in the
+    unnormalised-rfft convention; Hermitian-consistent because it is the rfft of a real field."""
+    rng = np.random.default_rng(seed)
+    kr = np.arange(n // 2 + 1)[None, :]
+    l = np.fft.fftfreq(n, 1 / n)[:, None]
+    K = np.sqrt(kr**2 + l**2)
+    A = K / np.sqrt(1 + (K / 6) ** 4)
+    th = rng.uniform(0, 2 * np.pi, K.shape)
+    bh = A * np.exp(1j * th)
+    b = np.fft.irfft2(bh, s=(n, n))
+    b /= np.sqrt(np.mean(b * b))
+    return np.fft.rfft2(b)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_problem(cfg):
+    from oracle import gfo
+    gfo.set_workers(os.cpu_count() or 1)
+    po = gfo.surfaceqg.Problem(nx=cfg["nx"], Lx=cfg["Lx"], nu=cfg["nu"], nnu=cfg["nnu"], H=cfg["H"], dt=cfg["dt"],
+                               stepper=cfg["stepper"])
+    return gfo, po
+
+
+def cpu_steps(cfg, bh0, nsteps, warmup):
+    """The reference path on the host cores: numpy elementwise (serial, as Julia's broadcast) + pocketfft
+    (scipy.fft, workers = all cores, the stand-in for threaded FFTW).  Returns seconds per step."""
+    gfo, po = oracle_problem(cfg)
+    po.sol[...] = bh0
+    po.sol[0, 0] = 0
+    gfo.stepforward_(po, warmup)
+    t0 = time.perf_counter()
+    gfo.stepforward_(po, nsteps)
+    return (time.perf_counter() - t0) / nsteps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = workload(args.workload)
+    n = cfg["nx"]
+    bh0 = initial_bh(n)
+    # bounded sample: one untimed step measures the cost, then as many of the K steps as fit ~150 s
+    t0 = time.perf_counter()
+    gfo, po = oracle_problem(cfg)
+    po.sol[...] = bh0
+    po.sol[0, 0] = 0
+    gfo.stepforward_(po, 1)
+    t1 = time.perf_counter() - t0
+    budget = float(os.environ.get("GFB_REF_BUDGET_S", "150"))
+    k = max(1, min(args.steps, int(budget / max(t1, 1e-3))))
+    t0 = time.perf_counter()
+    gfo.stepforward_(po, k)
+    per = (time.perf_counter() - t0) / k
+    val = n * n / per
+    cores = os.cpu_count() or 1
+    sample = "%d of %d requested ETDRK4 steps at %d^2 timed after 1 warm-up step (bounded to ~%.0f s)" % (k, args.steps, n, budget)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "SurfaceQG decaying %d^2 ETDRK4 Float64 (BASELINE.json configs[3])" % n,
+                       "impl": "oracle port of the reference CPU path: numpy broadcast + scipy.fft(pocketfft) workers=%d; "
+                               "the Julia/FFTW reference itself cannot run here (no Julia, FourierFlows.jl not vendored)" % cores},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="sqg4096")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import gfb_loader
+    pkg = gfb_loader.load()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    dev = pkg.GPU(local)
+    torch.cuda.set_device(local)
+    cfg = workload(args.workload)
+    n = cfg["nx"]
+    prob = pkg.SurfaceQG.Problem(dev, nx=n, Lx=cfg["Lx"], nu=cfg["nu"], nnu=cfg["nnu"], H=cfg["H"], dt=cfg["dt"],
+                                 stepper=cfg["stepper"])
+    bh0 = initial_bh(n)
+    bh0[0, 0] = 0
+    host_sol = torch.from_numpy(bh0).pin_memory()
+    prob.sol.copy_(host_sol, non_blocking=True)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ---------------------------------------------------------
+    pkg.stepforward_(prob, args.warmup)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    prob.profile_begin()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    pkg.stepforward_(prob, args.steps)
+    e1.record()
+    barrier()
+    prof = prob.profile_end()
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * n * n * args.steps / (ms * 1e-3)
+    finite = bool(torch.isfinite(prob.sol.real).all().item())
+
+    # ---- end to end through the public API with host buffers ----------------------------------
+    # every step: state uploaded from pinned host memory, one stepforward!, state + two diagnostics back
+    out_host = torch.empty_like(host_sol).pin_memory()
+    h2d = host_sol.numel() * 16
+    d2h = out_host.numel() * 16 + 16
+    for _ in range(2):
+        prob.sol.copy_(host_sol, non_blocking=True)
+        pkg.stepforward_(prob, 1)
+        out_host.copy_(prob.sol, non_blocking=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        prob.sol.copy_(host_sol, non_blocking=True)
+        pkg.stepforward_(prob, 1)
+        out_host.copy_(prob.sol, non_blocking=True)
+        ke = pkg.SurfaceQG.kinetic_energy(prob)  # device->host scalar (synchronises the stream)
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = world * n * n / float(te.item())
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------------
+    peak, peak_src = peaks()
+    g = prob.grid
+    kcut, nkr, ny = g.kr_alias0, g.nkr, g.ny
+    kbytes = {  # algorithmic bytes per launch (DESIGN.md "kernels"): 16 B per complex element
+        "k_col_inv": 16.0 * ny * kcut * (1 + 3) + 8.0 * ny * kcut,  # read sol + G column band, write u,v,q bands
+        "k_row": 16.0 * ny * (3 * kcut + 2 * nkr),                   # read 3 bands, write 2 full half-spectra
+        "k_col_fwd": 16.0 * ny * nkr * (2 + 3 + 2.5),                # read 2 products + ~3 state/acc reads + tables, write ~2
+    }
+    top = max(("k_col_inv", "k_row", "k_col_fwd"), key=lambda k: prof[k]["ms"])
+    avg_ms = prof[top]["ms"] / max(prof[top]["launches"], 1)
+    achieved = kbytes[top] / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else None
+    step_gbs = ALGO_BYTES_PER_POINT_STEP * n * n / (ms_per_step * 1e-3) / 1e9
+    launches = sum(v["launches"] for v in prof.values())
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "SurfaceQG decaying %d^2 ETDRK4 Float64 (BASELINE.json configs[3])" % n,
+                   "grid": [n, n], "stepper": cfg["stepper"], "dt": cfg["dt"],
+                   "initial_condition": "random-phase b_h ~ |k|(1+(|k|/6)^4)^-1/2, rms b = 1, numpy default_rng(0)",
+                   "l2": "working set (>= 12 fields x %.0f MB) exceeds the 126 MB L2; no flush needed" % (16.0 * ny * nkr / 1e6),
+                   "parallelism": "1 GPU" if world == 1 else "%d independent replicas (slab-sharded path not built yet)" % world,
+                   "state_finite": finite},
+        "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": kbytes[top], "avg_launch_ms": avg_ms},
+        "step_roofline": {"algorithmic_bytes_per_step": ALGO_BYTES_PER_POINT_STEP * n * n, "achieved_gbs": step_gbs,
+                          "frac_of_measured_peak": step_gbs / peak, "frac_of_8tbs_nominal": step_gbs / 8000.0},
+        "kernels": {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps} for k, v in prof.items()},
+        "gpu_launches": launches,
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_s * 1e3, "what": "per step: pinned-host sol -> device, stepforward!(prob, 1), sol + kinetic_energy -> host"},
+        "clocks": sampler.summary(),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        nsamp = 2 if n >= 4096 else 4
+        per = cpu_steps(cfg, bh0, nsamp, 1)
+        line["cpu_baseline"] = {"value": n * n / per, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                                "sample": "%d ETDRK4 steps at %d^2 after 1 warm-up step; numpy broadcast + scipy.fft workers=%d"
+                                          % (nsamp, n, os.cpu_count() or 1), "ms_per_step": per * 1e3}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

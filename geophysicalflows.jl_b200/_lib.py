@@ -33,7 +33,8 @@ class GfbConfig(C.Structure):
 
 EXPORTS = ["gfb_version", "gfb_last_error", "gfb_create", "gfb_destroy", "gfb_get_clock", "gfb_set_clock",
            "gfb_rfft", "gfb_irfft", "gfb_dealias", "gfb_calcN", "gfb_step", "gfb_nstages", "gfb_stage", "gfb_diag",
-           "gfb_streamfunction_from_pv", "gfb_pv_from_streamfunction", "gfb_updatevars", "gfb_device_bytes"]
+           "gfb_streamfunction_from_pv", "gfb_pv_from_streamfunction", "gfb_updatevars", "gfb_device_bytes",
+           "gfb_profile_begin", "gfb_profile_end"]
 
 
 class GfbError(RuntimeError):
@@ -60,6 +61,8 @@ def _prototype(lib):
     lib.gfb_streamfunction_from_pv.argtypes = [vp, vp, vp, vp]
     lib.gfb_pv_from_streamfunction.argtypes = [vp, vp, vp, vp]
     lib.gfb_updatevars.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    lib.gfb_profile_begin.argtypes = [vp]
+    lib.gfb_profile_end.argtypes = [vp, C.POINTER(dp), C.POINTER(C.c_longlong)]
     lib.gfb_device_bytes.argtypes = [vp]
     lib.gfb_device_bytes.restype = C.c_longlong
     for name in EXPORTS:

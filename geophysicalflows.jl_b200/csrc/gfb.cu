@@ -44,6 +44,31 @@ struct gfb_ctx {
   cplx* st[4] = {nullptr, nullptr, nullptr, nullptr};  // stage states / accumulators / histories
   double *dpart = nullptr, *dout = nullptr;
   int dblocks = 0;
+  // optional per-kernel event timing
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_ev;   // pairs (start, stop)
+  std::vector<int> prof_cls;
+  size_t prof_used = 0;
+  long long prof_launches[4] = {0, 0, 0, 0};
+};
+
+// RAII: records an event pair around one launch when profiling is on
+struct ProfScope {
+  gfb_ctx* c;
+  cudaStream_t st;
+  cudaEvent_t stop = nullptr;
+  ProfScope(gfb_ctx* c_, int cls, cudaStream_t st_) : c(c_), st(st_) {
+    if (!c->prof_on) return;
+    c->prof_launches[cls]++;
+    if (c->prof_used + 2 > c->prof_ev.size()) return;
+    cudaEventRecord(c->prof_ev[c->prof_used], st);
+    stop = c->prof_ev[c->prof_used + 1];
+    c->prof_cls.push_back(cls);
+    c->prof_used += 2;
+  }
+  ~ProfScope() {
+    if (stop) cudaEventRecord(stop, st);
+  }
 };
 
 static int fail(gfb_ctx* c, int code, const char* fmt, ...) {
@@ -154,6 +179,7 @@ long long gfb_device_bytes(const gfb_ctx* ctx) { return ctx ? ctx->bytes : 0; }
 int gfb_destroy(gfb_ctx* c) {
   if (!c) return GFB_OK;
   for (void* p : c->allocs) cudaFree(p);
+  for (auto& e : c->prof_ev) cudaEventDestroy(e);
   delete c;
   return GFB_OK;
 }
@@ -268,6 +294,40 @@ int gfb_create(gfb_ctx** out, const gfb_config* cfg) {
   return GFB_OK;
 }
 
+int gfb_profile_begin(gfb_ctx* c) {
+  if (!c) return GFB_ERR_INVALID;
+  if (c->prof_ev.empty()) {
+    c->prof_ev.resize(2 * 8192);
+    for (auto& e : c->prof_ev) GFB_CUDA(c, cudaEventCreate(&e));
+  }
+  c->prof_used = 0;
+  c->prof_cls.clear();
+  for (int i = 0; i < 4; ++i) c->prof_launches[i] = 0;
+  c->prof_on = true;
+  return GFB_OK;
+}
+
+int gfb_profile_end(gfb_ctx* c, double* ms4, long long* launches4) {
+  if (!c || !ms4 || !launches4) return GFB_ERR_INVALID;
+  c->prof_on = false;
+  double ms[4] = {0, 0, 0, 0};
+  long long timed[4] = {0, 0, 0, 0};
+  for (size_t i = 0; i + 1 < c->prof_used; i += 2) {
+    GFB_CUDA(c, cudaEventSynchronize(c->prof_ev[i + 1]));
+    float t = 0.f;
+    GFB_CUDA(c, cudaEventElapsedTime(&t, c->prof_ev[i], c->prof_ev[i + 1]));
+    const int cls = c->prof_cls[i / 2];
+    ms[cls] += t;
+    timed[cls]++;
+  }
+  for (int k = 0; k < 4; ++k) {
+    // launches beyond the event pool are extrapolated from the timed ones of the same class
+    ms4[k] = timed[k] ? ms[k] * (double)c->prof_launches[k] / (double)timed[k] : 0.0;
+    launches4[k] = c->prof_launches[k];
+  }
+  return GFB_OK;
+}
+
 int gfb_get_clock(const gfb_ctx* c, double* t, long long* step) {
   if (!c) return GFB_ERR_INVALID;
   if (t) *t = c->t;
@@ -346,6 +406,7 @@ static int run_col_inv_state(gfb_ctx* c, const Spec& sin, int nf, cudaStream_t s
     L.pm.nf = nf;
     L.nfields = nf * c->nlayers;
   }
+  ProfScope ps(c, 0, st);
   return check_launch(c, launch_col_inv(c->g.ny, L), "k_col_inv");
 }
 
@@ -370,6 +431,7 @@ static int run_row_product(gfb_ctx* c, cudaStream_t st) {
   R.nlayers = c->nlayers;
   R.tw = c->tw_x;
   R.st = st;
+  ProfScope ps(c, 1, st);
   return check_launch(c, launch_row(c->g.nx, R), "k_row");
 }
 
@@ -387,6 +449,7 @@ static int run_col_fwd(gfb_ctx* c, const EpiArgs& e, cudaStream_t st) {
   F.two = true;
   F.tw = c->tw_y;
   F.st = st;
+  ProfScope ps(c, 2, st);
   return check_launch(c, launch_col_fwd(c->g.ny, F), "k_col_fwd");
 }
 

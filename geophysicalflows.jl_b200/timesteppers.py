@@ -185,6 +185,16 @@ class Problem:
                                       self.dev.stream_ptr()), "gfb_diag")
         return [out[i] for i in range(nout)]
 
+    def profile_begin(self):
+        self._check(self.lib.gfb_profile_begin(self.ctx), "gfb_profile_begin")
+
+    def profile_end(self):
+        ms = (C.c_double * 4)()
+        n = (C.c_longlong * 4)()
+        self._check(self.lib.gfb_profile_end(self.ctx, ms, n), "gfb_profile_end")
+        names = ("k_col_inv", "k_row", "k_col_fwd", "other")
+        return {names[i]: {"ms": ms[i], "launches": int(n[i])} for i in range(4)}
+
     def parseval_factor(self):
         g = self.grid
         return g.Lx * g.Ly / (g.nx**2 * g.ny**2)

@@ -159,6 +159,12 @@ int gfb_pv_from_streamfunction(gfb_ctx* ctx, void* qh, const void* psih, void* s
  * (q, psi, u, v: double[nlayers][ny][nx]; u WITHOUT the imposed U, as vars.u in updatevars!). */
 int gfb_updatevars(gfb_ctx* ctx, void* sol, double* q, double* psi, double* u, double* v, void* stream);
 
+/* Per-kernel device timing (CUDA events on the caller's stream around every launch), for the roofline
+ * report of bench.py.  Classes: 0 = k_col_inv (K1), 1 = k_row (K2), 2 = k_col_fwd (K3), 3 = other.
+ * gfb_profile_end synchronises the recorded events and returns summed milliseconds and launch counts. */
+int gfb_profile_begin(gfb_ctx* ctx);
+int gfb_profile_end(gfb_ctx* ctx, double* ms4, long long* launches4);
+
 /* bytes of device memory owned by the context */
 long long gfb_device_bytes(const gfb_ctx* ctx);
 

@@ -80,6 +80,18 @@ static inline cudaError_t cudaPeekAtLastError() { return cudaSuccess; }
 static inline const char* cudaGetErrorString(cudaError_t e) { return e == 0 ? "no error" : "emulated error"; }
 template <class F>
 static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+typedef struct emuEvent* cudaEvent_t;
+static inline cudaError_t cudaEventCreate(cudaEvent_t* e) {
+  *e = nullptr;
+  return cudaSuccess;
+}
+static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) {
+  *ms = 0.f;
+  return cudaSuccess;
+}
 static inline cudaError_t cudaGetDevice(int* d) {
   *d = 0;
   return cudaSuccess;

@@ -1,0 +1,160 @@
+"""CPU (`-m "not gpu"`) checks of the PRODUCT's kernel sources, compiled by g++ through the test-only
+CUDA emulation layer (tests/emu/cuda_emu.h) and driven through the same C ABI + Python host code as
+on the GPU.  They compare against the oracle and the reference's analytic goldens at small
+power-of-two sizes.  The GPU parity tests proper are in tests/test_gpu_parity.py."""
+import numpy as np
+import pytest
+import torch
+
+import refcases as R
+
+RT = 1e-12  # the analytic cases hold to ~1e-15; FFT algorithms differ from pocketfft at the 1e-16 level
+
+
+@pytest.fixture(scope="module")
+def emu():
+    import backends
+    return backends.emu_backend()
+
+
+def test_plain_transforms(emu):
+    prob = emu.twodnavierstokes.Problem(nx=64, ny=32, Lx=2 * np.pi, Ly=3.0, stepper="ForwardEuler")
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((3, 32, 64))
+    ah = prob.rfft(emu.dev(a))
+    assert R.relerr(emu.host(ah), np.fft.rfft2(a)) < 1e-14
+    assert R.relerr(emu.host(prob.irfft(ah)), a) < 1e-14
+    # c2r must ignore the imaginary parts of the kr = 0 and kr = nx/2 columns like FFTW / pocketfft
+    bh = np.fft.rfft2(a) + 1j * rng.standard_normal((3, 32, 33)) * np.array([1.0] + [0.0] * 31 + [1.0])
+    assert R.relerr(emu.host(prob.irfft(emu.dev(bh))), np.fft.irfft2(bh, s=(32, 64))) < 1e-14
+
+
+@pytest.mark.parametrize("nx,ny", [(64, 64), (128, 32), (32, 128), (16, 16)])
+@pytest.mark.parametrize("stepper", ["ForwardEuler", "FilteredRK4", "RK4", "ETDRK4", "FilteredETDRK4", "FilteredAB3"])
+def test_twodns_steps_vs_oracle(emu, oracle_backend, nx, ny, stepper):
+    kw = dict(nx=nx, ny=ny, Lx=2 * np.pi, Ly=5.0, nu=1e-4, nnu=1, mu=0.02, nmu=0, dt=2e-3, stepper=stepper)
+    po = oracle_backend.twodnavierstokes.Problem(**kw)
+    pb = emu.twodnavierstokes.Problem(**kw)
+    rng = np.random.default_rng(nx * 7 + ny)
+    s0 = np.fft.rfft2(rng.standard_normal((ny, nx))) * 30 / (nx * ny)
+    po.sol[...] = s0
+    pb.sol.copy_(emu.dev(s0))
+    oracle_backend.stepforward_(po, 6)
+    emu.stepforward_(pb, 6)
+    # the whole state, INCLUDING the aliased band residue left by the last step
+    assert R.relerr(emu.host(pb.sol), po.sol) < 1e-13
+    assert pb.clock.t == po.clock.t and pb.clock.step == po.clock.step
+    M = emu.twodnavierstokes
+    O = oracle_backend.twodnavierstokes
+    assert abs(M.energy(pb) / O.energy(po) - 1) < 1e-13
+    assert abs(M.enstrophy(pb) / O.enstrophy(po) - 1) < 1e-13
+
+
+def test_calcN_dealiases_in_place(emu, oracle_backend):
+    kw = dict(nx=64, ny=64, Lx=2 * np.pi, stepper="RK4")
+    po = oracle_backend.twodnavierstokes.Problem(**kw)
+    pb = emu.twodnavierstokes.Problem(**kw)
+    rng = np.random.default_rng(5)
+    s0 = np.fft.rfft2(rng.standard_normal((64, 64)))
+    so, No = s0.copy(), np.zeros_like(s0)
+    oracle_backend.twodnavierstokes.calcN_(No, so, 0.0, po.clock, po.vars, po.params, po.grid)
+    sb = emu.dev(s0)
+    Nb = torch.zeros_like(sb)
+    emu.twodnavierstokes.calcN_(Nb, sb, 0.0, pb.clock, pb.vars, pb.params, pb.grid)
+    assert np.array_equal(emu.host(sb), so)          # masked copy is bit-exact
+    assert R.relerr(emu.host(Nb), No) < 1e-14
+    assert np.any(No[:, po.grid.kr_alias_range[0]:] != 0)  # N itself is NOT masked
+
+
+def test_stochastic_forcing_semantics(emu, oracle_backend):
+    """Forcing drawn once per step at t == clock.t, frozen over the stages, prevsol = dealiased state."""
+    n = 32
+    rng = np.random.default_rng(3)
+    draws = [np.fft.rfft2(rng.standard_normal((n, n))) * 1e-2 for _ in range(4)]
+
+    def mk(B):
+        it = iter(draws)
+
+        def calcF(Fh, sol, t, clock, vars, params, grid):
+            B.assign(Fh, B.dev(next(it)))
+        return calcF
+    kw = dict(nx=n, Lx=2 * np.pi, nu=1e-3, dt=1e-2, stepper="RK4", stochastic=True)
+    po = oracle_backend.twodnavierstokes.Problem(calcF=mk(oracle_backend), **kw)
+    pb = emu.twodnavierstokes.Problem(calcF=mk(emu), **kw)
+    s0 = np.fft.rfft2(rng.standard_normal((n, n))) / n
+    po.sol[...] = s0
+    pb.sol.copy_(emu.dev(s0))
+    oracle_backend.stepforward_(po, 4)
+    emu.stepforward_(pb, 4)
+    assert R.relerr(emu.host(pb.sol), po.sol) < 1e-13
+    assert R.relerr(emu.host(pb.vars.prevsol), po.vars.prevsol) < 1e-13
+    assert abs(emu.twodnavierstokes.energy_work(pb) / oracle_backend.twodnavierstokes.energy_work(po) - 1) < 1e-12
+
+
+def test_reference_cases_twodns_sqg(emu):
+    assert R.twodns_advection(emu, dt=0.005, stepper="RK4", n=64, tf=0.1) < RT
+    assert max(abs(e) for e in R.twodns_energyenstrophypalinstrophy(emu, nx=128, ny=64)) < RT
+    assert R.sqg_advection(emu, dt=0.005, stepper="FilteredRK4", n=64, tf=0.1) < RT
+    assert R.sqg_advection(emu, dt=0.005, stepper="ETDRK4", H=1.0, n=64, tf=0.1) < RT
+    for H in (np.inf, 1.0):
+        assert max(abs(e) for e in R.sqg_energy_buoyancyvariance(emu, H=H, nx=64, ny=32)) < RT
+
+
+def test_reference_cases_slqg(emu):
+    for stepper, dt, ns in (("RK4", 1e-2, 20), ("FilteredETDRK4", 1e-2, 20), ("ForwardEuler", 1e-4, 100)):
+        for ell, U in ((np.inf, 0.0), (1.23, 0.3), (np.inf, 0.3 * np.ones(64))):
+            err, rtol = R.slqg_rossbywave(emu, stepper, dt, ns, deformation_radius=ell, U=U)
+            assert err < rtol, (stepper, ell)
+    for kw in (dict(), dict(add_topography=True),
+               dict(add_background_flow=True, background_flow_vary_in_y=False, add_topography=True),
+               dict(add_background_flow=True, background_flow_vary_in_y=True)):
+        assert R.slqg_nonlinearadvection(emu, dt=0.005, stepper="RK4", n=64, tf=0.1, **kw) < RT
+    assert R.slqg_nonlinearadvection_deformation(emu, dt=0.005, stepper="RK4", n=64, tf=0.1) < RT
+    e, z, pe = R.slqg_energyenstrophy(emu)
+    assert abs(e) < RT and abs(z) < RT and pe == 0
+    assert max(abs(e) for e in R.slqg_energyenstrophy(emu, deformation_radius=1.23)) < RT
+    M = emu.singlelayerqg
+    prob = M.Problem(nx=16, deformation_radius=2.23)
+    for f in (M.energy_dissipation, M.enstrophy_dissipation, M.energy_work, M.enstrophy_work, M.energy_drag,
+              M.enstrophy_drag):
+        with pytest.raises(RuntimeError, match="not implemented for finite deformation radius"):
+            f(prob)
+
+
+def test_reference_cases_mqg(emu):
+    for n in (2, 3):
+        assert R.mqg_pvtofromstreamfunction(emu, n, n=64) < 1e-13
+        eq, epsi = R.mqg_nonlinearadvection(emu, n, nx=64, ny=64, nsteps=20)
+        assert eq < RT and epsi < RT
+    assert max(abs(e) for e in R.mqg_energies(emu, nx=64, ny=64)) < RT
+    assert abs(R.mqg_energysinglelayer(emu)) < RT
+    lat, ver = R.mqg_fluxes(emu, 2, nx=128, ny=128)
+    assert abs(lat[0] / 0.00626267 - 1) < 1e-6 and abs(lat[1]) < 1e-12 and abs(ver[0] / -0.196539 - 1) < 1e-6
+    assert abs(R.mqg_fluxessinglelayer(emu, nx=128, ny=128) - 0.0313134) < 1e-7
+    assert max(R.mqg_setqsetpsi(emu, nx=32, ny=32)) < RT
+    assert max(R.mqg_topographicPV_gradient(emu, nx=32, ny=32)) < RT
+    err, rtol = R.mqg_rossbywave(emu)
+    assert err < rtol
+
+
+@pytest.mark.parametrize("nlayers", [2, 5])
+def test_mqg_steps_vs_oracle(emu, oracle_backend, nlayers):
+    """Random multi-layer state with U(y), topography, beta, drag: full-state parity incl. alias band."""
+    nx, ny = 32, 64
+    rng = np.random.default_rng(11)
+    y = np.linspace(-np.pi, np.pi, ny, endpoint=False)
+    U = np.stack([0.1 * (j + 1) * np.cos(y) for j in range(nlayers)], axis=1)
+    eta = 0.3 * rng.standard_normal((ny, nx))
+    kw = dict(nx=nx, ny=ny, Lx=2 * np.pi, Ly=2 * np.pi, f0=1.0, beta=0.5, U=U, eta=eta, mu=0.05, nu=1e-4,
+              topographic_pv_gradient=(0.01, 0.02), dt=2e-3, stepper="FilteredRK4")
+    po = oracle_backend.multilayerqg.Problem(nlayers, **kw)
+    pb = emu.multilayerqg.Problem(nlayers, **kw)
+    s0 = np.fft.rfft2(rng.standard_normal((nlayers, ny, nx))) * 5 / (nx * ny)
+    po.sol[...] = s0
+    pb.sol.copy_(emu.dev(s0))
+    oracle_backend.stepforward_(po, 4)
+    emu.stepforward_(pb, 4)
+    assert R.relerr(emu.host(pb.sol), po.sol) < 1e-13
+    KEo, PEo = oracle_backend.multilayerqg.energies(po)
+    KEb, PEb = emu.multilayerqg.energies(pb)
+    assert np.allclose(KEb, KEo, rtol=1e-12) and np.allclose(PEb, PEo, rtol=1e-12)
