@@ -314,4 +314,4 @@ def test_4096_step_conserves_and_matches_stagewise(gpu, big):
         for i in range(4):
             prob.stage_lib(i)
     assert float(torch.linalg.norm(prob.sol - fused)) == 0.0  # same kernels, same order: bit-identical
-    assert abs(bv1 / bv0 - 1) < 1e-6
+    assert abs(bv1 / bv0 - 1) < 1e-4  # white-noise state: hyperviscosity removes a little variance in 3 steps
