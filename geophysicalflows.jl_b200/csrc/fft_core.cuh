@@ -157,6 +157,27 @@ struct Plan {
   static_assert((1 << lg) == N && N >= 16 && N <= 8192, "N must be a power of two in [16, 8192]");
 };
 
+// x[s] *= w1^s for s = 1..R-1.  Powers are built from the binary decomposition of s
+// (w[s] = w[s - lowbit(s)] * w[lowbit(s)], powers of two by squaring): log-depth rounding error, the same
+// 14 complex products as a plain chain for R = 16, and only w1, w2, w4, w8 plus one running product alive.
+template <int R>
+__device__ __forceinline__ void twiddle_apply(cplx* x, const cplx w1) {
+  cplx w[R];
+  w[1] = w1;
+  x[1] = cmul(x[1], w1);
+#pragma unroll
+  for (int s = 2; s < R; ++s) {
+    const int low = s & (-s);
+    if (low == s) {
+      const cplx h = w[s / 2];
+      w[s] = cmake(h.x * h.x - h.y * h.y, 2.0 * h.x * h.y);
+    } else {
+      w[s] = cmul(w[s - low], w[low]);
+    }
+    x[s] = cmul(x[s], w[s]);
+  }
+}
+
 // One Stockham pass of radix R with Ns = product of earlier radices.
 //   tw: W_N^i (forward sign), i < N.   xb: this group's exchange buffer (xbuf_elems(N) cplx),
 // LAST pass leaves the result in registers in natural strided layout; other passes exchange.
@@ -176,19 +197,7 @@ __device__ __forceinline__ void fft_pass(cplx (&v)[PT], const int j, cplx* __res
       cplx w1 = __ldg(&tw[k * (N / (Ns * R))]);
       if (DIR == INV) w1.y = -w1.y;
       // powers by a log-depth chain: w[2a] = w[a]^2, w[2a+1] = w[2a]*w1
-      cplx w[R];
-      w[1] = w1;
-#pragma unroll
-      for (int s = 2; s < R; ++s) {
-        if ((s & 1) == 0) {
-          const cplx h = w[s / 2];
-          w[s] = cmake(h.x * h.x - h.y * h.y, 2.0 * h.x * h.y);
-        } else {
-          w[s] = cmul(w[s - 1], w1);
-        }
-      }
-#pragma unroll
-      for (int s = 1; s < R; ++s) x[s] = cmul(x[s], w[s]);
+      twiddle_apply<R>(x, w1);
     }
     Dft<DIR, R>::run(x);
     if (LAST) {
@@ -243,5 +252,86 @@ __device__ __forceinline__ void block_fft(cplx (&v)[PT], const int j, cplx* __re
     }
   }
 }
+
+// Split (re / im) exchange variant: the exchange buffer holds N doubles (+pad) instead of N complex, so it
+// costs half the shared memory (two CTAs of a 4096-point kernel fit one SM) for twice the barriers.
+template <int N, int DIR, int R, int Ns, bool LAST>
+__device__ __forceinline__ void fft_pass_split(cplx (&v)[PT], const int j, double* __restrict__ xb,
+                                               const cplx* __restrict__ tw) {
+  constexpr int T = N / PT;
+  constexpr int M = PT / R;
+  int base[M];
+#pragma unroll
+  for (int i = 0; i < M; ++i) {
+    const int b = j + i * T;
+    cplx x[R];
+#pragma unroll
+    for (int s = 0; s < R; ++s) x[s] = v[i + s * M];
+    if (Ns > 1) {
+      const int k = b & (Ns - 1);
+      cplx w1 = __ldg(&tw[k * (N / (Ns * R))]);
+      if (DIR == INV) w1.y = -w1.y;
+      twiddle_apply<R>(x, w1);
+    }
+    Dft<DIR, R>::run(x);
+#pragma unroll
+    for (int s = 0; s < R; ++s) v[i + s * M] = x[s];
+    const int k = b & (Ns - 1);
+    base[i] = (b - k) * R + k;
+  }
+  if (!LAST) {
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+#pragma unroll
+      for (int s = 0; s < R; ++s) xb[xpad(base[i] + s * Ns)] = v[i + s * M].x;
+    __syncthreads();
+    double re[PT];
+#pragma unroll
+    for (int r = 0; r < PT; ++r) re[r] = xb[xpad(j + r * T)];
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+#pragma unroll
+      for (int s = 0; s < R; ++s) xb[xpad(base[i] + s * Ns)] = v[i + s * M].y;
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < PT; ++r) v[r] = cmake(re[r], xb[xpad(j + r * T)]);
+    __syncthreads();
+  }
+}
+
+template <int N, int DIR>
+__device__ __forceinline__ void block_fft_split(cplx (&v)[PT], const int j, double* __restrict__ xb,
+                                                const cplx* __restrict__ tw) {
+  using P = Plan<N>;
+  constexpr int rem = P::rem;
+  constexpr int RR = rem > 1 ? rem : 2;
+  if constexpr (P::n16 == 1) {
+    if constexpr (rem == 1) {
+      fft_pass_split<N, DIR, 16, 1, true>(v, j, xb, tw);
+    } else {
+      fft_pass_split<N, DIR, 16, 1, false>(v, j, xb, tw);
+      fft_pass_split<N, DIR, RR, 16, true>(v, j, xb, tw);
+    }
+  } else if constexpr (P::n16 == 2) {
+    fft_pass_split<N, DIR, 16, 1, false>(v, j, xb, tw);
+    if constexpr (rem == 1) {
+      fft_pass_split<N, DIR, 16, 16, true>(v, j, xb, tw);
+    } else {
+      fft_pass_split<N, DIR, 16, 16, false>(v, j, xb, tw);
+      fft_pass_split<N, DIR, RR, 256, true>(v, j, xb, tw);
+    }
+  } else {
+    fft_pass_split<N, DIR, 16, 1, false>(v, j, xb, tw);
+    fft_pass_split<N, DIR, 16, 16, false>(v, j, xb, tw);
+    if constexpr (rem == 1) {
+      fft_pass_split<N, DIR, 16, 256, true>(v, j, xb, tw);
+    } else {
+      fft_pass_split<N, DIR, 16, 256, false>(v, j, xb, tw);
+      fft_pass_split<N, DIR, RR, 4096, true>(v, j, xb, tw);
+    }
+  }
+}
+
 
 }  // namespace gfb

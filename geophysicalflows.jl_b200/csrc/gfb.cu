@@ -44,6 +44,8 @@ struct gfb_ctx {
   cplx* st[4] = {nullptr, nullptr, nullptr, nullptr};  // stage states / accumulators / histories
   double *dpart = nullptr, *dout = nullptr;
   int dblocks = 0;
+  cplx* scratch = nullptr;  // K3 per-CTA parking space (L2-resident)
+  int max_ctas = 296;
   // optional per-kernel event timing
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev;   // pairs (start, stop)
@@ -129,7 +131,7 @@ static int upload_padded(gfb_ctx* c, void** out, const void* host, int nlay, boo
   return 0;
 }
 
-static bool pow2_ok(int n) { return n >= 16 && n <= 8192 && (n & (n - 1)) == 0; }
+static bool pow2_ok(int n) { return n >= 32 && n <= 8192 && (n & (n - 1)) == 0; }
 
 static int make_twiddles(gfb_ctx* c, cplx** out, int N) {
   std::vector<cplx> h(N);
@@ -145,7 +147,7 @@ namespace gfb {
 int launch_col_inv(int NY, const ColInvLaunch& L) {
   switch (NY) {
 #define GFB_CASE(N) case N: return launch_col_inv_##N(L);
-    GFB_CASE(16) GFB_CASE(32) GFB_CASE(64) GFB_CASE(128) GFB_CASE(256) GFB_CASE(512) GFB_CASE(1024) GFB_CASE(2048) GFB_CASE(4096) GFB_CASE(8192)
+    GFB_CASE(32) GFB_CASE(64) GFB_CASE(128) GFB_CASE(256) GFB_CASE(512) GFB_CASE(1024) GFB_CASE(2048) GFB_CASE(4096) GFB_CASE(8192)
 #undef GFB_CASE
   }
   return -1;
@@ -153,7 +155,7 @@ int launch_col_inv(int NY, const ColInvLaunch& L) {
 int launch_row(int NX, const RowLaunch& L) {
   switch (NX) {
 #define GFB_CASE(N) case N: return launch_row_##N(L);
-    GFB_CASE(16) GFB_CASE(32) GFB_CASE(64) GFB_CASE(128) GFB_CASE(256) GFB_CASE(512) GFB_CASE(1024) GFB_CASE(2048) GFB_CASE(4096) GFB_CASE(8192)
+    GFB_CASE(32) GFB_CASE(64) GFB_CASE(128) GFB_CASE(256) GFB_CASE(512) GFB_CASE(1024) GFB_CASE(2048) GFB_CASE(4096) GFB_CASE(8192)
 #undef GFB_CASE
   }
   return -1;
@@ -161,7 +163,7 @@ int launch_row(int NX, const RowLaunch& L) {
 int launch_col_fwd(int NY, const ColFwdLaunch& L) {
   switch (NY) {
 #define GFB_CASE(N) case N: return launch_col_fwd_##N(L);
-    GFB_CASE(16) GFB_CASE(32) GFB_CASE(64) GFB_CASE(128) GFB_CASE(256) GFB_CASE(512) GFB_CASE(1024) GFB_CASE(2048) GFB_CASE(4096) GFB_CASE(8192)
+    GFB_CASE(32) GFB_CASE(64) GFB_CASE(128) GFB_CASE(256) GFB_CASE(512) GFB_CASE(1024) GFB_CASE(2048) GFB_CASE(4096) GFB_CASE(8192)
 #undef GFB_CASE
   }
   return -1;
@@ -188,7 +190,7 @@ int gfb_create(gfb_ctx** out, const gfb_config* cfg) {
   if (!out || !cfg) return fail(nullptr, GFB_ERR_INVALID, "null argument");
   *out = nullptr;
   if (!pow2_ok(cfg->nx) || !pow2_ok(cfg->ny))
-    return fail(nullptr, GFB_ERR_UNSUPPORTED, "nx=%d, ny=%d: sizes must be powers of two in [16, 8192]", cfg->nx, cfg->ny);
+    return fail(nullptr, GFB_ERR_UNSUPPORTED, "nx=%d, ny=%d: sizes must be powers of two in [32, 8192]", cfg->nx, cfg->ny);
   if (cfg->nlayers < 1 || cfg->nlayers > MAX_LAYERS) return fail(nullptr, GFB_ERR_UNSUPPORTED, "nlayers=%d not in [1, %d]", cfg->nlayers, MAX_LAYERS);
   if (cfg->kind == GFB_KIND_SINGLE && cfg->nlayers != 1) return fail(nullptr, GFB_ERR_INVALID, "GFB_KIND_SINGLE needs nlayers == 1");
   if (cfg->kind != GFB_KIND_SINGLE && cfg->kind != GFB_KIND_LAYERED) return fail(nullptr, GFB_ERR_INVALID, "unknown kind %d", cfg->kind);
@@ -284,6 +286,13 @@ int gfb_create(gfb_ctx** out, const gfb_config* cfg) {
   if (cfg->stepper == GFB_ETDRK4 || cfg->stepper == GFB_FILTERED_ETDRK4) {
     // ETDRK4 needs s1, s2, s3, acc, N1: the fifth array aliases W's fourth field block (unused on the step path)
   }
+  {
+    int devid = 0;
+    cudaDeviceProp prop;
+    if (cudaGetDevice(&devid) == cudaSuccess && cudaGetDeviceProperties(&prop, devid) == cudaSuccess && prop.multiProcessorCount > 0)
+      c->max_ctas = 2 * prop.multiProcessorCount;
+  }
+  TRY(dev_alloc(c, &c->scratch, (size_t)col_fwd_scratch_per_cta(g.ny) * c->max_ctas * (size_t)(2 * n > 4 ? 2 * n : 4)));
   c->dblocks = 592;
   TRY(dev_alloc(c, &c->dpart, (size_t)c->dblocks * DIAG_MAXOUT));
   TRY(dev_alloc(c, &c->dout, (size_t)DIAG_MAXOUT));
@@ -404,13 +413,14 @@ static int run_col_inv_state(gfb_ctx* c, const Spec& sin, int nf, cudaStream_t s
     L.pm.Sinv = c->Sinv;
     L.pm.ldS = c->g.nkr;
     L.pm.nf = nf;
+    L.pm.nl = c->nlayers;
     L.nfields = nf * c->nlayers;
   }
   ProfScope ps(c, 0, st);
   return check_launch(c, launch_col_inv(c->g.ny, L), "k_col_inv");
 }
 
-static int run_row_product(gfb_ctx* c, cudaStream_t st) {
+static int run_row_product(gfb_ctx* c, cudaStream_t st, bool prune) {
   RowLaunch R;
   std::memset(&R, 0, sizeof R);
   R.mode = (c->kind == GFB_KIND_LAYERED) ? ROW_PRODUCT_Q : ROW_PRODUCT;
@@ -421,7 +431,7 @@ static int run_row_product(gfb_ctx* c, cudaStream_t st) {
   R.a.P = c->P;
   R.a.ldp = c->ldp;
   R.a.pfs = c->pfs;
-  R.a.kout = c->g.nkr;
+  R.a.kout = prune ? c->g.kcut : c->g.nkr;
   R.a.eta = c->eta;
   R.a.U = c->U;
   R.a.Qx = c->Qx;
@@ -443,7 +453,9 @@ static int run_col_fwd(gfb_ctx* c, const EpiArgs& e, cudaStream_t st) {
   F.ldp = c->ldp;
   F.pfs = c->pfs;
   F.e = e;
-  F.ncols = c->g.nkr;
+  F.ncols = e.prune ? c->g.kcut : c->g.nkr;
+  F.max_ctas = c->max_ctas;
+  F.scratch = c->scratch;
   F.nlayers = c->nlayers;
   F.nl = c->nlayers;
   F.two = true;
@@ -471,7 +483,7 @@ static EpiArgs base_epi(const gfb_ctx* c, const void* Fh) {
 static int run_stage_kernels(gfb_ctx* c, const Spec& sin, EpiArgs& e, cudaStream_t st) {
   int rc = run_col_inv_state(c, sin, 3, st);
   if (rc) return rc;
-  rc = run_row_product(c, st);
+  rc = run_row_product(c, st, e.prune != 0);
   if (rc) return rc;
   e.sin = sin;
   return run_col_fwd(c, e, st);
@@ -534,12 +546,16 @@ int gfb_nstages(const gfb_ctx* c) {
   }
 }
 
-int gfb_stage(gfb_ctx* c, void* sol, int istage, const void* Fh, void* prevsol, void* stream) {
+// prune = 1 ("lazy alias band"): the aliased band of N -- which only ever lands in the aliased band of the
+// next state, where the next stage-1 dealias! wipes it -- is not computed.  Used by
+// gfb_step for every step but the last of a call, so the state the caller sees is always exact.
+static int do_stage(gfb_ctx* c, void* sol, int istage, const void* Fh, void* prevsol, void* stream, int prune) {
   if (!c || !sol) return fail(c, GFB_ERR_INVALID, "gfb_stage: null argument");
   const int ns = gfb_nstages(c);
   if (istage < 0 || istage >= ns) return fail(c, GFB_ERR_INVALID, "gfb_stage: stage %d out of range", istage);
   cudaStream_t st = (cudaStream_t)stream;
   EpiArgs e = base_epi(c, Fh);
+  e.prune = (prune && c->g.kcut < c->g.nkr) ? 1 : 0;
   const Spec S0 = user_spec(c, sol);
   const double dt = c->dt;
   if (c->filtered) {
@@ -608,7 +624,7 @@ int gfb_stage(gfb_ctx* c, void* sol, int istage, const void* Fh, void* prevsol, 
       // the epilogue stores rhs through e.sin, so run the kernels by hand
       rc = run_col_inv_state(c, S0, 3, st);
       if (rc) return rc;
-      rc = run_row_product(c, st);
+      rc = run_row_product(c, st, e.prune != 0);
       if (rc) return rc;
       e.sin = int_spec(c, cur);
       rc = run_col_fwd(c, e, st);
@@ -627,14 +643,21 @@ int gfb_stage(gfb_ctx* c, void* sol, int istage, const void* Fh, void* prevsol, 
   return GFB_OK;
 }
 
+int gfb_stage(gfb_ctx* c, void* sol, int istage, const void* Fh, void* prevsol, void* stream) {
+  return do_stage(c, sol, istage, Fh, prevsol, stream, 0);
+}
+
 int gfb_step(gfb_ctx* c, void* sol, int nsteps, const void* Fh, void* prevsol, void* stream) {
   if (!c || !sol || nsteps < 0) return fail(c, GFB_ERR_INVALID, "gfb_step: bad argument");
   const int ns = gfb_nstages(c);
-  for (int s = 0; s < nsteps; ++s)
+  const bool ab3 = c->stepper == GFB_AB3 || c->stepper == GFB_FILTERED_AB3;  // AB3 keeps RHS history incl. the aliased band
+  for (int s = 0; s < nsteps; ++s) {
+    const bool last = (s == nsteps - 1);
     for (int i = 0; i < ns; ++i) {
-      int rc = gfb_stage(c, sol, i, Fh, (s == nsteps - 1) ? prevsol : nullptr, stream);
+      int rc = do_stage(c, sol, i, Fh, last ? prevsol : nullptr, stream, (!last && !ab3 && !c->cfg.no_dealias_in_calcN) ? 1 : 0);
       if (rc) return rc;
     }
+  }
   return GFB_OK;
 }
 
@@ -714,6 +737,8 @@ int gfb_rfft(gfb_ctx* c, void* out_spec, const double* in_phys, int batch, void*
     F.nlayers = nb;
     F.nl = 1;
     F.two = false;
+    F.max_ctas = c->max_ctas;
+    F.scratch = c->scratch;
     F.tw = c->tw_y;
     F.st = st;
     rc = check_launch(c, launch_col_fwd(c->g.ny, F), "k_col_fwd(plain)");

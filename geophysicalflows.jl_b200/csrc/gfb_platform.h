@@ -5,6 +5,8 @@
 #ifdef GFB_EMULATE
 #include "cuda_emu.h"  // found via -I tests/emu (test builds only)
 #define GFB_HD
+#define __noinline__ __attribute__((noinline))
+#define __grid_constant__
 #else
 #include <cuda_runtime.h>
 #define GFB_HD __host__ __device__
@@ -17,6 +19,22 @@
 #include <cstdint>
 
 namespace gfb {
+
+// 16-byte asynchronous global->shared copy (LDGSTS): no destination registers, so a whole column can be
+// in flight while the registers hold another one.  The emulation build copies synchronously.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+#ifdef GFB_EMULATE
+  *reinterpret_cast<double2*>(smem_dst) = *reinterpret_cast<const double2*>(gmem_src);
+#else
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+#ifndef GFB_EMULATE
+  asm volatile("cp.async.wait_all;\n" ::: "memory");
+#endif
+}
 
 typedef double2 cplx;
 

@@ -46,62 +46,93 @@ struct SpecR {  // real-valued table with the same indexing
   __device__ __forceinline__ double at(int layer, int l, int kr) const { return p[layer * ls + (long long)l * ld + kr]; }
 };
 
-// threads per CTA for a column kernel of length NY and columns per CTA
-template <int NY>
-struct ColCfg {
-  static constexpr int T = NY / PT;
-  static constexpr int THREADS = (T >= 256) ? 512 : 256;
-  static constexpr int C = THREADS / T;  // adjacent kr columns per CTA (2 at 4096)
-  // group stride of the exchange buffers (in elements) so that the C interleaved lanes of a
-  // quarter-warp land in different banks
-  static constexpr int want = (C >= 8) ? 1 : (C == 1 ? 0 : 8 / C);
-  static constexpr int GS = xbuf_elems(NY) + ((want - xbuf_elems(NY) % 8) + 8) % 8;
+// One "FFT group" = T = N/16 threads transforming one length-N line at a time.  A CTA has G groups
+// (256 threads, or T when T > 256).  Shared memory per CTA: G split-exchange buffers of N(+pad) doubles
+// and thread-private stashes of PT complex per thread (`stash[r*THREADS + tid]`, conflict-free, no
+// barrier needed) -- 34 KB + 64 KB at N = 4096, so two CTAs share an SM and one CTA's global-memory
+// phases overlap the other's butterflies.
+template <int N>
+struct GroupCfg {
+  static constexpr int T = N / PT;
+  static constexpr int THREADS = (T >= 256) ? T : 256;
+  static constexpr int G = THREADS / T;
+  static constexpr int GSD = (xbuf_elems(N) + 1) & ~1;  // doubles per group buffer; 17*T keeps groups in distinct banks
+  static constexpr int XB_DOUBLES = G * GSD;
+  static constexpr int STASH = PT * THREADS;           // complex elements per stash
+  static constexpr int MINB = (THREADS == 256) ? 2 : 1;
 };
+
+__device__ __forceinline__ void swap_stash(cplx (&v)[PT], cplx* __restrict__ X, const int tid, const int threads) {
+#pragma unroll
+  for (int r = 0; r < PT; ++r) {
+    const cplx t = X[r * threads + tid];
+    X[r * threads + tid] = v[r];
+    v[r] = t;
+  }
+}
 
 // ------------------------------------------------------------------------------------------------
 // K1 pre-pass functors: value of `field` at (l, col) ready for the inverse y-FFT
 // ------------------------------------------------------------------------------------------------
+// Every functor offers two equivalent ways to produce the value of `field` at (l, col):
+//   load(g, field, l, col)                 -- direct (registers)
+//   src(...) + apply(g, field, l, col, raw) -- `raw` is the complex at src(), fetched by cp.async into the
+//                                             stash (kAsync functors only); live(g, l) says whether the row
+//                                             survives the dealias mask (else the value is 0 and nothing is read)
 struct PrepPlain {  // irfft of arbitrary spectra: field = batch index
+  static constexpr bool kAsync = true;
   const cplx* in;
   int ld;
   long long ls;
   double scale;
-  __device__ __forceinline__ cplx load(const GridDesc&, int field, int l, int col) const {
-    return cscale(in[field * ls + (long long)l * ld + col], scale);
+  __device__ __forceinline__ bool live(const GridDesc&, int) const { return true; }
+  __device__ __forceinline__ const cplx* src(int field, int l, int col) const { return in + field * ls + (long long)l * ld + col; }
+  __device__ __forceinline__ cplx apply(const GridDesc&, int, int, int, cplx raw) const { return cscale(raw, scale); }
+  __device__ __forceinline__ cplx load(const GridDesc& g, int field, int l, int col) const {
+    return apply(g, field, l, col, *src(field, l, col));
   }
 };
 
 struct PrepSingle {  // single-layer modules: psi_h = -G*sol ; uh = i l G sol ; vh = -i kr G sol ; qh = sol
+  static constexpr bool kAsync = true;
   const cplx* sol;
   int ld;
   SpecR G;
-  __device__ __forceinline__ cplx load(const GridDesc& g, int field, int l, int col) const {
-    if (l_aliased(g, l)) return cmake(0.0, 0.0);
-    cplx s = cscale(sol[(long long)l * ld + col], g.invN);
+  __device__ __forceinline__ bool live(const GridDesc& g, int l) const { return !l_aliased(g, l); }
+  __device__ __forceinline__ const cplx* src(int, int l, int col) const { return sol + (long long)l * ld + col; }
+  __device__ __forceinline__ cplx apply(const GridDesc& g, int field, int l, int col, cplx raw) const {
+    const cplx s = cscale(raw, g.invN);
     if (field == 2) return s;
     const double gg = G.at(0, l, col);
     if (field == 0) return cscale(cmul_i(s), wav_l(g, l) * gg);
     if (field == 1) return cscale(cmul_mi(s), wav_kr(g, col) * gg);
     return cscale(s, -gg);  // field 3: psi_h (updatevars! only)
   }
+  __device__ __forceinline__ cplx load(const GridDesc& g, int field, int l, int col) const {
+    if (!live(g, l)) return cmake(0.0, 0.0);
+    return apply(g, field, l, col, *src(field, l, col));
+  }
 };
 
-template <int NL>
-struct PrepMulti {  // MultiLayerQG: psi_h = S^-1 q_h ; uh = -i l psi_h ; vh = i kr psi_h ; field = 3*layer + {u,v,q}
+struct PrepMulti {  // MultiLayerQG: psi_h = S^-1 q_h ; uh = -i l psi_h ; vh = i kr psi_h ; field = nf*layer + {u,v,q[,psi]}
+  static constexpr bool kAsync = false;
   const cplx* sol;
   int ld;
   long long ls;
   const double* Sinv;  // [l][kr][row][col] row-major NLxNL, ld = nkr
   int ldS;
   int nf;              // fields per layer: 3 (u, v, q) on the hot path, 4 (+psi) for updatevars!
+  int nl;              // layers
+  __device__ __forceinline__ bool live(const GridDesc& g, int l) const { return !l_aliased(g, l); }
+  __device__ __forceinline__ const cplx* src(int, int, int) const { return nullptr; }
+  __device__ __forceinline__ cplx apply(const GridDesc&, int, int, int, cplx raw) const { return raw; }
   __device__ __forceinline__ cplx load(const GridDesc& g, int field, int l, int col) const {
     if (l_aliased(g, l)) return cmake(0.0, 0.0);
     const int layer = field / nf, what = field - nf * layer;
     if (what == 2) return cscale(sol[layer * ls + (long long)l * ld + col], g.invN);
-    const double* M = Sinv + ((long long)l * ldS + col) * (NL * NL) + layer * NL;
+    const double* M = Sinv + ((long long)l * ldS + col) * (nl * nl) + layer * nl;
     cplx psi = cmake(0.0, 0.0);
-#pragma unroll
-    for (int m = 0; m < NL; ++m) {
+    for (int m = 0; m < nl; ++m) {
       const cplx q = sol[m * ls + (long long)l * ld + col];
       const double a = __ldg(&M[m]);
       psi.x += a * q.x;
@@ -114,40 +145,68 @@ struct PrepMulti {  // MultiLayerQG: psi_h = S^-1 q_h ; uh = -i l psi_h ; vh = i
   }
 };
 
+// K1.  Each group takes a PAIR of adjacent kr columns (32-byte sectors on both the spectral and the
+// W side), transforms them one after the other in the same registers and parks the other column in the
+// thread-private stash.
 template <int NY, class Prep>
-__global__ void __launch_bounds__(ColCfg<NY>::THREADS, ColCfg<NY>::THREADS == 512 ? 1 : 2)
+__global__ void __launch_bounds__(GroupCfg<NY>::THREADS, GroupCfg<NY>::MINB)
     k_col_inv(const GridDesc g, const Prep prep, cplx* __restrict__ W, const int ldw, const long long wfs,
               const int ncols, const cplx* __restrict__ tw) {
-  using CC = ColCfg<NY>;
-  constexpr int T = CC::T, C = CC::C;
-  GFB_DYN_SMEM(cplx, sm);
-  const int c = threadIdx.x % C, j = threadIdx.x / C;
-  const int col = blockIdx.x * C + c;
+  using GC = GroupCfg<NY>;
+  constexpr int T = GC::T, THREADS = GC::THREADS;
+  GFB_DYN_SMEM(double, smd);
+  const int tid = threadIdx.x;
+  const int gi = tid / T, j = tid % T;
+  const int colA = 2 * (blockIdx.x * GC::G + gi), colB = colA + 1;
   const int field = blockIdx.y;
-  const bool live = col < ncols;
-  cplx* xb = sm + c * CC::GS;
+  const bool liveA = colA < ncols, liveB = colB < ncols;
+  double* xb = smd + gi * GC::GSD;
+  cplx* X = reinterpret_cast<cplx*>(smd + GC::XB_DOUBLES);
   cplx v[PT];
+  if constexpr (Prep::kAsync) {
+    // column B: raw values straight into the stash (no registers), prepared when swapped in
 #pragma unroll
-  for (int r = 0; r < PT; ++r) v[r] = live ? prep.load(g, field, j + r * T, col) : cmake(0.0, 0.0);
-  block_fft<NY, INV>(v, j, xb, tw);
-  if (live) {
-    cplx* out = W + field * wfs + col;
+    for (int r = 0; r < PT; ++r) {
+      const int l = j + r * T;
+      if (liveB && prep.live(g, l)) cp_async16(&X[r * THREADS + tid], prep.src(field, l, colB));
+    }
 #pragma unroll
-    for (int r = 0; r < PT; ++r) out[(long long)(j + r * T) * ldw] = v[r];
+    for (int r = 0; r < PT; ++r) v[r] = liveA ? prep.load(g, field, j + r * T, colA) : cmake(0.0, 0.0);
+    block_fft_split<NY, INV>(v, j, xb, tw);
+    cp_async_wait_all();
+#pragma unroll
+    for (int r = 0; r < PT; ++r) {
+      const int l = j + r * T;
+      cplx t = cmake(0.0, 0.0);
+      if (liveB && prep.live(g, l)) t = prep.apply(g, field, l, colB, X[r * THREADS + tid]);
+      X[r * THREADS + tid] = v[r];
+      v[r] = t;
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < PT; ++r) {
+      const int l = j + r * T;
+      v[r] = liveA ? prep.load(g, field, l, colA) : cmake(0.0, 0.0);
+      X[r * THREADS + tid] = liveB ? prep.load(g, field, l, colB) : cmake(0.0, 0.0);
+    }
+    block_fft_split<NY, INV>(v, j, xb, tw);
+    swap_stash(v, X, tid, THREADS);
+  }
+  block_fft_split<NY, INV>(v, j, xb, tw);
+  if (liveA) {
+    cplx* out = W + field * wfs + colA;
+#pragma unroll
+    for (int r = 0; r < PT; ++r) {
+      cplx* o = out + (long long)(j + r * T) * ldw;
+      o[0] = X[r * THREADS + tid];
+      if (liveB) o[1] = v[r];
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // K2 row pass
 // ------------------------------------------------------------------------------------------------
-template <int NX>
-struct RowCfg {
-  static constexpr int T = NX / PT;
-  static constexpr int THREADS = (T >= 256) ? T : 256;  // 8192 -> 512 threads
-  static constexpr int G = THREADS / T;                 // row pairs per CTA
-  static constexpr int GS = xbuf_elems(NX) + ((T < 8 ? 4 : 0) + 8 - xbuf_elems(NX) % 8) % 8;
-};
-
 // Z[k] = A[k] + i B[k] with Hermitian extension, A/B half-spectra rows known for k < kc (else 0).
 // c2r semantics of FFTW/cuFFT/pocketfft: imaginary parts of the k = 0 and k = N/2 entries are ignored.
 template <int N>
@@ -174,23 +233,32 @@ __device__ __forceinline__ void load_hermitian(cplx (&v)[PT], const int j, const
 }
 
 // After a forward FFT of z = a + i b (a, b real rows): thread holds Z[k], k = j + r*T.  Exchanges
-// through shared memory to fetch Z[N-k] and returns A[k], B[k] for r = 0..8 (r = 8 only valid
+// through shared memory (re then im) to fetch Z[N-k] and returns A[k], B[k] for r = 0..8 (r = 8 only valid
 // for j == 0, k = N/2).
 template <int N>
-__device__ __forceinline__ void unpack_pair(const cplx (&v)[PT], const int j, cplx* __restrict__ xb,
+__device__ __forceinline__ void unpack_pair(const cplx (&v)[PT], const int j, double* __restrict__ xb,
                                             cplx (&A)[9], cplx (&B)[9]) {
   constexpr int T = N / PT;
+  double wre[9];
 #pragma unroll
-  for (int r = 0; r < PT; ++r) xb[xpad(j + r * T)] = v[r];
+  for (int r = 0; r < PT; ++r) xb[xpad(j + r * T)] = v[r].x;
   __syncthreads();
 #pragma unroll
   for (int r = 0; r < 9; ++r) {
-    const int k = j + r * T;
-    const int m = (N - k) & (N - 1);
-    cplx o = v[r];
-    cplx w = (r < 8 || j == 0) ? xb[xpad(m)] : o;
-    A[r] = cmake(0.5 * (o.x + w.x), 0.5 * (o.y - w.y));
-    B[r] = cmake(0.5 * (o.y + w.y), -0.5 * (o.x - w.x));
+    const int m = (N - (j + r * T)) & (N - 1);
+    wre[r] = (r < 8 || j == 0) ? xb[xpad(m)] : v[r].x;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < PT; ++r) xb[xpad(j + r * T)] = v[r].y;
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 9; ++r) {
+    const int m = (N - (j + r * T)) & (N - 1);
+    const double wim = (r < 8 || j == 0) ? xb[xpad(m)] : v[r].y;
+    const cplx o = v[r];
+    A[r] = cmake(0.5 * (o.x + wre[r]), 0.5 * (o.y - wim));
+    B[r] = cmake(0.5 * (o.y + wim), -0.5 * (o.x - wre[r]));
   }
   __syncthreads();
 }
@@ -219,18 +287,18 @@ struct RowArgs {
 };
 
 template <int NX, int MODE>
-__global__ void __launch_bounds__(RowCfg<NX>::THREADS, RowCfg<NX>::THREADS == 256 ? 2 : 1)
+__global__ void __launch_bounds__(GroupCfg<NX>::THREADS, GroupCfg<NX>::MINB)
     k_row(const RowArgs a, const cplx* __restrict__ tw) {
-  using RC = RowCfg<NX>;
+  using RC = GroupCfg<NX>;
   constexpr int T = RC::T, THREADS = RC::THREADS;
-  GFB_DYN_SMEM(cplx, sm);
+  GFB_DYN_SMEM(double, smd);
   const int gi = threadIdx.x / T, j = threadIdx.x % T;
   const int unit = blockIdx.x * RC::G + gi;  // row pair
   const int layer = blockIdx.y;
   const int ya = 2 * unit, yb = ya + 1;
   const bool live = yb < a.ny;
-  cplx* xb = sm + gi * RC::GS;
-  cplx* stash = sm + RC::G * RC::GS;  // thread-private: stash[r*THREADS + tid]
+  double* xb = smd + gi * RC::GSD;
+  cplx* stash = reinterpret_cast<cplx*>(smd + RC::XB_DOUBLES);  // thread-private: stash[r*THREADS + tid]
   const int tid = threadIdx.x;
   cplx v[PT];
   cplx A[9], B[9];
@@ -243,7 +311,7 @@ __global__ void __launch_bounds__(RowCfg<NX>::THREADS, RowCfg<NX>::THREADS == 25
 #pragma unroll
       for (int r = 0; r < PT; ++r) v[r] = cmake(0.0, 0.0);
     }
-    block_fft<NX, INV>(v, j, xb, tw);
+    block_fft_split<NX, INV>(v, j, xb, tw);
     if (live) {
       double* oa = a.phys + ((long long)layer * a.ny + ya) * NX;
       double* ob = oa + NX;
@@ -265,7 +333,7 @@ __global__ void __launch_bounds__(RowCfg<NX>::THREADS, RowCfg<NX>::THREADS == 25
 #pragma unroll
       for (int r = 0; r < PT; ++r) v[r] = cmake(0.0, 0.0);
     }
-    block_fft<NX, FWD>(v, j, xb, tw);
+    block_fft_split<NX, FWD>(v, j, xb, tw);
     unpack_pair<NX>(v, j, xb, A, B);
     if (live) {
       cplx* pa = a.P + layer * a.pfs + (long long)ya * a.ldp;
@@ -293,7 +361,7 @@ __global__ void __launch_bounds__(RowCfg<NX>::THREADS, RowCfg<NX>::THREADS == 25
 #pragma unroll
     for (int r = 0; r < PT; ++r) v[r] = cmake(0.0, 0.0);
   }
-  block_fft<NX, INV>(v, j, xb, tw);
+  block_fft_split<NX, INV>(v, j, xb, tw);
   if (a.eta != nullptr && live) {
     const double* ea = a.eta + (long long)ya * NX;
     const double* eb = ea + NX;
@@ -316,7 +384,7 @@ __global__ void __launch_bounds__(RowCfg<NX>::THREADS, RowCfg<NX>::THREADS == 25
 #pragma unroll
       for (int r = 0; r < PT; ++r) v[r] = cmake(0.0, 0.0);
     }
-    block_fft<NX, INV>(v, j, xb, tw);
+    block_fft_split<NX, INV>(v, j, xb, tw);
     if (withQ && live) {
       const double Uy = a.U ? a.U[(long long)layer * a.ny + y] : 0.0;
       const double* qx = a.Qx + ((long long)layer * a.ny + y) * NX;
@@ -336,7 +404,7 @@ __global__ void __launch_bounds__(RowCfg<NX>::THREADS, RowCfg<NX>::THREADS == 25
       v[r].x *= q;
       v[r].y *= q;
     }
-    block_fft<NX, FWD>(v, j, xb, tw);
+    block_fft_split<NX, FWD>(v, j, xb, tw);
     unpack_pair<NX>(v, j, xb, A, B);  // A = (uq)_h, B = (vq)_h
     if (live) {
       cplx* pd = a.P + (2 * layer + 0) * a.pfs + (long long)y * a.ldp;
@@ -356,7 +424,7 @@ __global__ void __launch_bounds__(RowCfg<NX>::THREADS, RowCfg<NX>::THREADS == 25
   if (withQ) {
 #pragma unroll
     for (int r = 0; r < PT; ++r) v[r] = live ? gst[r * THREADS + tid] : cmake(0.0, 0.0);
-    block_fft<NX, FWD>(v, j, xb, tw);
+    block_fft_split<NX, FWD>(v, j, xb, tw);
     unpack_pair<NX>(v, j, xb, A, B);
     if (live) {
       cplx* pa = a.P + (2 * layer + 0) * a.pfs + (long long)ya * a.ldp;
@@ -405,6 +473,7 @@ struct Coef {  // real or complex coefficient table [layer][l][kr]
 struct EpiArgs {
   int kind;
   int nlayers;
+  int prune;       // 1: rows in the aliased l band are neither read nor written (non-final steps)
   Spec out;        // EPI_STORE / EPI_PLAIN: destination of N ; stage kinds: the state written this stage
   Spec sol;        // s0 source (the problem state `sol`), masked on load
   Spec sin;        // stage input (== sol for stage 1), masked on load
@@ -423,14 +492,13 @@ struct EpiArgs {
   int ldS;
 };
 
-template <int NL>
 __device__ __forceinline__ cplx masked(const GridDesc& g, const Spec& s, int layer, int l, int col) {
   if (col >= g.kcut || l_aliased(g, l)) return cmake(0.0, 0.0);
   return s.at(layer, l, col);
 }
 
-template <int NL>
 __device__ __forceinline__ void epilogue(const GridDesc& g, const EpiArgs& e, int layer, int l, int col, cplx N) {
+  const int NL = e.nlayers;
   if (e.kind == EPI_PLAIN) {
     e.out.at(layer, l, col) = N;
     return;
@@ -440,9 +508,8 @@ __device__ __forceinline__ void epilogue(const GridDesc& g, const EpiArgs& e, in
     // bottom drag on the stage input (dealiased): psi_n = sum_m Sinv[n-1][m] q_m
     cplx psi = cmake(0.0, 0.0);
     const double* M = e.Sinv + ((long long)l * e.ldS + col) * (NL * NL) + (NL - 1) * NL;
-#pragma unroll
     for (int m = 0; m < NL; ++m) {
-      const cplx q = masked<NL>(g, e.sin, m, l, col);
+      const cplx q = masked(g, e.sin, m, l, col);
       psi.x += M[m] * q.x;
       psi.y += M[m] * q.y;
     }
@@ -458,47 +525,47 @@ __device__ __forceinline__ void epilogue(const GridDesc& g, const EpiArgs& e, in
       e.out.at(layer, l, col) = N;
       break;
     case EPI_RK_FIRST: {
-      const cplx s0 = masked<NL>(g, e.sol, layer, l, col);
+      const cplx s0 = masked(g, e.sol, layer, l, col);
       const cplx rhs = cadd(N, e.L.mul(layer, l, col, s0));
       e.out.at(layer, l, col) = cmake(s0.x + e.a * rhs.x, s0.y + e.a * rhs.y);
       e.acc.at(layer, l, col) = cmake(s0.x + e.b * rhs.x, s0.y + e.b * rhs.y);
       if (e.prevsol.p) e.prevsol.at(layer, l, col) = s0;
     } break;
     case EPI_RK_MID: {
-      const cplx s0 = masked<NL>(g, e.sol, layer, l, col);
-      const cplx si = masked<NL>(g, e.sin, layer, l, col);
+      const cplx s0 = masked(g, e.sol, layer, l, col);
+      const cplx si = masked(g, e.sin, layer, l, col);
       const cplx rhs = cadd(N, e.L.mul(layer, l, col, si));
       cplx ac = e.acc.at(layer, l, col);
       e.out.at(layer, l, col) = cmake(s0.x + e.a * rhs.x, s0.y + e.a * rhs.y);
       e.acc.at(layer, l, col) = cmake(ac.x + e.b * rhs.x, ac.y + e.b * rhs.y);
     } break;
     case EPI_RK_LAST: {
-      const cplx si = masked<NL>(g, e.sin, layer, l, col);
+      const cplx si = masked(g, e.sin, layer, l, col);
       const cplx rhs = cadd(N, e.L.mul(layer, l, col, si));
       const cplx ac = e.acc.at(layer, l, col);
       e.out.at(layer, l, col) = cmake((ac.x + e.b * rhs.x) * filt, (ac.y + e.b * rhs.y) * filt);
     } break;
     case EPI_RK_ONLY: {
-      const cplx s0 = masked<NL>(g, e.sol, layer, l, col);
+      const cplx s0 = masked(g, e.sol, layer, l, col);
       const cplx rhs = cadd(N, e.L.mul(layer, l, col, s0));
       if (e.prevsol.p) e.prevsol.at(layer, l, col) = s0;
       e.out.at(layer, l, col) = cmake((s0.x + e.b * rhs.x) * filt, (s0.y + e.b * rhs.y) * filt);
     } break;
     case EPI_ETD_1: {  // c1 = exp(L dt/2), c2 = zeta, c3 = exp(L dt), c4 = alpha
-      const cplx s0 = masked<NL>(g, e.sol, layer, l, col);
+      const cplx s0 = masked(g, e.sol, layer, l, col);
       e.out.at(layer, l, col) = cadd(e.c1.mul(layer, l, col, s0), e.c2.mul(layer, l, col, N));
       e.acc.at(layer, l, col) = cadd(e.c3.mul(layer, l, col, s0), e.c4.mul(layer, l, col, N));
       e.n1.at(layer, l, col) = N;
       if (e.prevsol.p) e.prevsol.at(layer, l, col) = s0;
     } break;
     case EPI_ETD_2: {  // c1 = exp(L dt/2), c2 = zeta, c4 = beta (2*beta applied here)
-      const cplx s0 = masked<NL>(g, e.sol, layer, l, col);
+      const cplx s0 = masked(g, e.sol, layer, l, col);
       e.out.at(layer, l, col) = cadd(e.c1.mul(layer, l, col, s0), e.c2.mul(layer, l, col, N));
       const cplx ac = e.acc.at(layer, l, col);
       e.acc.at(layer, l, col) = cadd(ac, e.c4.mul(layer, l, col, cscale(N, 2.0)));
     } break;
     case EPI_ETD_3: {  // sin = sol2 (input of N3); sol here = sol1 (dealiased on load); out = sol2
-      const cplx s1 = masked<NL>(g, e.sol, layer, l, col);
+      const cplx s1 = masked(g, e.sol, layer, l, col);
       const cplx n1 = e.n1.at(layer, l, col);
       const cplx t = cmake(2.0 * N.x - n1.x, 2.0 * N.y - n1.y);
       e.out.at(layer, l, col) = cadd(e.c1.mul(layer, l, col, s1), e.c2.mul(layer, l, col, t));
@@ -511,7 +578,7 @@ __device__ __forceinline__ void epilogue(const GridDesc& g, const EpiArgs& e, in
       e.out.at(layer, l, col) = cscale(r, filt);
     } break;
     case EPI_AB3: {  // out = sol (in place); acc = rhs-1 ; n1 = rhs-2 ; sin = where rhs is stored
-      const cplx s0 = masked<NL>(g, e.sol, layer, l, col);
+      const cplx s0 = masked(g, e.sol, layer, l, col);
       const cplx rhs = cadd(N, e.L.mul(layer, l, col, s0));
       cplx upd = cscale(rhs, e.a);
       if (e.b != 0.0 || e.d != 0.0) {
@@ -528,143 +595,121 @@ __device__ __forceinline__ void epilogue(const GridDesc& g, const EpiArgs& e, in
   }
 }
 
-// Split (re / im) exchange variant of the FFT for kernels that also need a large stash.
-template <int N, int DIR, int R, int Ns, bool LAST>
-__device__ __forceinline__ void fft_pass_split(cplx (&v)[PT], const int j, double* __restrict__ xb,
-                                               const cplx* __restrict__ tw) {
-  constexpr int T = N / PT;
-  constexpr int M = PT / R;
-  int base[M];
+// K3.  TWO = true: N = FFTy(Pd) - i l FFTy(Pv) ; TWO = false: plain forward transform of one field.
+// Persistent CTAs loop over column-pair tiles.  Per pair four transforms run back to back in the same
+// registers: the two (-i l)-weighted v-transforms are parked in a CTA-private, L2-resident scratch
+// (written and read back by the same thread, 128 KB per CTA), the stash holds the other column, and the
+// epilogue then touches every spectral array with complete 32-byte sectors (both columns of a row).
+// The per-tile work lives in two non-inlined functions: inside a persistent loop the compiler would hoist
+// ~64 registers of loop invariants (row offsets, wavenumbers) out of the loop and spill the butterflies.
+// phase V: both columns of -i l FFTy(Pv) -> scratch; leaves the cp.async of column B of Pd in flight
+template <int NY>
+__device__ __noinline__ void col_fwd_tile_v(const GridDesc& g, const cplx* __restrict__ pv, const cplx* __restrict__ pd,
+                                            const int ldp, const cplx* __restrict__ tw, cplx* __restrict__ sc,
+                                            double* __restrict__ xb, cplx* __restrict__ X, const bool liveA,
+                                            const bool liveB, const int j, const int tid) {
+  using GC = GroupCfg<NY>;
+  constexpr int T = GC::T, THREADS = GC::THREADS;
+  cplx v[PT];
+  if (liveB) {
 #pragma unroll
-  for (int i = 0; i < M; ++i) {
-    const int b = j + i * T;
-    cplx x[R];
-#pragma unroll
-    for (int s = 0; s < R; ++s) x[s] = v[i + s * M];
-    if (Ns > 1) {
-      const int k = b & (Ns - 1);
-      cplx w1 = __ldg(&tw[k * (N / (Ns * R))]);
-      if (DIR == INV) w1.y = -w1.y;
-      cplx w[R];
-      w[1] = w1;
-#pragma unroll
-      for (int s = 2; s < R; ++s) {
-        if ((s & 1) == 0) {
-          const cplx h = w[s / 2];
-          w[s] = cmake(h.x * h.x - h.y * h.y, 2.0 * h.x * h.y);
-        } else {
-          w[s] = cmul(w[s - 1], w1);
-        }
-      }
-#pragma unroll
-      for (int s = 1; s < R; ++s) x[s] = cmul(x[s], w[s]);
-    }
-    Dft<DIR, R>::run(x);
-#pragma unroll
-    for (int s = 0; s < R; ++s) v[i + s * M] = x[s];
-    const int k = b & (Ns - 1);
-    base[i] = (b - k) * R + k;
+    for (int r = 0; r < PT; ++r) cp_async16(&X[r * THREADS + tid], pv + (long long)(j + r * T) * ldp + 1);
   }
-  if (!LAST) {
 #pragma unroll
-    for (int i = 0; i < M; ++i)
+  for (int r = 0; r < PT; ++r) v[r] = liveA ? pv[(long long)(j + r * T) * ldp] : cmake(0.0, 0.0);
+  block_fft_split<NY, FWD>(v, j, xb, tw);
+  cp_async_wait_all();
 #pragma unroll
-      for (int s = 0; s < R; ++s) xb[xpad(base[i] + s * Ns)] = v[i + s * M].x;
-    __syncthreads();
-    double re[PT];
+  for (int r = 0; r < PT; ++r) {
+    const double ll = wav_l(g, j + r * T);
+    sc[r * THREADS + tid] = cmake(ll * v[r].y, -ll * v[r].x);  // -i l (vq)_h, column A
+    v[r] = liveB ? X[r * THREADS + tid] : cmake(0.0, 0.0);
+  }
+  // the stash is free again: start fetching column B of the d field behind the next transform
+  if (liveB) {
 #pragma unroll
-    for (int r = 0; r < PT; ++r) re[r] = xb[xpad(j + r * T)];
-    __syncthreads();
+    for (int r = 0; r < PT; ++r) cp_async16(&X[r * THREADS + tid], pd + (long long)(j + r * T) * ldp + 1);
+  }
+  block_fft_split<NY, FWD>(v, j, xb, tw);
 #pragma unroll
-    for (int i = 0; i < M; ++i)
-#pragma unroll
-      for (int s = 0; s < R; ++s) xb[xpad(base[i] + s * Ns)] = v[i + s * M].y;
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < PT; ++r) v[r] = cmake(re[r], xb[xpad(j + r * T)]);
-    __syncthreads();
+  for (int r = 0; r < PT; ++r) {
+    const double ll = wav_l(g, j + r * T);
+    sc[GC::STASH + r * THREADS + tid] = cmake(ll * v[r].y, -ll * v[r].x);  // column B
   }
 }
 
-template <int N, int DIR>
-__device__ __forceinline__ void block_fft_split(cplx (&v)[PT], const int j, double* __restrict__ xb,
-                                                const cplx* __restrict__ tw) {
-  using P = Plan<N>;
-  constexpr int rem = P::rem;
-  constexpr int RR = rem > 1 ? rem : 2;
-  if constexpr (P::n16 == 1) {
-    if constexpr (rem == 1) {
-      fft_pass_split<N, DIR, 16, 1, true>(v, j, xb, tw);
-    } else {
-      fft_pass_split<N, DIR, 16, 1, false>(v, j, xb, tw);
-      fft_pass_split<N, DIR, RR, 16, true>(v, j, xb, tw);
-    }
-  } else if constexpr (P::n16 == 2) {
-    fft_pass_split<N, DIR, 16, 1, false>(v, j, xb, tw);
-    if constexpr (rem == 1) {
-      fft_pass_split<N, DIR, 16, 16, true>(v, j, xb, tw);
-    } else {
-      fft_pass_split<N, DIR, 16, 16, false>(v, j, xb, tw);
-      fft_pass_split<N, DIR, RR, 256, true>(v, j, xb, tw);
+// phase D: FFTy(Pd) of both columns (+ the parked phase-V results), then the epilogue on the column pair
+template <int NY, bool TWO>
+__device__ __noinline__ void col_fwd_tile_d(const GridDesc& g, const cplx* __restrict__ pd, const int ldp, const EpiArgs& e,
+                                            const cplx* __restrict__ tw, cplx* __restrict__ sc, double* __restrict__ xb,
+                                            cplx* __restrict__ X, const int colA, const bool liveA, const bool liveB,
+                                            const int layer, const int j, const int tid) {
+  using GC = GroupCfg<NY>;
+  constexpr int T = GC::T, THREADS = GC::THREADS;
+  cplx v[PT];
+  if (!TWO && liveB) {
+#pragma unroll
+    for (int r = 0; r < PT; ++r) cp_async16(&X[r * THREADS + tid], pd + (long long)(j + r * T) * ldp + 1);
+  }
+#pragma unroll
+  for (int r = 0; r < PT; ++r) v[r] = liveA ? pd[(long long)(j + r * T) * ldp] : cmake(0.0, 0.0);
+  block_fft_split<NY, FWD>(v, j, xb, tw);
+  cp_async_wait_all();
+#pragma unroll
+  for (int r = 0; r < PT; ++r) {
+    cplx t = liveB ? X[r * THREADS + tid] : cmake(0.0, 0.0);
+    cplx n = v[r];
+    if (TWO) n = cadd(n, sc[r * THREADS + tid]);
+    X[r * THREADS + tid] = n;
+    v[r] = t;
+  }
+  block_fft_split<NY, FWD>(v, j, xb, tw);
+  const int colB = colA + 1;
+  if constexpr (!TWO) {
+    if (liveA) {
+#pragma unroll
+      for (int r = 0; r < PT; ++r) {
+        const int l = j + r * T;
+        e.out.at(layer, l, colA) = X[r * THREADS + tid];
+        if (liveB) e.out.at(layer, l, colB) = v[r];
+      }
     }
   } else {
-    fft_pass_split<N, DIR, 16, 1, false>(v, j, xb, tw);
-    fft_pass_split<N, DIR, 16, 16, false>(v, j, xb, tw);
-    if constexpr (rem == 1) {
-      fft_pass_split<N, DIR, 16, 256, true>(v, j, xb, tw);
-    } else {
-      fft_pass_split<N, DIR, 16, 256, false>(v, j, xb, tw);
-      fft_pass_split<N, DIR, RR, 4096, true>(v, j, xb, tw);
+    // park column B next to column A so the (large) epilogue is instantiated once in a rolled loop
+#pragma unroll
+    for (int r = 0; r < PT; ++r) sc[r * THREADS + tid] = cadd(v[r], sc[GC::STASH + r * THREADS + tid]);
+    if (liveA) {
+#pragma unroll 1
+      for (int r = 0; r < PT; ++r) {
+        const int l = j + r * T;
+        if (e.prune && l_aliased(g, l)) continue;
+        epilogue(g, e, layer, l, colA, X[r * THREADS + tid]);
+        if (liveB) epilogue(g, e, layer, l, colB, sc[r * THREADS + tid]);
+      }
     }
   }
 }
 
-template <int NY>
-struct ColSplitCfg {
-  using CC = ColCfg<NY>;
-  // doubles; half-warp (16 lanes) of 8-byte accesses: C interleaved lanes -> offsets of 16/C doubles
-  static constexpr int want = (CC::C >= 16) ? 1 : (CC::C == 1 ? 0 : 16 / CC::C);
-  static constexpr int GS = xbuf_elems(NY) + ((want - xbuf_elems(NY) % 16) + 16) % 16;
-};
-
-// K3.  TWO = true: N = FFTy(Pd) - i l FFTy(Pv) ; TWO = false: plain forward transform of one field.
-template <int NY, int NL, bool TWO>
-__global__ void __launch_bounds__(ColCfg<NY>::THREADS, ColCfg<NY>::THREADS == 512 ? 1 : 2)
-    k_col_fwd(const GridDesc g, const cplx* __restrict__ P, const int ldp, const long long pfs,
-              const EpiArgs e, const int ncols, const cplx* __restrict__ tw) {
-  using CC = ColCfg<NY>;
-  constexpr int T = CC::T, C = CC::C, THREADS = CC::THREADS;
+template <int NY, bool TWO>
+__global__ void __launch_bounds__(GroupCfg<NY>::THREADS, GroupCfg<NY>::MINB)
+    k_col_fwd(const __grid_constant__ GridDesc g, const cplx* __restrict__ P, const int ldp, const long long pfs,
+              const __grid_constant__ EpiArgs e, const int ncols, const cplx* __restrict__ tw, cplx* __restrict__ scratch) {
+  using GC = GroupCfg<NY>;
+  constexpr int T = GC::T;
   GFB_DYN_SMEM(double, smd);
   const int tid = threadIdx.x;
-  const int c = tid % C, j = tid / C;
-  const int col = blockIdx.x * C + c;
+  const int gi = tid / T, j = tid % T;
   const int layer = blockIdx.y;
-  const bool live = col < ncols;
-  double* xb = smd + c * ColSplitCfg<NY>::GS;
-  cplx* stash = reinterpret_cast<cplx*>(smd + ((C * ColSplitCfg<NY>::GS + 1) & ~1));
-  cplx v[PT];
-  if (TWO) {
-    const cplx* pv = P + (2 * layer + 1) * pfs + col;
-#pragma unroll
-    for (int r = 0; r < PT; ++r) v[r] = live ? pv[(long long)(j + r * T) * ldp] : cmake(0.0, 0.0);
-    block_fft_split<NY, FWD>(v, j, xb, tw);
-#pragma unroll
-    for (int r = 0; r < PT; ++r) {
-      const double ll = wav_l(g, j + r * T);
-      stash[r * THREADS + tid] = cmake(ll * v[r].y, -ll * v[r].x);  // -i l (vq)_h
-    }
-  }
-  const cplx* pd = P + (TWO ? 2 * layer : layer) * pfs + col;
-#pragma unroll
-  for (int r = 0; r < PT; ++r) v[r] = live ? pd[(long long)(j + r * T) * ldp] : cmake(0.0, 0.0);
-  block_fft_split<NY, FWD>(v, j, xb, tw);
-  if (live) {
-#pragma unroll
-    for (int r = 0; r < PT; ++r) {
-      cplx N = v[r];
-      if (TWO) N = cadd(N, stash[r * THREADS + tid]);
-      epilogue<NL>(g, e, layer, j + r * T, col, N);
-    }
+  double* xb = smd + gi * GC::GSD;
+  cplx* X = reinterpret_cast<cplx*>(smd + GC::XB_DOUBLES);
+  cplx* sc = scratch + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * (2 * GC::STASH);
+  const int ntiles = ((ncols + 1) / 2 + GC::G - 1) / GC::G;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int colA = 2 * (tile * GC::G + gi);
+    const bool liveA = colA < ncols, liveB = colA + 1 < ncols;
+    const cplx* pd = P + (TWO ? 2 * layer : layer) * pfs + colA;
+    if (TWO) col_fwd_tile_v<NY>(g, P + (2 * layer + 1) * pfs + colA, pd, ldp, tw, sc, xb, X, liveA, liveB, j, tid);
+    col_fwd_tile_d<NY, TWO>(g, pd, ldp, e, tw, sc, xb, X, colA, liveA, liveB, layer, j, tid);
   }
 }
 

@@ -5,15 +5,6 @@
 
 namespace gfb {
 
-struct PrepMultiArgs {
-  const cplx* sol;
-  int ld;
-  long long ls;
-  const double* Sinv;
-  int ldS;
-  int nf;
-};
-
 enum PrepKind { PREP_PLAIN = 0, PREP_SINGLE = 1, PREP_MULTI = 2 };
 
 struct ColInvLaunch {
@@ -21,7 +12,7 @@ struct ColInvLaunch {
   int prep;            // PrepKind
   PrepPlain pp;
   PrepSingle ps;
-  PrepMultiArgs pm;
+  PrepMulti pm;
   int nl;              // layers (PREP_MULTI template argument)
   cplx* W;
   int ldw;
@@ -50,6 +41,8 @@ struct ColFwdLaunch {
   int nlayers;         // grid.y
   int nl;              // template NL (layers coupled in the epilogue)
   bool two;
+  int max_ctas;        // persistent grid width (per layer); scratch has nlayers*max_ctas slots
+  cplx* scratch;       // 2*PT*THREADS complex per CTA slot
   const cplx* tw;
   cudaStream_t st;
 };
@@ -60,7 +53,6 @@ constexpr int MAX_LAYERS = 5;
   int launch_col_inv_##N(const ColInvLaunch& L);    \
   int launch_row_##N(const RowLaunch& L);           \
   int launch_col_fwd_##N(const ColFwdLaunch& L);
-GFB_DECL_SIZE(16)
 GFB_DECL_SIZE(32)
 GFB_DECL_SIZE(64)
 GFB_DECL_SIZE(128)
@@ -76,4 +68,13 @@ int launch_col_inv(int NY, const ColInvLaunch& L);
 int launch_row(int NX, const RowLaunch& L);
 int launch_col_fwd(int NY, const ColFwdLaunch& L);
 
+}  // namespace gfb
+
+namespace gfb {
+// complex elements of K3 scratch needed per CTA slot for FFT length NY
+inline long long col_fwd_scratch_per_cta(int NY) {
+  const int T = NY / PT;
+  const int threads = T >= 256 ? T : 256;
+  return 2LL * PT * threads;
+}
 }  // namespace gfb

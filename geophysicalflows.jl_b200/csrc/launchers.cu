@@ -18,51 +18,33 @@ static inline int set_smem(K kernel, size_t bytes) {
 
 template <class Prep>
 static int do_col_inv(const ColInvLaunch& L, const Prep& prep) {
-  using CC = ColCfg<GFB_N>;
-  const size_t smem = (size_t)CC::C * CC::GS * sizeof(cplx);
+  using GC = GroupCfg<GFB_N>;
+  const size_t smem = (size_t)GC::XB_DOUBLES * sizeof(double) + (size_t)GC::STASH * sizeof(cplx);
   static bool attr = false;
   if (!attr) {
     if (set_smem(k_col_inv<GFB_N, Prep>, smem)) return -2;
     attr = true;
   }
-  dim3 grid((L.ncols + CC::C - 1) / CC::C, L.nfields);
-  GFB_LAUNCH((k_col_inv<GFB_N, Prep>), grid, dim3(CC::THREADS), smem, L.st, L.g, prep, L.W, L.ldw, L.wfs, L.ncols, L.tw);
+  const int npairs = (L.ncols + 1) / 2;
+  dim3 grid((npairs + GC::G - 1) / GC::G, L.nfields);
+  GFB_LAUNCH((k_col_inv<GFB_N, Prep>), grid, dim3(GC::THREADS), smem, L.st, L.g, prep, L.W, L.ldw, L.wfs, L.ncols, L.tw);
   return 0;
-}
-
-template <int NL>
-static int do_col_inv_multi(const ColInvLaunch& L) {
-  PrepMulti<NL> p;
-  p.sol = L.pm.sol;
-  p.ld = L.pm.ld;
-  p.ls = L.pm.ls;
-  p.Sinv = L.pm.Sinv;
-  p.ldS = L.pm.ldS;
-  p.nf = L.pm.nf;
-  return do_col_inv(L, p);
 }
 
 int GFB_CAT(launch_col_inv_, GFB_N)(const ColInvLaunch& L) {
   switch (L.prep) {
     case PREP_PLAIN: return do_col_inv(L, L.pp);
     case PREP_SINGLE: return do_col_inv(L, L.ps);
-    case PREP_MULTI:
-      switch (L.nl) {
-        case 1: return do_col_inv_multi<1>(L);
-        case 2: return do_col_inv_multi<2>(L);
-        case 3: return do_col_inv_multi<3>(L);
-        case 4: return do_col_inv_multi<4>(L);
-        case 5: return do_col_inv_multi<5>(L);
-      }
+    case PREP_MULTI: return do_col_inv(L, L.pm);
   }
   return -1;
 }
 
 template <int MODE>
 static int do_row(const RowLaunch& L) {
-  using RC = RowCfg<GFB_N>;
+  using RC = GroupCfg<GFB_N>;
   const int nst = (MODE == ROW_PRODUCT) ? 1 : (MODE == ROW_PRODUCT_Q ? 2 : 0);
-  const size_t smem = ((size_t)RC::G * RC::GS + (size_t)nst * PT * RC::THREADS) * sizeof(cplx);
+  const size_t smem = (size_t)RC::XB_DOUBLES * sizeof(double) + (size_t)nst * RC::STASH * sizeof(cplx);
   static bool attr = false;
   if (!attr) {
     if (set_smem(k_row<GFB_N, MODE>, smem)) return -2;
@@ -84,31 +66,25 @@ int GFB_CAT(launch_row_, GFB_N)(const RowLaunch& L) {
   return -1;
 }
 
-template <int NL, bool TWO>
+template <bool TWO>
 static int do_col_fwd(const ColFwdLaunch& L) {
-  using CC = ColCfg<GFB_N>;
-  const size_t xch = ((size_t)CC::C * ColSplitCfg<GFB_N>::GS + 1) & ~(size_t)1;
-  const size_t smem = xch * sizeof(double) + (TWO ? (size_t)PT * CC::THREADS * sizeof(cplx) : 0);
+  using GC = GroupCfg<GFB_N>;
+  const size_t smem = (size_t)GC::XB_DOUBLES * sizeof(double) + (size_t)GC::STASH * sizeof(cplx);
   static bool attr = false;
   if (!attr) {
-    if (set_smem(k_col_fwd<GFB_N, NL, TWO>, smem)) return -2;
+    if (set_smem(k_col_fwd<GFB_N, TWO>, smem)) return -2;
     attr = true;
   }
-  dim3 grid((L.ncols + CC::C - 1) / CC::C, L.nlayers);
-  GFB_LAUNCH((k_col_fwd<GFB_N, NL, TWO>), grid, dim3(CC::THREADS), smem, L.st, L.g, L.P, L.ldp, L.pfs, L.e, L.ncols, L.tw);
+  const int ntiles = ((L.ncols + 1) / 2 + GC::G - 1) / GC::G;
+  int gx = ntiles < L.max_ctas ? ntiles : L.max_ctas;
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, L.nlayers);
+  GFB_LAUNCH((k_col_fwd<GFB_N, TWO>), grid, dim3(GC::THREADS), smem, L.st, L.g, L.P, L.ldp, L.pfs, L.e, L.ncols, L.tw, L.scratch);
   return 0;
 }
 
 int GFB_CAT(launch_col_fwd_, GFB_N)(const ColFwdLaunch& L) {
-  if (!L.two) return do_col_fwd<1, false>(L);
-  switch (L.nl) {
-    case 1: return do_col_fwd<1, true>(L);
-    case 2: return do_col_fwd<2, true>(L);
-    case 3: return do_col_fwd<3, true>(L);
-    case 4: return do_col_fwd<4, true>(L);
-    case 5: return do_col_fwd<5, true>(L);
-  }
-  return -1;
+  return L.two ? do_col_fwd<true>(L) : do_col_fwd<false>(L);
 }
 
 }  // namespace gfb

@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "geophysicalflows.jl_b200", "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libgfb_emu.so")
-SIZES = [16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192]
+SIZES = [32, 64, 128, 256, 512, 1024, 2048, 4096, 8192]
 FLAGS = ["-std=c++17", "-O1", "-fPIC", "-DGFB_EMULATE", "-x", "c++", "-I", HERE, "-I", CSRC, "-w"]
 
 

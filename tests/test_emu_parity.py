@@ -29,7 +29,7 @@ def test_plain_transforms(emu):
     assert R.relerr(emu.host(prob.irfft(emu.dev(bh))), np.fft.irfft2(bh, s=(32, 64))) < 1e-14
 
 
-@pytest.mark.parametrize("nx,ny", [(64, 64), (128, 32), (32, 128), (16, 16)])
+@pytest.mark.parametrize("nx,ny", [(64, 64), (128, 32), (32, 128), (32, 32)])
 @pytest.mark.parametrize("stepper", ["ForwardEuler", "FilteredRK4", "RK4", "ETDRK4", "FilteredETDRK4", "FilteredAB3"])
 def test_twodns_steps_vs_oracle(emu, oracle_backend, nx, ny, stepper):
     kw = dict(nx=nx, ny=ny, Lx=2 * np.pi, Ly=5.0, nu=1e-4, nnu=1, mu=0.02, nmu=0, dt=2e-3, stepper=stepper)
@@ -114,7 +114,7 @@ def test_reference_cases_slqg(emu):
     assert abs(e) < RT and abs(z) < RT and pe == 0
     assert max(abs(e) for e in R.slqg_energyenstrophy(emu, deformation_radius=1.23)) < RT
     M = emu.singlelayerqg
-    prob = M.Problem(nx=16, deformation_radius=2.23)
+    prob = M.Problem(nx=32, deformation_radius=2.23)
     for f in (M.energy_dissipation, M.enstrophy_dissipation, M.energy_work, M.enstrophy_work, M.energy_drag,
               M.enstrophy_drag):
         with pytest.raises(RuntimeError, match="not implemented for finite deformation radius"):

@@ -36,7 +36,7 @@ def test_native_library_is_loaded(gpu):
     assert "libgfb.so" in maps
 
 
-@pytest.mark.parametrize("nx,ny", [(16, 16), (64, 32), (128, 128), (256, 1024), (2048, 512), (4096, 64), (64, 8192), (8192, 32)])
+@pytest.mark.parametrize("nx,ny", [(32, 32), (64, 32), (128, 128), (256, 1024), (2048, 512), (4096, 64), (64, 8192), (8192, 32)])
 def test_plain_transforms(gpu, nx, ny):
     prob = gpu.twodnavierstokes.Problem(nx=nx, ny=ny, Lx=2 * np.pi, Ly=3.0, stepper="ForwardEuler")
     rng = np.random.default_rng(nx + ny)

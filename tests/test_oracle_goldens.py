@@ -92,7 +92,7 @@ def test_slqg_energies_equivalentbarotropic(oracle_backend):
 def test_slqg_finite_deformation_errors(oracle_backend):
     """test/runtests.jl:82-87."""
     M = oracle_backend.singlelayerqg
-    prob = M.Problem(nx=16, deformation_radius=2.23)
+    prob = M.Problem(nx=32, deformation_radius=2.23)
     for f in (M.energy_dissipation, M.enstrophy_dissipation, M.energy_work, M.enstrophy_work, M.energy_drag,
               M.enstrophy_drag):
         with pytest.raises(RuntimeError, match="not implemented for finite deformation radius"):
