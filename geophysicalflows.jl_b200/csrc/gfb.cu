@@ -42,6 +42,7 @@ struct gfb_ctx {
   int ldw = 0, ldp = 0, ldi = 0;
   long long wfs = 0, pfs = 0, ils = 0;  // field / layer strides
   cplx* st[4] = {nullptr, nullptr, nullptr, nullptr};  // stage states / accumulators / histories
+  cplx *S0 = nullptr, *Fint = nullptr, *PV = nullptr, *Cin = nullptr, *Nint = nullptr;  // aligned copies of user arrays
   double *dpart = nullptr, *dout = nullptr;
   int dblocks = 0;
   cplx* scratch = nullptr;  // K3 per-CTA parking space (L2-resident)
@@ -238,18 +239,30 @@ int gfb_create(gfb_ctx** out, const gfb_config* cfg) {
   const size_t nspec = (size_t)nl * nkr, nphys = (size_t)g.ny * g.nx;
   if (c->kind == GFB_KIND_SINGLE) {
     if (!cfg->G) { fail(c, GFB_ERR_INVALID, "GFB_KIND_SINGLE needs config.G"); TRY(GFB_ERR_INVALID); }
-    TRY(dev_upload(c, &c->G, cfg->G, nspec));
+    {
+      void* gp = nullptr;
+      TRY(upload_padded(c, &gp, cfg->G, 1, false));
+      c->G = (double*)gp;
+    }
     if (cfg->eta) TRY(dev_upload(c, &c->eta, cfg->eta, nphys));
   } else {
     if (!cfg->Sinv || !cfg->Qx || !cfg->Qy) { fail(c, GFB_ERR_INVALID, "GFB_KIND_LAYERED needs config.Sinv, Qx, Qy"); TRY(GFB_ERR_INVALID); }
     TRY(dev_upload(c, &c->Sinv, cfg->Sinv, nspec * n * n));
-    if (cfg->G) TRY(dev_upload(c, &c->G, cfg->G, nspec));  // optional: only the G-weighted diagnostics use it
+    if (cfg->G) {  // optional: only the G-weighted diagnostics use it
+      void* gp = nullptr;
+      TRY(upload_padded(c, &gp, cfg->G, 1, false));
+      c->G = (double*)gp;
+    }
     if (cfg->S) TRY(dev_upload(c, &c->S, cfg->S, nspec * n * n));
     if (cfg->U) TRY(dev_upload(c, &c->U, cfg->U, (size_t)n * g.ny));
     TRY(dev_upload(c, &c->Qx, cfg->Qx, nphys * n));
     TRY(dev_upload(c, &c->Qy, cfg->Qy, nphys * n));
   }
-  if (cfg->Nconst) TRY(dev_upload(c, &c->Nconst, cfg->Nconst, nspec * n));
+  if (cfg->Nconst) {
+    void* np = nullptr;
+    TRY(upload_padded(c, &np, cfg->Nconst, n, true));
+    c->Nconst = (cplx*)np;
+  }
   TRY(upload_padded(c, &c->L, cfg->L, n, c->cplxL));
   if (c->filtered) {
     if (!cfg->filter) { fail(c, GFB_ERR_INVALID, "filtered stepper needs config.filter"); TRY(GFB_ERR_INVALID); }
@@ -293,6 +306,13 @@ int gfb_create(gfb_ctx** out, const gfb_config* cfg) {
       c->max_ctas = 2 * prop.multiProcessorCount;
   }
   TRY(dev_alloc(c, &c->scratch, (size_t)col_fwd_scratch_per_cta(g.ny) * c->max_ctas * (size_t)(2 * n > 4 ? 2 * n : 4)));
+  {
+    cplx** arrs[5] = {&c->S0, &c->Fint, &c->PV, &c->Cin, &c->Nint};
+    for (auto a : arrs) {
+      TRY(dev_alloc(c, a, (size_t)n * c->ils));
+      GFB_CUDA(c, cudaMemset(*a, 0, (size_t)n * c->ils * sizeof(cplx)));
+    }
+  }
   c->dblocks = 592;
   TRY(dev_alloc(c, &c->dpart, (size_t)c->dblocks * DIAG_MAXOUT));
   TRY(dev_alloc(c, &c->dout, (size_t)DIAG_MAXOUT));
@@ -385,6 +405,17 @@ static Coef coef(const gfb_ctx* c, const void* p) {
   return k;
 }
 
+static int repack(gfb_ctx* c, cplx* dst, int ldd, long long lsd, const cplx* src, int lds, long long lss, cudaStream_t st) {
+  GFB_LAUNCH(k_repack, dim3(1184), dim3(256), 0, st, c->g.ny, c->g.nkr, c->nlayers, dst, ldd, lsd, src, lds, lss);
+  return check_launch(c, 0, "k_repack");
+}
+static int import_spec(gfb_ctx* c, cplx* internal, const void* user, cudaStream_t st) {
+  return repack(c, internal, c->ldi, c->ils, (const cplx*)user, c->g.nkr, (long long)c->g.ny * c->g.nkr, st);
+}
+static int export_spec(gfb_ctx* c, void* user, const cplx* internal, cudaStream_t st) {
+  return repack(c, (cplx*)user, c->g.nkr, (long long)c->g.ny * c->g.nkr, internal, c->ldi, c->ils, st);
+}
+
 // K1 on a stage input (hot path): fields u, v, q (+psi if nf == 4) for every layer -> W
 static int run_col_inv_state(gfb_ctx* c, const Spec& sin, int nf, cudaStream_t st) {
   ColInvLaunch L;
@@ -401,9 +432,8 @@ static int run_col_inv_state(gfb_ctx* c, const Spec& sin, int nf, cudaStream_t s
     L.prep = PREP_SINGLE;
     L.ps.sol = sin.p;
     L.ps.ld = sin.ld;
-    L.ps.G.p = c->G;
-    L.ps.G.ld = c->g.nkr;
-    L.ps.G.ls = 0;
+    L.ps.G = c->G;
+    L.ps.ldg = c->ldi;
     L.nfields = nf;
   } else {
     L.prep = PREP_MULTI;
@@ -469,8 +499,9 @@ static EpiArgs base_epi(const gfb_ctx* c, const void* Fh) {
   EpiArgs e;
   std::memset(&e, 0, sizeof e);
   e.nlayers = c->nlayers;
-  e.F = Fh ? user_spec(c, Fh) : null_spec();
-  e.Nconst = c->Nconst ? user_spec(c, c->Nconst) : null_spec();
+  e.F = Fh ? int_spec(c, c->Fint) : null_spec();  // callers import the user's Fh into Fint first
+  e.Nconst = c->Nconst ? int_spec(c, c->Nconst) : null_spec();
+  e.cplxL = c->cplxL ? 1 : 0;
   e.L = coef(c, c->L);
   e.mu = (c->kind == GFB_KIND_LAYERED) ? c->cfg.mu : 0.0;
   e.Sinv = c->Sinv;
@@ -507,10 +538,13 @@ static int matvec(gfb_ctx* c, void* y, const void* x, const double* M, void* str
   return check_launch(c, 0, "k_matvec");
 }
 
-static __global__ void k_scale_by_table(const long long n, cplx* __restrict__ y, const cplx* __restrict__ x,
-                                 const double* __restrict__ G, const double sign) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    y[i] = cscale(x[i], sign * G[i]);
+static __global__ void k_scale_by_table(const int nl, const int nkr, cplx* __restrict__ y, const cplx* __restrict__ x,
+                                 const double* __restrict__ G, const int ldg, const double sign) {
+  const long long n = (long long)nl * nkr;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int l = (int)(i / nkr), k = (int)(i - (long long)l * nkr);
+    y[i] = cscale(x[i], sign * G[(long long)l * ldg + k]);
+  }
 }
 
 template <int NL>
@@ -532,10 +566,13 @@ int gfb_calcN(gfb_ctx* c, void* N, void* sol, const void* Fh, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   int rc = gfb_dealias(c, sol, stream);
   if (rc) return rc;
+  if ((rc = import_spec(c, c->Cin, sol, st))) return rc;
+  if (Fh && (rc = import_spec(c, c->Fint, Fh, st))) return rc;
   EpiArgs e = base_epi(c, Fh);
   e.kind = EPI_STORE;
-  e.out = user_spec(c, N);
-  return run_stage_kernels(c, user_spec(c, sol), e, st);
+  e.out = int_spec(c, c->Nint);
+  if ((rc = run_stage_kernels(c, int_spec(c, c->Cin), e, st))) return rc;
+  return export_spec(c, N, c->Nint, st);
 }
 
 int gfb_nstages(const gfb_ctx* c) {
@@ -556,7 +593,8 @@ static int do_stage(gfb_ctx* c, void* sol, int istage, const void* Fh, void* pre
   cudaStream_t st = (cudaStream_t)stream;
   EpiArgs e = base_epi(c, Fh);
   e.prune = (prune && c->g.kcut < c->g.nkr) ? 1 : 0;
-  const Spec S0 = user_spec(c, sol);
+  (void)sol;
+  const Spec S0 = int_spec(c, c->S0);  // callers import/export the user's sol
   const double dt = c->dt;
   if (c->filtered) {
     e.filter.p = c->filter;
@@ -571,14 +609,14 @@ static int do_stage(gfb_ctx* c, void* sol, int istage, const void* Fh, void* pre
       e.kind = EPI_RK_ONLY;
       e.b = dt;
       e.out = S0;
-      e.prevsol = prevsol ? user_spec(c, prevsol) : null_spec();
+      e.prevsol = prevsol ? int_spec(c, c->PV) : null_spec();
       break;
     case GFB_RK4: case GFB_FILTERED_RK4: {
       const Spec s1 = int_spec(c, c->st[0]), s2 = int_spec(c, c->st[1]), acc = int_spec(c, c->st[2]);
       e.acc = acc;
       if (istage == 0) {
         e.kind = EPI_RK_FIRST; e.a = dt / 2; e.b = dt / 6; sin = S0; e.out = s1;
-        e.prevsol = prevsol ? user_spec(c, prevsol) : null_spec();
+        e.prevsol = prevsol ? int_spec(c, c->PV) : null_spec();
       } else if (istage == 1) {
         e.kind = EPI_RK_MID; e.a = dt / 2; e.b = dt / 3; sin = s1; e.out = s2;
       } else if (istage == 2) {
@@ -600,7 +638,7 @@ static int do_stage(gfb_ctx* c, void* sol, int istage, const void* Fh, void* pre
       e.c2 = coef(c, c->zeta);
       if (istage == 0) {
         e.kind = EPI_ETD_1; sin = S0; e.out = s1; e.c3 = coef(c, c->E); e.c4 = coef(c, c->alpha);
-        e.prevsol = prevsol ? user_spec(c, prevsol) : null_spec();
+        e.prevsol = prevsol ? int_spec(c, c->PV) : null_spec();
       } else if (istage == 1) {
         e.kind = EPI_ETD_2; sin = s1; e.out = s2; e.c4 = coef(c, c->beta);
       } else if (istage == 2) {
@@ -620,13 +658,14 @@ static int do_stage(gfb_ctx* c, void* sol, int istage, const void* Fh, void* pre
       e.out = S0;
       e.acc = int_spec(c, m1);
       e.n1 = int_spec(c, m2);
-      e.prevsol = prevsol ? user_spec(c, prevsol) : null_spec();
+      e.prevsol = prevsol ? int_spec(c, c->PV) : null_spec();
       // the epilogue stores rhs through e.sin, so run the kernels by hand
       rc = run_col_inv_state(c, S0, 3, st);
       if (rc) return rc;
       rc = run_row_product(c, st, e.prune != 0);
       if (rc) return rc;
-      e.sin = int_spec(c, cur);
+      e.sin = S0;
+      e.rhs = int_spec(c, cur);
       rc = run_col_fwd(c, e, st);
       if (rc) return rc;
       c->t += c->dt;
@@ -644,21 +683,35 @@ static int do_stage(gfb_ctx* c, void* sol, int istage, const void* Fh, void* pre
 }
 
 int gfb_stage(gfb_ctx* c, void* sol, int istage, const void* Fh, void* prevsol, void* stream) {
-  return do_stage(c, sol, istage, Fh, prevsol, stream, 0);
+  if (!c || !sol) return fail(c, GFB_ERR_INVALID, "gfb_stage: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = 0;
+  if (istage == 0 && (rc = import_spec(c, c->S0, sol, st))) return rc;  // later stages continue from the ctx copy
+  if (Fh && (rc = import_spec(c, c->Fint, Fh, st))) return rc;
+  if ((rc = do_stage(c, sol, istage, Fh, prevsol, stream, 0))) return rc;
+  if (istage == 0 && prevsol && (rc = export_spec(c, prevsol, c->PV, st))) return rc;
+  if (istage == gfb_nstages(c) - 1) return export_spec(c, sol, c->S0, st);
+  return GFB_OK;
 }
 
 int gfb_step(gfb_ctx* c, void* sol, int nsteps, const void* Fh, void* prevsol, void* stream) {
   if (!c || !sol || nsteps < 0) return fail(c, GFB_ERR_INVALID, "gfb_step: bad argument");
+  if (nsteps == 0) return GFB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
   const int ns = gfb_nstages(c);
   const bool ab3 = c->stepper == GFB_AB3 || c->stepper == GFB_FILTERED_AB3;  // AB3 keeps RHS history incl. the aliased band
+  int rc = import_spec(c, c->S0, sol, st);
+  if (rc) return rc;
+  if (Fh && (rc = import_spec(c, c->Fint, Fh, st))) return rc;
   for (int s = 0; s < nsteps; ++s) {
     const bool last = (s == nsteps - 1);
     for (int i = 0; i < ns; ++i) {
-      int rc = do_stage(c, sol, i, Fh, last ? prevsol : nullptr, stream, (!last && !ab3 && !c->cfg.no_dealias_in_calcN) ? 1 : 0);
+      rc = do_stage(c, sol, i, Fh, last ? prevsol : nullptr, stream, (!last && !ab3) ? 1 : 0);
       if (rc) return rc;
     }
   }
-  return GFB_OK;
+  if (prevsol && (rc = export_spec(c, prevsol, c->PV, st))) return rc;
+  return export_spec(c, sol, c->S0, st);
 }
 
 int gfb_irfft(gfb_ctx* c, double* out_phys, const void* in_spec, int batch, void* stream) {
@@ -753,7 +806,8 @@ int gfb_updatevars(gfb_ctx* c, void* sol, double* q, double* psi, double* u, dou
   int rc = gfb_dealias(c, sol, stream);
   if (rc) return rc;
   const int nf = 4;
-  rc = run_col_inv_state(c, user_spec(c, sol), nf, st);
+  if ((rc = import_spec(c, c->Cin, sol, st))) return rc;
+  rc = run_col_inv_state(c, int_spec(c, c->Cin), nf, st);
   if (rc) return rc;
   double* outs[4] = {u, v, q, psi};
   for (int f = 0; f < 4; ++f) {
@@ -779,8 +833,8 @@ int gfb_updatevars(gfb_ctx* c, void* sol, double* q, double* psi, double* u, dou
 int gfb_streamfunction_from_pv(gfb_ctx* c, void* psih, const void* qh, void* stream) {
   if (!c || !psih || !qh) return fail(c, GFB_ERR_INVALID, "gfb_streamfunction_from_pv: null argument");
   if (c->kind == GFB_KIND_SINGLE) {
-    GFB_LAUNCH(k_scale_by_table, dim3(592), dim3(256), 0, (cudaStream_t)stream, (long long)c->g.ny * c->g.nkr,
-               (cplx*)psih, (const cplx*)qh, (const double*)c->G, -1.0);
+    GFB_LAUNCH(k_scale_by_table, dim3(592), dim3(256), 0, (cudaStream_t)stream, c->g.ny, c->g.nkr,
+               (cplx*)psih, (const cplx*)qh, (const double*)c->G, c->ldi, -1.0);
     return check_launch(c, 0, "k_scale_by_table");
   }
   return matvec(c, psih, qh, c->Sinv, stream);
@@ -803,6 +857,7 @@ int gfb_diag(gfb_ctx* c, int kind, const void* sol, const void* aux, const void*
   d.aux = (const cplx*)aux;
   d.aux2 = (const cplx*)aux2;
   d.G = c->G;
+  d.ldg = c->ldi;
   d.Sinv = c->Sinv;
   d.p = p;
   d.scale = 1.0;

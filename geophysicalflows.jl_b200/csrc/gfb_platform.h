@@ -30,6 +30,35 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
 #endif
 }
+// Two adjacent complex values (a column pair of one row) = one 32-byte sector.  On sm_100a this is a
+// single LDG.E.256 / STG.E.256; `p` must be 32-byte aligned (all ctx-owned arrays have an even leading
+// dimension, so a pair starting at an even column always is).
+struct cpair {
+  double2 a, b;
+};
+__device__ __forceinline__ cpair ldpair(const double2* p) {
+  cpair r;
+#ifdef GFB_EMULATE
+  r.a = p[0];
+  r.b = p[1];
+#else
+  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.a.x), "=d"(r.a.y), "=d"(r.b.x), "=d"(r.b.y) : "l"(p));
+#endif
+  return r;
+}
+__device__ __forceinline__ void stpair(double2* p, double2 a, double2 b) {
+#ifdef GFB_EMULATE
+  p[0] = a;
+  p[1] = b;
+#else
+  asm volatile("st.global.v4.f64 [%4], {%0,%1,%2,%3};" ::"d"(a.x), "d"(a.y), "d"(b.x), "d"(b.y), "l"(p) : "memory");
+#endif
+}
+__device__ __forceinline__ double2 ldpair_d(const double* p) {  // two adjacent doubles, 16-byte aligned
+  return *reinterpret_cast<const double2*>(p);
+}
+__device__ __forceinline__ void compiler_fence() { asm volatile("" ::: "memory"); }
+
 __device__ __forceinline__ void cp_async_wait_all() {
 #ifndef GFB_EMULATE
   asm volatile("cp.async.wait_all;\n" ::: "memory");

@@ -74,80 +74,98 @@ __device__ __forceinline__ void swap_stash(cplx (&v)[PT], cplx* __restrict__ X, 
 // ------------------------------------------------------------------------------------------------
 // K1 pre-pass functors: value of `field` at (l, col) ready for the inverse y-FFT
 // ------------------------------------------------------------------------------------------------
-// Every functor offers two equivalent ways to produce the value of `field` at (l, col):
-//   load(g, field, l, col)                 -- direct (registers)
-//   src(...) + apply(g, field, l, col, raw) -- `raw` is the complex at src(), fetched by cp.async into the
-//                                             stash (kAsync functors only); live(g, l) says whether the row
-//                                             survives the dealias mask (else the value is 0 and nothing is read)
-struct PrepPlain {  // irfft of arbitrary spectra: field = batch index
-  static constexpr bool kAsync = true;
+// load_pair(g, field, l, colA, liveB, a, b): values of `field` at (l, colA) and (l, colA+1), ready for the
+// inverse y-FFT.  Sources that are ctx-owned (kAligned) are read with one 256-bit access per row.
+struct PrepPlain {  // irfft of arbitrary (user, dense) spectra: field = batch index
   const cplx* in;
   int ld;
   long long ls;
   double scale;
-  __device__ __forceinline__ bool live(const GridDesc&, int) const { return true; }
-  __device__ __forceinline__ const cplx* src(int field, int l, int col) const { return in + field * ls + (long long)l * ld + col; }
-  __device__ __forceinline__ cplx apply(const GridDesc&, int, int, int, cplx raw) const { return cscale(raw, scale); }
-  __device__ __forceinline__ cplx load(const GridDesc& g, int field, int l, int col) const {
-    return apply(g, field, l, col, *src(field, l, col));
+  __device__ __forceinline__ void load_pair(const GridDesc&, int field, int l, int colA, bool liveB, cplx& a, cplx& b) const {
+    const cplx* p = in + field * ls + (long long)l * ld + colA;
+    a = cscale(p[0], scale);
+    b = liveB ? cscale(p[1], scale) : cmake(0.0, 0.0);
   }
 };
 
 struct PrepSingle {  // single-layer modules: psi_h = -G*sol ; uh = i l G sol ; vh = -i kr G sol ; qh = sol
-  static constexpr bool kAsync = true;
-  const cplx* sol;
+  const cplx* sol;   // ctx-owned, ld even
   int ld;
-  SpecR G;
-  __device__ __forceinline__ bool live(const GridDesc& g, int l) const { return !l_aliased(g, l); }
-  __device__ __forceinline__ const cplx* src(int, int l, int col) const { return sol + (long long)l * ld + col; }
-  __device__ __forceinline__ cplx apply(const GridDesc& g, int field, int l, int col, cplx raw) const {
+  const double* G;   // ctx-owned, ld = ldg even
+  int ldg;
+  __device__ __forceinline__ cplx apply(const GridDesc& g, int field, double ll, double kr, double gg, cplx raw) const {
     const cplx s = cscale(raw, g.invN);
     if (field == 2) return s;
-    const double gg = G.at(0, l, col);
-    if (field == 0) return cscale(cmul_i(s), wav_l(g, l) * gg);
-    if (field == 1) return cscale(cmul_mi(s), wav_kr(g, col) * gg);
+    if (field == 0) return cscale(cmul_i(s), ll * gg);
+    if (field == 1) return cscale(cmul_mi(s), kr * gg);
     return cscale(s, -gg);  // field 3: psi_h (updatevars! only)
   }
-  __device__ __forceinline__ cplx load(const GridDesc& g, int field, int l, int col) const {
-    if (!live(g, l)) return cmake(0.0, 0.0);
-    return apply(g, field, l, col, *src(field, l, col));
+  __device__ __forceinline__ void load_pair(const GridDesc& g, int field, int l, int colA, bool, cplx& a, cplx& b) const {
+    if (l_aliased(g, l)) {
+      a = b = cmake(0.0, 0.0);
+      return;
+    }
+    const cpair p = ldpair(sol + (long long)l * ld + colA);
+    double2 gg = make_double2(0.0, 0.0);
+    if (field != 2) gg = ldpair_d(G + (long long)l * ldg + colA);
+    const double ll = wav_l(g, l);
+    a = apply(g, field, ll, wav_kr(g, colA), gg.x, p.a);
+    b = apply(g, field, ll, wav_kr(g, colA + 1), gg.y, p.b);
   }
 };
 
 struct PrepMulti {  // MultiLayerQG: psi_h = S^-1 q_h ; uh = -i l psi_h ; vh = i kr psi_h ; field = nf*layer + {u,v,q[,psi]}
-  static constexpr bool kAsync = false;
-  const cplx* sol;
+  const cplx* sol;     // ctx-owned, ld even
   int ld;
   long long ls;
-  const double* Sinv;  // [l][kr][row][col] row-major NLxNL, ld = nkr
+  const double* Sinv;  // [l][kr][row][col] row-major nl x nl, dense ld = ldS
   int ldS;
   int nf;              // fields per layer: 3 (u, v, q) on the hot path, 4 (+psi) for updatevars!
   int nl;              // layers
-  __device__ __forceinline__ bool live(const GridDesc& g, int l) const { return !l_aliased(g, l); }
-  __device__ __forceinline__ const cplx* src(int, int, int) const { return nullptr; }
-  __device__ __forceinline__ cplx apply(const GridDesc&, int, int, int, cplx raw) const { return raw; }
-  __device__ __forceinline__ cplx load(const GridDesc& g, int field, int l, int col) const {
-    if (l_aliased(g, l)) return cmake(0.0, 0.0);
-    const int layer = field / nf, what = field - nf * layer;
-    if (what == 2) return cscale(sol[layer * ls + (long long)l * ld + col], g.invN);
-    const double* M = Sinv + ((long long)l * ldS + col) * (nl * nl) + layer * nl;
-    cplx psi = cmake(0.0, 0.0);
-    for (int m = 0; m < nl; ++m) {
-      const cplx q = sol[m * ls + (long long)l * ld + col];
-      const double a = __ldg(&M[m]);
-      psi.x += a * q.x;
-      psi.y += a * q.y;
+  __device__ __forceinline__ void load_pair(const GridDesc& g, int field, int l, int colA, bool liveB, cplx& a, cplx& b) const {
+    if (l_aliased(g, l)) {
+      a = b = cmake(0.0, 0.0);
+      return;
     }
-    psi = cscale(psi, g.invN);
-    if (what == 0) return cscale(cmul_mi(psi), wav_l(g, l));
-    if (what == 1) return cscale(cmul_i(psi), wav_kr(g, col));
-    return psi;
+    const int layer = field / nf, what = field - nf * layer;
+    if (what == 2) {
+      const cpair p = ldpair(sol + layer * ls + (long long)l * ld + colA);
+      a = cscale(p.a, g.invN);
+      b = cscale(p.b, g.invN);
+      return;
+    }
+    const double* MA = Sinv + ((long long)l * ldS + colA) * (nl * nl) + layer * nl;
+    const double* MB = MA + nl * nl;
+    cplx pa = cmake(0.0, 0.0), pb = cmake(0.0, 0.0);
+    for (int m = 0; m < nl; ++m) {
+      const cpair q = ldpair(sol + m * ls + (long long)l * ld + colA);
+      const double ca = __ldg(&MA[m]);
+      const double cb = liveB ? __ldg(&MB[m]) : 0.0;
+      pa.x += ca * q.a.x;
+      pa.y += ca * q.a.y;
+      pb.x += cb * q.b.x;
+      pb.y += cb * q.b.y;
+    }
+    pa = cscale(pa, g.invN);
+    pb = cscale(pb, g.invN);
+    if (what == 0) {
+      const double ll = wav_l(g, l);
+      a = cscale(cmul_mi(pa), ll);
+      b = cscale(cmul_mi(pb), ll);
+    } else if (what == 1) {
+      a = cscale(cmul_i(pa), wav_kr(g, colA));
+      b = cscale(cmul_i(pb), wav_kr(g, colA + 1));
+    } else {
+      a = pa;
+      b = pb;
+    }
   }
 };
 
-// K1.  Each group takes a PAIR of adjacent kr columns (32-byte sectors on both the spectral and the
-// W side), transforms them one after the other in the same registers and parks the other column in the
-// thread-private stash.
+// K1.  Each group takes a PAIR of adjacent kr columns: one 256-bit access per row on the spectral side and
+// on the W side.  The two columns are transformed one after the other in the same registers; the other
+// column waits in the thread-private stash.  Loads are issued four rows at a time (bounded registers,
+// ~200 bytes in flight per thread).
 template <int NY, class Prep>
 __global__ void __launch_bounds__(GroupCfg<NY>::THREADS, GroupCfg<NY>::MINB)
     k_col_inv(const GridDesc g, const Prep prep, cplx* __restrict__ W, const int ldw, const long long wfs,
@@ -163,44 +181,25 @@ __global__ void __launch_bounds__(GroupCfg<NY>::THREADS, GroupCfg<NY>::MINB)
   double* xb = smd + gi * GC::GSD;
   cplx* X = reinterpret_cast<cplx*>(smd + GC::XB_DOUBLES);
   cplx v[PT];
-  if constexpr (Prep::kAsync) {
-    // column B: raw values straight into the stash (no registers), prepared when swapped in
 #pragma unroll
-    for (int r = 0; r < PT; ++r) {
-      const int l = j + r * T;
-      if (liveB && prep.live(g, l)) cp_async16(&X[r * THREADS + tid], prep.src(field, l, colB));
+  for (int c0 = 0; c0 < PT; c0 += 4) {
+    cplx bb[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (liveA) prep.load_pair(g, field, j + (c0 + q) * T, colA, liveB, v[c0 + q], bb[q]);
+      else v[c0 + q] = bb[q] = cmake(0.0, 0.0);
     }
 #pragma unroll
-    for (int r = 0; r < PT; ++r) v[r] = liveA ? prep.load(g, field, j + r * T, colA) : cmake(0.0, 0.0);
-    block_fft_split<NY, INV>(v, j, xb, tw);
-    cp_async_wait_all();
-#pragma unroll
-    for (int r = 0; r < PT; ++r) {
-      const int l = j + r * T;
-      cplx t = cmake(0.0, 0.0);
-      if (liveB && prep.live(g, l)) t = prep.apply(g, field, l, colB, X[r * THREADS + tid]);
-      X[r * THREADS + tid] = v[r];
-      v[r] = t;
-    }
-  } else {
-#pragma unroll
-    for (int r = 0; r < PT; ++r) {
-      const int l = j + r * T;
-      v[r] = liveA ? prep.load(g, field, l, colA) : cmake(0.0, 0.0);
-      X[r * THREADS + tid] = liveB ? prep.load(g, field, l, colB) : cmake(0.0, 0.0);
-    }
-    block_fft_split<NY, INV>(v, j, xb, tw);
-    swap_stash(v, X, tid, THREADS);
+    for (int q = 0; q < 4; ++q) X[(c0 + q) * THREADS + tid] = bb[q];
+    compiler_fence();
   }
+  block_fft_split<NY, INV>(v, j, xb, tw);
+  swap_stash(v, X, tid, THREADS);
   block_fft_split<NY, INV>(v, j, xb, tw);
   if (liveA) {
     cplx* out = W + field * wfs + colA;
 #pragma unroll
-    for (int r = 0; r < PT; ++r) {
-      cplx* o = out + (long long)(j + r * T) * ldw;
-      o[0] = X[r * THREADS + tid];
-      if (liveB) o[1] = v[r];
-    }
+    for (int r = 0; r < PT; ++r) stpair(out + (long long)(j + r * T) * ldw, X[r * THREADS + tid], v[r]);
   }
 }
 
@@ -458,32 +457,45 @@ enum EpiKind {
   EPI_PLAIN        // plain forward transform: single field, store
 };
 
+// All spectral arrays the epilogue touches are ctx-owned (even leading dimension): every access below is a
+// 256-bit column-pair access.
 struct Coef {  // real or complex coefficient table [layer][l][kr]
   const double* r;
   const cplx* c;
   int ld;
   long long ls;
-  __device__ __forceinline__ cplx mul(int layer, int l, int kr, cplx x) const {
-    const long long i = layer * ls + (long long)l * ld + kr;
-    if (c != nullptr) return cmul(c[i], x);
-    return cscale(x, r[i]);
+  template <bool CL>
+  __device__ __forceinline__ cpair pair(int layer, int l, int col) const {
+    const long long i = layer * ls + (long long)l * ld + col;
+    if (CL) return ldpair(c + i);
+    const double2 t = ldpair_d(r + i);
+    cpair o;
+    o.a = cmake(t.x, 0.0);
+    o.b = cmake(t.y, 0.0);
+    return o;
   }
 };
+template <bool CL>
+__device__ __forceinline__ cplx coefmul(cplx c, cplx x) {
+  return CL ? cmul(c, x) : cscale(x, c.x);
+}
 
 struct EpiArgs {
   int kind;
   int nlayers;
   int prune;       // 1: rows in the aliased l band are neither read nor written (non-final steps)
+  int cplxL;       // coefficient tables are complex
   Spec out;        // EPI_STORE / EPI_PLAIN: destination of N ; stage kinds: the state written this stage
-  Spec sol;        // s0 source (the problem state `sol`), masked on load
+  Spec sol;        // s0 source (the problem state), masked on load
   Spec sin;        // stage input (== sol for stage 1), masked on load
-  Spec acc;        // accumulator
-  Spec n1;         // saved N1 (ETDRK4) / RHS history (AB3: rhs, rhs-1, rhs-2 via out/acc/n1)
+  Spec acc;        // accumulator (AB3: rhs of the previous step)
+  Spec n1;         // saved N1 (ETDRK4) / AB3: rhs two steps back
+  Spec rhs;        // AB3: where this step's rhs is stored
   Spec F;          // forcing or null
   Spec Nconst;     // constant addition to N or null (SingleLayerQG: -i kr U eta_h)
   Spec prevsol;    // if non-null at a first stage: receives the dealiased state
   Coef L;          // linear operator
-  Coef c1, c2, c3, c4;  // ETD: exp(L dt/2), zeta, exp(L dt) / alpha, 2*beta or Gamma  (see gfb.cu)
+  Coef c1, c2, c3, c4;  // ETD: exp(L dt/2), zeta, exp(L dt) / alpha, beta or Gamma  (see gfb.cu)
   SpecR filter;    // null p -> no filter (layer stride 0: shared by layers)
   double a, b, d;  // RK: a = c_i*dt (sub-step), b = weight*dt ; AB3: a, b, d = dt*(23/12, -16/12, 5/12)
   // MultiLayerQG bottom drag: N[nlayers-1] += mu * Krsq * psi_h[nlayers-1], psi = S^-1 q recomputed
@@ -492,106 +504,189 @@ struct EpiArgs {
   int ldS;
 };
 
-__device__ __forceinline__ cplx masked(const GridDesc& g, const Spec& s, int layer, int l, int col) {
-  if (col >= g.kcut || l_aliased(g, l)) return cmake(0.0, 0.0);
-  return s.at(layer, l, col);
+__device__ __forceinline__ cpair zero_pair() {
+  cpair z;
+  z.a = z.b = cmake(0.0, 0.0);
+  return z;
 }
 
-__device__ __forceinline__ void epilogue(const GridDesc& g, const EpiArgs& e, int layer, int l, int col, cplx N) {
+// dealias mask applied on load: rows in the aliased l band and columns >= kcut read as zero (and are not fetched)
+__device__ __forceinline__ cpair masked_pair(const GridDesc& g, const Spec& s, int layer, int l, int colA) {
+  if (colA >= g.kcut || l_aliased(g, l)) return zero_pair();
+  cpair p = ldpair(&s.at(layer, l, colA));
+  if (colA + 1 >= g.kcut) p.b = cmake(0.0, 0.0);
+  return p;
+}
+
+template <int KIND>
+struct EpiIn {
+  cpair s0, si, acc, n1, F, Nc, drag, c1, c2, c3, c4, L;
+  double2 filt;
+};
+
+// all loads of one row (column pair) ...
+template <int KIND, bool CL>
+__device__ __forceinline__ void epi_fetch(const GridDesc& g, const EpiArgs& e, int layer, int l, int colA, EpiIn<KIND>& in) {
+  if (e.F.p) in.F = ldpair(&e.F.at(layer, l, colA));
+  if (e.Nconst.p) in.Nc = ldpair(&e.Nconst.at(layer, l, colA));
   const int NL = e.nlayers;
-  if (e.kind == EPI_PLAIN) {
-    e.out.at(layer, l, col) = N;
-    return;
-  }
-  if (e.Nconst.p) N = cadd(N, e.Nconst.at(layer, l, col));
   if (e.mu != 0.0 && layer == NL - 1) {
-    // bottom drag on the stage input (dealiased): psi_n = sum_m Sinv[n-1][m] q_m
-    cplx psi = cmake(0.0, 0.0);
-    const double* M = e.Sinv + ((long long)l * e.ldS + col) * (NL * NL) + (NL - 1) * NL;
+    // bottom drag on the (dealiased) stage input: psi_n = sum_m Sinv[n-1][m] q_m
+    cplx pa = cmake(0.0, 0.0), pb = cmake(0.0, 0.0);
+    const double* MA = e.Sinv + ((long long)l * e.ldS + colA) * (NL * NL) + (NL - 1) * NL;
+    const double* MB = MA + NL * NL;
+    const bool hasB = colA + 1 < g.nkr;
     for (int m = 0; m < NL; ++m) {
-      const cplx q = masked(g, e.sin, m, l, col);
-      psi.x += M[m] * q.x;
-      psi.y += M[m] * q.y;
+      const cpair q = masked_pair(g, e.sin, m, l, colA);
+      const double ca = MA[m], cb = hasB ? MB[m] : 0.0;
+      pa.x += ca * q.a.x;
+      pa.y += ca * q.a.y;
+      pb.x += cb * q.b.x;
+      pb.y += cb * q.b.y;
     }
-    const double kr = wav_kr(g, col), ll = wav_l(g, l);
-    const double K2 = kr * kr + ll * ll;
-    N.x += e.mu * K2 * psi.x;
-    N.y += e.mu * K2 * psi.y;
+    const double ll = wav_l(g, l), ka = wav_kr(g, colA), kb = wav_kr(g, colA + 1);
+    in.drag.a = cscale(pa, e.mu * (ka * ka + ll * ll));
+    in.drag.b = cscale(pb, e.mu * (kb * kb + ll * ll));
   }
-  if (e.F.p) N = cadd(N, e.F.at(layer, l, col));
-  const double filt = e.filter.p ? e.filter.at(0, l, col) : 1.0;
+  if (KIND == EPI_RK_LAST || KIND == EPI_RK_ONLY || KIND == EPI_ETD_4 || KIND == EPI_AB3) {
+    in.filt = e.filter.p ? ldpair_d(e.filter.p + (long long)l * e.filter.ld + colA) : make_double2(1.0, 1.0);
+  }
+  if (KIND == EPI_RK_FIRST || KIND == EPI_RK_MID || KIND == EPI_RK_ONLY || KIND == EPI_ETD_1 || KIND == EPI_ETD_2 ||
+      KIND == EPI_ETD_3 || KIND == EPI_AB3)
+    in.s0 = masked_pair(g, e.sol, layer, l, colA);
+  if (KIND == EPI_RK_MID || KIND == EPI_RK_LAST) in.si = masked_pair(g, e.sin, layer, l, colA);
+  if (KIND == EPI_RK_FIRST || KIND == EPI_RK_MID || KIND == EPI_RK_LAST || KIND == EPI_RK_ONLY || KIND == EPI_AB3)
+    in.L = e.L.pair<CL>(layer, l, colA);
+  if (KIND == EPI_RK_MID || KIND == EPI_RK_LAST || KIND == EPI_ETD_2 || KIND == EPI_ETD_3 || KIND == EPI_ETD_4)
+    in.acc = ldpair(&e.acc.at(layer, l, colA));
+  if (KIND == EPI_AB3 && (e.b != 0.0 || e.d != 0.0)) {
+    in.acc = ldpair(&e.acc.at(layer, l, colA));
+    in.n1 = ldpair(&e.n1.at(layer, l, colA));
+  }
+  if (KIND == EPI_ETD_3) in.n1 = ldpair(&e.n1.at(layer, l, colA));
+  if (KIND == EPI_ETD_1 || KIND == EPI_ETD_2 || KIND == EPI_ETD_3) {
+    in.c1 = e.c1.pair<CL>(layer, l, colA);
+    in.c2 = e.c2.pair<CL>(layer, l, colA);
+  }
+  if (KIND == EPI_ETD_1) in.c3 = e.c3.pair<CL>(layer, l, colA);
+  if (KIND == EPI_ETD_1 || KIND == EPI_ETD_2 || KIND == EPI_ETD_3 || KIND == EPI_ETD_4) in.c4 = e.c4.pair<CL>(layer, l, colA);
+}
+
+__device__ __forceinline__ cplx axpy(cplx y, double a, cplx x) { return cmake(y.x + a * x.x, y.y + a * x.y); }
+
+// ... then the arithmetic and all stores of that row
+template <int KIND, bool CL>
+__device__ __forceinline__ void epi_finish(const GridDesc& g, const EpiArgs& e, int layer, int l, int colA, cplx NA,
+                                           cplx NB, const EpiIn<KIND>& in) {
+  if (e.Nconst.p) {
+    NA = cadd(NA, in.Nc.a);
+    NB = cadd(NB, in.Nc.b);
+  }
+  if (e.mu != 0.0 && layer == e.nlayers - 1) {
+    NA = cadd(NA, in.drag.a);
+    NB = cadd(NB, in.drag.b);
+  }
+  if (e.F.p) {
+    NA = cadd(NA, in.F.a);
+    NB = cadd(NB, in.F.b);
+  }
+  cplx* out = &e.out.at(layer, l, colA);
+  if (KIND == EPI_STORE) {
+    stpair(out, NA, NB);
+  } else if (KIND == EPI_RK_FIRST) {
+    const cplx ra = cadd(NA, coefmul<CL>(in.L.a, in.s0.a)), rb = cadd(NB, coefmul<CL>(in.L.b, in.s0.b));
+    stpair(out, axpy(in.s0.a, e.a, ra), axpy(in.s0.b, e.a, rb));
+    stpair(&e.acc.at(layer, l, colA), axpy(in.s0.a, e.b, ra), axpy(in.s0.b, e.b, rb));
+    if (e.prevsol.p) stpair(&e.prevsol.at(layer, l, colA), in.s0.a, in.s0.b);
+  } else if (KIND == EPI_RK_MID) {
+    const cplx ra = cadd(NA, coefmul<CL>(in.L.a, in.si.a)), rb = cadd(NB, coefmul<CL>(in.L.b, in.si.b));
+    stpair(out, axpy(in.s0.a, e.a, ra), axpy(in.s0.b, e.a, rb));
+    stpair(&e.acc.at(layer, l, colA), axpy(in.acc.a, e.b, ra), axpy(in.acc.b, e.b, rb));
+  } else if (KIND == EPI_RK_LAST) {
+    const cplx ra = cadd(NA, coefmul<CL>(in.L.a, in.si.a)), rb = cadd(NB, coefmul<CL>(in.L.b, in.si.b));
+    stpair(out, cscale(axpy(in.acc.a, e.b, ra), in.filt.x), cscale(axpy(in.acc.b, e.b, rb), in.filt.y));
+  } else if (KIND == EPI_RK_ONLY) {
+    const cplx ra = cadd(NA, coefmul<CL>(in.L.a, in.s0.a)), rb = cadd(NB, coefmul<CL>(in.L.b, in.s0.b));
+    if (e.prevsol.p) stpair(&e.prevsol.at(layer, l, colA), in.s0.a, in.s0.b);
+    stpair(out, cscale(axpy(in.s0.a, e.b, ra), in.filt.x), cscale(axpy(in.s0.b, e.b, rb), in.filt.y));
+  } else if (KIND == EPI_ETD_1) {  // c1 = exp(L dt/2), c2 = zeta, c3 = exp(L dt), c4 = alpha
+    stpair(out, cadd(coefmul<CL>(in.c1.a, in.s0.a), coefmul<CL>(in.c2.a, NA)),
+           cadd(coefmul<CL>(in.c1.b, in.s0.b), coefmul<CL>(in.c2.b, NB)));
+    stpair(&e.acc.at(layer, l, colA), cadd(coefmul<CL>(in.c3.a, in.s0.a), coefmul<CL>(in.c4.a, NA)),
+           cadd(coefmul<CL>(in.c3.b, in.s0.b), coefmul<CL>(in.c4.b, NB)));
+    stpair(&e.n1.at(layer, l, colA), NA, NB);
+    if (e.prevsol.p) stpair(&e.prevsol.at(layer, l, colA), in.s0.a, in.s0.b);
+  } else if (KIND == EPI_ETD_2) {  // c4 = beta
+    stpair(out, cadd(coefmul<CL>(in.c1.a, in.s0.a), coefmul<CL>(in.c2.a, NA)),
+           cadd(coefmul<CL>(in.c1.b, in.s0.b), coefmul<CL>(in.c2.b, NB)));
+    stpair(&e.acc.at(layer, l, colA), cadd(in.acc.a, coefmul<CL>(in.c4.a, cscale(NA, 2.0))),
+           cadd(in.acc.b, coefmul<CL>(in.c4.b, cscale(NB, 2.0))));
+  } else if (KIND == EPI_ETD_3) {  // e.sol = sol1 (dealiased on load), out = next stage input
+    const cplx ta = cmake(2.0 * NA.x - in.n1.a.x, 2.0 * NA.y - in.n1.a.y);
+    const cplx tb = cmake(2.0 * NB.x - in.n1.b.x, 2.0 * NB.y - in.n1.b.y);
+    stpair(out, cadd(coefmul<CL>(in.c1.a, in.s0.a), coefmul<CL>(in.c2.a, ta)),
+           cadd(coefmul<CL>(in.c1.b, in.s0.b), coefmul<CL>(in.c2.b, tb)));
+    stpair(&e.acc.at(layer, l, colA), cadd(in.acc.a, coefmul<CL>(in.c4.a, cscale(NA, 2.0))),
+           cadd(in.acc.b, coefmul<CL>(in.c4.b, cscale(NB, 2.0))));
+  } else if (KIND == EPI_ETD_4) {  // c4 = Gamma
+    stpair(out, cscale(cadd(in.acc.a, coefmul<CL>(in.c4.a, NA)), in.filt.x),
+           cscale(cadd(in.acc.b, coefmul<CL>(in.c4.b, NB)), in.filt.y));
+  } else if (KIND == EPI_AB3) {
+    const cplx ra = cadd(NA, coefmul<CL>(in.L.a, in.s0.a)), rb = cadd(NB, coefmul<CL>(in.L.b, in.s0.b));
+    cplx ua = cscale(ra, e.a), ub = cscale(rb, e.a);
+    if (e.b != 0.0 || e.d != 0.0) {
+      ua = axpy(axpy(ua, e.b, in.acc.a), e.d, in.n1.a);
+      ub = axpy(axpy(ub, e.b, in.acc.b), e.d, in.n1.b);
+    }
+    if (e.prevsol.p) stpair(&e.prevsol.at(layer, l, colA), in.s0.a, in.s0.b);
+    stpair(&e.rhs.at(layer, l, colA), ra, rb);
+    stpair(out, cscale(cadd(in.s0.a, ua), in.filt.x), cscale(cadd(in.s0.b, ub), in.filt.y));
+  }
+}
+
+// Epilogue of one column-pair tile: N of column A waits in the stash X, of column B in the scratch slot.
+// Two rows (four wavenumbers) are fetched before anything is stored, so ~10 independent 256-bit loads per
+// thread are in flight; the kind is a template parameter so only the arrays a stage needs are touched.
+template <int NY, int KIND, bool CL>
+__device__ __noinline__ void epilogue_tile(const GridDesc& g, const EpiArgs& e, const int layer, const int colA,
+                                           const cplx* __restrict__ X, const cplx* __restrict__ sc, const int j, const int tid) {
+  using GC = GroupCfg<NY>;
+  constexpr int T = GC::T, THREADS = GC::THREADS;
+#pragma unroll 1
+  for (int r0 = 0; r0 < PT; r0 += 2) {
+    EpiIn<KIND> in[2];
+    bool act[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int l = j + (r0 + q) * T;
+      act[q] = !(e.prune && l_aliased(g, l));
+      if (act[q]) epi_fetch<KIND, CL>(g, e, layer, l, colA, in[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int l = j + (r0 + q) * T;
+      if (act[q]) epi_finish<KIND, CL>(g, e, layer, l, colA, X[(r0 + q) * THREADS + tid], sc[(r0 + q) * THREADS + tid], in[q]);
+    }
+  }
+}
+
+template <int NY, bool CL>
+__device__ __forceinline__ void epilogue_dispatch(const GridDesc& g, const EpiArgs& e, int layer, int colA, const cplx* X,
+                                                  const cplx* sc, int j, int tid) {
   switch (e.kind) {
-    case EPI_STORE:
-      e.out.at(layer, l, col) = N;
-      break;
-    case EPI_RK_FIRST: {
-      const cplx s0 = masked(g, e.sol, layer, l, col);
-      const cplx rhs = cadd(N, e.L.mul(layer, l, col, s0));
-      e.out.at(layer, l, col) = cmake(s0.x + e.a * rhs.x, s0.y + e.a * rhs.y);
-      e.acc.at(layer, l, col) = cmake(s0.x + e.b * rhs.x, s0.y + e.b * rhs.y);
-      if (e.prevsol.p) e.prevsol.at(layer, l, col) = s0;
-    } break;
-    case EPI_RK_MID: {
-      const cplx s0 = masked(g, e.sol, layer, l, col);
-      const cplx si = masked(g, e.sin, layer, l, col);
-      const cplx rhs = cadd(N, e.L.mul(layer, l, col, si));
-      cplx ac = e.acc.at(layer, l, col);
-      e.out.at(layer, l, col) = cmake(s0.x + e.a * rhs.x, s0.y + e.a * rhs.y);
-      e.acc.at(layer, l, col) = cmake(ac.x + e.b * rhs.x, ac.y + e.b * rhs.y);
-    } break;
-    case EPI_RK_LAST: {
-      const cplx si = masked(g, e.sin, layer, l, col);
-      const cplx rhs = cadd(N, e.L.mul(layer, l, col, si));
-      const cplx ac = e.acc.at(layer, l, col);
-      e.out.at(layer, l, col) = cmake((ac.x + e.b * rhs.x) * filt, (ac.y + e.b * rhs.y) * filt);
-    } break;
-    case EPI_RK_ONLY: {
-      const cplx s0 = masked(g, e.sol, layer, l, col);
-      const cplx rhs = cadd(N, e.L.mul(layer, l, col, s0));
-      if (e.prevsol.p) e.prevsol.at(layer, l, col) = s0;
-      e.out.at(layer, l, col) = cmake((s0.x + e.b * rhs.x) * filt, (s0.y + e.b * rhs.y) * filt);
-    } break;
-    case EPI_ETD_1: {  // c1 = exp(L dt/2), c2 = zeta, c3 = exp(L dt), c4 = alpha
-      const cplx s0 = masked(g, e.sol, layer, l, col);
-      e.out.at(layer, l, col) = cadd(e.c1.mul(layer, l, col, s0), e.c2.mul(layer, l, col, N));
-      e.acc.at(layer, l, col) = cadd(e.c3.mul(layer, l, col, s0), e.c4.mul(layer, l, col, N));
-      e.n1.at(layer, l, col) = N;
-      if (e.prevsol.p) e.prevsol.at(layer, l, col) = s0;
-    } break;
-    case EPI_ETD_2: {  // c1 = exp(L dt/2), c2 = zeta, c4 = beta (2*beta applied here)
-      const cplx s0 = masked(g, e.sol, layer, l, col);
-      e.out.at(layer, l, col) = cadd(e.c1.mul(layer, l, col, s0), e.c2.mul(layer, l, col, N));
-      const cplx ac = e.acc.at(layer, l, col);
-      e.acc.at(layer, l, col) = cadd(ac, e.c4.mul(layer, l, col, cscale(N, 2.0)));
-    } break;
-    case EPI_ETD_3: {  // sin = sol2 (input of N3); sol here = sol1 (dealiased on load); out = sol2
-      const cplx s1 = masked(g, e.sol, layer, l, col);
-      const cplx n1 = e.n1.at(layer, l, col);
-      const cplx t = cmake(2.0 * N.x - n1.x, 2.0 * N.y - n1.y);
-      e.out.at(layer, l, col) = cadd(e.c1.mul(layer, l, col, s1), e.c2.mul(layer, l, col, t));
-      const cplx ac = e.acc.at(layer, l, col);
-      e.acc.at(layer, l, col) = cadd(ac, e.c4.mul(layer, l, col, cscale(N, 2.0)));
-    } break;
-    case EPI_ETD_4: {  // c4 = Gamma
-      const cplx ac = e.acc.at(layer, l, col);
-      const cplx r = cadd(ac, e.c4.mul(layer, l, col, N));
-      e.out.at(layer, l, col) = cscale(r, filt);
-    } break;
-    case EPI_AB3: {  // out = sol (in place); acc = rhs-1 ; n1 = rhs-2 ; sin = where rhs is stored
-      const cplx s0 = masked(g, e.sol, layer, l, col);
-      const cplx rhs = cadd(N, e.L.mul(layer, l, col, s0));
-      cplx upd = cscale(rhs, e.a);
-      if (e.b != 0.0 || e.d != 0.0) {
-        const cplx r1 = e.acc.at(layer, l, col), r2 = e.n1.at(layer, l, col);
-        upd.x += e.b * r1.x + e.d * r2.x;
-        upd.y += e.b * r1.y + e.d * r2.y;
-      }
-      if (e.prevsol.p) e.prevsol.at(layer, l, col) = s0;
-      e.sin.at(layer, l, col) = rhs;
-      e.out.at(layer, l, col) = cmake((s0.x + upd.x) * filt, (s0.y + upd.y) * filt);
-    } break;
-    default:
-      break;
+#define GFB_EPI_CASE(K) case K: epilogue_tile<NY, K, CL>(g, e, layer, colA, X, sc, j, tid); break;
+    GFB_EPI_CASE(EPI_STORE)
+    GFB_EPI_CASE(EPI_RK_FIRST)
+    GFB_EPI_CASE(EPI_RK_MID)
+    GFB_EPI_CASE(EPI_RK_LAST)
+    GFB_EPI_CASE(EPI_RK_ONLY)
+    GFB_EPI_CASE(EPI_ETD_1)
+    GFB_EPI_CASE(EPI_ETD_2)
+    GFB_EPI_CASE(EPI_ETD_3)
+    GFB_EPI_CASE(EPI_ETD_4)
+    GFB_EPI_CASE(EPI_AB3)
+#undef GFB_EPI_CASE
+    default: break;
   }
 }
 
@@ -600,35 +695,47 @@ __device__ __forceinline__ void epilogue(const GridDesc& g, const EpiArgs& e, in
 // registers: the two (-i l)-weighted v-transforms are parked in a CTA-private, L2-resident scratch
 // (written and read back by the same thread, 128 KB per CTA), the stash holds the other column, and the
 // epilogue then touches every spectral array with complete 32-byte sectors (both columns of a row).
-// The per-tile work lives in two non-inlined functions: inside a persistent loop the compiler would hoist
+// The per-tile work lives in non-inlined functions: inside a persistent loop the compiler would hoist
 // ~64 registers of loop invariants (row offsets, wavenumbers) out of the loop and spill the butterflies.
-// phase V: both columns of -i l FFTy(Pv) -> scratch; leaves the cp.async of column B of Pd in flight
 template <int NY>
-__device__ __noinline__ void col_fwd_tile_v(const GridDesc& g, const cplx* __restrict__ pv, const cplx* __restrict__ pd,
-                                            const int ldp, const cplx* __restrict__ tw, cplx* __restrict__ sc,
-                                            double* __restrict__ xb, cplx* __restrict__ X, const bool liveA,
-                                            const bool liveB, const int j, const int tid) {
+__device__ __forceinline__ void load_pair_column(cplx (&v)[PT], cplx* __restrict__ X, const cplx* __restrict__ p, const int ldp,
+                                                 const bool liveA, const int j, const int tid) {
+  using GC = GroupCfg<NY>;
+  constexpr int T = GC::T, THREADS = GC::THREADS;
+#pragma unroll
+  for (int c0 = 0; c0 < PT; c0 += 4) {
+    cplx bb[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (liveA) {
+        const cpair t = ldpair(p + (long long)(j + (c0 + q) * T) * ldp);
+        v[c0 + q] = t.a;
+        bb[q] = t.b;
+      } else {
+        v[c0 + q] = bb[q] = cmake(0.0, 0.0);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) X[(c0 + q) * THREADS + tid] = bb[q];
+    compiler_fence();
+  }
+}
+
+// phase V: both columns of -i l FFTy(Pv) -> scratch
+template <int NY>
+__device__ __noinline__ void col_fwd_tile_v(const GridDesc& g, const cplx* __restrict__ pv, const int ldp,
+                                            const cplx* __restrict__ tw, cplx* __restrict__ sc, double* __restrict__ xb,
+                                            cplx* __restrict__ X, const bool liveA, const int j, const int tid) {
   using GC = GroupCfg<NY>;
   constexpr int T = GC::T, THREADS = GC::THREADS;
   cplx v[PT];
-  if (liveB) {
-#pragma unroll
-    for (int r = 0; r < PT; ++r) cp_async16(&X[r * THREADS + tid], pv + (long long)(j + r * T) * ldp + 1);
-  }
-#pragma unroll
-  for (int r = 0; r < PT; ++r) v[r] = liveA ? pv[(long long)(j + r * T) * ldp] : cmake(0.0, 0.0);
+  load_pair_column<NY>(v, X, pv, ldp, liveA, j, tid);
   block_fft_split<NY, FWD>(v, j, xb, tw);
-  cp_async_wait_all();
 #pragma unroll
   for (int r = 0; r < PT; ++r) {
     const double ll = wav_l(g, j + r * T);
     sc[r * THREADS + tid] = cmake(ll * v[r].y, -ll * v[r].x);  // -i l (vq)_h, column A
-    v[r] = liveB ? X[r * THREADS + tid] : cmake(0.0, 0.0);
-  }
-  // the stash is free again: start fetching column B of the d field behind the next transform
-  if (liveB) {
-#pragma unroll
-    for (int r = 0; r < PT; ++r) cp_async16(&X[r * THREADS + tid], pd + (long long)(j + r * T) * ldp + 1);
+    v[r] = X[r * THREADS + tid];
   }
   block_fft_split<NY, FWD>(v, j, xb, tw);
 #pragma unroll
@@ -642,50 +749,39 @@ __device__ __noinline__ void col_fwd_tile_v(const GridDesc& g, const cplx* __res
 template <int NY, bool TWO>
 __device__ __noinline__ void col_fwd_tile_d(const GridDesc& g, const cplx* __restrict__ pd, const int ldp, const EpiArgs& e,
                                             const cplx* __restrict__ tw, cplx* __restrict__ sc, double* __restrict__ xb,
-                                            cplx* __restrict__ X, const int colA, const bool liveA, const bool liveB,
-                                            const int layer, const int j, const int tid) {
+                                            cplx* __restrict__ X, const int colA, const bool liveA, const int layer,
+                                            const int j, const int tid) {
   using GC = GroupCfg<NY>;
   constexpr int T = GC::T, THREADS = GC::THREADS;
   cplx v[PT];
-  if (!TWO && liveB) {
-#pragma unroll
-    for (int r = 0; r < PT; ++r) cp_async16(&X[r * THREADS + tid], pd + (long long)(j + r * T) * ldp + 1);
-  }
-#pragma unroll
-  for (int r = 0; r < PT; ++r) v[r] = liveA ? pd[(long long)(j + r * T) * ldp] : cmake(0.0, 0.0);
+  load_pair_column<NY>(v, X, pd, ldp, liveA, j, tid);
   block_fft_split<NY, FWD>(v, j, xb, tw);
-  cp_async_wait_all();
 #pragma unroll
   for (int r = 0; r < PT; ++r) {
-    cplx t = liveB ? X[r * THREADS + tid] : cmake(0.0, 0.0);
+    const cplx t = X[r * THREADS + tid];
     cplx n = v[r];
     if (TWO) n = cadd(n, sc[r * THREADS + tid]);
     X[r * THREADS + tid] = n;
     v[r] = t;
   }
   block_fft_split<NY, FWD>(v, j, xb, tw);
-  const int colB = colA + 1;
   if constexpr (!TWO) {
     if (liveA) {
 #pragma unroll
       for (int r = 0; r < PT; ++r) {
         const int l = j + r * T;
-        e.out.at(layer, l, colA) = X[r * THREADS + tid];
-        if (liveB) e.out.at(layer, l, colB) = v[r];
+        cplx* o = &e.out.at(layer, l, colA);  // EPI_PLAIN writes a dense user array: no pair store
+        o[0] = X[r * THREADS + tid];
+        if (colA + 1 < g.nkr) o[1] = v[r];
       }
     }
   } else {
-    // park column B next to column A so the (large) epilogue is instantiated once in a rolled loop
+    // park column B next to column A: the epilogue runs in its own (kind-specialised) function
 #pragma unroll
     for (int r = 0; r < PT; ++r) sc[r * THREADS + tid] = cadd(v[r], sc[GC::STASH + r * THREADS + tid]);
     if (liveA) {
-#pragma unroll 1
-      for (int r = 0; r < PT; ++r) {
-        const int l = j + r * T;
-        if (e.prune && l_aliased(g, l)) continue;
-        epilogue(g, e, layer, l, colA, X[r * THREADS + tid]);
-        if (liveB) epilogue(g, e, layer, l, colB, sc[r * THREADS + tid]);
-      }
+      if (e.cplxL) epilogue_dispatch<NY, true>(g, e, layer, colA, X, sc, j, tid);
+      else epilogue_dispatch<NY, false>(g, e, layer, colA, X, sc, j, tid);
     }
   }
 }
@@ -706,16 +802,28 @@ __global__ void __launch_bounds__(GroupCfg<NY>::THREADS, GroupCfg<NY>::MINB)
   const int ntiles = ((ncols + 1) / 2 + GC::G - 1) / GC::G;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int colA = 2 * (tile * GC::G + gi);
-    const bool liveA = colA < ncols, liveB = colA + 1 < ncols;
+    const bool liveA = colA < ncols;
     const cplx* pd = P + (TWO ? 2 * layer : layer) * pfs + colA;
-    if (TWO) col_fwd_tile_v<NY>(g, P + (2 * layer + 1) * pfs + colA, pd, ldp, tw, sc, xb, X, liveA, liveB, j, tid);
-    col_fwd_tile_d<NY, TWO>(g, pd, ldp, e, tw, sc, xb, X, colA, liveA, liveB, layer, j, tid);
+    if (TWO) col_fwd_tile_v<NY>(g, P + (2 * layer + 1) * pfs + colA, ldp, tw, sc, xb, X, liveA, j, tid);
+    col_fwd_tile_d<NY, TWO>(g, pd, ldp, e, tw, sc, xb, X, colA, liveA, layer, j, tid);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // small elementwise kernels
 // ------------------------------------------------------------------------------------------------
+// dense user array [layer][l][nkr] <-> ctx-owned array with even leading dimension
+static __global__ void k_repack(const int nl, const int nkr, const int nlayers, cplx* __restrict__ dst, const int ldd,
+                                const long long lsd, const cplx* __restrict__ src, const int lds, const long long lss) {
+  const long long n = (long long)nl * nkr;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n * nlayers; i += (long long)gridDim.x * blockDim.x) {
+    const int layer = (int)(i / n);
+    const long long rr = i - layer * n;
+    const int l = (int)(rr / nkr), k = (int)(rr - (long long)l * nkr);
+    dst[layer * lsd + (long long)l * ldd + k] = src[layer * lss + (long long)l * lds + k];
+  }
+}
+
 static __global__ void k_dealias(const GridDesc g, cplx* __restrict__ a, const int ld, const long long ls, const int nlayers) {
   const long long n = (long long)g.ny * g.nkr;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n * nlayers; i += (long long)gridDim.x * blockDim.x) {
@@ -776,7 +884,8 @@ struct DiagArgs {
   const cplx* s;
   const cplx* aux;   // eta_h or F
   const cplx* aux2;  // prevsol
-  const double* G;   // [l][kr]
+  const double* G;   // [l][ldg]
+  int ldg;
   const double* Sinv;
   double p;
   double scale;      // multiplies every term (e.g. 0.5)
@@ -822,9 +931,9 @@ __global__ void __launch_bounds__(256) k_diag_partial(const GridDesc g, const Di
       case DIAG_INVK_ABS2: t = (i == 0) ? 0.0 : cabs2(s) / K2; break;
       case DIAG_K_ABS2: t = K2 * cabs2(s); break;
       case DIAG_KP_ABS2: t = (i == 0) ? 0.0 : pow(K2, d.p) * cabs2(s); break;
-      case DIAG_G_ABS2: t = d.G[i] * cabs2(s); break;
-      case DIAG_G2_ABS2: t = d.G[i] * d.G[i] * cabs2(s); break;
-      case DIAG_KG2_ABS2: t = K2 * d.G[i] * d.G[i] * cabs2(s); break;
+      case DIAG_G_ABS2: t = d.G[(long long)l * d.ldg + k] * cabs2(s); break;
+      case DIAG_G2_ABS2: { const double gg = d.G[(long long)l * d.ldg + k]; t = gg * gg * cabs2(s); } break;
+      case DIAG_KG2_ABS2: { const double gg = d.G[(long long)l * d.ldg + k]; t = K2 * gg * gg * cabs2(s); } break;
       case DIAG_ABS2_PLUS: t = cabs2(cadd(s, d.aux[i])); break;
       case DIAG_WORK:
       case DIAG_WORK_INVK: {

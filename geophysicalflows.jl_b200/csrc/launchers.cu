@@ -13,6 +13,10 @@ namespace gfb {
 template <class K>
 static inline int set_smem(K kernel, size_t bytes) {
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) return -2;
+  // ask for the largest shared-memory carveout: the kernels are sized so that TWO CTAs (2 x ~100 KB at
+  // N = 4096) share an SM; with the default carveout the driver only guarantees room for one
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   return e == cudaSuccess ? 0 : -2;
 }
 
