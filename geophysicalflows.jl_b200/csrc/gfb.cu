@@ -116,14 +116,16 @@ static int dev_upload(gfb_ctx* c, T** p, const void* host, size_t n) {
   return 0;
 }
 
-// upload a dense host table [nlayers][nl][nkr] (double or cplx) into the padded internal layout (ld = ldi)
+// upload a dense host table [nlayers][nl][nkr] (double or cplx) into the ctx-owned tiled layout (toff, ld = ldi)
 static int upload_padded(gfb_ctx* c, void** out, const void* host, int nlay, bool is_cplx) {
   const int nl = c->g.ny, nkr = c->g.nkr, ldi = c->ldi;
   const size_t es = is_cplx ? sizeof(cplx) : sizeof(double);
   std::vector<char> tmp((size_t)nlay * nl * ldi * es, 0);
   for (int a = 0; a < nlay; ++a)
     for (int l = 0; l < nl; ++l)
-      std::memcpy(&tmp[((size_t)(a * nl + l) * ldi) * es], (const char*)host + ((size_t)(a * nl + l) * nkr) * es, nkr * es);
+      for (int k = 0; k < nkr; ++k)
+        std::memcpy(&tmp[((size_t)a * nl * ldi + (size_t)toff(l, k, ldi)) * es],
+                    (const char*)host + ((size_t)(a * nl + l) * nkr + k) * es, es);
   char* d = nullptr;
   int rc = dev_alloc(c, &d, tmp.size());
   if (rc) return rc;
@@ -405,15 +407,17 @@ static Coef coef(const gfb_ctx* c, const void* p) {
   return k;
 }
 
-static int repack(gfb_ctx* c, cplx* dst, int ldd, long long lsd, const cplx* src, int lds, long long lss, cudaStream_t st) {
-  GFB_LAUNCH(k_repack, dim3(1184), dim3(256), 0, st, c->g.ny, c->g.nkr, c->nlayers, dst, ldd, lsd, src, lds, lss);
+static int repack(gfb_ctx* c, cplx* dst, int ldd, long long lsd, const cplx* src, int lds, long long lss, int to_tiled,
+                  cudaStream_t st) {
+  ProfScope ps(c, 3, st);
+  GFB_LAUNCH(k_repack, dim3(1184), dim3(256), 0, st, c->g.ny, c->g.nkr, c->nlayers, dst, ldd, lsd, src, lds, lss, to_tiled);
   return check_launch(c, 0, "k_repack");
 }
 static int import_spec(gfb_ctx* c, cplx* internal, const void* user, cudaStream_t st) {
-  return repack(c, internal, c->ldi, c->ils, (const cplx*)user, c->g.nkr, (long long)c->g.ny * c->g.nkr, st);
+  return repack(c, internal, c->ldi, c->ils, (const cplx*)user, c->g.nkr, (long long)c->g.ny * c->g.nkr, 1, st);
 }
 static int export_spec(gfb_ctx* c, void* user, const cplx* internal, cudaStream_t st) {
-  return repack(c, (cplx*)user, c->g.nkr, (long long)c->g.ny * c->g.nkr, internal, c->ldi, c->ils, st);
+  return repack(c, (cplx*)user, c->g.nkr, (long long)c->g.ny * c->g.nkr, internal, c->ldi, c->ils, 0, st);
 }
 
 // K1 on a stage input (hot path): fields u, v, q (+psi if nf == 4) for every layer -> W
@@ -543,7 +547,7 @@ static __global__ void k_scale_by_table(const int nl, const int nkr, cplx* __res
   const long long n = (long long)nl * nkr;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int l = (int)(i / nkr), k = (int)(i - (long long)l * nkr);
-    y[i] = cscale(x[i], sign * G[(long long)l * ldg + k]);
+    y[i] = cscale(x[i], sign * G[toff(l, k, ldg)]);
   }
 }
 

@@ -27,7 +27,7 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
   *reinterpret_cast<double2*>(smem_dst) = *reinterpret_cast<const double2*>(gmem_src);
 #else
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
 #endif
 }
 // Two adjacent complex values (a column pair of one row) = one 32-byte sector.  On sm_100a this is a

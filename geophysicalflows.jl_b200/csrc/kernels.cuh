@@ -32,18 +32,38 @@ __device__ __forceinline__ double wav_l(const GridDesc& g, int n) { return (n < 
 __device__ __forceinline__ double wav_kr(const GridDesc& g, int m) { return m * g.dkx; }
 __device__ __forceinline__ bool l_aliased(const GridDesc& g, int n) { return n >= g.la0 && n < g.la1; }
 
-// a spectral array view: element (layer, l, kr) = p[layer*ls + l*ld + kr]
+// Ctx-owned arrays (states, tables, W, P) use an 8-row TILED layout: element (row, col) of an array with
+// even leading dimension ld lives at
+//     toff = ((row/8)*(ld/2) + col/2)*16 + (row%8)*2 + col%2
+// i.e. [row/8][column pair][row%8][2].  Same footprint as row-major [rows][ld] (rows % 8 == 0), but a column
+// kernel whose lanes hold consecutive rows of one column pair now touches 256 contiguous bytes per 8 lanes
+// (DRAM-page friendly even when CTAs drift apart), while the row kernel still reads/writes whole 32-byte
+// sectors.  User arrays at the C ABI stay dense row-major; k_repack converts.
+// (32-bit: one field of the largest supported grid, 8192 x 4098, has 3.4e7 elements)
+__host__ __device__ __forceinline__ int toff(int row, int col, int ld) {
+  return ((row >> 3) * (ld >> 1) + (col >> 1)) * 16 + ((row & 7) << 1) + (col & 1);
+}
+
+// offset of row j + r*T given the offset of row j: when T is a multiple of 8 the tiled layout is affine in r
+// with the same stride as a row-major array (T*ld) -- one base register plus immediates
+template <int T>
+__device__ __forceinline__ int toff_row(const int off_j, const int j, const int r, const int col, const int ld) {
+  if (T % 8 == 0) return off_j + r * T * ld;
+  return toff(j + r * T, col, ld);
+}
+
+// a ctx-owned spectral array view: element (layer, l, kr) = p[layer*ls + toff(l, kr, ld)]
 struct Spec {
   cplx* p;
   int ld;
   long long ls;
-  __device__ __forceinline__ cplx& at(int layer, int l, int kr) const { return p[layer * ls + (long long)l * ld + kr]; }
+  __device__ __forceinline__ cplx& at(int layer, int l, int kr) const { return p[layer * ls + toff(l, kr, ld)]; }
 };
 struct SpecR {  // real-valued table with the same indexing
   const double* p;
   int ld;
   long long ls;
-  __device__ __forceinline__ double at(int layer, int l, int kr) const { return p[layer * ls + (long long)l * ld + kr]; }
+  __device__ __forceinline__ double at(int layer, int l, int kr) const { return p[layer * ls + toff(l, kr, ld)]; }
 };
 
 // One "FFT group" = T = N/16 threads transforming one length-N line at a time.  A CTA has G groups
@@ -78,10 +98,10 @@ __device__ __forceinline__ void swap_stash(cplx (&v)[PT], cplx* __restrict__ X, 
 // inverse y-FFT.  Sources that are ctx-owned (kAligned) are read with one 256-bit access per row.
 struct PrepPlain {  // irfft of arbitrary (user, dense) spectra: field = batch index
   const cplx* in;
-  int ld;
+  int ld;  // dense (user) leading dimension; offsets are computed inside
   long long ls;
   double scale;
-  __device__ __forceinline__ void load_pair(const GridDesc&, int field, int l, int colA, bool liveB, cplx& a, cplx& b) const {
+  __device__ __forceinline__ void load_pair(const GridDesc&, int field, int l, int colA, bool liveB, int, cplx& a, cplx& b) const {
     const cplx* p = in + field * ls + (long long)l * ld + colA;
     a = cscale(p[0], scale);
     b = liveB ? cscale(p[1], scale) : cmake(0.0, 0.0);
@@ -100,14 +120,14 @@ struct PrepSingle {  // single-layer modules: psi_h = -G*sol ; uh = i l G sol ; 
     if (field == 1) return cscale(cmul_mi(s), kr * gg);
     return cscale(s, -gg);  // field 3: psi_h (updatevars! only)
   }
-  __device__ __forceinline__ void load_pair(const GridDesc& g, int field, int l, int colA, bool, cplx& a, cplx& b) const {
+  __device__ __forceinline__ void load_pair(const GridDesc& g, int field, int l, int colA, bool, int off, cplx& a, cplx& b) const {
     if (l_aliased(g, l)) {
       a = b = cmake(0.0, 0.0);
       return;
     }
-    const cpair p = ldpair(sol + (long long)l * ld + colA);
+    const cpair p = ldpair(sol + off);
     double2 gg = make_double2(0.0, 0.0);
-    if (field != 2) gg = ldpair_d(G + (long long)l * ldg + colA);
+    if (field != 2) gg = ldpair_d(G + off);  // G shares the state's leading dimension
     const double ll = wav_l(g, l);
     a = apply(g, field, ll, wav_kr(g, colA), gg.x, p.a);
     b = apply(g, field, ll, wav_kr(g, colA + 1), gg.y, p.b);
@@ -122,14 +142,14 @@ struct PrepMulti {  // MultiLayerQG: psi_h = S^-1 q_h ; uh = -i l psi_h ; vh = i
   int ldS;
   int nf;              // fields per layer: 3 (u, v, q) on the hot path, 4 (+psi) for updatevars!
   int nl;              // layers
-  __device__ __forceinline__ void load_pair(const GridDesc& g, int field, int l, int colA, bool liveB, cplx& a, cplx& b) const {
+  __device__ __forceinline__ void load_pair(const GridDesc& g, int field, int l, int colA, bool liveB, int off, cplx& a, cplx& b) const {
     if (l_aliased(g, l)) {
       a = b = cmake(0.0, 0.0);
       return;
     }
     const int layer = field / nf, what = field - nf * layer;
     if (what == 2) {
-      const cpair p = ldpair(sol + layer * ls + (long long)l * ld + colA);
+      const cpair p = ldpair(sol + layer * ls + off);
       a = cscale(p.a, g.invN);
       b = cscale(p.b, g.invN);
       return;
@@ -138,7 +158,7 @@ struct PrepMulti {  // MultiLayerQG: psi_h = S^-1 q_h ; uh = -i l psi_h ; vh = i
     const double* MB = MA + nl * nl;
     cplx pa = cmake(0.0, 0.0), pb = cmake(0.0, 0.0);
     for (int m = 0; m < nl; ++m) {
-      const cpair q = ldpair(sol + m * ls + (long long)l * ld + colA);
+      const cpair q = ldpair(sol + m * ls + off);
       const double ca = __ldg(&MA[m]);
       const double cb = liveB ? __ldg(&MB[m]) : 0.0;
       pa.x += ca * q.a.x;
@@ -181,12 +201,13 @@ __global__ void __launch_bounds__(GroupCfg<NY>::THREADS, GroupCfg<NY>::MINB)
   double* xb = smd + gi * GC::GSD;
   cplx* X = reinterpret_cast<cplx*>(smd + GC::XB_DOUBLES);
   cplx v[PT];
+  const int inoff = toff(j, colA, prep.ld);
 #pragma unroll
   for (int c0 = 0; c0 < PT; c0 += 4) {
     cplx bb[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      if (liveA) prep.load_pair(g, field, j + (c0 + q) * T, colA, liveB, v[c0 + q], bb[q]);
+      if (liveA) prep.load_pair(g, field, j + (c0 + q) * T, colA, liveB, toff_row<T>(inoff, j, c0 + q, colA, prep.ld), v[c0 + q], bb[q]);
       else v[c0 + q] = bb[q] = cmake(0.0, 0.0);
     }
 #pragma unroll
@@ -197,9 +218,10 @@ __global__ void __launch_bounds__(GroupCfg<NY>::THREADS, GroupCfg<NY>::MINB)
   swap_stash(v, X, tid, THREADS);
   block_fft_split<NY, INV>(v, j, xb, tw);
   if (liveA) {
-    cplx* out = W + field * wfs + colA;
+    cplx* out = W + field * wfs;
+    const int ooff = toff(j, colA, ldw);
 #pragma unroll
-    for (int r = 0; r < PT; ++r) stpair(out + (long long)(j + r * T) * ldw, X[r * THREADS + tid], v[r]);
+    for (int r = 0; r < PT; ++r) stpair(out + toff_row<T>(ooff, j, r, colA, ldw), X[r * THREADS + tid], v[r]);
   }
 }
 
@@ -209,8 +231,8 @@ __global__ void __launch_bounds__(GroupCfg<NY>::THREADS, GroupCfg<NY>::MINB)
 // Z[k] = A[k] + i B[k] with Hermitian extension, A/B half-spectra rows known for k < kc (else 0).
 // c2r semantics of FFTW/cuFFT/pocketfft: imaginary parts of the k = 0 and k = N/2 entries are ignored.
 template <int N>
-__device__ __forceinline__ void load_hermitian(cplx (&v)[PT], const int j, const cplx* __restrict__ A,
-                                               const cplx* __restrict__ B, const int kc) {
+__device__ __forceinline__ void load_hermitian(cplx (&v)[PT], const int j, const cplx* __restrict__ A, const int rowA,
+                                               const cplx* __restrict__ B, const int rowB, const int ld, const int kc) {
   constexpr int T = N / PT;
 #pragma unroll
   for (int r = 0; r < PT; ++r) {
@@ -218,8 +240,8 @@ __device__ __forceinline__ void load_hermitian(cplx (&v)[PT], const int j, const
     const int kk = (k <= N / 2) ? k : N - k;
     cplx a = cmake(0.0, 0.0), b = cmake(0.0, 0.0);
     if (kk < kc) {
-      a = A[kk];
-      b = B[kk];
+      a = A[toff(rowA, kk, ld)];
+      b = B[toff(rowB, kk, ld)];
     }
     if (k == 0 || k == N / 2) {
       v[r] = cmake(a.x, b.x);
@@ -303,9 +325,8 @@ __global__ void __launch_bounds__(GroupCfg<NX>::THREADS, GroupCfg<NX>::MINB)
   cplx A[9], B[9];
 
   if (MODE == ROW_C2R) {
-    const cplx* Wa = a.W + layer * a.wfs + (long long)ya * a.ldw;
-    const cplx* Wb = Wa + a.ldw;
-    if (live) load_hermitian<NX>(v, j, Wa, Wb, a.kc);
+    const cplx* Wf = a.W + layer * a.wfs;
+    if (live) load_hermitian<NX>(v, j, Wf, ya, Wf, yb, a.ldw, a.kc);
     else {
 #pragma unroll
       for (int r = 0; r < PT; ++r) v[r] = cmake(0.0, 0.0);
@@ -335,14 +356,13 @@ __global__ void __launch_bounds__(GroupCfg<NX>::THREADS, GroupCfg<NX>::MINB)
     block_fft_split<NX, FWD>(v, j, xb, tw);
     unpack_pair<NX>(v, j, xb, A, B);
     if (live) {
-      cplx* pa = a.P + layer * a.pfs + (long long)ya * a.ldp;
-      cplx* pb = pa + a.ldp;
+      cplx* pf = a.P + layer * a.pfs;
 #pragma unroll
       for (int r = 0; r < 9; ++r) {
         const int k = j + r * T;
         if ((r < 8 || j == 0) && k < a.kout) {
-          pa[k] = A[r];
-          pb[k] = B[r];
+          pf[toff(ya, k, a.ldp)] = A[r];
+          pf[toff(yb, k, a.ldp)] = B[r];
         }
       }
     }
@@ -355,7 +375,7 @@ __global__ void __launch_bounds__(GroupCfg<NX>::THREADS, GroupCfg<NX>::MINB)
   const cplx* Wv = a.W + (3 * layer + 1) * a.wfs;
   const cplx* Wq = a.W + (3 * layer + 2) * a.wfs;
   // 1. q of both rows: one complex transform gives q_a + i q_b
-  if (live) load_hermitian<NX>(v, j, Wq + (long long)ya * a.ldw, Wq + (long long)yb * a.ldw, a.kc);
+  if (live) load_hermitian<NX>(v, j, Wq, ya, Wq, yb, a.ldw, a.kc);
   else {
 #pragma unroll
     for (int r = 0; r < PT; ++r) v[r] = cmake(0.0, 0.0);
@@ -378,7 +398,7 @@ __global__ void __launch_bounds__(GroupCfg<NX>::THREADS, GroupCfg<NX>::MINB)
 #pragma unroll 1
   for (int h = 0; h < 2; ++h) {
     const int y = ya + h;
-    if (live) load_hermitian<NX>(v, j, Wu + (long long)y * a.ldw, Wv + (long long)y * a.ldw, a.kc);
+    if (live) load_hermitian<NX>(v, j, Wu, y, Wv, y, a.ldw, a.kc);
     else {
 #pragma unroll
       for (int r = 0; r < PT; ++r) v[r] = cmake(0.0, 0.0);
@@ -406,15 +426,15 @@ __global__ void __launch_bounds__(GroupCfg<NX>::THREADS, GroupCfg<NX>::MINB)
     block_fft_split<NX, FWD>(v, j, xb, tw);
     unpack_pair<NX>(v, j, xb, A, B);  // A = (uq)_h, B = (vq)_h
     if (live) {
-      cplx* pd = a.P + (2 * layer + 0) * a.pfs + (long long)y * a.ldp;
-      cplx* pv = a.P + (2 * layer + 1) * a.pfs + (long long)y * a.ldp;
+      cplx* pd = a.P + (2 * layer + 0) * a.pfs;
+      cplx* pv = a.P + (2 * layer + 1) * a.pfs;
 #pragma unroll
       for (int r = 0; r < 9; ++r) {
         const int k = j + r * T;
         if ((r < 8 || j == 0) && k < a.kout) {
           const double kr = k * a.dkx;
-          pd[k] = cmake(kr * A[r].y, -kr * A[r].x);  // -i kr (uq)_h
-          pv[k] = B[r];
+          pd[toff(y, k, a.ldp)] = cmake(kr * A[r].y, -kr * A[r].x);  // -i kr (uq)_h
+          pv[toff(y, k, a.ldp)] = B[r];
         }
       }
     }
@@ -426,14 +446,15 @@ __global__ void __launch_bounds__(GroupCfg<NX>::THREADS, GroupCfg<NX>::MINB)
     block_fft_split<NX, FWD>(v, j, xb, tw);
     unpack_pair<NX>(v, j, xb, A, B);
     if (live) {
-      cplx* pa = a.P + (2 * layer + 0) * a.pfs + (long long)ya * a.ldp;
-      cplx* pb = pa + a.ldp;
+      cplx* pf = a.P + (2 * layer + 0) * a.pfs;
 #pragma unroll
       for (int r = 0; r < 9; ++r) {
         const int k = j + r * T;
         if ((r < 8 || j == 0) && k < a.kout) {
-          pa[k] = csub(pa[k], A[r]);  // same thread wrote pa[k] in step 2
-          pb[k] = csub(pb[k], B[r]);
+          cplx& ea = pf[toff(ya, k, a.ldp)];  // same thread wrote these in step 2
+          cplx& eb = pf[toff(yb, k, a.ldp)];
+          ea = csub(ea, A[r]);
+          eb = csub(eb, B[r]);
         }
       }
     }
@@ -465,8 +486,8 @@ struct Coef {  // real or complex coefficient table [layer][l][kr]
   int ld;
   long long ls;
   template <bool CL>
-  __device__ __forceinline__ cpair pair(int layer, int l, int col) const {
-    const long long i = layer * ls + (long long)l * ld + col;
+  __device__ __forceinline__ cpair pair(int layer, int off) const {
+    const long long i = layer * ls + off;
     if (CL) return ldpair(c + i);
     const double2 t = ldpair_d(r + i);
     cpair o;
@@ -511,9 +532,9 @@ __device__ __forceinline__ cpair zero_pair() {
 }
 
 // dealias mask applied on load: rows in the aliased l band and columns >= kcut read as zero (and are not fetched)
-__device__ __forceinline__ cpair masked_pair(const GridDesc& g, const Spec& s, int layer, int l, int colA) {
+__device__ __forceinline__ cpair masked_pair(const GridDesc& g, const Spec& s, int layer, int l, int colA, int off) {
   if (colA >= g.kcut || l_aliased(g, l)) return zero_pair();
-  cpair p = ldpair(&s.at(layer, l, colA));
+  cpair p = ldpair(s.p + layer * s.ls + off);
   if (colA + 1 >= g.kcut) p.b = cmake(0.0, 0.0);
   return p;
 }
@@ -526,9 +547,10 @@ struct EpiIn {
 
 // all loads of one row (column pair) ...
 template <int KIND, bool CL>
-__device__ __forceinline__ void epi_fetch(const GridDesc& g, const EpiArgs& e, int layer, int l, int colA, EpiIn<KIND>& in) {
-  if (e.F.p) in.F = ldpair(&e.F.at(layer, l, colA));
-  if (e.Nconst.p) in.Nc = ldpair(&e.Nconst.at(layer, l, colA));
+__device__ __forceinline__ void epi_fetch(const GridDesc& g, const EpiArgs& e, int layer, int l, int colA, int off,
+                                          EpiIn<KIND>& in) {
+  if (e.F.p) in.F = ldpair(e.F.p + layer * e.F.ls + off);
+  if (e.Nconst.p) in.Nc = ldpair(e.Nconst.p + layer * e.Nconst.ls + off);
   const int NL = e.nlayers;
   if (e.mu != 0.0 && layer == NL - 1) {
     // bottom drag on the (dealiased) stage input: psi_n = sum_m Sinv[n-1][m] q_m
@@ -537,7 +559,7 @@ __device__ __forceinline__ void epi_fetch(const GridDesc& g, const EpiArgs& e, i
     const double* MB = MA + NL * NL;
     const bool hasB = colA + 1 < g.nkr;
     for (int m = 0; m < NL; ++m) {
-      const cpair q = masked_pair(g, e.sin, m, l, colA);
+      const cpair q = masked_pair(g, e.sin, m, l, colA, off);
       const double ca = MA[m], cb = hasB ? MB[m] : 0.0;
       pa.x += ca * q.a.x;
       pa.y += ca * q.a.y;
@@ -549,34 +571,34 @@ __device__ __forceinline__ void epi_fetch(const GridDesc& g, const EpiArgs& e, i
     in.drag.b = cscale(pb, e.mu * (kb * kb + ll * ll));
   }
   if (KIND == EPI_RK_LAST || KIND == EPI_RK_ONLY || KIND == EPI_ETD_4 || KIND == EPI_AB3) {
-    in.filt = e.filter.p ? ldpair_d(e.filter.p + (long long)l * e.filter.ld + colA) : make_double2(1.0, 1.0);
+    in.filt = e.filter.p ? ldpair_d(e.filter.p + off) : make_double2(1.0, 1.0);
   }
   if (KIND == EPI_RK_FIRST || KIND == EPI_RK_MID || KIND == EPI_RK_ONLY || KIND == EPI_ETD_1 || KIND == EPI_ETD_2 ||
       KIND == EPI_ETD_3 || KIND == EPI_AB3)
-    in.s0 = masked_pair(g, e.sol, layer, l, colA);
-  if (KIND == EPI_RK_MID || KIND == EPI_RK_LAST) in.si = masked_pair(g, e.sin, layer, l, colA);
+    in.s0 = masked_pair(g, e.sol, layer, l, colA, off);
+  if (KIND == EPI_RK_MID || KIND == EPI_RK_LAST) in.si = masked_pair(g, e.sin, layer, l, colA, off);
   if (KIND == EPI_RK_FIRST || KIND == EPI_RK_MID || KIND == EPI_RK_LAST || KIND == EPI_RK_ONLY || KIND == EPI_AB3)
-    in.L = e.L.pair<CL>(layer, l, colA);
+    in.L = e.L.pair<CL>(layer, off);
   if (KIND == EPI_RK_MID || KIND == EPI_RK_LAST || KIND == EPI_ETD_2 || KIND == EPI_ETD_3 || KIND == EPI_ETD_4)
-    in.acc = ldpair(&e.acc.at(layer, l, colA));
+    in.acc = ldpair(e.acc.p + layer * e.acc.ls + off);
   if (KIND == EPI_AB3 && (e.b != 0.0 || e.d != 0.0)) {
-    in.acc = ldpair(&e.acc.at(layer, l, colA));
-    in.n1 = ldpair(&e.n1.at(layer, l, colA));
+    in.acc = ldpair(e.acc.p + layer * e.acc.ls + off);
+    in.n1 = ldpair(e.n1.p + layer * e.n1.ls + off);
   }
-  if (KIND == EPI_ETD_3) in.n1 = ldpair(&e.n1.at(layer, l, colA));
+  if (KIND == EPI_ETD_3) in.n1 = ldpair(e.n1.p + layer * e.n1.ls + off);
   if (KIND == EPI_ETD_1 || KIND == EPI_ETD_2 || KIND == EPI_ETD_3) {
-    in.c1 = e.c1.pair<CL>(layer, l, colA);
-    in.c2 = e.c2.pair<CL>(layer, l, colA);
+    in.c1 = e.c1.pair<CL>(layer, off);
+    in.c2 = e.c2.pair<CL>(layer, off);
   }
-  if (KIND == EPI_ETD_1) in.c3 = e.c3.pair<CL>(layer, l, colA);
-  if (KIND == EPI_ETD_1 || KIND == EPI_ETD_2 || KIND == EPI_ETD_3 || KIND == EPI_ETD_4) in.c4 = e.c4.pair<CL>(layer, l, colA);
+  if (KIND == EPI_ETD_1) in.c3 = e.c3.pair<CL>(layer, off);
+  if (KIND == EPI_ETD_1 || KIND == EPI_ETD_2 || KIND == EPI_ETD_3 || KIND == EPI_ETD_4) in.c4 = e.c4.pair<CL>(layer, off);
 }
 
 __device__ __forceinline__ cplx axpy(cplx y, double a, cplx x) { return cmake(y.x + a * x.x, y.y + a * x.y); }
 
 // ... then the arithmetic and all stores of that row
 template <int KIND, bool CL>
-__device__ __forceinline__ void epi_finish(const GridDesc& g, const EpiArgs& e, int layer, int l, int colA, cplx NA,
+__device__ __forceinline__ void epi_finish(const GridDesc& g, const EpiArgs& e, int layer, int off, cplx NA,
                                            cplx NB, const EpiIn<KIND>& in) {
   if (e.Nconst.p) {
     NA = cadd(NA, in.Nc.a);
@@ -590,43 +612,43 @@ __device__ __forceinline__ void epi_finish(const GridDesc& g, const EpiArgs& e, 
     NA = cadd(NA, in.F.a);
     NB = cadd(NB, in.F.b);
   }
-  cplx* out = &e.out.at(layer, l, colA);
+  cplx* out = e.out.p + layer * e.out.ls + off;
   if (KIND == EPI_STORE) {
     stpair(out, NA, NB);
   } else if (KIND == EPI_RK_FIRST) {
     const cplx ra = cadd(NA, coefmul<CL>(in.L.a, in.s0.a)), rb = cadd(NB, coefmul<CL>(in.L.b, in.s0.b));
     stpair(out, axpy(in.s0.a, e.a, ra), axpy(in.s0.b, e.a, rb));
-    stpair(&e.acc.at(layer, l, colA), axpy(in.s0.a, e.b, ra), axpy(in.s0.b, e.b, rb));
-    if (e.prevsol.p) stpair(&e.prevsol.at(layer, l, colA), in.s0.a, in.s0.b);
+    stpair(e.acc.p + layer * e.acc.ls + off, axpy(in.s0.a, e.b, ra), axpy(in.s0.b, e.b, rb));
+    if (e.prevsol.p) stpair(e.prevsol.p + layer * e.prevsol.ls + off, in.s0.a, in.s0.b);
   } else if (KIND == EPI_RK_MID) {
     const cplx ra = cadd(NA, coefmul<CL>(in.L.a, in.si.a)), rb = cadd(NB, coefmul<CL>(in.L.b, in.si.b));
     stpair(out, axpy(in.s0.a, e.a, ra), axpy(in.s0.b, e.a, rb));
-    stpair(&e.acc.at(layer, l, colA), axpy(in.acc.a, e.b, ra), axpy(in.acc.b, e.b, rb));
+    stpair(e.acc.p + layer * e.acc.ls + off, axpy(in.acc.a, e.b, ra), axpy(in.acc.b, e.b, rb));
   } else if (KIND == EPI_RK_LAST) {
     const cplx ra = cadd(NA, coefmul<CL>(in.L.a, in.si.a)), rb = cadd(NB, coefmul<CL>(in.L.b, in.si.b));
     stpair(out, cscale(axpy(in.acc.a, e.b, ra), in.filt.x), cscale(axpy(in.acc.b, e.b, rb), in.filt.y));
   } else if (KIND == EPI_RK_ONLY) {
     const cplx ra = cadd(NA, coefmul<CL>(in.L.a, in.s0.a)), rb = cadd(NB, coefmul<CL>(in.L.b, in.s0.b));
-    if (e.prevsol.p) stpair(&e.prevsol.at(layer, l, colA), in.s0.a, in.s0.b);
+    if (e.prevsol.p) stpair(e.prevsol.p + layer * e.prevsol.ls + off, in.s0.a, in.s0.b);
     stpair(out, cscale(axpy(in.s0.a, e.b, ra), in.filt.x), cscale(axpy(in.s0.b, e.b, rb), in.filt.y));
   } else if (KIND == EPI_ETD_1) {  // c1 = exp(L dt/2), c2 = zeta, c3 = exp(L dt), c4 = alpha
     stpair(out, cadd(coefmul<CL>(in.c1.a, in.s0.a), coefmul<CL>(in.c2.a, NA)),
            cadd(coefmul<CL>(in.c1.b, in.s0.b), coefmul<CL>(in.c2.b, NB)));
-    stpair(&e.acc.at(layer, l, colA), cadd(coefmul<CL>(in.c3.a, in.s0.a), coefmul<CL>(in.c4.a, NA)),
+    stpair(e.acc.p + layer * e.acc.ls + off, cadd(coefmul<CL>(in.c3.a, in.s0.a), coefmul<CL>(in.c4.a, NA)),
            cadd(coefmul<CL>(in.c3.b, in.s0.b), coefmul<CL>(in.c4.b, NB)));
-    stpair(&e.n1.at(layer, l, colA), NA, NB);
-    if (e.prevsol.p) stpair(&e.prevsol.at(layer, l, colA), in.s0.a, in.s0.b);
+    stpair(e.n1.p + layer * e.n1.ls + off, NA, NB);
+    if (e.prevsol.p) stpair(e.prevsol.p + layer * e.prevsol.ls + off, in.s0.a, in.s0.b);
   } else if (KIND == EPI_ETD_2) {  // c4 = beta
     stpair(out, cadd(coefmul<CL>(in.c1.a, in.s0.a), coefmul<CL>(in.c2.a, NA)),
            cadd(coefmul<CL>(in.c1.b, in.s0.b), coefmul<CL>(in.c2.b, NB)));
-    stpair(&e.acc.at(layer, l, colA), cadd(in.acc.a, coefmul<CL>(in.c4.a, cscale(NA, 2.0))),
+    stpair(e.acc.p + layer * e.acc.ls + off, cadd(in.acc.a, coefmul<CL>(in.c4.a, cscale(NA, 2.0))),
            cadd(in.acc.b, coefmul<CL>(in.c4.b, cscale(NB, 2.0))));
   } else if (KIND == EPI_ETD_3) {  // e.sol = sol1 (dealiased on load), out = next stage input
     const cplx ta = cmake(2.0 * NA.x - in.n1.a.x, 2.0 * NA.y - in.n1.a.y);
     const cplx tb = cmake(2.0 * NB.x - in.n1.b.x, 2.0 * NB.y - in.n1.b.y);
     stpair(out, cadd(coefmul<CL>(in.c1.a, in.s0.a), coefmul<CL>(in.c2.a, ta)),
            cadd(coefmul<CL>(in.c1.b, in.s0.b), coefmul<CL>(in.c2.b, tb)));
-    stpair(&e.acc.at(layer, l, colA), cadd(in.acc.a, coefmul<CL>(in.c4.a, cscale(NA, 2.0))),
+    stpair(e.acc.p + layer * e.acc.ls + off, cadd(in.acc.a, coefmul<CL>(in.c4.a, cscale(NA, 2.0))),
            cadd(in.acc.b, coefmul<CL>(in.c4.b, cscale(NB, 2.0))));
   } else if (KIND == EPI_ETD_4) {  // c4 = Gamma
     stpair(out, cscale(cadd(in.acc.a, coefmul<CL>(in.c4.a, NA)), in.filt.x),
@@ -638,8 +660,8 @@ __device__ __forceinline__ void epi_finish(const GridDesc& g, const EpiArgs& e, 
       ua = axpy(axpy(ua, e.b, in.acc.a), e.d, in.n1.a);
       ub = axpy(axpy(ub, e.b, in.acc.b), e.d, in.n1.b);
     }
-    if (e.prevsol.p) stpair(&e.prevsol.at(layer, l, colA), in.s0.a, in.s0.b);
-    stpair(&e.rhs.at(layer, l, colA), ra, rb);
+    if (e.prevsol.p) stpair(e.prevsol.p + layer * e.prevsol.ls + off, in.s0.a, in.s0.b);
+    stpair(e.rhs.p + layer * e.rhs.ls + off, ra, rb);
     stpair(out, cscale(cadd(in.s0.a, ua), in.filt.x), cscale(cadd(in.s0.b, ub), in.filt.y));
   }
 }
@@ -656,16 +678,17 @@ __device__ __noinline__ void epilogue_tile(const GridDesc& g, const EpiArgs& e, 
   for (int r0 = 0; r0 < PT; r0 += 2) {
     EpiIn<KIND> in[2];
     bool act[2];
+    int off[2];
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
       const int l = j + (r0 + q) * T;
       act[q] = !(e.prune && l_aliased(g, l));
-      if (act[q]) epi_fetch<KIND, CL>(g, e, layer, l, colA, in[q]);
+      off[q] = toff(l, colA, e.out.ld);  // every ctx-owned array shares this leading dimension
+      if (act[q]) epi_fetch<KIND, CL>(g, e, layer, l, colA, off[q], in[q]);
     }
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
-      const int l = j + (r0 + q) * T;
-      if (act[q]) epi_finish<KIND, CL>(g, e, layer, l, colA, X[(r0 + q) * THREADS + tid], sc[(r0 + q) * THREADS + tid], in[q]);
+      if (act[q]) epi_finish<KIND, CL>(g, e, layer, off[q], X[(r0 + q) * THREADS + tid], sc[(r0 + q) * THREADS + tid], in[q]);
     }
   }
 }
@@ -697,27 +720,26 @@ __device__ __forceinline__ void epilogue_dispatch(const GridDesc& g, const EpiAr
 // epilogue then touches every spectral array with complete 32-byte sectors (both columns of a row).
 // The per-tile work lives in non-inlined functions: inside a persistent loop the compiler would hoist
 // ~64 registers of loop invariants (row offsets, wavenumbers) out of the loop and spill the butterflies.
+// Column A of a pair goes to registers (16 x LDG.128), column B -- the other half of the same 32-byte sectors --
+// straight into the thread-private stash with cp.async.ca (no registers; merged with A's sector fetch in L1).
+// The caller must cp_async_wait_all() before touching X.
 template <int NY>
 __device__ __forceinline__ void load_pair_column(cplx (&v)[PT], cplx* __restrict__ X, const cplx* __restrict__ p, const int ldp,
-                                                 const bool liveA, const int j, const int tid) {
+                                                 const int colA, const bool liveA, const int j, const int tid) {
   using GC = GroupCfg<NY>;
   constexpr int T = GC::T, THREADS = GC::THREADS;
+  const int off0 = toff(j, colA, ldp);
+  if (liveA) {
 #pragma unroll
-  for (int c0 = 0; c0 < PT; c0 += 4) {
-    cplx bb[4];
+    for (int r = 0; r < PT; ++r) cp_async16(&X[r * THREADS + tid], p + toff_row<T>(off0, j, r, colA, ldp) + 1);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (liveA) {
-        const cpair t = ldpair(p + (long long)(j + (c0 + q) * T) * ldp);
-        v[c0 + q] = t.a;
-        bb[q] = t.b;
-      } else {
-        v[c0 + q] = bb[q] = cmake(0.0, 0.0);
-      }
+    for (int r = 0; r < PT; ++r) v[r] = p[toff_row<T>(off0, j, r, colA, ldp)];
+  } else {
+#pragma unroll
+    for (int r = 0; r < PT; ++r) {
+      v[r] = cmake(0.0, 0.0);
+      X[r * THREADS + tid] = cmake(0.0, 0.0);
     }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) X[(c0 + q) * THREADS + tid] = bb[q];
-    compiler_fence();
   }
 }
 
@@ -725,12 +747,13 @@ __device__ __forceinline__ void load_pair_column(cplx (&v)[PT], cplx* __restrict
 template <int NY>
 __device__ __noinline__ void col_fwd_tile_v(const GridDesc& g, const cplx* __restrict__ pv, const int ldp,
                                             const cplx* __restrict__ tw, cplx* __restrict__ sc, double* __restrict__ xb,
-                                            cplx* __restrict__ X, const bool liveA, const int j, const int tid) {
+                                            cplx* __restrict__ X, const int colA, const bool liveA, const int j, const int tid) {
   using GC = GroupCfg<NY>;
   constexpr int T = GC::T, THREADS = GC::THREADS;
   cplx v[PT];
-  load_pair_column<NY>(v, X, pv, ldp, liveA, j, tid);
+  load_pair_column<NY>(v, X, pv, ldp, colA, liveA, j, tid);
   block_fft_split<NY, FWD>(v, j, xb, tw);
+  cp_async_wait_all();
 #pragma unroll
   for (int r = 0; r < PT; ++r) {
     const double ll = wav_l(g, j + r * T);
@@ -754,8 +777,9 @@ __device__ __noinline__ void col_fwd_tile_d(const GridDesc& g, const cplx* __res
   using GC = GroupCfg<NY>;
   constexpr int T = GC::T, THREADS = GC::THREADS;
   cplx v[PT];
-  load_pair_column<NY>(v, X, pd, ldp, liveA, j, tid);
+  load_pair_column<NY>(v, X, pd, ldp, colA, liveA, j, tid);
   block_fft_split<NY, FWD>(v, j, xb, tw);
+  cp_async_wait_all();
 #pragma unroll
   for (int r = 0; r < PT; ++r) {
     const cplx t = X[r * THREADS + tid];
@@ -770,7 +794,7 @@ __device__ __noinline__ void col_fwd_tile_d(const GridDesc& g, const cplx* __res
 #pragma unroll
       for (int r = 0; r < PT; ++r) {
         const int l = j + r * T;
-        cplx* o = &e.out.at(layer, l, colA);  // EPI_PLAIN writes a dense user array: no pair store
+        cplx* o = e.out.p + layer * e.out.ls + (long long)l * e.out.ld + colA;  // EPI_PLAIN: dense user array
         o[0] = X[r * THREADS + tid];
         if (colA + 1 < g.nkr) o[1] = v[r];
       }
@@ -803,8 +827,8 @@ __global__ void __launch_bounds__(GroupCfg<NY>::THREADS, GroupCfg<NY>::MINB)
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int colA = 2 * (tile * GC::G + gi);
     const bool liveA = colA < ncols;
-    const cplx* pd = P + (TWO ? 2 * layer : layer) * pfs + colA;
-    if (TWO) col_fwd_tile_v<NY>(g, P + (2 * layer + 1) * pfs + colA, ldp, tw, sc, xb, X, liveA, j, tid);
+    const cplx* pd = P + (TWO ? 2 * layer : layer) * pfs;
+    if (TWO) col_fwd_tile_v<NY>(g, P + (2 * layer + 1) * pfs, ldp, tw, sc, xb, X, colA, liveA, j, tid);
     col_fwd_tile_d<NY, TWO>(g, pd, ldp, e, tw, sc, xb, X, colA, liveA, layer, j, tid);
   }
 }
@@ -812,15 +836,17 @@ __global__ void __launch_bounds__(GroupCfg<NY>::THREADS, GroupCfg<NY>::MINB)
 // ------------------------------------------------------------------------------------------------
 // small elementwise kernels
 // ------------------------------------------------------------------------------------------------
-// dense user array [layer][l][nkr] <-> ctx-owned array with even leading dimension
+// dense user array [layer][l][nkr] <-> ctx-owned tiled array (toff); to_tiled selects the direction
 static __global__ void k_repack(const int nl, const int nkr, const int nlayers, cplx* __restrict__ dst, const int ldd,
-                                const long long lsd, const cplx* __restrict__ src, const int lds, const long long lss) {
+                                const long long lsd, const cplx* __restrict__ src, const int lds, const long long lss,
+                                const int to_tiled) {
   const long long n = (long long)nl * nkr;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n * nlayers; i += (long long)gridDim.x * blockDim.x) {
     const int layer = (int)(i / n);
     const long long rr = i - layer * n;
     const int l = (int)(rr / nkr), k = (int)(rr - (long long)l * nkr);
-    dst[layer * lsd + (long long)l * ldd + k] = src[layer * lss + (long long)l * lds + k];
+    if (to_tiled) dst[layer * lsd + toff(l, k, ldd)] = src[layer * lss + (long long)l * lds + k];
+    else dst[layer * lsd + (long long)l * ldd + k] = src[layer * lss + toff(l, k, lds)];
   }
 }
 
@@ -931,9 +957,9 @@ __global__ void __launch_bounds__(256) k_diag_partial(const GridDesc g, const Di
       case DIAG_INVK_ABS2: t = (i == 0) ? 0.0 : cabs2(s) / K2; break;
       case DIAG_K_ABS2: t = K2 * cabs2(s); break;
       case DIAG_KP_ABS2: t = (i == 0) ? 0.0 : pow(K2, d.p) * cabs2(s); break;
-      case DIAG_G_ABS2: t = d.G[(long long)l * d.ldg + k] * cabs2(s); break;
-      case DIAG_G2_ABS2: { const double gg = d.G[(long long)l * d.ldg + k]; t = gg * gg * cabs2(s); } break;
-      case DIAG_KG2_ABS2: { const double gg = d.G[(long long)l * d.ldg + k]; t = K2 * gg * gg * cabs2(s); } break;
+      case DIAG_G_ABS2: t = d.G[toff(l, k, d.ldg)] * cabs2(s); break;
+      case DIAG_G2_ABS2: { const double gg = d.G[toff(l, k, d.ldg)]; t = gg * gg * cabs2(s); } break;
+      case DIAG_KG2_ABS2: { const double gg = d.G[toff(l, k, d.ldg)]; t = K2 * gg * gg * cabs2(s); } break;
       case DIAG_ABS2_PLUS: t = cabs2(cadd(s, d.aux[i])); break;
       case DIAG_WORK:
       case DIAG_WORK_INVK: {
