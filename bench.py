@@ -26,6 +26,9 @@ sys.path.insert(0, ROOT)
 METRIC = "grid-point-steps/sec"
 UNIT = "grid-point-steps/s"
 ALGO_BYTES_PER_POINT_STEP = 480.0  # 60 field passes x 8 B (Float64), RK4/ETDRK4 families
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the same
+# command (profiles/): full-mode (un-pruned) launches of the 4096^2 workload
+NCU_TRAFFIC = {}
 
 
 def workload(name):
@@ -246,10 +249,18 @@ def main():
     peak, peak_src = peaks()
     g = prob.grid
     kcut, nkr, ny = g.kr_alias0, g.nkr, g.ny
-    kbytes = {  # algorithmic bytes per launch (DESIGN.md "kernels"): 16 B per complex element
-        "k_col_inv": 16.0 * ny * kcut * (1 + 3) + 8.0 * ny * kcut,  # read sol + G column band, write u,v,q bands
-        "k_row": 16.0 * ny * (3 * kcut + 2 * nkr),                   # read 3 bands, write 2 full half-spectra
-        "k_col_fwd": 16.0 * ny * nkr * (2 + 3 + 2.5),                # read 2 products + ~3 state/acc reads + tables, write ~2
+    nlive = ny - (g.l_alias[1] - g.l_alias[0])         # rows that survive the dealias mask
+    band = kcut * nlive                                 # live wavenumbers of a dealiased state
+    # K3 epilogue bytes per output wavenumber, ETDRK4 stages 1-4 (real coefficient tables):
+    epi = [16 + 4 * 8 + 3 * 16, 16 + 3 * 8 + 16 + 2 * 16, 2 * 16 + 16 + 3 * 8 + 2 * 16, 16 + 8 + 16]
+
+    def k3_bytes(ncols, nout):
+        return 2 * 16.0 * ny * ncols + sum(epi) / 4.0 * nout
+    wfull = 1.0 / float(args.steps)                     # one full (un-pruned) step per stepforward! call,
+    kbytes = {                                          # the others skip the aliased band of N
+        "k_col_inv": (16.0 + 8.0) * band + 3 * 16.0 * ny * kcut,
+        "k_row": 3 * 16.0 * ny * kcut + 2 * 16.0 * ny * (wfull * nkr + (1 - wfull) * kcut),
+        "k_col_fwd": wfull * k3_bytes(nkr, nkr * ny) + (1 - wfull) * k3_bytes(kcut, band),
     }
     top = max(("k_col_inv", "k_row", "k_col_fwd"), key=lambda k: prof[k]["ms"])
     avg_ms = prof[top]["ms"] / max(prof[top]["launches"], 1)
@@ -267,8 +278,11 @@ def main():
                    "parallelism": "1 GPU" if world == 1 else "%d independent replicas (slab-sharded path not built yet)" % world,
                    "state_finite": finite},
         "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": kbytes[top], "avg_launch_ms": avg_ms},
+                     "frac": (achieved / peak) if achieved else None, "traffic": NCU_TRAFFIC.get(top), "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": kbytes[top], "avg_launch_ms": avg_ms,
+                     "all_kernels": {k: {"achieved_gbs": kbytes[k] / (prof[k]["ms"] / max(prof[k]["launches"], 1) * 1e-3) / 1e9
+                                         if prof[k]["ms"] > 0 else None,
+                                         "algorithmic_bytes_per_launch": kbytes[k]} for k in kbytes}},
         "step_roofline": {"algorithmic_bytes_per_step": ALGO_BYTES_PER_POINT_STEP * n * n, "achieved_gbs": step_gbs,
                           "frac_of_measured_peak": step_gbs / peak, "frac_of_8tbs_nominal": step_gbs / 8000.0},
         "kernels": {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps} for k, v in prof.items()},

@@ -485,21 +485,24 @@ struct Coef {  // real or complex coefficient table [layer][l][kr]
   const cplx* c;
   int ld;
   long long ls;
-  template <bool CL>
-  __device__ __forceinline__ cpair pair(int layer, int off) const {
-    const long long i = layer * ls + off;
-    if (CL) return ldpair(c + i);
-    const double2 t = ldpair_d(r + i);
-    cpair o;
-    o.a = cmake(t.x, 0.0);
-    o.b = cmake(t.y, 0.0);
-    return o;
-  }
 };
+// a pair of coefficients: complex tables keep 8 registers, real tables only 4
 template <bool CL>
-__device__ __forceinline__ cplx coefmul(cplx c, cplx x) {
-  return CL ? cmul(c, x) : cscale(x, c.x);
-}
+struct CoefPair;
+template <>
+struct CoefPair<true> {
+  cpair v;
+  __device__ __forceinline__ void load(const Coef& t, int layer, int off) { v = ldpair(t.c + layer * t.ls + off); }
+  __device__ __forceinline__ cplx mulA(cplx x) const { return cmul(v.a, x); }
+  __device__ __forceinline__ cplx mulB(cplx x) const { return cmul(v.b, x); }
+};
+template <>
+struct CoefPair<false> {
+  double2 v;
+  __device__ __forceinline__ void load(const Coef& t, int layer, int off) { v = ldpair_d(t.r + layer * t.ls + off); }
+  __device__ __forceinline__ cplx mulA(cplx x) const { return cscale(x, v.x); }
+  __device__ __forceinline__ cplx mulB(cplx x) const { return cscale(x, v.y); }
+};
 
 struct EpiArgs {
   int kind;
@@ -539,18 +542,22 @@ __device__ __forceinline__ cpair masked_pair(const GridDesc& g, const Spec& s, i
   return p;
 }
 
-template <int KIND>
+template <int KIND, bool CL>
 struct EpiIn {
-  cpair s0, si, acc, n1, F, Nc, drag, c1, c2, c3, c4, L;
+  cpair s0, si, acc, n1;
+  CoefPair<CL> c1, c2, c3, c4, L;
   double2 filt;
 };
 
-// all loads of one row (column pair) ...
-template <int KIND, bool CL>
-__device__ __forceinline__ void epi_fetch(const GridDesc& g, const EpiArgs& e, int layer, int l, int colA, int off,
-                                          EpiIn<KIND>& in) {
-  if (e.F.p) in.F = ldpair(e.F.p + layer * e.F.ls + off);
-  if (e.Nconst.p) in.Nc = ldpair(e.Nconst.p + layer * e.Nconst.ls + off);
+// N += Nconst + drag + F for one row of the column pair (the optional additive terms of calcN!), done in a
+// separate light pass so the stage-update pass below carries only what its kind needs
+__device__ __forceinline__ void epi_addends(const GridDesc& g, const EpiArgs& e, int layer, int l, int colA, int off, cplx& NA,
+                                            cplx& NB) {
+  if (e.Nconst.p) {
+    const cpair t = ldpair(e.Nconst.p + layer * e.Nconst.ls + off);
+    NA = cadd(NA, t.a);
+    NB = cadd(NB, t.b);
+  }
   const int NL = e.nlayers;
   if (e.mu != 0.0 && layer == NL - 1) {
     // bottom drag on the (dealiased) stage input: psi_n = sum_m Sinv[n-1][m] q_m
@@ -567,9 +574,20 @@ __device__ __forceinline__ void epi_fetch(const GridDesc& g, const EpiArgs& e, i
       pb.y += cb * q.b.y;
     }
     const double ll = wav_l(g, l), ka = wav_kr(g, colA), kb = wav_kr(g, colA + 1);
-    in.drag.a = cscale(pa, e.mu * (ka * ka + ll * ll));
-    in.drag.b = cscale(pb, e.mu * (kb * kb + ll * ll));
+    NA = cadd(NA, cscale(pa, e.mu * (ka * ka + ll * ll)));
+    NB = cadd(NB, cscale(pb, e.mu * (kb * kb + ll * ll)));
   }
+  if (e.F.p) {
+    const cpair t = ldpair(e.F.p + layer * e.F.ls + off);
+    NA = cadd(NA, t.a);
+    NB = cadd(NB, t.b);
+  }
+}
+
+// all loads of one row (column pair) ...
+template <int KIND, bool CL>
+__device__ __forceinline__ void epi_fetch(const GridDesc& g, const EpiArgs& e, int layer, int l, int colA, int off,
+                                          EpiIn<KIND, CL>& in) {
   if (KIND == EPI_RK_LAST || KIND == EPI_RK_ONLY || KIND == EPI_ETD_4 || KIND == EPI_AB3) {
     in.filt = e.filter.p ? ldpair_d(e.filter.p + off) : make_double2(1.0, 1.0);
   }
@@ -578,7 +596,7 @@ __device__ __forceinline__ void epi_fetch(const GridDesc& g, const EpiArgs& e, i
     in.s0 = masked_pair(g, e.sol, layer, l, colA, off);
   if (KIND == EPI_RK_MID || KIND == EPI_RK_LAST) in.si = masked_pair(g, e.sin, layer, l, colA, off);
   if (KIND == EPI_RK_FIRST || KIND == EPI_RK_MID || KIND == EPI_RK_LAST || KIND == EPI_RK_ONLY || KIND == EPI_AB3)
-    in.L = e.L.pair<CL>(layer, off);
+    in.L.load(e.L, layer, off);
   if (KIND == EPI_RK_MID || KIND == EPI_RK_LAST || KIND == EPI_ETD_2 || KIND == EPI_ETD_3 || KIND == EPI_ETD_4)
     in.acc = ldpair(e.acc.p + layer * e.acc.ls + off);
   if (KIND == EPI_AB3 && (e.b != 0.0 || e.d != 0.0)) {
@@ -587,11 +605,11 @@ __device__ __forceinline__ void epi_fetch(const GridDesc& g, const EpiArgs& e, i
   }
   if (KIND == EPI_ETD_3) in.n1 = ldpair(e.n1.p + layer * e.n1.ls + off);
   if (KIND == EPI_ETD_1 || KIND == EPI_ETD_2 || KIND == EPI_ETD_3) {
-    in.c1 = e.c1.pair<CL>(layer, off);
-    in.c2 = e.c2.pair<CL>(layer, off);
+    in.c1.load(e.c1, layer, off);
+    in.c2.load(e.c2, layer, off);
   }
-  if (KIND == EPI_ETD_1) in.c3 = e.c3.pair<CL>(layer, off);
-  if (KIND == EPI_ETD_1 || KIND == EPI_ETD_2 || KIND == EPI_ETD_3 || KIND == EPI_ETD_4) in.c4 = e.c4.pair<CL>(layer, off);
+  if (KIND == EPI_ETD_1) in.c3.load(e.c3, layer, off);
+  if (KIND == EPI_ETD_1 || KIND == EPI_ETD_2 || KIND == EPI_ETD_3 || KIND == EPI_ETD_4) in.c4.load(e.c4, layer, off);
 }
 
 __device__ __forceinline__ cplx axpy(cplx y, double a, cplx x) { return cmake(y.x + a * x.x, y.y + a * x.y); }
@@ -599,62 +617,50 @@ __device__ __forceinline__ cplx axpy(cplx y, double a, cplx x) { return cmake(y.
 // ... then the arithmetic and all stores of that row
 template <int KIND, bool CL>
 __device__ __forceinline__ void epi_finish(const GridDesc& g, const EpiArgs& e, int layer, int off, cplx NA,
-                                           cplx NB, const EpiIn<KIND>& in) {
-  if (e.Nconst.p) {
-    NA = cadd(NA, in.Nc.a);
-    NB = cadd(NB, in.Nc.b);
-  }
-  if (e.mu != 0.0 && layer == e.nlayers - 1) {
-    NA = cadd(NA, in.drag.a);
-    NB = cadd(NB, in.drag.b);
-  }
-  if (e.F.p) {
-    NA = cadd(NA, in.F.a);
-    NB = cadd(NB, in.F.b);
-  }
+                                           cplx NB, const EpiIn<KIND, CL>& in) {
   cplx* out = e.out.p + layer * e.out.ls + off;
   if (KIND == EPI_STORE) {
     stpair(out, NA, NB);
   } else if (KIND == EPI_RK_FIRST) {
-    const cplx ra = cadd(NA, coefmul<CL>(in.L.a, in.s0.a)), rb = cadd(NB, coefmul<CL>(in.L.b, in.s0.b));
+    const cplx ra = cadd(NA, in.L.mulA(in.s0.a)), rb = cadd(NB, in.L.mulB(in.s0.b));
     stpair(out, axpy(in.s0.a, e.a, ra), axpy(in.s0.b, e.a, rb));
     stpair(e.acc.p + layer * e.acc.ls + off, axpy(in.s0.a, e.b, ra), axpy(in.s0.b, e.b, rb));
     if (e.prevsol.p) stpair(e.prevsol.p + layer * e.prevsol.ls + off, in.s0.a, in.s0.b);
   } else if (KIND == EPI_RK_MID) {
-    const cplx ra = cadd(NA, coefmul<CL>(in.L.a, in.si.a)), rb = cadd(NB, coefmul<CL>(in.L.b, in.si.b));
+    const cplx ra = cadd(NA, in.L.mulA(in.si.a)), rb = cadd(NB, in.L.mulB(in.si.b));
     stpair(out, axpy(in.s0.a, e.a, ra), axpy(in.s0.b, e.a, rb));
     stpair(e.acc.p + layer * e.acc.ls + off, axpy(in.acc.a, e.b, ra), axpy(in.acc.b, e.b, rb));
   } else if (KIND == EPI_RK_LAST) {
-    const cplx ra = cadd(NA, coefmul<CL>(in.L.a, in.si.a)), rb = cadd(NB, coefmul<CL>(in.L.b, in.si.b));
+    const cplx ra = cadd(NA, in.L.mulA(in.si.a)), rb = cadd(NB, in.L.mulB(in.si.b));
     stpair(out, cscale(axpy(in.acc.a, e.b, ra), in.filt.x), cscale(axpy(in.acc.b, e.b, rb), in.filt.y));
   } else if (KIND == EPI_RK_ONLY) {
-    const cplx ra = cadd(NA, coefmul<CL>(in.L.a, in.s0.a)), rb = cadd(NB, coefmul<CL>(in.L.b, in.s0.b));
+    const cplx ra = cadd(NA, in.L.mulA(in.s0.a)), rb = cadd(NB, in.L.mulB(in.s0.b));
     if (e.prevsol.p) stpair(e.prevsol.p + layer * e.prevsol.ls + off, in.s0.a, in.s0.b);
     stpair(out, cscale(axpy(in.s0.a, e.b, ra), in.filt.x), cscale(axpy(in.s0.b, e.b, rb), in.filt.y));
   } else if (KIND == EPI_ETD_1) {  // c1 = exp(L dt/2), c2 = zeta, c3 = exp(L dt), c4 = alpha
-    stpair(out, cadd(coefmul<CL>(in.c1.a, in.s0.a), coefmul<CL>(in.c2.a, NA)),
-           cadd(coefmul<CL>(in.c1.b, in.s0.b), coefmul<CL>(in.c2.b, NB)));
-    stpair(e.acc.p + layer * e.acc.ls + off, cadd(coefmul<CL>(in.c3.a, in.s0.a), coefmul<CL>(in.c4.a, NA)),
-           cadd(coefmul<CL>(in.c3.b, in.s0.b), coefmul<CL>(in.c4.b, NB)));
+    stpair(out, cadd(in.c1.mulA(in.s0.a), in.c2.mulA(NA)),
+           cadd(in.c1.mulB(in.s0.b), in.c2.mulB(NB)));
+    stpair(e.acc.p + layer * e.acc.ls + off, cadd(in.c3.mulA(in.s0.a), in.c4.mulA(NA)),
+           cadd(in.c3.mulB(in.s0.b), in.c4.mulB(NB)));
     stpair(e.n1.p + layer * e.n1.ls + off, NA, NB);
     if (e.prevsol.p) stpair(e.prevsol.p + layer * e.prevsol.ls + off, in.s0.a, in.s0.b);
   } else if (KIND == EPI_ETD_2) {  // c4 = beta
-    stpair(out, cadd(coefmul<CL>(in.c1.a, in.s0.a), coefmul<CL>(in.c2.a, NA)),
-           cadd(coefmul<CL>(in.c1.b, in.s0.b), coefmul<CL>(in.c2.b, NB)));
-    stpair(e.acc.p + layer * e.acc.ls + off, cadd(in.acc.a, coefmul<CL>(in.c4.a, cscale(NA, 2.0))),
-           cadd(in.acc.b, coefmul<CL>(in.c4.b, cscale(NB, 2.0))));
+    stpair(out, cadd(in.c1.mulA(in.s0.a), in.c2.mulA(NA)),
+           cadd(in.c1.mulB(in.s0.b), in.c2.mulB(NB)));
+    stpair(e.acc.p + layer * e.acc.ls + off, cadd(in.acc.a, in.c4.mulA(cscale(NA, 2.0))),
+           cadd(in.acc.b, in.c4.mulB(cscale(NB, 2.0))));
   } else if (KIND == EPI_ETD_3) {  // e.sol = sol1 (dealiased on load), out = next stage input
     const cplx ta = cmake(2.0 * NA.x - in.n1.a.x, 2.0 * NA.y - in.n1.a.y);
     const cplx tb = cmake(2.0 * NB.x - in.n1.b.x, 2.0 * NB.y - in.n1.b.y);
-    stpair(out, cadd(coefmul<CL>(in.c1.a, in.s0.a), coefmul<CL>(in.c2.a, ta)),
-           cadd(coefmul<CL>(in.c1.b, in.s0.b), coefmul<CL>(in.c2.b, tb)));
-    stpair(e.acc.p + layer * e.acc.ls + off, cadd(in.acc.a, coefmul<CL>(in.c4.a, cscale(NA, 2.0))),
-           cadd(in.acc.b, coefmul<CL>(in.c4.b, cscale(NB, 2.0))));
+    stpair(out, cadd(in.c1.mulA(in.s0.a), in.c2.mulA(ta)),
+           cadd(in.c1.mulB(in.s0.b), in.c2.mulB(tb)));
+    stpair(e.acc.p + layer * e.acc.ls + off, cadd(in.acc.a, in.c4.mulA(cscale(NA, 2.0))),
+           cadd(in.acc.b, in.c4.mulB(cscale(NB, 2.0))));
   } else if (KIND == EPI_ETD_4) {  // c4 = Gamma
-    stpair(out, cscale(cadd(in.acc.a, coefmul<CL>(in.c4.a, NA)), in.filt.x),
-           cscale(cadd(in.acc.b, coefmul<CL>(in.c4.b, NB)), in.filt.y));
+    stpair(out, cscale(cadd(in.acc.a, in.c4.mulA(NA)), in.filt.x),
+           cscale(cadd(in.acc.b, in.c4.mulB(NB)), in.filt.y));
   } else if (KIND == EPI_AB3) {
-    const cplx ra = cadd(NA, coefmul<CL>(in.L.a, in.s0.a)), rb = cadd(NB, coefmul<CL>(in.L.b, in.s0.b));
+    const cplx ra = cadd(NA, in.L.mulA(in.s0.a)), rb = cadd(NB, in.L.mulB(in.s0.b));
     cplx ua = cscale(ra, e.a), ub = cscale(rb, e.a);
     if (e.b != 0.0 || e.d != 0.0) {
       ua = axpy(axpy(ua, e.b, in.acc.a), e.d, in.n1.a);
@@ -671,31 +677,44 @@ __device__ __forceinline__ void epi_finish(const GridDesc& g, const EpiArgs& e, 
 // thread are in flight; the kind is a template parameter so only the arrays a stage needs are touched.
 template <int NY, int KIND, bool CL>
 __device__ __noinline__ void epilogue_tile(const GridDesc& g, const EpiArgs& e, const int layer, const int colA,
-                                           const cplx* __restrict__ X, const cplx* __restrict__ sc, const int j, const int tid) {
+                                           cplx* __restrict__ X, cplx* __restrict__ sc, const int j, const int tid) {
   using GC = GroupCfg<NY>;
   constexpr int T = GC::T, THREADS = GC::THREADS;
+  constexpr int CH = 4;  // rows fetched before anything is stored: ~4 x (3..5) independent 128/256-bit loads in flight
+  const int off0 = toff(j, colA, e.out.ld);  // every ctx-owned array shares this leading dimension
+  if (e.Nconst.p || e.F.p || (e.mu != 0.0 && layer == e.nlayers - 1)) {
+#pragma unroll 4
+    for (int r = 0; r < PT; ++r) {
+      const int l = j + r * T;
+      if (e.prune && l_aliased(g, l)) continue;
+      cplx NA = X[r * THREADS + tid], NB = sc[r * THREADS + tid];
+      epi_addends(g, e, layer, l, colA, toff_row<T>(off0, j, r, colA, e.out.ld), NA, NB);
+      X[r * THREADS + tid] = NA;
+      sc[r * THREADS + tid] = NB;
+    }
+  }
 #pragma unroll 1
-  for (int r0 = 0; r0 < PT; r0 += 2) {
-    EpiIn<KIND> in[2];
-    bool act[2];
-    int off[2];
+  for (int r0 = 0; r0 < PT; r0 += CH) {
+    EpiIn<KIND, CL> in[CH];
+    bool act[CH];
+    int off[CH];
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
+    for (int q = 0; q < CH; ++q) {
       const int l = j + (r0 + q) * T;
       act[q] = !(e.prune && l_aliased(g, l));
-      off[q] = toff(l, colA, e.out.ld);  // every ctx-owned array shares this leading dimension
+      off[q] = toff_row<T>(off0, j, r0 + q, colA, e.out.ld);
       if (act[q]) epi_fetch<KIND, CL>(g, e, layer, l, colA, off[q], in[q]);
     }
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
+    for (int q = 0; q < CH; ++q) {
       if (act[q]) epi_finish<KIND, CL>(g, e, layer, off[q], X[(r0 + q) * THREADS + tid], sc[(r0 + q) * THREADS + tid], in[q]);
     }
   }
 }
 
 template <int NY, bool CL>
-__device__ __forceinline__ void epilogue_dispatch(const GridDesc& g, const EpiArgs& e, int layer, int colA, const cplx* X,
-                                                  const cplx* sc, int j, int tid) {
+__device__ __forceinline__ void epilogue_dispatch(const GridDesc& g, const EpiArgs& e, int layer, int colA, cplx* X,
+                                                  cplx* sc, int j, int tid) {
   switch (e.kind) {
 #define GFB_EPI_CASE(K) case K: epilogue_tile<NY, K, CL>(g, e, layer, colA, X, sc, j, tid); break;
     GFB_EPI_CASE(EPI_STORE)
