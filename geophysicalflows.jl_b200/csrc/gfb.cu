@@ -45,8 +45,6 @@ struct gfb_ctx {
   cplx *S0 = nullptr, *Fint = nullptr, *PV = nullptr, *Cin = nullptr, *Nint = nullptr;  // aligned copies of user arrays
   double *dpart = nullptr, *dout = nullptr;
   int dblocks = 0;
-  cplx* scratch = nullptr;  // K3 per-CTA parking space (L2-resident)
-  int max_ctas = 296;
   // optional per-kernel event timing
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev;   // pairs (start, stop)
@@ -302,13 +300,6 @@ int gfb_create(gfb_ctx** out, const gfb_config* cfg) {
     // ETDRK4 needs s1, s2, s3, acc, N1: the fifth array aliases W's fourth field block (unused on the step path)
   }
   {
-    int devid = 0;
-    cudaDeviceProp prop;
-    if (cudaGetDevice(&devid) == cudaSuccess && cudaGetDeviceProperties(&prop, devid) == cudaSuccess && prop.multiProcessorCount > 0)
-      c->max_ctas = 2 * prop.multiProcessorCount;
-  }
-  TRY(dev_alloc(c, &c->scratch, (size_t)col_fwd_scratch_per_cta(g.ny) * c->max_ctas * (size_t)(2 * n > 4 ? 2 * n : 4)));
-  {
     cplx** arrs[5] = {&c->S0, &c->Fint, &c->PV, &c->Cin, &c->Nint};
     for (auto a : arrs) {
       TRY(dev_alloc(c, a, (size_t)n * c->ils));
@@ -488,8 +479,6 @@ static int run_col_fwd(gfb_ctx* c, const EpiArgs& e, cudaStream_t st) {
   F.pfs = c->pfs;
   F.e = e;
   F.ncols = e.prune ? c->g.kcut : c->g.nkr;
-  F.max_ctas = c->max_ctas;
-  F.scratch = c->scratch;
   F.nlayers = c->nlayers;
   F.nl = c->nlayers;
   F.two = true;
@@ -794,8 +783,6 @@ int gfb_rfft(gfb_ctx* c, void* out_spec, const double* in_phys, int batch, void*
     F.nlayers = nb;
     F.nl = 1;
     F.two = false;
-    F.max_ctas = c->max_ctas;
-    F.scratch = c->scratch;
     F.tw = c->tw_y;
     F.st = st;
     rc = check_launch(c, launch_col_fwd(c->g.ny, F), "k_col_fwd(plain)");

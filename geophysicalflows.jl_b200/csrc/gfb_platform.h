@@ -59,6 +59,77 @@ __device__ __forceinline__ double2 ldpair_d(const double* p) {  // two adjacent 
 }
 __device__ __forceinline__ void compiler_fence() { asm volatile("" ::: "memory"); }
 
+// ---- Tensor Memory (TMEM) as thread-private parking space ------------------------------------------------
+// 256 KB per SM, 512 columns x 128 lanes x 32 bit, reachable only through tcgen05.st / tcgen05.ld.  With the
+// 32x32b shape every thread reads and writes its OWN lane (warp w owns lanes 32*(w%4) ..), which is exactly
+// what a thread-private stash needs -- and it costs neither shared memory nor LSU bandwidth.  Warps w and
+// w+4 share lanes, so they use different column ranges.  All tcgen05 calls are warp-collective
+// (.sync.aligned): never call them under divergent control flow.
+#ifdef GFB_EMULATE
+__device__ __forceinline__ uint32_t tmem_setup(uint32_t*, int) {
+  __syncthreads();
+  return 0u;
+}
+__device__ __forceinline__ void tmem_release(uint32_t, int) { __syncthreads(); }
+__device__ __forceinline__ uint32_t tmem_thread_base(uint32_t base, int cols_per_warpgroup) {
+  const int warp = (int)threadIdx.x / 32;
+  return base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * cols_per_warpgroup);
+}
+__device__ __forceinline__ uint32_t* emu_tmem_cell(uint32_t taddr) {
+  const int lane = (int)(taddr >> 16) + ((int)threadIdx.x & 31);
+  const int col = (int)(taddr & 0xffffu);
+  return emu::tmem_storage() + (size_t)lane * 512 + col;
+}
+__device__ __forceinline__ void tmem_store(uint32_t taddr, double2 v) { std::memcpy(emu_tmem_cell(taddr), &v, 16); }
+__device__ __forceinline__ double2 tmem_load(uint32_t taddr) {
+  double2 v;
+  std::memcpy(&v, emu_tmem_cell(taddr), 16);
+  return v;
+}
+__device__ __forceinline__ void tmem_wait_st() {}
+__device__ __forceinline__ void tmem_wait_ld() {}
+#else
+// all threads of the CTA call this; warp 0 allocates `cols` (power of two >= 32) columns
+__device__ __forceinline__ uint32_t tmem_setup(uint32_t* smem_word, int cols) {
+  if (threadIdx.x < 32) {
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_word);
+    if (cols == 512) asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(dst) : "memory");
+    else if (cols == 256) asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(dst) : "memory");
+    else asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(dst) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  return *reinterpret_cast<volatile uint32_t*>(smem_word);
+}
+__device__ __forceinline__ void tmem_release(uint32_t base, int cols) {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    if (cols == 512) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(base) : "memory");
+    else if (cols == 256) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(base) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(base) : "memory");
+  }
+}
+__device__ __forceinline__ uint32_t tmem_thread_base(uint32_t base, int cols_per_warpgroup) {
+  const int warp = (int)threadIdx.x / 32;
+  return base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * cols_per_warpgroup);
+}
+__device__ __forceinline__ void tmem_store(uint32_t taddr, double2 v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(__double2loint(v.x)),
+               "r"(__double2hiint(v.x)), "r"(__double2loint(v.y)), "r"(__double2hiint(v.y))
+               : "memory");
+}
+__device__ __forceinline__ double2 tmem_load(uint32_t taddr) {  // result valid after tmem_wait_ld()
+  uint32_t a, b, c, d;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(taddr) : "memory");
+  return make_double2(__hiloint2double((int)b, (int)a), __hiloint2double((int)d, (int)c));
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+#endif
+
 __device__ __forceinline__ void cp_async_wait_all() {
 #ifndef GFB_EMULATE
   asm volatile("cp.async.wait_all;\n" ::: "memory");

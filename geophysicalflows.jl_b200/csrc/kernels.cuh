@@ -97,6 +97,7 @@ __device__ __forceinline__ void swap_stash(cplx (&v)[PT], cplx* __restrict__ X, 
 // load_pair(g, field, l, colA, liveB, a, b): values of `field` at (l, colA) and (l, colA+1), ready for the
 // inverse y-FFT.  Sources that are ctx-owned (kAligned) are read with one 256-bit access per row.
 struct PrepPlain {  // irfft of arbitrary (user, dense) spectra: field = batch index
+  static constexpr bool kAsync = false;
   const cplx* in;
   int ld;  // dense (user) leading dimension; offsets are computed inside
   long long ls;
@@ -109,6 +110,18 @@ struct PrepPlain {  // irfft of arbitrary (user, dense) spectra: field = batch i
 };
 
 struct PrepSingle {  // single-layer modules: psi_h = -G*sol ; uh = i l G sol ; vh = -i kr G sol ; qh = sol
+  static constexpr bool kAsync = true;  // column B: raw value by cp.async into the stash, prepared when swapped in
+  __device__ __forceinline__ bool live(const GridDesc& g, int l) const { return !l_aliased(g, l); }
+  __device__ __forceinline__ const cplx* src(int, int off) const { return sol + off; }
+  __device__ __forceinline__ cplx prepare(const GridDesc& g, int field, int l, int col, int off, cplx raw) const {
+    double gg = 0.0;
+    if (field != 2) gg = G[off];
+    return apply(g, field, wav_l(g, l), wav_kr(g, col), gg, raw);
+  }
+  __device__ __forceinline__ cplx load_one(const GridDesc& g, int field, int l, int col, int off) const {
+    if (l_aliased(g, l)) return cmake(0.0, 0.0);
+    return prepare(g, field, l, col, off, sol[off]);
+  }
   const cplx* sol;   // ctx-owned, ld even
   int ld;
   const double* G;   // ctx-owned, ld = ldg even
@@ -135,6 +148,7 @@ struct PrepSingle {  // single-layer modules: psi_h = -G*sol ; uh = i l G sol ; 
 };
 
 struct PrepMulti {  // MultiLayerQG: psi_h = S^-1 q_h ; uh = -i l psi_h ; vh = i kr psi_h ; field = nf*layer + {u,v,q[,psi]}
+  static constexpr bool kAsync = false;
   const cplx* sol;     // ctx-owned, ld even
   int ld;
   long long ls;
@@ -202,20 +216,43 @@ __global__ void __launch_bounds__(GroupCfg<NY>::THREADS, GroupCfg<NY>::MINB)
   cplx* X = reinterpret_cast<cplx*>(smd + GC::XB_DOUBLES);
   cplx v[PT];
   const int inoff = toff(j, colA, prep.ld);
+  if constexpr (Prep::kAsync) {
+    if (liveA) {
 #pragma unroll
-  for (int c0 = 0; c0 < PT; c0 += 4) {
-    cplx bb[4];
+      for (int r = 0; r < PT; ++r)
+        if (prep.live(g, j + r * T)) cp_async16(&X[r * THREADS + tid], prep.src(field, toff_row<T>(inoff, j, r, colA, prep.ld) + 1));
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (liveA) prep.load_pair(g, field, j + (c0 + q) * T, colA, liveB, toff_row<T>(inoff, j, c0 + q, colA, prep.ld), v[c0 + q], bb[q]);
-      else v[c0 + q] = bb[q] = cmake(0.0, 0.0);
+      for (int r = 0; r < PT; ++r) v[r] = prep.load_one(g, field, j + r * T, colA, toff_row<T>(inoff, j, r, colA, prep.ld));
+    } else {
+#pragma unroll
+      for (int r = 0; r < PT; ++r) v[r] = cmake(0.0, 0.0);
     }
+    block_fft_split<NY, INV>(v, j, xb, tw);
+    cp_async_wait_all();
 #pragma unroll
-    for (int q = 0; q < 4; ++q) X[(c0 + q) * THREADS + tid] = bb[q];
-    compiler_fence();
+    for (int r = 0; r < PT; ++r) {
+      const int l = j + r * T;
+      cplx t = cmake(0.0, 0.0);
+      if (liveA && prep.live(g, l)) t = prep.prepare(g, field, l, colB, toff_row<T>(inoff, j, r, colA, prep.ld) + 1, X[r * THREADS + tid]);
+      X[r * THREADS + tid] = v[r];
+      v[r] = t;
+    }
+  } else {
+#pragma unroll
+    for (int c0 = 0; c0 < PT; c0 += 4) {
+      cplx bb[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (liveA) prep.load_pair(g, field, j + (c0 + q) * T, colA, liveB, toff_row<T>(inoff, j, c0 + q, colA, prep.ld), v[c0 + q], bb[q]);
+        else v[c0 + q] = bb[q] = cmake(0.0, 0.0);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) X[(c0 + q) * THREADS + tid] = bb[q];
+      compiler_fence();
+    }
+    block_fft_split<NY, INV>(v, j, xb, tw);
+    swap_stash(v, X, tid, THREADS);
   }
-  block_fft_split<NY, INV>(v, j, xb, tw);
-  swap_stash(v, X, tid, THREADS);
   block_fft_split<NY, INV>(v, j, xb, tw);
   if (liveA) {
     cplx* out = W + field * wfs;
@@ -675,23 +712,36 @@ __device__ __forceinline__ void epi_finish(const GridDesc& g, const EpiArgs& e, 
 // Epilogue of one column-pair tile: N of column A waits in the stash X, of column B in the scratch slot.
 // Two rows (four wavenumbers) are fetched before anything is stored, so ~10 independent 256-bit loads per
 // thread are in flight; the kind is a template parameter so only the arrays a stage needs are touched.
+// N of column A waits in the shared-memory stash X, N of column B in the thread's TMEM slot `tb`.
+// TMEM accesses are warp-collective, so they sit outside every row-dependent branch.
 template <int NY, int KIND, bool CL>
-__device__ __noinline__ void epilogue_tile(const GridDesc& g, const EpiArgs& e, const int layer, const int colA,
-                                           cplx* __restrict__ X, cplx* __restrict__ sc, const int j, const int tid) {
+__device__ __forceinline__ void epilogue_tile(const GridDesc& g, const EpiArgs& e, const int layer, const int colA,
+                                              const bool liveA, cplx* __restrict__ X, const uint32_t tb, const int j,
+                                              const int tid) {
   using GC = GroupCfg<NY>;
   constexpr int T = GC::T, THREADS = GC::THREADS;
   constexpr int CH = 4;  // rows fetched before anything is stored: ~4 x (3..5) independent 128/256-bit loads in flight
   const int off0 = toff(j, colA, e.out.ld);  // every ctx-owned array shares this leading dimension
   if (e.Nconst.p || e.F.p || (e.mu != 0.0 && layer == e.nlayers - 1)) {
-#pragma unroll 4
-    for (int r = 0; r < PT; ++r) {
-      const int l = j + r * T;
-      if (e.prune && l_aliased(g, l)) continue;
-      cplx NA = X[r * THREADS + tid], NB = sc[r * THREADS + tid];
-      epi_addends(g, e, layer, l, colA, toff_row<T>(off0, j, r, colA, e.out.ld), NA, NB);
-      X[r * THREADS + tid] = NA;
-      sc[r * THREADS + tid] = NB;
+#pragma unroll 1
+    for (int r0 = 0; r0 < PT; r0 += CH) {
+      cplx nb[CH];
+#pragma unroll
+      for (int q = 0; q < CH; ++q) nb[q] = tmem_load(tb + 4 * (r0 + q));
+      tmem_wait_ld();
+#pragma unroll
+      for (int q = 0; q < CH; ++q) {
+        const int r = r0 + q, l = j + r * T;
+        if (liveA && !(e.prune && l_aliased(g, l))) {
+          cplx NA = X[r * THREADS + tid];
+          epi_addends(g, e, layer, l, colA, toff_row<T>(off0, j, r, colA, e.out.ld), NA, nb[q]);
+          X[r * THREADS + tid] = NA;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < CH; ++q) tmem_store(tb + 4 * (r0 + q), nb[q]);
     }
+    tmem_wait_st();
   }
 #pragma unroll 1
   for (int r0 = 0; r0 < PT; r0 += CH) {
@@ -701,22 +751,24 @@ __device__ __noinline__ void epilogue_tile(const GridDesc& g, const EpiArgs& e, 
 #pragma unroll
     for (int q = 0; q < CH; ++q) {
       const int l = j + (r0 + q) * T;
-      act[q] = !(e.prune && l_aliased(g, l));
+      act[q] = liveA && !(e.prune && l_aliased(g, l));
       off[q] = toff_row<T>(off0, j, r0 + q, colA, e.out.ld);
       if (act[q]) epi_fetch<KIND, CL>(g, e, layer, l, colA, off[q], in[q]);
     }
 #pragma unroll
     for (int q = 0; q < CH; ++q) {
-      if (act[q]) epi_finish<KIND, CL>(g, e, layer, off[q], X[(r0 + q) * THREADS + tid], sc[(r0 + q) * THREADS + tid], in[q]);
+      const cplx nb = tmem_load(tb + 4 * (r0 + q));  // TMEM latency is tiny next to the global loads above
+      tmem_wait_ld();
+      if (act[q]) epi_finish<KIND, CL>(g, e, layer, off[q], X[(r0 + q) * THREADS + tid], nb, in[q]);
     }
   }
 }
 
 template <int NY, bool CL>
-__device__ __forceinline__ void epilogue_dispatch(const GridDesc& g, const EpiArgs& e, int layer, int colA, cplx* X,
-                                                  cplx* sc, int j, int tid) {
+__device__ __forceinline__ void epilogue_dispatch(const GridDesc& g, const EpiArgs& e, int layer, int colA, bool liveA, cplx* X,
+                                                  uint32_t tb, int j, int tid) {
   switch (e.kind) {
-#define GFB_EPI_CASE(K) case K: epilogue_tile<NY, K, CL>(g, e, layer, colA, X, sc, j, tid); break;
+#define GFB_EPI_CASE(K) case K: epilogue_tile<NY, K, CL>(g, e, layer, colA, liveA, X, tb, j, tid); break;
     GFB_EPI_CASE(EPI_STORE)
     GFB_EPI_CASE(EPI_RK_FIRST)
     GFB_EPI_CASE(EPI_RK_MID)
@@ -733,12 +785,12 @@ __device__ __forceinline__ void epilogue_dispatch(const GridDesc& g, const EpiAr
 }
 
 // K3.  TWO = true: N = FFTy(Pd) - i l FFTy(Pv) ; TWO = false: plain forward transform of one field.
-// Persistent CTAs loop over column-pair tiles.  Per pair four transforms run back to back in the same
-// registers: the two (-i l)-weighted v-transforms are parked in a CTA-private, L2-resident scratch
-// (written and read back by the same thread, 128 KB per CTA), the stash holds the other column, and the
-// epilogue then touches every spectral array with complete 32-byte sectors (both columns of a row).
-// The per-tile work lives in non-inlined functions: inside a persistent loop the compiler would hoist
-// ~64 registers of loop invariants (row offsets, wavenumbers) out of the loop and spill the butterflies.
+// One CTA group per column pair.  Four transforms run back to back in the same registers; the other column
+// waits in the shared-memory stash X (fetched by cp.async behind the first transform) and the two
+// (-i l)-weighted v-transforms are parked in the thread's TMEM slots (2 x 64 columns per thread, 256 of the
+// SM's 512 columns per CTA -- two CTAs per SM use all of it).  The epilogue then touches every spectral array
+// with complete 32-byte sectors (both columns of a row).
+
 // Column A of a pair goes to registers (16 x LDG.128), column B -- the other half of the same 32-byte sectors --
 // straight into the thread-private stash with cp.async.ca (no registers; merged with A's sector fetch in L1).
 // The caller must cp_async_wait_all() before touching X.
@@ -762,50 +814,72 @@ __device__ __forceinline__ void load_pair_column(cplx (&v)[PT], cplx* __restrict
   }
 }
 
-// phase V: both columns of -i l FFTy(Pv) -> scratch
 template <int NY>
-__device__ __noinline__ void col_fwd_tile_v(const GridDesc& g, const cplx* __restrict__ pv, const int ldp,
-                                            const cplx* __restrict__ tw, cplx* __restrict__ sc, double* __restrict__ xb,
-                                            cplx* __restrict__ X, const int colA, const bool liveA, const int j, const int tid) {
-  using GC = GroupCfg<NY>;
-  constexpr int T = GC::T, THREADS = GC::THREADS;
-  cplx v[PT];
-  load_pair_column<NY>(v, X, pv, ldp, colA, liveA, j, tid);
-  block_fft_split<NY, FWD>(v, j, xb, tw);
-  cp_async_wait_all();
-#pragma unroll
-  for (int r = 0; r < PT; ++r) {
-    const double ll = wav_l(g, j + r * T);
-    sc[r * THREADS + tid] = cmake(ll * v[r].y, -ll * v[r].x);  // -i l (vq)_h, column A
-    v[r] = X[r * THREADS + tid];
-  }
-  block_fft_split<NY, FWD>(v, j, xb, tw);
-#pragma unroll
-  for (int r = 0; r < PT; ++r) {
-    const double ll = wav_l(g, j + r * T);
-    sc[GC::STASH + r * THREADS + tid] = cmake(ll * v[r].y, -ll * v[r].x);  // column B
-  }
-}
+struct TmemCfg {
+  static constexpr int PER_WG = 128;                                  // two 64-column slots per thread
+  static constexpr int COLS = (GroupCfg<NY>::THREADS / 128) * PER_WG;  // 256 (512 for 512-thread CTAs)
+};
 
-// phase D: FFTy(Pd) of both columns (+ the parked phase-V results), then the epilogue on the column pair
 template <int NY, bool TWO>
-__device__ __noinline__ void col_fwd_tile_d(const GridDesc& g, const cplx* __restrict__ pd, const int ldp, const EpiArgs& e,
-                                            const cplx* __restrict__ tw, cplx* __restrict__ sc, double* __restrict__ xb,
-                                            cplx* __restrict__ X, const int colA, const bool liveA, const int layer,
-                                            const int j, const int tid) {
+__global__ void __launch_bounds__(GroupCfg<NY>::THREADS, GroupCfg<NY>::MINB)
+    k_col_fwd(const __grid_constant__ GridDesc g, const cplx* __restrict__ P, const int ldp, const long long pfs,
+              const __grid_constant__ EpiArgs e, const int ncols, const cplx* __restrict__ tw) {
   using GC = GroupCfg<NY>;
   constexpr int T = GC::T, THREADS = GC::THREADS;
+  GFB_DYN_SMEM(double, smd);
+  const int tid = threadIdx.x;
+  const int gi = tid / T, j = tid % T;
+  const int layer = blockIdx.y;
+  double* xb = smd + gi * GC::GSD;
+  cplx* X = reinterpret_cast<cplx*>(smd + GC::XB_DOUBLES);
+  const int colA = 2 * (blockIdx.x * GC::G + gi);
+  const bool liveA = colA < ncols;
+  const cplx* pd = P + (TWO ? 2 * layer : layer) * pfs;
   cplx v[PT];
+  uint32_t tbase = 0, tA = 0, tB = 0;
+  if (TWO) {
+    tbase = tmem_setup(reinterpret_cast<uint32_t*>(X + GC::STASH), TmemCfg<NY>::COLS);
+    tA = tmem_thread_base(tbase, TmemCfg<NY>::PER_WG);
+    tB = tA + 64;
+    // ---- phase V: -i l FFTy(Pv) of both columns -> TMEM
+    const cplx* pv = P + (2 * layer + 1) * pfs;
+    load_pair_column<NY>(v, X, pv, ldp, colA, liveA, j, tid);
+    block_fft_split<NY, FWD>(v, j, xb, tw);
+    cp_async_wait_all();
+#pragma unroll
+    for (int r = 0; r < PT; ++r) {
+      const double ll = wav_l(g, j + r * T);
+      tmem_store(tA + 4 * r, cmake(ll * v[r].y, -ll * v[r].x));  // -i l (vq)_h, column A
+      v[r] = X[r * THREADS + tid];
+    }
+    block_fft_split<NY, FWD>(v, j, xb, tw);
+#pragma unroll
+    for (int r = 0; r < PT; ++r) {
+      const double ll = wav_l(g, j + r * T);
+      tmem_store(tB + 4 * r, cmake(ll * v[r].y, -ll * v[r].x));  // column B
+    }
+    tmem_wait_st();
+  }
+  // ---- phase D: FFTy(Pd) of both columns (+ the parked phase-V results)
   load_pair_column<NY>(v, X, pd, ldp, colA, liveA, j, tid);
   block_fft_split<NY, FWD>(v, j, xb, tw);
   cp_async_wait_all();
+  if (TWO) {
 #pragma unroll
-  for (int r = 0; r < PT; ++r) {
-    const cplx t = X[r * THREADS + tid];
-    cplx n = v[r];
-    if (TWO) n = cadd(n, sc[r * THREADS + tid]);
-    X[r * THREADS + tid] = n;
-    v[r] = t;
+    for (int c0 = 0; c0 < PT; c0 += 4) {
+      cplx a[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) a[q] = tmem_load(tA + 4 * (c0 + q));
+      tmem_wait_ld();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const cplx t = X[(c0 + q) * THREADS + tid];
+        X[(c0 + q) * THREADS + tid] = cadd(v[c0 + q], a[q]);
+        v[c0 + q] = t;
+      }
+    }
+  } else {
+    swap_stash(v, X, tid, THREADS);
   }
   block_fft_split<NY, FWD>(v, j, xb, tw);
   if constexpr (!TWO) {
@@ -819,36 +893,20 @@ __device__ __noinline__ void col_fwd_tile_d(const GridDesc& g, const cplx* __res
       }
     }
   } else {
-    // park column B next to column A: the epilogue runs in its own (kind-specialised) function
+    // N of column B -> TMEM slot A (its phase-V partner is consumed), then the kind-specialised epilogue
 #pragma unroll
-    for (int r = 0; r < PT; ++r) sc[r * THREADS + tid] = cadd(v[r], sc[GC::STASH + r * THREADS + tid]);
-    if (liveA) {
-      if (e.cplxL) epilogue_dispatch<NY, true>(g, e, layer, colA, X, sc, j, tid);
-      else epilogue_dispatch<NY, false>(g, e, layer, colA, X, sc, j, tid);
+    for (int c0 = 0; c0 < PT; c0 += 4) {
+      cplx b[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) b[q] = tmem_load(tB + 4 * (c0 + q));
+      tmem_wait_ld();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) tmem_store(tA + 4 * (c0 + q), cadd(v[c0 + q], b[q]));
     }
-  }
-}
-
-template <int NY, bool TWO>
-__global__ void __launch_bounds__(GroupCfg<NY>::THREADS, GroupCfg<NY>::MINB)
-    k_col_fwd(const __grid_constant__ GridDesc g, const cplx* __restrict__ P, const int ldp, const long long pfs,
-              const __grid_constant__ EpiArgs e, const int ncols, const cplx* __restrict__ tw, cplx* __restrict__ scratch) {
-  using GC = GroupCfg<NY>;
-  constexpr int T = GC::T;
-  GFB_DYN_SMEM(double, smd);
-  const int tid = threadIdx.x;
-  const int gi = tid / T, j = tid % T;
-  const int layer = blockIdx.y;
-  double* xb = smd + gi * GC::GSD;
-  cplx* X = reinterpret_cast<cplx*>(smd + GC::XB_DOUBLES);
-  cplx* sc = scratch + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * (2 * GC::STASH);
-  const int ntiles = ((ncols + 1) / 2 + GC::G - 1) / GC::G;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int colA = 2 * (tile * GC::G + gi);
-    const bool liveA = colA < ncols;
-    const cplx* pd = P + (TWO ? 2 * layer : layer) * pfs;
-    if (TWO) col_fwd_tile_v<NY>(g, P + (2 * layer + 1) * pfs, ldp, tw, sc, xb, X, colA, liveA, j, tid);
-    col_fwd_tile_d<NY, TWO>(g, pd, ldp, e, tw, sc, xb, X, colA, liveA, layer, j, tid);
+    tmem_wait_st();
+    if (e.cplxL) epilogue_dispatch<NY, true>(g, e, layer, colA, liveA, X, tA, j, tid);
+    else epilogue_dispatch<NY, false>(g, e, layer, colA, liveA, X, tA, j, tid);
+    tmem_release(tbase, TmemCfg<NY>::COLS);
   }
 }
 

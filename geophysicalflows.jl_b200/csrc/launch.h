@@ -41,8 +41,6 @@ struct ColFwdLaunch {
   int nlayers;         // grid.y
   int nl;              // template NL (layers coupled in the epilogue)
   bool two;
-  int max_ctas;        // persistent grid width (per layer); scratch has nlayers*max_ctas slots
-  cplx* scratch;       // 2*PT*THREADS complex per CTA slot
   const cplx* tw;
   cudaStream_t st;
 };
@@ -70,11 +68,3 @@ int launch_col_fwd(int NY, const ColFwdLaunch& L);
 
 }  // namespace gfb
 
-namespace gfb {
-// complex elements of K3 scratch needed per CTA slot for FFT length NY
-inline long long col_fwd_scratch_per_cta(int NY) {
-  const int T = NY / PT;
-  const int threads = T >= 256 ? T : 256;
-  return 2LL * PT * threads;
-}
-}  // namespace gfb

@@ -73,17 +73,15 @@ int GFB_CAT(launch_row_, GFB_N)(const RowLaunch& L) {
 template <bool TWO>
 static int do_col_fwd(const ColFwdLaunch& L) {
   using GC = GroupCfg<GFB_N>;
-  const size_t smem = (size_t)GC::XB_DOUBLES * sizeof(double) + (size_t)GC::STASH * sizeof(cplx);
+  const size_t smem = (size_t)GC::XB_DOUBLES * sizeof(double) + (size_t)GC::STASH * sizeof(cplx) + 16;  // + TMEM base word
   static bool attr = false;
   if (!attr) {
     if (set_smem(k_col_fwd<GFB_N, TWO>, smem)) return -2;
     attr = true;
   }
   const int ntiles = ((L.ncols + 1) / 2 + GC::G - 1) / GC::G;
-  int gx = ntiles < L.max_ctas ? ntiles : L.max_ctas;
-  if (gx < 1) gx = 1;
-  dim3 grid(gx, L.nlayers);
-  GFB_LAUNCH((k_col_fwd<GFB_N, TWO>), grid, dim3(GC::THREADS), smem, L.st, L.g, L.P, L.ldp, L.pfs, L.e, L.ncols, L.tw, L.scratch);
+  dim3 grid(ntiles, L.nlayers);
+  GFB_LAUNCH((k_col_fwd<GFB_N, TWO>), grid, dim3(GC::THREADS), smem, L.st, L.g, L.P, L.ldp, L.pfs, L.e, L.ncols, L.tw);
   return 0;
 }
 

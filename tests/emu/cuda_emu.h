@@ -130,9 +130,11 @@ struct BlockState {
   const std::function<void()>* body = nullptr;
   char* smem = nullptr;
   size_t smem_cap = 0;
+  uint32_t* tmem = nullptr;  // emulated tensor memory: 128 lanes x 512 columns
   ~BlockState() {
     for (char* s : stacks) std::free(s);
     std::free(smem);
+    std::free(tmem);
   }
 };
 
@@ -141,6 +143,8 @@ extern thread_local uint3 tl_threadIdx, tl_blockIdx;
 extern thread_local dim3 tl_blockDim, tl_gridDim;
 
 static const size_t kStack = 256 * 1024;
+
+inline uint32_t* tmem_storage();
 
 inline void yield_to_sched() {
   BlockState* b = tl_block;
@@ -186,6 +190,12 @@ inline T shfl_idx(T v, int src_lane) {
   T out;
   std::memcpy(&out, &got, sizeof(T));
   return out;
+}
+
+inline uint32_t* tmem_storage() {
+  BlockState* b = tl_block;
+  if (!b->tmem) b->tmem = (uint32_t*)std::calloc((size_t)128 * 512, sizeof(uint32_t));
+  return b->tmem;
 }
 
 void fiber_entry();

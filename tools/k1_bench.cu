@@ -5,7 +5,9 @@
 #include "kernels.cuh"
 using namespace gfb;
 
-template <int NY, int MODE>  // MODE 0 full, 1 no-fft, 2 no-global
+__device__ int g_tok[256];
+__device__ __forceinline__ unsigned smid() { unsigned r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
+template <int NY, int MODE>  // MODE 0 full, 1 no-fft, 2 no-global, 3 full + one-CTA-per-SM compute token
 __global__ void __launch_bounds__(GroupCfg<NY>::THREADS, GroupCfg<NY>::MINB)
     k_var(const GridDesc g, const PrepSingle prep, cplx* __restrict__ W, const int ldw, const long long wfs,
           const int ncols, const cplx* __restrict__ tw, int never) {
@@ -25,19 +27,27 @@ __global__ void __launch_bounds__(GroupCfg<NY>::THREADS, GroupCfg<NY>::MINB)
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       if (MODE == 2) { v[c0 + q] = cmake(tid * 1e-3, c0 + q); bb[q] = cmake(q, tid); }
-      else prep.load_pair(g, field, j + (c0 + q) * T, colA, true, v[c0 + q], bb[q]);
+      else prep.load_pair(g, field, j + (c0 + q) * T, colA, true, toff(j + (c0 + q) * T, colA, prep.ld), v[c0 + q], bb[q]);
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) X[(c0 + q) * THREADS + tid] = bb[q];
     compiler_fence();
   }
+  if (MODE == 3) {
+    if (tid == 0) { while (atomicCAS(&g_tok[smid()], 0, 1) != 0) __nanosleep(100); }
+    __syncthreads();
+  }
   if (MODE != 1) block_fft_split<NY, INV>(v, j, xb, tw);
   swap_stash(v, X, tid, THREADS);
   if (MODE != 1) block_fft_split<NY, INV>(v, j, xb, tw);
+  if (MODE == 3) {
+    __syncthreads();
+    if (tid == 0) atomicExch(&g_tok[smid()], 0);
+  }
   if (MODE != 2 || never) {
-    cplx* out = W + field * wfs + colA;
+    cplx* out = W + field * wfs;
 #pragma unroll
-    for (int r = 0; r < PT; ++r) stpair(out + (long long)(j + r * T) * ldw, X[r * THREADS + tid], v[r]);
+    for (int r = 0; r < PT; ++r) stpair(out + toff(j + r * T, colA, ldw), X[r * THREADS + tid], v[r]);
   }
 }
 
@@ -70,5 +80,6 @@ int main() {
   run<0>(g, ps, W, ld, (long long)n * ld, g.kcut, tw, 0);
   run<1>(g, ps, W, ld, (long long)n * ld, g.kcut, tw, 0);
   run<2>(g, ps, W, ld, (long long)n * ld, g.kcut, tw, 0);
+  run<3>(g, ps, W, ld, (long long)n * ld, g.kcut, tw, 0);
   return 0;
 }
