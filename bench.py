@@ -182,10 +182,15 @@ def main():
     torch.cuda.set_device(local)
     cfg = workload(args.workload)
     n = cfg["nx"]
+    # N > 1: the SAME 4096^2 problem slab-sharded over the N GPUs (strong scaling): y-slabs in physical space,
+    # round-robin kr column pairs in spectral space, one NCCL all-to-all per 2-D transform direction and stage
+    shard = (rank, world) if world > 1 else None
     prob = pkg.SurfaceQG.Problem(dev, nx=n, Lx=cfg["Lx"], nu=cfg["nu"], nnu=cfg["nnu"], H=cfg["H"], dt=cfg["dt"],
-                                 stepper=cfg["stepper"])
+                                 stepper=cfg["stepper"], shard=shard)
     bh0 = initial_bh(n)
     bh0[0, 0] = 0
+    if world > 1:
+        bh0 = prob.shard.spec_local(bh0)
     host_sol = torch.from_numpy(bh0).pin_memory()
     prob.sol.copy_(host_sol, non_blocking=True)
 
@@ -214,14 +219,14 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     ms_per_step = ms / args.steps
-    value = world * n * n * args.steps / (ms * 1e-3)
+    value = n * n * args.steps / (ms * 1e-3)  # one problem, however many GPUs share it
     finite = bool(torch.isfinite(prob.sol.real).all().item())
 
     # ---- end to end through the public API with host buffers ----------------------------------
     # every step: state uploaded from pinned host memory, one stepforward!, state + two diagnostics back
     out_host = torch.empty_like(host_sol).pin_memory()
-    h2d = host_sol.numel() * 16
-    d2h = out_host.numel() * 16 + 16
+    h2d = host_sol.numel() * 16 * world
+    d2h = (out_host.numel() * 16 + 16) * world
     for _ in range(2):
         prob.sol.copy_(host_sol, non_blocking=True)
         pkg.stepforward_(prob, 1)
@@ -238,13 +243,17 @@ def main():
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_val = world * n * n / float(te.item())
+    e2e_val = n * n / float(te.item())
 
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
+    # all-to-all volume per GPU per step: W (3 fields) + P (2 fields) buffers, (P-1)/P of each leaves the GPU
+    a2a_bytes = 0.0
+    if world > 1:
+        a2a_bytes = 4 * 16.0 * (prob._wbuf[0].numel() + prob._pbuf[0].numel()) * (world - 1) / world
     # ---- roofline of the dominant kernel ---------------------------------------------------------
     peak, peak_src = peaks()
     g = prob.grid
@@ -262,6 +271,7 @@ def main():
         "k_row": 3 * 16.0 * ny * kcut + 2 * 16.0 * ny * (wfull * nkr + (1 - wfull) * kcut),
         "k_col_fwd": wfull * k3_bytes(nkr, nkr * ny) + (1 - wfull) * k3_bytes(kcut, band),
     }
+    kbytes = {k: v / world for k, v in kbytes.items()}  # each GPU launches the kernels on its 1/N share
     top = max(("k_col_inv", "k_row", "k_col_fwd"), key=lambda k: prof[k]["ms"])
     avg_ms = prof[top]["ms"] / max(prof[top]["launches"], 1)
     achieved = kbytes[top] / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else None
@@ -269,13 +279,15 @@ def main():
     launches = sum(v["launches"] for v in prof.values())
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": "SurfaceQG decaying %d^2 ETDRK4 Float64 (BASELINE.json configs[3])" % n,
                    "grid": [n, n], "stepper": cfg["stepper"], "dt": cfg["dt"],
                    "initial_condition": "random-phase b_h ~ |k|(1+(|k|/6)^4)^-1/2, rms b = 0.1, numpy default_rng(0)",
                    "l2": "working set (>= 12 fields x %.0f MB) exceeds the 126 MB L2; no flush needed" % (16.0 * ny * nkr / 1e6),
-                   "parallelism": "1 GPU" if world == 1 else "%d independent replicas (slab-sharded path not built yet)" % world,
+                   "parallelism": "1 GPU" if world == 1 else
+                   "%d GPUs, one %d^2 problem: y-slabs / round-robin kr column pairs, 2 NCCL all-to-all per stage "
+                   "(%.0f MB sent per GPU per step)" % (world, n, a2a_bytes / 1e6),
                    "state_finite": finite},
         "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": NCU_TRAFFIC.get(top), "peak_source": peak_src,
@@ -291,6 +303,10 @@ def main():
                 "ms_per_step": e2e_s * 1e3, "what": "per step: pinned-host sol -> device, stepforward!(prob, 1), sol + kinetic_energy -> host"},
         "clocks": sampler.summary(),
     }
+    if world > 1:
+        # NVLink roofline of the sharded step: bytes that must leave each GPU / measured peer bandwidth (770 GB/s/dir)
+        line["nvlink"] = {"a2a_bytes_per_gpu_per_step": a2a_bytes, "floor_ms_at_770GBs": a2a_bytes / 770e9 * 1e3,
+                          "collectives_per_step": 8, "note": "all-to-all not yet overlapped with the passes"}
     if world == 1 and not args.no_cpu_baseline:
         nsamp = 2 if n >= 4096 else 4
         per = cpu_steps(cfg, bh0, nsamp, 1)

@@ -11,7 +11,7 @@ from . import _lib, device, grid, timesteppers, twodnavierstokes, surfaceqg, sin
 from ._lib import GfbError  # noqa: F401
 from .device import GPU, CPU, Device  # noqa: F401
 from .grid import TwoDGrid  # noqa: F401
-from .timesteppers import stepforward_, Diagnostic  # noqa: F401
+from .timesteppers import stepforward_, Diagnostic, Shard  # noqa: F401
 
 TwoDNavierStokes = twodnavierstokes
 SurfaceQG = surfaceqg

@@ -28,13 +28,15 @@ class GfbConfig(C.Structure):
         ("G", C.c_void_p), ("eta", C.c_void_p), ("Nconst", C.c_void_p),
         ("Sinv", C.c_void_p), ("S", C.c_void_p), ("U", C.c_void_p), ("Qx", C.c_void_p), ("Qy", C.c_void_p),
         ("mu", C.c_double), ("no_dealias_in_calcN", C.c_int),
+        ("rank", C.c_int), ("nranks", C.c_int),
     ]
 
 
 EXPORTS = ["gfb_version", "gfb_last_error", "gfb_create", "gfb_destroy", "gfb_get_clock", "gfb_set_clock",
            "gfb_rfft", "gfb_irfft", "gfb_dealias", "gfb_calcN", "gfb_step", "gfb_nstages", "gfb_stage", "gfb_diag",
            "gfb_streamfunction_from_pv", "gfb_pv_from_streamfunction", "gfb_updatevars", "gfb_device_bytes",
-           "gfb_profile_begin", "gfb_profile_end"]
+           "gfb_profile_begin", "gfb_profile_end", "gfb_shard_info", "gfb_state_import", "gfb_state_export",
+           "gfb_stage_pre", "gfb_stage_mid", "gfb_stage_post"]
 
 
 class GfbError(RuntimeError):
@@ -63,6 +65,12 @@ def _prototype(lib):
     lib.gfb_updatevars.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     lib.gfb_profile_begin.argtypes = [vp]
     lib.gfb_profile_end.argtypes = [vp, C.POINTER(dp), C.POINTER(C.c_longlong)]
+    lib.gfb_shard_info.argtypes = [vp, C.POINTER(C.c_longlong)]
+    lib.gfb_state_import.argtypes = [vp, vp, vp]
+    lib.gfb_state_export.argtypes = [vp, vp, vp]
+    lib.gfb_stage_pre.argtypes = [vp, ip, vp, vp]
+    lib.gfb_stage_mid.argtypes = [vp, vp, vp, ip, vp]
+    lib.gfb_stage_post.argtypes = [vp, ip, vp, vp, vp, ip, vp]
     lib.gfb_device_bytes.argtypes = [vp]
     lib.gfb_device_bytes.restype = C.c_longlong
     for name in EXPORTS:

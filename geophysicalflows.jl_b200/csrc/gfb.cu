@@ -28,6 +28,9 @@ struct gfb_ctx {
   std::string err;
   long long bytes = 0;
   std::vector<void*> allocs;
+  // sharding (single GPU: rank 0 of 1, ny_loc = ny)
+  int ny_loc = 0;   // physical rows owned by this rank (row pass)
+  int nkpl = 0;     // column pairs per rank (ldi = 2 * nkpl)
   // tables
   cplx *tw_x = nullptr, *tw_y = nullptr;
   double* G = nullptr;
@@ -37,12 +40,12 @@ struct gfb_ctx {
   void* L = nullptr;
   double* filter = nullptr;
   void *E = nullptr, *Eh = nullptr, *zeta = nullptr, *alpha = nullptr, *beta = nullptr, *Gamma = nullptr;
-  // work
+  // work (ctx-owned W/P only on a single GPU; sharded runs pass the all-to-all buffers in)
   cplx *W = nullptr, *P = nullptr;
-  int ldw = 0, ldp = 0, ldi = 0;
-  long long wfs = 0, pfs = 0, ils = 0;  // field / layer strides
-  cplx* st[4] = {nullptr, nullptr, nullptr, nullptr};  // stage states / accumulators / histories
-  cplx *S0 = nullptr, *Fint = nullptr, *PV = nullptr, *Cin = nullptr, *Nint = nullptr;  // aligned copies of user arrays
+  int ldi = 0;
+  long long ils = 0;  // layer stride of ctx-owned spectral arrays
+  cplx* st[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // stage states / accumulators / histories
+  cplx *S0 = nullptr, *Fint = nullptr, *PV = nullptr, *Cin = nullptr, *Nint = nullptr;  // tiled copies of user arrays
   double *dpart = nullptr, *dout = nullptr;
   int dblocks = 0;
   // optional per-kernel event timing
@@ -116,7 +119,7 @@ static int dev_upload(gfb_ctx* c, T** p, const void* host, size_t n) {
 
 // upload a dense host table [nlayers][nl][nkr] (double or cplx) into the ctx-owned tiled layout (toff, ld = ldi)
 static int upload_padded(gfb_ctx* c, void** out, const void* host, int nlay, bool is_cplx) {
-  const int nl = c->g.ny, nkr = c->g.nkr, ldi = c->ldi;
+  const int nl = c->g.ny, nkr = c->g.nkl, ldi = c->ldi;
   const size_t es = is_cplx ? sizeof(cplx) : sizeof(double);
   std::vector<char> tmp((size_t)nlay * nl * ldi * es, 0);
   for (int a = 0; a < nlay; ++a)
@@ -171,9 +174,31 @@ int launch_col_fwd(int NY, const ColFwdLaunch& L) {
 }
 }  // namespace gfb
 
+
+// ---------------------------------------------------------------------------------------------
+// geometry helpers
+// ---------------------------------------------------------------------------------------------
+static int local_cols_below(const gfb_ctx* c, int gbound) {  // local columns whose global index is < gbound
+  int n = 0;
+  for (int col = 0; col < 2 * c->nkpl; ++col) {
+    const int gc = ((col >> 1) * c->g.nranks + c->g.rank) * 2 + (col & 1);
+    if (gc < gbound) n = col + 1;  // live columns form a prefix of the local ones
+  }
+  return n;
+}
+static long long w_elems(const gfb_ctx* c, int nf) { return (long long)c->g.ny * nf * c->ldi; }
+static RowLayout row_layout(const gfb_ctx* c, int nf) {
+  RowLayout r;
+  r.nranks = c->g.nranks;
+  r.rbs = 8 * nf * c->ldi;
+  r.fstr = 8 * c->ldi;
+  r.chunk = (long long)(c->ny_loc / 8) * r.rbs;
+  return r;
+}
+
 extern "C" {
 
-const char* gfb_version(void) { return "gfb 0.1 (sm_100a)"; }
+const char* gfb_version(void) { return "gfb 0.2 (sm_100a)"; }
 
 const char* gfb_last_error(const gfb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
@@ -201,6 +226,10 @@ int gfb_create(gfb_ctx** out, const gfb_config* cfg) {
   const int nkr = cfg->nx / 2 + 1;
   if (cfg->kr_alias0 < 1 || cfg->kr_alias0 > nkr || cfg->l_alias0 < 0 || cfg->l_alias1 > cfg->ny || cfg->l_alias0 > cfg->l_alias1)
     return fail(nullptr, GFB_ERR_INVALID, "bad alias ranges");
+  const int nranks = cfg->nranks > 0 ? cfg->nranks : 1;
+  const int rank = cfg->nranks > 0 ? cfg->rank : 0;
+  if (rank < 0 || rank >= nranks || (nranks & (nranks - 1)) != 0 || cfg->ny % (8 * nranks) != 0)
+    return fail(nullptr, GFB_ERR_INVALID, "bad sharding: rank %d of %d (power of two, ny divisible by 8*nranks)", rank, nranks);
   gfb_ctx* c = new gfb_ctx();
   c->cfg = *cfg;
   c->nlayers = cfg->nlayers;
@@ -220,9 +249,14 @@ int gfb_create(gfb_ctx** out, const gfb_config* cfg) {
   g.dkx = (2.0 * M_PI / cfg->Lx * cfg->nx) / cfg->nx;
   g.dky = (2.0 * M_PI / cfg->Ly * cfg->ny) / cfg->ny;
   g.invN = 1.0 / ((double)cfg->nx * (double)cfg->ny);
+  g.rank = rank;
+  g.nranks = nranks;
+  const int nkp_total = (nkr + 1) / 2;
+  c->nkpl = (nkp_total + nranks - 1) / nranks;
+  c->ldi = 2 * c->nkpl;
+  c->ny_loc = cfg->ny / nranks;
+  g.nkl = local_cols_below(c, nkr);
   const int n = c->nlayers, nl = g.ny;
-  c->ldw = c->ldp = c->ldi = (nkr + 1) & ~1;
-  c->wfs = c->pfs = (long long)nl * c->ldw;
   c->ils = (long long)nl * c->ldi;
   int rc = 0;
 #define TRY(x)             \
@@ -236,25 +270,20 @@ int gfb_create(gfb_ctx** out, const gfb_config* cfg) {
   } while (0)
   TRY(make_twiddles(c, &c->tw_x, g.nx));
   TRY(make_twiddles(c, &c->tw_y, g.ny));
-  const size_t nspec = (size_t)nl * nkr, nphys = (size_t)g.ny * g.nx;
+  const size_t nspec = (size_t)nl * g.nkl, nphys = (size_t)c->ny_loc * g.nx;
+  if (cfg->G) {
+    void* gp = nullptr;
+    TRY(upload_padded(c, &gp, cfg->G, 1, false));
+    c->G = (double*)gp;
+  }
   if (c->kind == GFB_KIND_SINGLE) {
     if (!cfg->G) { fail(c, GFB_ERR_INVALID, "GFB_KIND_SINGLE needs config.G"); TRY(GFB_ERR_INVALID); }
-    {
-      void* gp = nullptr;
-      TRY(upload_padded(c, &gp, cfg->G, 1, false));
-      c->G = (double*)gp;
-    }
     if (cfg->eta) TRY(dev_upload(c, &c->eta, cfg->eta, nphys));
   } else {
     if (!cfg->Sinv || !cfg->Qx || !cfg->Qy) { fail(c, GFB_ERR_INVALID, "GFB_KIND_LAYERED needs config.Sinv, Qx, Qy"); TRY(GFB_ERR_INVALID); }
     TRY(dev_upload(c, &c->Sinv, cfg->Sinv, nspec * n * n));
-    if (cfg->G) {  // optional: only the G-weighted diagnostics use it
-      void* gp = nullptr;
-      TRY(upload_padded(c, &gp, cfg->G, 1, false));
-      c->G = (double*)gp;
-    }
     if (cfg->S) TRY(dev_upload(c, &c->S, cfg->S, nspec * n * n));
-    if (cfg->U) TRY(dev_upload(c, &c->U, cfg->U, (size_t)n * g.ny));
+    if (cfg->U) TRY(dev_upload(c, &c->U, cfg->U, (size_t)n * c->ny_loc));
     TRY(dev_upload(c, &c->Qx, cfg->Qx, nphys * n));
     TRY(dev_upload(c, &c->Qy, cfg->Qy, nphys * n));
   }
@@ -283,21 +312,20 @@ int gfb_create(gfb_ctx** out, const gfb_config* cfg) {
     TRY(upload_padded(c, &c->beta, cfg->beta, n, c->cplxL));
     TRY(upload_padded(c, &c->Gamma, cfg->Gamma, n, c->cplxL));
   }
-  TRY(dev_alloc(c, &c->W, (size_t)4 * n * c->wfs));
-  TRY(dev_alloc(c, &c->P, (size_t)2 * n * c->pfs));
+  if (nranks == 1) {
+    TRY(dev_alloc(c, &c->W, (size_t)w_elems(c, 4 * n)));
+    TRY(dev_alloc(c, &c->P, (size_t)w_elems(c, 2 * n)));
+  }
   int nstate = 0;
   switch (cfg->stepper) {
     case GFB_FORWARD_EULER: case GFB_FILTERED_FORWARD_EULER: nstate = 0; break;
-    case GFB_RK4: case GFB_FILTERED_RK4: nstate = 3; break;     // s1, s2 (ping-pong), acc
-    case GFB_ETDRK4: case GFB_FILTERED_ETDRK4: nstate = 4; break;  // s1, s2 / s3 reuse, acc, N1
-    default: nstate = 3; break;                                  // AB3: rhs, rhs-1, rhs-2
+    case GFB_RK4: case GFB_FILTERED_RK4: nstate = 3; break;        // s1, s2 (ping-pong), acc
+    case GFB_ETDRK4: case GFB_FILTERED_ETDRK4: nstate = 5; break;  // s1, s2, acc, N1, s3
+    default: nstate = 3; break;                                    // AB3: rhs, rhs-1, rhs-2
   }
   for (int i = 0; i < nstate; ++i) {
     TRY(dev_alloc(c, &c->st[i], (size_t)n * c->ils));
     GFB_CUDA(c, cudaMemset(c->st[i], 0, (size_t)n * c->ils * sizeof(cplx)));
-  }
-  if (cfg->stepper == GFB_ETDRK4 || cfg->stepper == GFB_FILTERED_ETDRK4) {
-    // ETDRK4 needs s1, s2, s3, acc, N1: the fifth array aliases W's fourth field block (unused on the step path)
   }
   {
     cplx** arrs[5] = {&c->S0, &c->Fint, &c->PV, &c->Cin, &c->Nint};
@@ -310,9 +338,21 @@ int gfb_create(gfb_ctx** out, const gfb_config* cfg) {
   TRY(dev_alloc(c, &c->dpart, (size_t)c->dblocks * DIAG_MAXOUT));
   TRY(dev_alloc(c, &c->dout, (size_t)DIAG_MAXOUT));
 #undef TRY
-  // host pointers are not retained
-  c->cfg.L = c->cfg.filter = nullptr;
+  c->cfg.L = c->cfg.filter = nullptr;  // host pointers are not retained
   *out = c;
+  return GFB_OK;
+}
+
+int gfb_shard_info(const gfb_ctx* c, long long* info8) {
+  if (!c || !info8) return GFB_ERR_INVALID;
+  info8[0] = c->g.rank;
+  info8[1] = c->g.nranks;
+  info8[2] = c->g.nkl;                       // local dense spectral columns
+  info8[3] = c->ldi;                         // padded local columns (2 * pairs per rank)
+  info8[4] = c->ny_loc;                      // local physical rows
+  info8[5] = w_elems(c, 3 * c->nlayers);     // complex elements of the W all-to-all buffers
+  info8[6] = w_elems(c, 2 * c->nlayers);     // complex elements of the P all-to-all buffers
+  info8[7] = c->nkpl;
   return GFB_OK;
 }
 
@@ -368,13 +408,6 @@ int gfb_set_clock(gfb_ctx* c, double t, long long step) {
 // ---------------------------------------------------------------------------------------------
 // internal building blocks
 // ---------------------------------------------------------------------------------------------
-static Spec user_spec(const gfb_ctx* c, const void* p) {
-  Spec s;
-  s.p = (cplx*)p;
-  s.ld = c->g.nkr;
-  s.ls = (long long)c->g.ny * c->g.nkr;
-  return s;
-}
 static Spec int_spec(const gfb_ctx* c, cplx* p) {
   Spec s;
   s.p = p;
@@ -398,31 +431,34 @@ static Coef coef(const gfb_ctx* c, const void* p) {
   return k;
 }
 
+// dense local user array [layer][l][nkl] <-> ctx-owned tiled array
 static int repack(gfb_ctx* c, cplx* dst, int ldd, long long lsd, const cplx* src, int lds, long long lss, int to_tiled,
                   cudaStream_t st) {
   ProfScope ps(c, 3, st);
-  GFB_LAUNCH(k_repack, dim3(1184), dim3(256), 0, st, c->g.ny, c->g.nkr, c->nlayers, dst, ldd, lsd, src, lds, lss, to_tiled);
+  GFB_LAUNCH(k_repack, dim3(1184), dim3(256), 0, st, c->g.ny, c->g.nkl, c->nlayers, dst, ldd, lsd, src, lds, lss, to_tiled);
   return check_launch(c, 0, "k_repack");
 }
 static int import_spec(gfb_ctx* c, cplx* internal, const void* user, cudaStream_t st) {
-  return repack(c, internal, c->ldi, c->ils, (const cplx*)user, c->g.nkr, (long long)c->g.ny * c->g.nkr, 1, st);
+  return repack(c, internal, c->ldi, c->ils, (const cplx*)user, c->g.nkl, (long long)c->g.ny * c->g.nkl, 1, st);
 }
 static int export_spec(gfb_ctx* c, void* user, const cplx* internal, cudaStream_t st) {
-  return repack(c, (cplx*)user, c->g.nkr, (long long)c->g.ny * c->g.nkr, internal, c->ldi, c->ils, 0, st);
+  return repack(c, (cplx*)user, c->g.nkl, (long long)c->g.ny * c->g.nkl, internal, c->ldi, c->ils, 0, st);
 }
 
-// K1 on a stage input (hot path): fields u, v, q (+psi if nf == 4) for every layer -> W
-static int run_col_inv_state(gfb_ctx* c, const Spec& sin, int nf, cudaStream_t st) {
+// K1 on a stage input: fields u, v, q (+psi if nf == 4) for every layer of the LOCAL columns -> W
+// (tiled, row-block major, fields interleaved per row block: ld = nf*n*ldi, field stride = 8*ldi)
+static int run_col_inv_state(gfb_ctx* c, const Spec& sin, int nf, cplx* W, cudaStream_t st) {
   ColInvLaunch L;
   std::memset(&L, 0, sizeof L);
   L.g = c->g;
-  L.W = c->W;
-  L.ldw = c->ldw;
-  L.wfs = c->wfs;
-  L.ncols = c->g.kcut;
+  L.W = W;
+  L.ldw = nf * c->nlayers * c->ldi;
+  L.wfs = 8LL * c->ldi;
+  L.ncols = local_cols_below(c, c->g.kcut);
   L.tw = c->tw_y;
   L.st = st;
   L.nl = c->nlayers;
+  if (L.ncols == 0) return 0;
   if (c->kind == GFB_KIND_SINGLE) {
     L.prep = PREP_SINGLE;
     L.ps.sol = sin.p;
@@ -436,7 +472,7 @@ static int run_col_inv_state(gfb_ctx* c, const Spec& sin, int nf, cudaStream_t s
     L.pm.ld = sin.ld;
     L.pm.ls = sin.ls;
     L.pm.Sinv = c->Sinv;
-    L.pm.ldS = c->g.nkr;
+    L.pm.ldS = c->g.nkl;
     L.pm.nf = nf;
     L.pm.nl = c->nlayers;
     L.nfields = nf * c->nlayers;
@@ -445,24 +481,23 @@ static int run_col_inv_state(gfb_ctx* c, const Spec& sin, int nf, cudaStream_t s
   return check_launch(c, launch_col_inv(c->g.ny, L), "k_col_inv");
 }
 
-static int run_row_product(gfb_ctx* c, cudaStream_t st, bool prune) {
+static int run_row_product(gfb_ctx* c, const cplx* Wrecv, cplx* Psend, bool prune, cudaStream_t st) {
   RowLaunch R;
   std::memset(&R, 0, sizeof R);
   R.mode = (c->kind == GFB_KIND_LAYERED) ? ROW_PRODUCT_Q : ROW_PRODUCT;
-  R.a.W = c->W;
-  R.a.ldw = c->ldw;
-  R.a.wfs = c->wfs;
+  R.a.W = Wrecv;
+  R.a.wl = row_layout(c, 3 * c->nlayers);
+  R.a.wstride = 3;
   R.a.kc = c->g.kcut;
-  R.a.P = c->P;
-  R.a.ldp = c->ldp;
-  R.a.pfs = c->pfs;
+  R.a.P = Psend;
+  R.a.pl = row_layout(c, 2 * c->nlayers);
   R.a.kout = prune ? c->g.kcut : c->g.nkr;
   R.a.eta = c->eta;
   R.a.U = c->U;
   R.a.Qx = c->Qx;
   R.a.Qy = c->Qy;
   R.a.dkx = c->g.dkx;
-  R.a.ny = c->g.ny;
+  R.a.ny = c->ny_loc;
   R.nlayers = c->nlayers;
   R.tw = c->tw_x;
   R.st = st;
@@ -470,52 +505,139 @@ static int run_row_product(gfb_ctx* c, cudaStream_t st, bool prune) {
   return check_launch(c, launch_row(c->g.nx, R), "k_row");
 }
 
-static int run_col_fwd(gfb_ctx* c, const EpiArgs& e, cudaStream_t st) {
+static int run_col_fwd(gfb_ctx* c, const EpiArgs& e, const cplx* Precv, cudaStream_t st) {
   ColFwdLaunch F;
   std::memset(&F, 0, sizeof F);
   F.g = c->g;
-  F.P = c->P;
-  F.ldp = c->ldp;
-  F.pfs = c->pfs;
+  F.P = Precv;
+  F.ldp = 2 * c->nlayers * c->ldi;
+  F.pfs = 8LL * c->ldi;
   F.e = e;
-  F.ncols = e.prune ? c->g.kcut : c->g.nkr;
+  F.ncols = e.prune ? local_cols_below(c, c->g.kcut) : c->g.nkl;
   F.nlayers = c->nlayers;
   F.nl = c->nlayers;
   F.two = true;
   F.tw = c->tw_y;
   F.st = st;
+  if (F.ncols == 0) return 0;
   ProfScope ps(c, 2, st);
   return check_launch(c, launch_col_fwd(c->g.ny, F), "k_col_fwd");
 }
 
-static EpiArgs base_epi(const gfb_ctx* c, const void* Fh) {
+static EpiArgs base_epi(const gfb_ctx* c, bool forced) {
   EpiArgs e;
   std::memset(&e, 0, sizeof e);
   e.nlayers = c->nlayers;
-  e.F = Fh ? int_spec(c, c->Fint) : null_spec();  // callers import the user's Fh into Fint first
+  e.F = forced ? int_spec(c, c->Fint) : null_spec();  // callers import the user's Fh into Fint first
   e.Nconst = c->Nconst ? int_spec(c, c->Nconst) : null_spec();
   e.cplxL = c->cplxL ? 1 : 0;
   e.L = coef(c, c->L);
   e.mu = (c->kind == GFB_KIND_LAYERED) ? c->cfg.mu : 0.0;
   e.Sinv = c->Sinv;
-  e.ldS = c->g.nkr;
+  e.ldS = c->g.nkl;
   e.filter.p = nullptr;
   return e;
 }
 
-// one full calcN + epilogue on stage input `sin`
-static int run_stage_kernels(gfb_ctx* c, const Spec& sin, EpiArgs& e, cudaStream_t st) {
-  int rc = run_col_inv_state(c, sin, 3, st);
-  if (rc) return rc;
-  rc = run_row_product(c, st, e.prune != 0);
-  if (rc) return rc;
+static int nstages_of(const gfb_ctx* c) {
+  switch (c->stepper) {
+    case GFB_RK4: case GFB_FILTERED_RK4: case GFB_ETDRK4: case GFB_FILTERED_ETDRK4: return 4;
+    default: return 1;
+  }
+}
+
+// Which array feeds stage `istage` and what its epilogue does.
+// prune = 1 ("lazy alias band"): the aliased band of N -- which only ever lands in the aliased band of the next
+// state, where the next stage-1 dealias! wipes it -- is not computed.
+static int plan_stage(gfb_ctx* c, int istage, bool forced, bool want_prevsol, int prune, Spec& sin, EpiArgs& e) {
+  const int ns = nstages_of(c);
+  if (istage < 0 || istage >= ns) return fail(c, GFB_ERR_INVALID, "stage %d out of range", istage);
+  e = base_epi(c, forced);
+  e.prune = (prune && c->g.kcut < c->g.nkr) ? 1 : 0;
+  const Spec S0 = int_spec(c, c->S0);
+  const double dt = c->dt;
+  if (c->filtered) {
+    e.filter.p = c->filter;
+    e.filter.ld = c->ldi;
+    e.filter.ls = 0;
+  }
+  const Spec pv = want_prevsol ? int_spec(c, c->PV) : null_spec();
+  sin = S0;
+  e.sol = S0;
+  switch (c->stepper) {
+    case GFB_FORWARD_EULER: case GFB_FILTERED_FORWARD_EULER:
+      e.kind = EPI_RK_ONLY;
+      e.b = dt;
+      e.out = S0;
+      e.prevsol = pv;
+      break;
+    case GFB_RK4: case GFB_FILTERED_RK4: {
+      const Spec s1 = int_spec(c, c->st[0]), s2 = int_spec(c, c->st[1]), acc = int_spec(c, c->st[2]);
+      e.acc = acc;
+      if (istage == 0) {
+        e.kind = EPI_RK_FIRST; e.a = dt / 2; e.b = dt / 6; sin = S0; e.out = s1; e.prevsol = pv;
+      } else if (istage == 1) {
+        e.kind = EPI_RK_MID; e.a = dt / 2; e.b = dt / 3; sin = s1; e.out = s2;
+      } else if (istage == 2) {
+        e.kind = EPI_RK_MID; e.a = dt; e.b = dt / 3; sin = s2; e.out = s1;
+      } else {
+        e.kind = EPI_RK_LAST; e.b = dt / 6; sin = s1; e.out = S0;
+      }
+    } break;
+    case GFB_ETDRK4: case GFB_FILTERED_ETDRK4: {
+      const Spec s1 = int_spec(c, c->st[0]), s2 = int_spec(c, c->st[1]), acc = int_spec(c, c->st[2]);
+      const Spec n1 = int_spec(c, c->st[3]), s3 = int_spec(c, c->st[4]);
+      e.acc = acc;
+      e.n1 = n1;
+      e.c1 = coef(c, c->Eh);
+      e.c2 = coef(c, c->zeta);
+      if (istage == 0) {
+        e.kind = EPI_ETD_1; sin = S0; e.out = s1; e.c3 = coef(c, c->E); e.c4 = coef(c, c->alpha); e.prevsol = pv;
+      } else if (istage == 1) {
+        e.kind = EPI_ETD_2; sin = s1; e.out = s2; e.c4 = coef(c, c->beta);
+      } else if (istage == 2) {
+        e.kind = EPI_ETD_3; sin = s2; e.sol = s1; e.out = s3; e.c4 = coef(c, c->beta);
+      } else {
+        e.kind = EPI_ETD_4; sin = s3; e.out = S0; e.c4 = coef(c, c->Gamma);
+      }
+    } break;
+    default: {  // AB3
+      const long long k = c->step;
+      e.kind = EPI_AB3;
+      if (k < 3) { e.a = dt; e.b = 0; e.d = 0; }
+      else { e.a = dt * 23.0 / 12.0; e.b = -dt * 16.0 / 12.0; e.d = dt * 5.0 / 12.0; }
+      e.out = S0;
+      e.rhs = int_spec(c, c->st[k % 3]);
+      e.acc = int_spec(c, c->st[(k + 2) % 3]);
+      e.n1 = int_spec(c, c->st[(k + 1) % 3]);
+      e.prevsol = pv;
+    } break;
+  }
   e.sin = sin;
-  return run_col_fwd(c, e, st);
+  return 0;
+}
+
+static bool is_ab3(const gfb_ctx* c) { return c->stepper == GFB_AB3 || c->stepper == GFB_FILTERED_AB3; }
+
+// one stage on ctx-owned W/P (single GPU)
+static int do_stage(gfb_ctx* c, int istage, bool forced, bool want_prevsol, int prune, cudaStream_t st) {
+  Spec sin;
+  EpiArgs e;
+  int rc = plan_stage(c, istage, forced, want_prevsol, prune, sin, e);
+  if (rc) return rc;
+  if ((rc = run_col_inv_state(c, sin, 3, c->W, st))) return rc;
+  if ((rc = run_row_product(c, c->W, c->P, e.prune != 0, st))) return rc;
+  if ((rc = run_col_fwd(c, e, c->P, st))) return rc;
+  if (istage == nstages_of(c) - 1) {
+    c->t += c->dt;
+    c->step += 1;
+  }
+  return 0;
 }
 
 template <int NL>
 static void launch_matvec(const gfb_ctx* c, cplx* y, const cplx* x, const double* M, cudaStream_t st) {
-  GFB_LAUNCH((k_matvec<NL>), dim3(592), dim3(256), 0, st, c->g.ny, c->g.nkr, y, x, M);
+  GFB_LAUNCH((k_matvec<NL>), dim3(592), dim3(256), 0, st, c->g.ny, c->g.nkl, y, x, M);
 }
 
 static int matvec(gfb_ctx* c, void* y, const void* x, const double* M, void* stream) {
@@ -545,170 +667,112 @@ static void launch_diag(const gfb_ctx* c, const DiagArgs& d, cudaStream_t st) {
   GFB_LAUNCH((k_diag_partial<NL>), dim3(c->dblocks), dim3(256), 0, st, c->g, d, c->dpart);
 }
 
+#define NEED_SINGLE_GPU(c, what) \
+  if ((c)->g.nranks != 1) return fail((c), GFB_ERR_UNSUPPORTED, what ": not available on a sharded context (use the gfb_stage_pre/mid/post path)")
+
 extern "C" {
 
 int gfb_dealias(gfb_ctx* c, void* sol, void* stream) {
   if (!c || !sol) return fail(c, GFB_ERR_INVALID, "gfb_dealias: null argument");
-  const Spec s = user_spec(c, sol);
-  GFB_LAUNCH(k_dealias, dim3(592), dim3(256), 0, (cudaStream_t)stream, c->g, s.p, s.ld, s.ls, c->nlayers);
+  GFB_LAUNCH(k_dealias, dim3(592), dim3(256), 0, (cudaStream_t)stream, c->g, (cplx*)sol, c->g.nkl,
+             (long long)c->g.ny * c->g.nkl, c->nlayers);
   return check_launch(c, 0, "k_dealias");
 }
 
 int gfb_calcN(gfb_ctx* c, void* N, void* sol, const void* Fh, void* stream) {
   if (!c || !N || !sol) return fail(c, GFB_ERR_INVALID, "gfb_calcN: null argument");
+  NEED_SINGLE_GPU(c, "gfb_calcN");
   cudaStream_t st = (cudaStream_t)stream;
   int rc = gfb_dealias(c, sol, stream);
   if (rc) return rc;
   if ((rc = import_spec(c, c->Cin, sol, st))) return rc;
   if (Fh && (rc = import_spec(c, c->Fint, Fh, st))) return rc;
-  EpiArgs e = base_epi(c, Fh);
+  EpiArgs e = base_epi(c, Fh != nullptr);
   e.kind = EPI_STORE;
   e.out = int_spec(c, c->Nint);
-  if ((rc = run_stage_kernels(c, int_spec(c, c->Cin), e, st))) return rc;
+  const Spec sin = int_spec(c, c->Cin);
+  e.sin = sin;
+  if ((rc = run_col_inv_state(c, sin, 3, c->W, st))) return rc;
+  if ((rc = run_row_product(c, c->W, c->P, false, st))) return rc;
+  if ((rc = run_col_fwd(c, e, c->P, st))) return rc;
   return export_spec(c, N, c->Nint, st);
 }
 
-int gfb_nstages(const gfb_ctx* c) {
-  if (!c) return GFB_ERR_INVALID;
-  switch (c->stepper) {
-    case GFB_RK4: case GFB_FILTERED_RK4: case GFB_ETDRK4: case GFB_FILTERED_ETDRK4: return 4;
-    default: return 1;
-  }
+int gfb_nstages(const gfb_ctx* c) { return c ? nstages_of(c) : GFB_ERR_INVALID; }
+
+int gfb_stage(gfb_ctx* c, void* sol, int istage, const void* Fh, void* prevsol, void* stream) {
+  if (!c || !sol) return fail(c, GFB_ERR_INVALID, "gfb_stage: null argument");
+  NEED_SINGLE_GPU(c, "gfb_stage");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = 0;
+  if (istage == 0 && (rc = import_spec(c, c->S0, sol, st))) return rc;  // later stages continue from the ctx copy
+  if (Fh && (rc = import_spec(c, c->Fint, Fh, st))) return rc;
+  if ((rc = do_stage(c, istage, Fh != nullptr, prevsol != nullptr, 0, st))) return rc;
+  if (istage == 0 && prevsol && (rc = export_spec(c, prevsol, c->PV, st))) return rc;
+  if (istage == nstages_of(c) - 1) return export_spec(c, sol, c->S0, st);
+  return GFB_OK;
 }
 
-// prune = 1 ("lazy alias band"): the aliased band of N -- which only ever lands in the aliased band of the
-// next state, where the next stage-1 dealias! wipes it -- is not computed.  Used by
-// gfb_step for every step but the last of a call, so the state the caller sees is always exact.
-static int do_stage(gfb_ctx* c, void* sol, int istage, const void* Fh, void* prevsol, void* stream, int prune) {
-  if (!c || !sol) return fail(c, GFB_ERR_INVALID, "gfb_stage: null argument");
-  const int ns = gfb_nstages(c);
-  if (istage < 0 || istage >= ns) return fail(c, GFB_ERR_INVALID, "gfb_stage: stage %d out of range", istage);
+int gfb_step(gfb_ctx* c, void* sol, int nsteps, const void* Fh, void* prevsol, void* stream) {
+  if (!c || !sol || nsteps < 0) return fail(c, GFB_ERR_INVALID, "gfb_step: bad argument");
+  NEED_SINGLE_GPU(c, "gfb_step");
+  if (nsteps == 0) return GFB_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  EpiArgs e = base_epi(c, Fh);
-  e.prune = (prune && c->g.kcut < c->g.nkr) ? 1 : 0;
-  (void)sol;
-  const Spec S0 = int_spec(c, c->S0);  // callers import/export the user's sol
-  const double dt = c->dt;
-  if (c->filtered) {
-    e.filter.p = c->filter;
-    e.filter.ld = c->ldi;
-    e.filter.ls = 0;
-  }
-  Spec sin = S0;
-  e.sol = S0;
-  int rc = 0;
-  switch (c->stepper) {
-    case GFB_FORWARD_EULER: case GFB_FILTERED_FORWARD_EULER:
-      e.kind = EPI_RK_ONLY;
-      e.b = dt;
-      e.out = S0;
-      e.prevsol = prevsol ? int_spec(c, c->PV) : null_spec();
-      break;
-    case GFB_RK4: case GFB_FILTERED_RK4: {
-      const Spec s1 = int_spec(c, c->st[0]), s2 = int_spec(c, c->st[1]), acc = int_spec(c, c->st[2]);
-      e.acc = acc;
-      if (istage == 0) {
-        e.kind = EPI_RK_FIRST; e.a = dt / 2; e.b = dt / 6; sin = S0; e.out = s1;
-        e.prevsol = prevsol ? int_spec(c, c->PV) : null_spec();
-      } else if (istage == 1) {
-        e.kind = EPI_RK_MID; e.a = dt / 2; e.b = dt / 3; sin = s1; e.out = s2;
-      } else if (istage == 2) {
-        e.kind = EPI_RK_MID; e.a = dt; e.b = dt / 3; sin = s2; e.out = s1;
-      } else {
-        e.kind = EPI_RK_LAST; e.b = dt / 6; sin = s1; e.out = S0;
-      }
-    } break;
-    case GFB_ETDRK4: case GFB_FILTERED_ETDRK4: {
-      const Spec s1 = int_spec(c, c->st[0]), s2 = int_spec(c, c->st[1]), acc = int_spec(c, c->st[2]), n1 = int_spec(c, c->st[3]);
-      // third stage state lives in the unused 4th field block of W (only updatevars! uses it)
-      Spec s3;
-      s3.p = c->W + (long long)3 * c->nlayers * c->wfs;
-      s3.ld = c->ldw;
-      s3.ls = c->wfs;
-      e.acc = acc;
-      e.n1 = n1;
-      e.c1 = coef(c, c->Eh);
-      e.c2 = coef(c, c->zeta);
-      if (istage == 0) {
-        e.kind = EPI_ETD_1; sin = S0; e.out = s1; e.c3 = coef(c, c->E); e.c4 = coef(c, c->alpha);
-        e.prevsol = prevsol ? int_spec(c, c->PV) : null_spec();
-      } else if (istage == 1) {
-        e.kind = EPI_ETD_2; sin = s1; e.out = s2; e.c4 = coef(c, c->beta);
-      } else if (istage == 2) {
-        e.kind = EPI_ETD_3; sin = s2; e.sol = s1; e.out = s3; e.c4 = coef(c, c->beta);
-      } else {
-        e.kind = EPI_ETD_4; sin = s3; e.out = S0; e.c4 = coef(c, c->Gamma);
-      }
-    } break;
-    default: {  // AB3
-      const long long k = c->step;
-      cplx* cur = c->st[k % 3];
-      cplx* m1 = c->st[(k + 2) % 3];
-      cplx* m2 = c->st[(k + 1) % 3];
-      e.kind = EPI_AB3;
-      if (k < 3) { e.a = dt; e.b = 0; e.d = 0; }
-      else { e.a = dt * 23.0 / 12.0; e.b = -dt * 16.0 / 12.0; e.d = dt * 5.0 / 12.0; }
-      e.out = S0;
-      e.acc = int_spec(c, m1);
-      e.n1 = int_spec(c, m2);
-      e.prevsol = prevsol ? int_spec(c, c->PV) : null_spec();
-      // the epilogue stores rhs through e.sin, so run the kernels by hand
-      rc = run_col_inv_state(c, S0, 3, st);
-      if (rc) return rc;
-      rc = run_row_product(c, st, e.prune != 0);
-      if (rc) return rc;
-      e.sin = S0;
-      e.rhs = int_spec(c, cur);
-      rc = run_col_fwd(c, e, st);
-      if (rc) return rc;
-      c->t += c->dt;
-      c->step += 1;
-      return GFB_OK;
-    }
-  }
-  rc = run_stage_kernels(c, sin, e, st);
+  const int ns = nstages_of(c);
+  int rc = import_spec(c, c->S0, sol, st);
   if (rc) return rc;
-  if (istage == ns - 1) {
+  if (Fh && (rc = import_spec(c, c->Fint, Fh, st))) return rc;
+  for (int s = 0; s < nsteps; ++s) {
+    const bool last = (s == nsteps - 1);
+    for (int i = 0; i < ns; ++i)
+      if ((rc = do_stage(c, i, Fh != nullptr, last && prevsol != nullptr, (!last && !is_ab3(c)) ? 1 : 0, st))) return rc;
+  }
+  if (prevsol && (rc = export_spec(c, prevsol, c->PV, st))) return rc;
+  return export_spec(c, sol, c->S0, st);
+}
+
+// ---- sharded (multi-GPU) stepping: the caller owns the all-to-all buffers and runs the exchange -------------
+int gfb_state_import(gfb_ctx* c, const void* sol_local, void* stream) {
+  if (!c || !sol_local) return fail(c, GFB_ERR_INVALID, "gfb_state_import: null argument");
+  return import_spec(c, c->S0, sol_local, (cudaStream_t)stream);
+}
+int gfb_state_export(gfb_ctx* c, void* sol_local, void* stream) {
+  if (!c || !sol_local) return fail(c, GFB_ERR_INVALID, "gfb_state_export: null argument");
+  return export_spec(c, sol_local, c->S0, (cudaStream_t)stream);
+}
+int gfb_stage_pre(gfb_ctx* c, int istage, void* wsend, void* stream) {
+  if (!c || !wsend) return fail(c, GFB_ERR_INVALID, "gfb_stage_pre: null argument");
+  Spec sin;
+  EpiArgs e;
+  int rc = plan_stage(c, istage, false, false, 0, sin, e);
+  if (rc) return rc;
+  return run_col_inv_state(c, sin, 3, (cplx*)wsend, (cudaStream_t)stream);
+}
+int gfb_stage_mid(gfb_ctx* c, const void* wrecv, void* psend, int prune, void* stream) {
+  if (!c || !wrecv || !psend) return fail(c, GFB_ERR_INVALID, "gfb_stage_mid: null argument");
+  return run_row_product(c, (const cplx*)wrecv, (cplx*)psend, prune && c->g.kcut < c->g.nkr, (cudaStream_t)stream);
+}
+int gfb_stage_post(gfb_ctx* c, int istage, const void* precv, const void* Fh_local, void* prevsol_local, int prune,
+                   void* stream) {
+  if (!c || !precv) return fail(c, GFB_ERR_INVALID, "gfb_stage_post: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = 0;
+  if (Fh_local && (rc = import_spec(c, c->Fint, Fh_local, st))) return rc;
+  Spec sin;
+  EpiArgs e;
+  if ((rc = plan_stage(c, istage, Fh_local != nullptr, prevsol_local != nullptr, prune, sin, e))) return rc;
+  if ((rc = run_col_fwd(c, e, (const cplx*)precv, st))) return rc;
+  if (istage == 0 && prevsol_local && (rc = export_spec(c, prevsol_local, c->PV, st))) return rc;
+  if (istage == nstages_of(c) - 1) {
     c->t += c->dt;
     c->step += 1;
   }
   return GFB_OK;
 }
 
-int gfb_stage(gfb_ctx* c, void* sol, int istage, const void* Fh, void* prevsol, void* stream) {
-  if (!c || !sol) return fail(c, GFB_ERR_INVALID, "gfb_stage: null argument");
-  cudaStream_t st = (cudaStream_t)stream;
-  int rc = 0;
-  if (istage == 0 && (rc = import_spec(c, c->S0, sol, st))) return rc;  // later stages continue from the ctx copy
-  if (Fh && (rc = import_spec(c, c->Fint, Fh, st))) return rc;
-  if ((rc = do_stage(c, sol, istage, Fh, prevsol, stream, 0))) return rc;
-  if (istage == 0 && prevsol && (rc = export_spec(c, prevsol, c->PV, st))) return rc;
-  if (istage == gfb_nstages(c) - 1) return export_spec(c, sol, c->S0, st);
-  return GFB_OK;
-}
-
-int gfb_step(gfb_ctx* c, void* sol, int nsteps, const void* Fh, void* prevsol, void* stream) {
-  if (!c || !sol || nsteps < 0) return fail(c, GFB_ERR_INVALID, "gfb_step: bad argument");
-  if (nsteps == 0) return GFB_OK;
-  cudaStream_t st = (cudaStream_t)stream;
-  const int ns = gfb_nstages(c);
-  const bool ab3 = c->stepper == GFB_AB3 || c->stepper == GFB_FILTERED_AB3;  // AB3 keeps RHS history incl. the aliased band
-  int rc = import_spec(c, c->S0, sol, st);
-  if (rc) return rc;
-  if (Fh && (rc = import_spec(c, c->Fint, Fh, st))) return rc;
-  for (int s = 0; s < nsteps; ++s) {
-    const bool last = (s == nsteps - 1);
-    for (int i = 0; i < ns; ++i) {
-      rc = do_stage(c, sol, i, Fh, last ? prevsol : nullptr, stream, (!last && !ab3) ? 1 : 0);
-      if (rc) return rc;
-    }
-  }
-  if (prevsol && (rc = export_spec(c, prevsol, c->PV, st))) return rc;
-  return export_spec(c, sol, c->S0, st);
-}
-
 int gfb_irfft(gfb_ctx* c, double* out_phys, const void* in_spec, int batch, void* stream) {
   if (!c || !out_phys || !in_spec || batch < 1) return fail(c, GFB_ERR_INVALID, "gfb_irfft: bad argument");
+  NEED_SINGLE_GPU(c, "gfb_irfft");
   cudaStream_t st = (cudaStream_t)stream;
   const int maxb = 4 * c->nlayers;
   for (int b0 = 0; b0 < batch; b0 += maxb) {
@@ -722,8 +786,8 @@ int gfb_irfft(gfb_ctx* c, double* out_phys, const void* in_spec, int batch, void
     L.pp.ls = (long long)c->g.ny * c->g.nkr;
     L.pp.scale = c->g.invN;
     L.W = c->W;
-    L.ldw = c->ldw;
-    L.wfs = c->wfs;
+    L.ldw = nb * c->ldi;
+    L.wfs = 8LL * c->ldi;
     L.ncols = c->g.nkr;
     L.nfields = nb;
     L.tw = c->tw_y;
@@ -735,8 +799,9 @@ int gfb_irfft(gfb_ctx* c, double* out_phys, const void* in_spec, int batch, void
     std::memset(&R, 0, sizeof R);
     R.mode = ROW_C2R;
     R.a.W = c->W;
-    R.a.ldw = c->ldw;
-    R.a.wfs = c->wfs;
+    R.a.wl = row_layout(c, nb);
+    R.a.wstride = 1;
+    R.a.fsel = 0;
     R.a.kc = c->g.nkr;
     R.a.phys = out_phys + (long long)b0 * c->g.ny * c->g.nx;
     R.a.ny = c->g.ny;
@@ -751,6 +816,7 @@ int gfb_irfft(gfb_ctx* c, double* out_phys, const void* in_spec, int batch, void
 
 int gfb_rfft(gfb_ctx* c, void* out_spec, const double* in_phys, int batch, void* stream) {
   if (!c || !out_spec || !in_phys || batch < 1) return fail(c, GFB_ERR_INVALID, "gfb_rfft: bad argument");
+  NEED_SINGLE_GPU(c, "gfb_rfft");
   cudaStream_t st = (cudaStream_t)stream;
   const int maxb = 2 * c->nlayers;
   for (int b0 = 0; b0 < batch; b0 += maxb) {
@@ -759,8 +825,7 @@ int gfb_rfft(gfb_ctx* c, void* out_spec, const double* in_phys, int batch, void*
     std::memset(&R, 0, sizeof R);
     R.mode = ROW_R2C;
     R.a.P = c->P;
-    R.a.ldp = c->ldp;
-    R.a.pfs = c->pfs;
+    R.a.pl = row_layout(c, nb);
     R.a.kout = c->g.nkr;
     R.a.phys = const_cast<double*>(in_phys) + (long long)b0 * c->g.ny * c->g.nx;
     R.a.ny = c->g.ny;
@@ -773,8 +838,8 @@ int gfb_rfft(gfb_ctx* c, void* out_spec, const double* in_phys, int batch, void*
     std::memset(&F, 0, sizeof F);
     F.g = c->g;
     F.P = c->P;
-    F.ldp = c->ldp;
-    F.pfs = c->pfs;
+    F.ldp = nb * c->ldi;
+    F.pfs = 8LL * c->ldi;
     F.e.kind = EPI_PLAIN;
     F.e.out.p = (cplx*)out_spec + (long long)b0 * c->g.ny * c->g.nkr;
     F.e.out.ld = c->g.nkr;
@@ -793,12 +858,13 @@ int gfb_rfft(gfb_ctx* c, void* out_spec, const double* in_phys, int batch, void*
 
 int gfb_updatevars(gfb_ctx* c, void* sol, double* q, double* psi, double* u, double* v, void* stream) {
   if (!c || !sol) return fail(c, GFB_ERR_INVALID, "gfb_updatevars: null argument");
+  NEED_SINGLE_GPU(c, "gfb_updatevars");
   cudaStream_t st = (cudaStream_t)stream;
   int rc = gfb_dealias(c, sol, stream);
   if (rc) return rc;
   const int nf = 4;
   if ((rc = import_spec(c, c->Cin, sol, st))) return rc;
-  rc = run_col_inv_state(c, int_spec(c, c->Cin), nf, st);
+  rc = run_col_inv_state(c, int_spec(c, c->Cin), nf, c->W, st);
   if (rc) return rc;
   double* outs[4] = {u, v, q, psi};
   for (int f = 0; f < 4; ++f) {
@@ -806,9 +872,10 @@ int gfb_updatevars(gfb_ctx* c, void* sol, double* q, double* psi, double* u, dou
     RowLaunch R;
     std::memset(&R, 0, sizeof R);
     R.mode = ROW_C2R;
-    R.a.W = c->W + (long long)f * c->wfs;
-    R.a.ldw = c->ldw;
-    R.a.wfs = (long long)nf * c->wfs;  // consecutive layers of the same field
+    R.a.W = c->W;
+    R.a.wl = row_layout(c, nf * c->nlayers);
+    R.a.wstride = nf;
+    R.a.fsel = f;
     R.a.kc = c->g.kcut;
     R.a.phys = outs[f];
     R.a.ny = c->g.ny;
@@ -824,7 +891,7 @@ int gfb_updatevars(gfb_ctx* c, void* sol, double* q, double* psi, double* u, dou
 int gfb_streamfunction_from_pv(gfb_ctx* c, void* psih, const void* qh, void* stream) {
   if (!c || !psih || !qh) return fail(c, GFB_ERR_INVALID, "gfb_streamfunction_from_pv: null argument");
   if (c->kind == GFB_KIND_SINGLE) {
-    GFB_LAUNCH(k_scale_by_table, dim3(592), dim3(256), 0, (cudaStream_t)stream, c->g.ny, c->g.nkr,
+    GFB_LAUNCH(k_scale_by_table, dim3(592), dim3(256), 0, (cudaStream_t)stream, c->g.ny, c->g.nkl,
                (cplx*)psih, (const cplx*)qh, (const double*)c->G, c->ldi, -1.0);
     return check_launch(c, 0, "k_scale_by_table");
   }
@@ -837,6 +904,7 @@ int gfb_pv_from_streamfunction(gfb_ctx* c, void* qh, const void* psih, void* str
   return matvec(c, qh, psih, c->S, stream);
 }
 
+// On a sharded context the sums are LOCAL partial sums: the caller all-reduces them.
 int gfb_diag(gfb_ctx* c, int kind, const void* sol, const void* aux, const void* aux2, double p,
              double* out_host, int nout, void* stream) {
   if (!c || !sol || !out_host || nout < 1 || nout > DIAG_MAXOUT) return fail(c, GFB_ERR_INVALID, "gfb_diag: bad argument");
@@ -856,11 +924,9 @@ int gfb_diag(gfb_ctx* c, int kind, const void* sol, const void* aux, const void*
   if (kind == GFB_DIAG_LAYERED_ENERGIES) {
     if (c->kind != GFB_KIND_LAYERED) return fail(c, GFB_ERR_INVALID, "gfb_diag: layered energies need GFB_KIND_LAYERED");
     need = 2 * c->nlayers - 1;
-  } else if (c->nlayers != 1 && kind != GFB_DIAG_ABS2) {
-    // single-array kinds act on one layer: the caller passes a pointer to that layer
   }
   if ((kind == GFB_DIAG_G_ABS2 || kind == GFB_DIAG_G2_ABS2 || kind == GFB_DIAG_KG2_ABS2) && !c->G)
-    return fail(c, GFB_ERR_INVALID, "gfb_diag: kind %d needs the G table (GFB_KIND_SINGLE)", kind);
+    return fail(c, GFB_ERR_INVALID, "gfb_diag: kind %d needs the G table", kind);
   if ((kind == GFB_DIAG_ABS2_PLUS || kind == GFB_DIAG_WORK || kind == GFB_DIAG_WORK_INVK) && !aux)
     return fail(c, GFB_ERR_INVALID, "gfb_diag: kind %d needs aux", kind);
   if (kind < 0 || kind > GFB_DIAG_LAYERED_ENERGIES) return fail(c, GFB_ERR_INVALID, "gfb_diag: unknown kind %d", kind);

@@ -21,15 +21,22 @@
 namespace gfb {
 
 struct GridDesc {
-  int nx, ny, nkr;
-  int kcut;        // dealias!: kr columns [kcut, nkr) are zeroed
+  int nx, ny, nkr; // global grid (nkr = nx/2 + 1)
+  int kcut;        // dealias!: kr columns [kcut, nkr) are zeroed (global index)
   int la0, la1;    // dealias!: l rows [la0, la1) are zeroed
   double dkx, dky; // kr = m*dkx ; l = (n < ny/2 ? n : n - ny)*dky   (FourierFlows TwoDGrid)
   double invN;     // 1/(nx*ny): ldiv!(., rfftplan, .) normalisation
+  // kr-sharding of the spectral side (multi-GPU): column PAIRS are dealt round-robin, local pair p of rank r
+  // is global pair p*nranks + r (balanced for the live AND the aliased columns).  Single GPU: rank 0 of 1.
+  int rank, nranks;
+  int nkl;         // local dense columns (= nkr on one GPU)
 };
 
+// global kr index of local column `col`
+__device__ __forceinline__ int gcol(const GridDesc& g, int col) { return ((col >> 1) * g.nranks + g.rank) * 2 + (col & 1); }
+
 __device__ __forceinline__ double wav_l(const GridDesc& g, int n) { return (n < g.ny / 2 ? n : n - g.ny) * g.dky; }
-__device__ __forceinline__ double wav_kr(const GridDesc& g, int m) { return m * g.dkx; }
+__device__ __forceinline__ double wav_kr(const GridDesc& g, int m) { return gcol(g, m) * g.dkx; }  // m: LOCAL column
 __device__ __forceinline__ bool l_aliased(const GridDesc& g, int n) { return n >= g.la0 && n < g.la1; }
 
 // Ctx-owned arrays (states, tables, W, P) use an 8-row TILED layout: element (row, col) of an array with
@@ -265,11 +272,31 @@ __global__ void __launch_bounds__(GroupCfg<NY>::THREADS, GroupCfg<NY>::MINB)
 // ------------------------------------------------------------------------------------------------
 // K2 row pass
 // ------------------------------------------------------------------------------------------------
+// W and P as the row kernel sees them: LOCAL rows, ALL (global) kr.  Both are tiled, row-block major with the
+// fields interleaved per row block, and -- on several GPUs -- split into one chunk per peer rank, which is
+// exactly the send/receive buffer of the all-to-all (no packing):
+//   off(field, y, k) = (kp % nranks)*chunk + (y/8)*rbs + field*fstr + (kp / nranks)*16 + (y%8)*2 + k%2,  kp = k/2
+struct RowLayout {
+  int nranks;
+  long long chunk;  // elements per peer chunk = (local rows / 8) * rbs
+  int rbs;          // row-block stride = 8 * nfields * ldl
+  int fstr;         // field stride inside a row block = 8 * ldl
+  __device__ __forceinline__ long long off(int field, int y, int k) const {
+    const int kp = k >> 1;
+    int s = 0, kpl = kp;
+    if (nranks > 1) {
+      s = kp % nranks;
+      kpl = kp / nranks;
+    }
+    return s * chunk + (long long)(y >> 3) * rbs + field * fstr + kpl * 16 + ((y & 7) << 1) + (k & 1);
+  }
+};
+
 // Z[k] = A[k] + i B[k] with Hermitian extension, A/B half-spectra rows known for k < kc (else 0).
 // c2r semantics of FFTW/cuFFT/pocketfft: imaginary parts of the k = 0 and k = N/2 entries are ignored.
 template <int N>
-__device__ __forceinline__ void load_hermitian(cplx (&v)[PT], const int j, const cplx* __restrict__ A, const int rowA,
-                                               const cplx* __restrict__ B, const int rowB, const int ld, const int kc) {
+__device__ __forceinline__ void load_hermitian(cplx (&v)[PT], const int j, const cplx* __restrict__ W, const RowLayout& wl,
+                                               const int fA, const int rowA, const int fB, const int rowB, const int kc) {
   constexpr int T = N / PT;
 #pragma unroll
   for (int r = 0; r < PT; ++r) {
@@ -277,8 +304,8 @@ __device__ __forceinline__ void load_hermitian(cplx (&v)[PT], const int j, const
     const int kk = (k <= N / 2) ? k : N - k;
     cplx a = cmake(0.0, 0.0), b = cmake(0.0, 0.0);
     if (kk < kc) {
-      a = A[toff(rowA, kk, ld)];
-      b = B[toff(rowB, kk, ld)];
+      a = W[wl.off(fA, rowA, kk)];
+      b = W[wl.off(fB, rowB, kk)];
     }
     if (k == 0 || k == N / 2) {
       v[r] = cmake(a.x, b.x);
@@ -324,15 +351,12 @@ __device__ __forceinline__ void unpack_pair(const cplx (&v)[PT], const int j, do
 enum RowMode { ROW_PRODUCT = 0, ROW_C2R = 1, ROW_R2C = 2, ROW_PRODUCT_Q = 3 };
 
 struct RowArgs {
-  // inputs: per-field arrays [.][y][kr] with ld = ldw and field stride wfs; field = 3*layer + {u,v,q}
-  const cplx* W;
-  int ldw;
-  long long wfs;
+  const cplx* W;  // field = 3*layer + {u,v,q} (or the batch index for plain transforms)
+  RowLayout wl;
   int kc;  // live input columns (kcut, or nkr for plain transforms)
   // outputs of the forward part: field = 2*layer + {d, v}
   cplx* P;
-  int ldp;
-  long long pfs;
+  RowLayout pl;
   int kout;  // columns to write (nkr)
   // physical-space operands
   const double* eta;  // [y][x] or null              (SingleLayerQG: q + eta)
@@ -341,7 +365,9 @@ struct RowArgs {
   const double* Qy;   // [layer][y][x] or null
   double* phys;       // ROW_C2R output / ROW_R2C input, [batch][y][x]
   double dkx;
-  int ny;
+  int ny;       // LOCAL rows handled by this launch
+  int wstride;  // fields per layer in W (3, or 4 when updatevars! also wants psi; 1 for plain transforms)
+  int fsel;     // ROW_C2R: which of the wstride fields of each layer to transform
 };
 
 template <int NX, int MODE>
@@ -362,8 +388,8 @@ __global__ void __launch_bounds__(GroupCfg<NX>::THREADS, GroupCfg<NX>::MINB)
   cplx A[9], B[9];
 
   if (MODE == ROW_C2R) {
-    const cplx* Wf = a.W + layer * a.wfs;
-    if (live) load_hermitian<NX>(v, j, Wf, ya, Wf, yb, a.ldw, a.kc);
+    const int fc = a.wstride * layer + a.fsel;
+    if (live) load_hermitian<NX>(v, j, a.W, a.wl, fc, ya, fc, yb, a.kc);
     else {
 #pragma unroll
       for (int r = 0; r < PT; ++r) v[r] = cmake(0.0, 0.0);
@@ -393,13 +419,12 @@ __global__ void __launch_bounds__(GroupCfg<NX>::THREADS, GroupCfg<NX>::MINB)
     block_fft_split<NX, FWD>(v, j, xb, tw);
     unpack_pair<NX>(v, j, xb, A, B);
     if (live) {
-      cplx* pf = a.P + layer * a.pfs;
 #pragma unroll
       for (int r = 0; r < 9; ++r) {
         const int k = j + r * T;
         if ((r < 8 || j == 0) && k < a.kout) {
-          pf[toff(ya, k, a.ldp)] = A[r];
-          pf[toff(yb, k, a.ldp)] = B[r];
+          a.P[a.pl.off(layer, ya, k)] = A[r];
+          a.P[a.pl.off(layer, yb, k)] = B[r];
         }
       }
     }
@@ -408,11 +433,9 @@ __global__ void __launch_bounds__(GroupCfg<NX>::THREADS, GroupCfg<NX>::MINB)
 
   // ---- ROW_PRODUCT (+_Q: extra (u+U)*Qx + v*Qy term, MultiLayerQG / SingleLayerQG with U(y)) ----
   const bool withQ = (MODE == ROW_PRODUCT_Q);
-  const cplx* Wu = a.W + (3 * layer + 0) * a.wfs;
-  const cplx* Wv = a.W + (3 * layer + 1) * a.wfs;
-  const cplx* Wq = a.W + (3 * layer + 2) * a.wfs;
+  const int fu = a.wstride * layer + 0, fv = a.wstride * layer + 1, fq = a.wstride * layer + 2;
   // 1. q of both rows: one complex transform gives q_a + i q_b
-  if (live) load_hermitian<NX>(v, j, Wq, ya, Wq, yb, a.ldw, a.kc);
+  if (live) load_hermitian<NX>(v, j, a.W, a.wl, fq, ya, fq, yb, a.kc);
   else {
 #pragma unroll
     for (int r = 0; r < PT; ++r) v[r] = cmake(0.0, 0.0);
@@ -435,7 +458,7 @@ __global__ void __launch_bounds__(GroupCfg<NX>::THREADS, GroupCfg<NX>::MINB)
 #pragma unroll 1
   for (int h = 0; h < 2; ++h) {
     const int y = ya + h;
-    if (live) load_hermitian<NX>(v, j, Wu, y, Wv, y, a.ldw, a.kc);
+    if (live) load_hermitian<NX>(v, j, a.W, a.wl, fu, y, fv, y, a.kc);
     else {
 #pragma unroll
       for (int r = 0; r < PT; ++r) v[r] = cmake(0.0, 0.0);
@@ -463,15 +486,14 @@ __global__ void __launch_bounds__(GroupCfg<NX>::THREADS, GroupCfg<NX>::MINB)
     block_fft_split<NX, FWD>(v, j, xb, tw);
     unpack_pair<NX>(v, j, xb, A, B);  // A = (uq)_h, B = (vq)_h
     if (live) {
-      cplx* pd = a.P + (2 * layer + 0) * a.pfs;
-      cplx* pv = a.P + (2 * layer + 1) * a.pfs;
+      const int fd = 2 * layer, fw = 2 * layer + 1;
 #pragma unroll
       for (int r = 0; r < 9; ++r) {
         const int k = j + r * T;
         if ((r < 8 || j == 0) && k < a.kout) {
           const double kr = k * a.dkx;
-          pd[toff(y, k, a.ldp)] = cmake(kr * A[r].y, -kr * A[r].x);  // -i kr (uq)_h
-          pv[toff(y, k, a.ldp)] = B[r];
+          a.P[a.pl.off(fd, y, k)] = cmake(kr * A[r].y, -kr * A[r].x);  // -i kr (uq)_h
+          a.P[a.pl.off(fw, y, k)] = B[r];
         }
       }
     }
@@ -483,13 +505,12 @@ __global__ void __launch_bounds__(GroupCfg<NX>::THREADS, GroupCfg<NX>::MINB)
     block_fft_split<NX, FWD>(v, j, xb, tw);
     unpack_pair<NX>(v, j, xb, A, B);
     if (live) {
-      cplx* pf = a.P + (2 * layer + 0) * a.pfs;
 #pragma unroll
       for (int r = 0; r < 9; ++r) {
         const int k = j + r * T;
         if ((r < 8 || j == 0) && k < a.kout) {
-          cplx& ea = pf[toff(ya, k, a.ldp)];  // same thread wrote these in step 2
-          cplx& eb = pf[toff(yb, k, a.ldp)];
+          cplx& ea = a.P[a.pl.off(2 * layer, ya, k)];  // same thread wrote these in step 2
+          cplx& eb = a.P[a.pl.off(2 * layer, yb, k)];
           ea = csub(ea, A[r]);
           eb = csub(eb, B[r]);
         }
@@ -573,9 +594,10 @@ __device__ __forceinline__ cpair zero_pair() {
 
 // dealias mask applied on load: rows in the aliased l band and columns >= kcut read as zero (and are not fetched)
 __device__ __forceinline__ cpair masked_pair(const GridDesc& g, const Spec& s, int layer, int l, int colA, int off) {
-  if (colA >= g.kcut || l_aliased(g, l)) return zero_pair();
+  const int ga = gcol(g, colA);
+  if (ga >= g.kcut || l_aliased(g, l)) return zero_pair();
   cpair p = ldpair(s.p + layer * s.ls + off);
-  if (colA + 1 >= g.kcut) p.b = cmake(0.0, 0.0);
+  if (ga + 1 >= g.kcut) p.b = cmake(0.0, 0.0);
   return p;
 }
 
@@ -601,7 +623,7 @@ __device__ __forceinline__ void epi_addends(const GridDesc& g, const EpiArgs& e,
     cplx pa = cmake(0.0, 0.0), pb = cmake(0.0, 0.0);
     const double* MA = e.Sinv + ((long long)l * e.ldS + colA) * (NL * NL) + (NL - 1) * NL;
     const double* MB = MA + NL * NL;
-    const bool hasB = colA + 1 < g.nkr;
+    const bool hasB = colA + 1 < g.nkl;
     for (int m = 0; m < NL; ++m) {
       const cpair q = masked_pair(g, e.sin, m, l, colA, off);
       const double ca = MA[m], cb = hasB ? MB[m] : 0.0;
@@ -889,7 +911,7 @@ __global__ void __launch_bounds__(GroupCfg<NY>::THREADS, GroupCfg<NY>::MINB)
         const int l = j + r * T;
         cplx* o = e.out.p + layer * e.out.ls + (long long)l * e.out.ld + colA;  // EPI_PLAIN: dense user array
         o[0] = X[r * THREADS + tid];
-        if (colA + 1 < g.nkr) o[1] = v[r];
+        if (colA + 1 < g.nkl) o[1] = v[r];
       }
     }
   } else {
@@ -928,12 +950,12 @@ static __global__ void k_repack(const int nl, const int nkr, const int nlayers, 
 }
 
 static __global__ void k_dealias(const GridDesc g, cplx* __restrict__ a, const int ld, const long long ls, const int nlayers) {
-  const long long n = (long long)g.ny * g.nkr;
+  const long long n = (long long)g.ny * g.nkl;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n * nlayers; i += (long long)gridDim.x * blockDim.x) {
     const int layer = (int)(i / n);
     const long long rr = i - layer * n;
-    const int l = (int)(rr / g.nkr), k = (int)(rr - (long long)l * g.nkr);
-    if (k >= g.kcut || l_aliased(g, l)) a[layer * ls + (long long)l * ld + k] = cmake(0.0, 0.0);
+    const int l = (int)(rr / g.nkl), k = (int)(rr - (long long)l * g.nkl);
+    if (gcol(g, k) >= g.kcut || l_aliased(g, l)) a[layer * ls + (long long)l * ld + k] = cmake(0.0, 0.0);
   }
 }
 
@@ -998,14 +1020,16 @@ constexpr int DIAG_MAXOUT = 16;
 
 template <int NL>
 __global__ void __launch_bounds__(256) k_diag_partial(const GridDesc g, const DiagArgs d, double* __restrict__ partial) {
-  const long long n = (long long)g.ny * g.nkr;
+  const long long n = (long long)g.ny * g.nkl;
   constexpr int NOUT = (2 * NL - 1) > 1 ? (2 * NL - 1) : 1;
   double acc[NOUT];
 #pragma unroll
   for (int q = 0; q < NOUT; ++q) acc[q] = 0.0;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int l = (int)(i / g.nkr), k = (int)(i - (long long)l * g.nkr);
-    const double w = (k == 0 || k == g.nkr - 1) ? 1.0 : 2.0;
+    const int l = (int)(i / g.nkl), k = (int)(i - (long long)l * g.nkl);
+    const int kg = gcol(g, k);
+    const bool zero_mode = (l == 0 && kg == 0);
+    const double w = (kg == 0 || kg == g.nkr - 1) ? 1.0 : 2.0;
     const double kr = wav_kr(g, k), ll = wav_l(g, l);
     const double K2 = kr * kr + ll * ll;
     if (d.kind == DIAG_MLQG_ENERGIES) {
@@ -1031,9 +1055,9 @@ __global__ void __launch_bounds__(256) k_diag_partial(const GridDesc g, const Di
     double t = 0.0;
     switch (d.kind) {
       case DIAG_ABS2: t = cabs2(s); break;
-      case DIAG_INVK_ABS2: t = (i == 0) ? 0.0 : cabs2(s) / K2; break;
+      case DIAG_INVK_ABS2: t = zero_mode ? 0.0 : cabs2(s) / K2; break;
       case DIAG_K_ABS2: t = K2 * cabs2(s); break;
-      case DIAG_KP_ABS2: t = (i == 0) ? 0.0 : pow(K2, d.p) * cabs2(s); break;
+      case DIAG_KP_ABS2: t = zero_mode ? 0.0 : pow(K2, d.p) * cabs2(s); break;
       case DIAG_G_ABS2: t = d.G[toff(l, k, d.ldg)] * cabs2(s); break;
       case DIAG_G2_ABS2: { const double gg = d.G[toff(l, k, d.ldg)]; t = gg * gg * cabs2(s); } break;
       case DIAG_KG2_ABS2: { const double gg = d.G[toff(l, k, d.ldg)]; t = K2 * gg * gg * cabs2(s); } break;
@@ -1044,7 +1068,7 @@ __global__ void __launch_bounds__(256) k_diag_partial(const GridDesc g, const Di
         if (d.aux2) ss = cscale(cadd(ss, d.aux2[i]), 0.5);
         const cplx f = d.aux[i];
         t = ss.x * f.x + ss.y * f.y;  // Re(s conj f)
-        if (d.kind == DIAG_WORK_INVK) t = (i == 0) ? 0.0 : t / K2;
+        if (d.kind == DIAG_WORK_INVK) t = zero_mode ? 0.0 : t / K2;
       } break;
       default: break;
     }

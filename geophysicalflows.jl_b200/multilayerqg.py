@@ -10,6 +10,7 @@ from . import _lib
 from .device import GPU
 from .grid import TwoDGrid
 from .timesteppers import Equation, Problem as _Problem
+from .twodnavierstokes import _make_shard
 
 
 def convert_U_to_U3D(nlayers, grid, U):
@@ -30,7 +31,7 @@ def convert_U_to_U3D(nlayers, grid, U):
 
 def Problem(nlayers, dev=None, nx=128, ny=None, Lx=2 * np.pi, Ly=None, f0=1.0, beta=0.0, U=None, H=None, b=None,
             eta=None, topographic_pv_gradient=(0.0, 0.0), mu=0.0, nu=0.0, nnu=1, dt=0.01, stepper="RK4",
-            calcFq=None, stochastic=False, linear=False, aliased_fraction=1 / 3):
+            calcFq=None, stochastic=False, linear=False, aliased_fraction=1 / 3, shard=None):
     """src/multilayerqg.jl:87-135."""
     if linear:
         raise _lib.GfbError("MultiLayerQG linear=true (calcNlinear!) is not on the accelerated path yet")
@@ -41,15 +42,18 @@ def Problem(nlayers, dev=None, nx=128, ny=None, Lx=2 * np.pi, Ly=None, f0=1.0, b
     grid = TwoDGrid(dev, nx, Lx, ny, Ly, aliased_fraction=aliased_fraction)
     params = Params(nlayers, f0, beta, b, H, U, eta, topographic_pv_gradient, mu, nu, nnu, grid, calcFq)
     n = nlayers
+    shard = _make_shard(shard, grid)
+    nkl = grid.nkr if shard is None else shard.nkl
     v = SimpleNamespace(forced=calcFq is not None, stochastic=stochastic, Fqh=None, prevsol=None)
-    for name in ("q", "psi", "u", "v"):
-        setattr(v, name, dev.zeros((n, grid.ny, grid.nx), torch.float64))
-    for name in ("qh", "psih", "uh", "vh"):
-        setattr(v, name, dev.zeros((n, grid.nl, grid.nkr), torch.complex128))
+    if shard is None or shard.nranks == 1:
+        for name in ("q", "psi", "u", "v"):
+            setattr(v, name, dev.zeros((n, grid.ny, grid.nx), torch.float64))
+        for name in ("qh", "psih", "uh", "vh"):
+            setattr(v, name, dev.zeros((n, grid.nl, grid.nkr), torch.complex128))
     if v.forced:
-        v.Fqh = dev.zeros((n, grid.nl, grid.nkr), torch.complex128)
+        v.Fqh = dev.zeros((n, grid.nl, nkl), torch.complex128)
         if stochastic:
-            v.prevsol = dev.zeros((n, grid.nl, grid.nkr), torch.complex128)
+            v.prevsol = dev.zeros((n, grid.nl, nkl), torch.complex128)
     v.Fh = v.Fqh  # common name used by stepforward_
     params.calcF = calcFq
     L = np.ones((n, 1, 1)) * (-params.nu * grid.Krsq ** params.nnu)  # hyperviscosity, :338-347
@@ -60,7 +64,7 @@ def Problem(nlayers, dev=None, nx=128, ny=None, Lx=2 * np.pi, Ly=None, f0=1.0, b
               "U": (params.U[:, :, 0], np.float64, (n, grid.ny)),
               "Qx": (params.Qx, np.float64, (n,) + ph), "Qy": (params.Qy, np.float64, (n,) + ph),
               "mu": (params.mu, None, None)}
-    prob = _Problem(eqn, stepper, dt, grid, v, params, _lib.GFB_KIND_LAYERED, tables)
+    prob = _Problem(eqn, stepper, dt, grid, v, params, _lib.GFB_KIND_LAYERED, tables, shard=shard)
     return prob
 
 

@@ -12,18 +12,19 @@ from . import _lib
 from .device import GPU
 from .grid import TwoDGrid
 from .timesteppers import Equation, Problem as _Problem
-from .twodnavierstokes import _vars, _ps, _spectral_vars, calcN_ as _calcN_common
+from .twodnavierstokes import _vars, _ps, _spectral_vars, _make_shard, calcN_ as _calcN_common
 
 
 def Problem(dev=None, nx=256, ny=None, Lx=2 * np.pi, Ly=None, beta=0.0, deformation_radius=np.inf, U=0.0,
             eta=None, nu=0.0, nnu=1, mu=0.0, dt=0.01, stepper="RK4", calcF=None, stochastic=False,
-            aliased_fraction=1 / 3):
+            aliased_fraction=1 / 3, shard=None):
     """src/singlelayerqg.jl:80-121."""
     dev = GPU() if dev is None else dev
     grid = TwoDGrid(dev, nx, Lx, ny, Ly, aliased_fraction=aliased_fraction)
     params = Params(grid, deformation_radius, beta, U, eta, mu, nu, nnu, calcF)
+    shard = _make_shard(shard, grid)
     vars = _vars(dev, grid, calcF is not None, stochastic, phys=("q", "psi", "u", "v"),
-                 spec=("qh", "psih", "uh", "vh"))
+                 spec=("qh", "psih", "uh", "vh"), shard=shard)
     eqn = Equation_(params, grid)
     sp = (grid.nl, grid.nkr)
     ph = (grid.ny, grid.nx)
@@ -38,9 +39,9 @@ def Problem(dev=None, nx=256, ny=None, Lx=2 * np.pi, Ly=None, beta=0.0, deformat
                   "U": (params.U[:, 0], np.float64, (1, grid.ny)),
                   "Qx": (params.Qx, np.float64, (1,) + ph), "Qy": (params.Qy, np.float64, (1,) + ph)}
         kind = _lib.GFB_KIND_LAYERED
-    prob = _Problem(eqn, stepper, dt, grid, vars, params, kind, tables)
+    prob = _Problem(eqn, stepper, dt, grid, vars, params, kind, tables, shard=shard)
     # device copies of the arrays users read from params
-    params.etah_dev = dev.array(params.etah, torch.complex128)
+    params.etah_dev = dev.array(params.etah if shard is None else shard.spec_local(params.etah), torch.complex128)
     return prob
 
 

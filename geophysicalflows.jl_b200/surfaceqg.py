@@ -8,7 +8,7 @@ from . import _lib
 from .device import GPU
 from .grid import TwoDGrid
 from .timesteppers import Equation, Problem as _Problem
-from .twodnavierstokes import _vars, _ps
+from .twodnavierstokes import _vars, _ps, _make_shard
 
 
 def psihfrombh(H, grid):
@@ -21,17 +21,18 @@ def psihfrombh(H, grid):
 
 
 def Problem(dev=None, nx=256, ny=None, Lx=2 * np.pi, Ly=None, H=np.inf, nu=0.0, nnu=1, dt=0.01,
-            stepper="RK4", calcF=None, stochastic=False, aliased_fraction=1 / 3):
+            stepper="RK4", calcF=None, stochastic=False, aliased_fraction=1 / 3, shard=None):
     """src/surfaceqg.jl:65-93."""
     dev = GPU() if dev is None else dev
     grid = TwoDGrid(dev, nx, Lx, ny, Ly, aliased_fraction=aliased_fraction)
     params = SimpleNamespace(H=float(H), nu=float(nu), nnu=nnu, calcF=calcF, psihfrombh=psihfrombh(H, grid))
-    vars = _vars(dev, grid, calcF is not None, stochastic, phys=("b", "u", "v"), spec=("bh", "uh", "vh"))
+    shard = _make_shard(shard, grid)
+    vars = _vars(dev, grid, calcF is not None, stochastic, phys=("b", "u", "v"), spec=("bh", "uh", "vh"), shard=shard)
     L = -params.nu * grid.Krsq ** params.nnu  # src/surfaceqg.jl:153-158
     L[0, 0] = 0
     eqn = Equation(L, calcN_, grid, (grid.nl, grid.nkr))
     tables = {"G": (params.psihfrombh, np.float64, (grid.nl, grid.nkr))}
-    return _Problem(eqn, stepper, dt, grid, vars, params, _lib.GFB_KIND_SINGLE, tables)
+    return _Problem(eqn, stepper, dt, grid, vars, params, _lib.GFB_KIND_SINGLE, tables, shard=shard)
 
 
 def calcN_(N, sol, t, clock, vars, params, grid):

@@ -66,17 +66,57 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+# how each table of the config is cut for a sharded context: ("spec", axis of kr) or ("phys", axis of y)
+_SHARD_AXIS = {"L": ("spec", -1), "filter": ("spec", -1), "expLdt": ("spec", -1), "exphalfLdt": ("spec", -1),
+               "zeta": ("spec", -1), "alpha": ("spec", -1), "beta": ("spec", -1), "Gamma": ("spec", -1),
+               "G": ("spec", -1), "Nconst": ("spec", -1), "Sinv": ("spec", 1), "S": ("spec", 1),
+               "eta": ("phys", 0), "U": ("phys", 1), "Qx": ("phys", 1), "Qy": ("phys", 1)}
+
+
+class Shard:
+    """Slab decomposition of one Problem over `nranks` GPUs: spectral column PAIRS are dealt
+    round-robin (local pair p = global pair p*nranks + rank), physical rows are contiguous slabs."""
+
+    def __init__(self, rank, nranks, grid, group=None):
+        self.rank, self.nranks, self.group = int(rank), int(nranks), group
+        nkp = (grid.nkr + 1) // 2
+        self.nkpl = -(-nkp // nranks)
+        cols = []
+        for p_ in range(self.nkpl):
+            gp = p_ * nranks + rank
+            cols += [c for c in (2 * gp, 2 * gp + 1) if c < grid.nkr]
+        self.cols = np.array(cols, dtype=np.int64)     # global kr index of every local dense column
+        self.nkl = len(cols)
+        self.ny_loc = grid.ny // nranks
+        self.rows = slice(rank * self.ny_loc, (rank + 1) * self.ny_loc)
+
+    def cut(self, key, a):
+        kind, axis = _SHARD_AXIS[key]
+        a = np.asarray(a)
+        if kind == "spec":
+            return np.take(a, self.cols, axis=axis if axis >= 0 else a.ndim + axis)
+        idx = [slice(None)] * a.ndim
+        idx[axis] = self.rows
+        return a[tuple(idx)]
+
+    def spec_local(self, a_global):
+        """global [..., nl, nkr] numpy array -> local dense [..., nl, nkl]"""
+        return np.ascontiguousarray(np.take(np.asarray(a_global), self.cols, axis=-1))
+
+
 class Problem:
     """FourierFlows.Problem(equation, stepper, dt, grid, vars, params) on the B200 library."""
 
-    def __init__(self, eqn, stepper, dt, grid, vars, params, kind, tables):
+    def __init__(self, eqn, stepper, dt, grid, vars, params, kind, tables, shard=None):
         self.eqn, self.grid, self.vars, self.params = eqn, grid, vars, params
         self.clock = Clock(dt)
         self.timestepper = TimeStepper(stepper, eqn, dt)
         self.dev = grid.device
         self.lib = self.dev.lib
         self.nlayers = eqn.dims[0] if len(eqn.dims) == 3 else 1
-        self.sol = self.dev.zeros(eqn.dims, torch.complex128)
+        self.shard = shard
+        nkl = grid.nkr if shard is None else shard.nkl
+        self.sol = self.dev.zeros(tuple(eqn.dims[:-1]) + (nkl,), torch.complex128)
         self._keep = []  # host arrays referenced by the config during gfb_create
         cfg = _lib.GfbConfig()
         cfg.kind = kind
@@ -90,35 +130,43 @@ class Problem:
         cfg.L_is_complex = int(np.iscomplexobj(L))
         ldt = np.complex128 if cfg.L_is_complex else np.float64
         full = (self.nlayers, grid.nl, grid.nkr)
+        if shard is not None:
+            cfg.rank, cfg.nranks = shard.rank, shard.nranks
 
-        def table(a, dtype=ldt, shape=full):
+        def table(key, a, dtype=ldt, shape=full):
             if a is None:
                 return None
-            b = np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=dtype).reshape(
-                shape if np.ndim(a) == len(shape) else np.shape(a)), shape), dtype=dtype)
+            b = np.broadcast_to(np.asarray(a, dtype=dtype).reshape(shape if np.ndim(a) == len(shape) else np.shape(a)), shape)
+            if shard is not None:
+                b = shard.cut(key, b)
+            b = np.ascontiguousarray(b, dtype=dtype)
             self._keep.append(b)
             return b
-        cfg.L = _ptr(table(L))
+        cfg.L = _ptr(table("L", L))
         ts = self.timestepper
-        cfg.filter = _ptr(table(ts.filter, np.float64, (grid.nl, grid.nkr)))
+        cfg.filter = _ptr(table("filter", ts.filter, np.float64, (grid.nl, grid.nkr)))
         if ts.etd:
-            cfg.expLdt = _ptr(table(ts.expLdt))
-            cfg.exphalfLdt = _ptr(table(ts.exphalfLdt))
-            cfg.zeta = _ptr(table(ts.zeta))
-            cfg.alpha = _ptr(table(ts.alpha))
-            cfg.beta = _ptr(table(ts.beta))
-            cfg.Gamma = _ptr(table(ts.Gamma))
+            for key, arr in (("expLdt", ts.expLdt), ("exphalfLdt", ts.exphalfLdt), ("zeta", ts.zeta),
+                             ("alpha", ts.alpha), ("beta", ts.beta), ("Gamma", ts.Gamma)):
+                setattr(cfg, key, _ptr(table(key, arr)))
         for key, (arr, dtype, shape) in tables.items():
             if key == "mu":
                 cfg.mu = float(arr)
             else:
-                setattr(cfg, key, _ptr(table(arr, dtype, shape)))
+                setattr(cfg, key, _ptr(table(key, arr, dtype, shape)))
         ctx = C.c_void_p()
         rc = self.lib.gfb_create(C.byref(ctx), C.byref(cfg))
         if rc != 0:
             raise _lib.GfbError("gfb_create failed (%d): %s" % (rc, self.lib.gfb_last_error(None).decode()))
         self.ctx = ctx
         self._keep = []
+        if shard is not None and shard.nranks > 1:
+            info = (C.c_longlong * 8)()
+            self._check(self.lib.gfb_shard_info(ctx, info), "gfb_shard_info")
+            assert info[2] == shard.nkl and info[4] == shard.ny_loc
+            # all-to-all buffers: P equal contiguous chunks each, exactly what the kernels read and write
+            self._wbuf = [self.dev.zeros((int(info[5]),), torch.complex128) for _ in range(2)]
+            self._pbuf = [self.dev.zeros((int(info[6]),), torch.complex128) for _ in range(2)]
         if params is not None:
             params._prob = self
         grid._prob = self
@@ -143,8 +191,34 @@ class Problem:
         return t.data_ptr()
 
     def step_lib(self, nsteps, Fh=None, prevsol=None):
+        if self.shard is not None and self.shard.nranks > 1:
+            return self._step_sharded(nsteps, Fh, prevsol)
         self._check(self.lib.gfb_step(self.ctx, self._p(self.sol), int(nsteps), self._p(Fh), self._p(prevsol),
                                       self.dev.stream_ptr()), "gfb_step")
+
+    def _all_to_all(self, out, inp):
+        import torch.distributed as dist
+        # complex128 viewed as float64 pairs: every backend moves it; chunks stay contiguous
+        dist.all_to_all_single(torch.view_as_real(out), torch.view_as_real(inp), group=self.shard.group)
+
+    def _step_sharded(self, nsteps, Fh=None, prevsol=None):
+        """stepforward! on a slab-sharded problem: per stage K1 -> all-to-all -> K2 -> all-to-all -> K3."""
+        lib, ctx, sp = self.lib, self.ctx, self.dev.stream_ptr()
+        nst = lib.gfb_nstages(ctx)
+        ab3 = "AB3" in self.timestepper.name
+        (ws, wr), (ps, pr) = self._wbuf, self._pbuf
+        self._check(lib.gfb_state_import(ctx, self._p(self.sol), sp), "gfb_state_import")
+        for s in range(int(nsteps)):
+            last = s == nsteps - 1
+            prune = 0 if (last or ab3) else 1
+            for i in range(nst):
+                self._check(lib.gfb_stage_pre(ctx, i, self._p(ws), sp), "gfb_stage_pre")
+                self._all_to_all(wr, ws)
+                self._check(lib.gfb_stage_mid(ctx, self._p(wr), self._p(ps), prune, sp), "gfb_stage_mid")
+                self._all_to_all(pr, ps)
+                self._check(lib.gfb_stage_post(ctx, i, self._p(pr), self._p(Fh), self._p(prevsol) if last else None,
+                                               prune, sp), "gfb_stage_post")
+        self._check(lib.gfb_state_export(ctx, self._p(self.sol), sp), "gfb_state_export")
 
     def stage_lib(self, istage, Fh=None, prevsol=None):
         self._check(self.lib.gfb_stage(self.ctx, self._p(self.sol), int(istage), self._p(Fh), self._p(prevsol),
@@ -183,7 +257,13 @@ class Problem:
         sol = self.sol if sol is None else sol
         self._check(self.lib.gfb_diag(self.ctx, kind, self._p(sol), self._p(aux), self._p(aux2), float(p), out, 16,
                                       self.dev.stream_ptr()), "gfb_diag")
-        return [out[i] for i in range(nout)]
+        vals = [out[i] for i in range(nout)]
+        if self.shard is not None and self.shard.nranks > 1:  # local partial sums -> global
+            import torch.distributed as dist
+            t = torch.tensor(vals, dtype=torch.float64, device=self.sol.device)
+            dist.all_reduce(t, group=self.shard.group)
+            vals = [float(x) for x in t.cpu()]
+        return vals
 
     def profile_begin(self):
         self._check(self.lib.gfb_profile_begin(self.ctx), "gfb_profile_begin")

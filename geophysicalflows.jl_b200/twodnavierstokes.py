@@ -8,19 +8,27 @@ import torch
 from . import _lib
 from .device import GPU
 from .grid import TwoDGrid
-from .timesteppers import Equation, Problem as _Problem
+from .timesteppers import Equation, Problem as _Problem, Shard
 
 
 def Problem(dev=None, nx=256, ny=None, Lx=2 * np.pi, Ly=None, nu=0.0, nnu=1, mu=0.0, nmu=0, dt=0.01,
-            stepper="RK4", calcF=None, stochastic=False, aliased_fraction=1 / 3):
+            stepper="RK4", calcF=None, stochastic=False, aliased_fraction=1 / 3, shard=None):
     """src/twodnavierstokes.jl:71-100."""
     dev = GPU() if dev is None else dev
     grid = TwoDGrid(dev, nx, Lx, ny, Ly, aliased_fraction=aliased_fraction)
     params = SimpleNamespace(nu=float(nu), nnu=nnu, mu=float(mu), nmu=nmu, calcF=calcF)
-    vars = _vars(dev, grid, calcF is not None, stochastic)
+    shard = _make_shard(shard, grid)
+    vars = _vars(dev, grid, calcF is not None, stochastic, shard=shard)
     eqn = Equation_(params, grid)
     tables = {"G": (grid.invKrsq, np.float64, (grid.nl, grid.nkr))}
-    return _Problem(eqn, stepper, dt, grid, vars, params, _lib.GFB_KIND_SINGLE, tables)
+    return _Problem(eqn, stepper, dt, grid, vars, params, _lib.GFB_KIND_SINGLE, tables, shard=shard)
+
+
+def _make_shard(shard, grid):
+    """shard = None | Shard | (rank, nranks[, process_group])"""
+    if shard is None or isinstance(shard, Shard):
+        return shard
+    return Shard(shard[0], shard[1], grid, shard[2] if len(shard) > 2 else None)
 
 
 def Equation_(params, grid):
@@ -31,17 +39,20 @@ def Equation_(params, grid):
     return Equation(L, calcN_, grid, (grid.nl, grid.nkr))
 
 
-def _vars(dev, grid, forced, stochastic, phys=("zeta", "u", "v"), spec=("zetah", "uh", "vh")):
-    """DecayingVars / ForcedVars / StochasticForcedVars (src/twodnavierstokes.jl:170-236)."""
+def _vars(dev, grid, forced, stochastic, phys=("zeta", "u", "v"), spec=("zetah", "uh", "vh"), shard=None):
+    """DecayingVars / ForcedVars / StochasticForcedVars (src/twodnavierstokes.jl:170-236).  On a sharded
+    problem only the local spectral slices of Fh / prevsol exist (updatevars! needs a gathered state)."""
     v = SimpleNamespace(forced=forced, stochastic=stochastic, Fh=None, prevsol=None)
-    for n in phys:
-        setattr(v, n, dev.zeros((grid.ny, grid.nx), torch.float64))
-    for n in spec:
-        setattr(v, n, dev.zeros((grid.nl, grid.nkr), torch.complex128))
+    nkl = grid.nkr if shard is None else shard.nkl
+    if shard is None or shard.nranks == 1:
+        for n in phys:
+            setattr(v, n, dev.zeros((grid.ny, grid.nx), torch.float64))
+        for n in spec:
+            setattr(v, n, dev.zeros((grid.nl, grid.nkr), torch.complex128))
     if forced:
-        v.Fh = dev.zeros((grid.nl, grid.nkr), torch.complex128)
+        v.Fh = dev.zeros((grid.nl, nkl), torch.complex128)
         if stochastic:
-            v.prevsol = dev.zeros((grid.nl, grid.nkr), torch.complex128)
+            v.prevsol = dev.zeros((grid.nl, nkl), torch.complex128)
     return v
 
 

@@ -98,6 +98,12 @@ typedef struct gfb_config {
   const double* Qy;       /* [nlayers][ny][nx] */
   double mu;              /* bottom-layer linear drag (MultiLayerQG calcN!), 0 if none */
   int no_dealias_in_calcN; /* 1 for MultiLayerQG.calcNlinear! (src/multilayerqg.jl:675-683); not supported yet */
+  /* Multi-GPU slab decomposition (the reference is single-device).  nranks = 0 or 1: one GPU.
+   * nranks = P > 1 (power of two, ny % (8P) == 0): this context owns
+   *   - spectral side: column PAIRS dealt round-robin -- local pair p is global pair p*P + rank; every
+   *     spectral table above and every spectral array passed later is the LOCAL dense slice [..][nl][nkl];
+   *   - physical side: rows [rank*ny/P, (rank+1)*ny/P); eta/U/Qx/Qy are the local row slabs. */
+  int rank, nranks;
 } gfb_config;
 
 const char* gfb_version(void);
@@ -158,6 +164,22 @@ int gfb_pv_from_streamfunction(gfb_ctx* ctx, void* qh, const void* psih, void* s
 /* updatevars!: dealias sol in place, then any non-NULL output gets the physical field
  * (q, psi, u, v: double[nlayers][ny][nx]; u WITHOUT the imposed U, as vars.u in updatevars!). */
 int gfb_updatevars(gfb_ctx* ctx, void* sol, double* q, double* psi, double* u, double* v, void* stream);
+
+/* ---- sharded stepping (nranks > 1; also valid on one GPU) -------------------------------------------------
+ * One stage = gfb_stage_pre (spectral pre-pass + inverse y-FFT of the local columns -> wsend)
+ *           -> all-to-all (caller: NCCL) -> gfb_stage_mid (row pass on the local rows: wrecv -> psend)
+ *           -> all-to-all -> gfb_stage_post (forward y-FFT + stage update of the local columns).
+ * wsend/wrecv (psend/precv) are caller-owned buffers of info[5] (info[6]) complex elements whose P equal
+ * contiguous chunks are exactly the all-to-all send/receive blocks (8-row tiles, no packing).  The state lives
+ * in the context between gfb_state_import and gfb_state_export (local dense [nlayers][nl][nkl]).
+ * gfb_shard_info: info = {rank, nranks, nkl, padded local columns, local rows, W elements, P elements, pairs/rank}. */
+int gfb_shard_info(const gfb_ctx* ctx, long long* info8);
+int gfb_state_import(gfb_ctx* ctx, const void* sol_local, void* stream);
+int gfb_state_export(gfb_ctx* ctx, void* sol_local, void* stream);
+int gfb_stage_pre(gfb_ctx* ctx, int istage, void* wsend, void* stream);
+int gfb_stage_mid(gfb_ctx* ctx, const void* wrecv, void* psend, int prune, void* stream);
+int gfb_stage_post(gfb_ctx* ctx, int istage, const void* precv, const void* Fh_local, void* prevsol_local, int prune,
+                   void* stream);
 
 /* Per-kernel device timing (CUDA events on the caller's stream around every launch), for the roofline
  * report of bench.py.  Classes: 0 = k_col_inv (K1), 1 = k_row (K2), 2 = k_col_fwd (K3), 3 = other.
