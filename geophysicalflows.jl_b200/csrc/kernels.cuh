@@ -281,15 +281,16 @@ struct RowLayout {
   long long chunk;  // elements per peer chunk = (local rows / 8) * rbs
   int rbs;          // row-block stride = 8 * nfields * ldl
   int fstr;         // field stride inside a row block = 8 * ldl
-  __device__ __forceinline__ long long off(int field, int y, int k) const {
-    const int kp = k >> 1;
-    int s = 0, kpl = kp;
-    if (nranks > 1) {
-      s = kp % nranks;
-      kpl = kp / nranks;
-    }
-    return s * chunk + (long long)(y >> 3) * rbs + field * fstr + kpl * 16 + ((y & 7) << 1) + (k & 1);
+  // off(field, y, k) = rowbase(field, y) + coloff(k): the row part is hoisted out of the per-column loops
+  __device__ __forceinline__ long long rowbase(int field, int y) const {
+    return (long long)(y >> 3) * rbs + field * fstr + ((y & 7) << 1);
   }
+  __device__ __forceinline__ long long coloff(int k) const {
+    const int kp = k >> 1;
+    if (nranks == 1) return kp * 16 + (k & 1);
+    return (kp & (nranks - 1)) * chunk + (kp / nranks) * 16 + (k & 1);  // nranks is a power of two
+  }
+  __device__ __forceinline__ long long off(int field, int y, int k) const { return rowbase(field, y) + coloff(k); }
 };
 
 // Z[k] = A[k] + i B[k] with Hermitian extension, A/B half-spectra rows known for k < kc (else 0).
@@ -298,14 +299,17 @@ template <int N>
 __device__ __forceinline__ void load_hermitian(cplx (&v)[PT], const int j, const cplx* __restrict__ W, const RowLayout& wl,
                                                const int fA, const int rowA, const int fB, const int rowB, const int kc) {
   constexpr int T = N / PT;
+  const cplx* __restrict__ pa = W + wl.rowbase(fA, rowA);
+  const cplx* __restrict__ pb = W + wl.rowbase(fB, rowB);
 #pragma unroll
   for (int r = 0; r < PT; ++r) {
     const int k = j + r * T;
     const int kk = (k <= N / 2) ? k : N - k;
     cplx a = cmake(0.0, 0.0), b = cmake(0.0, 0.0);
     if (kk < kc) {
-      a = W[wl.off(fA, rowA, kk)];
-      b = W[wl.off(fB, rowB, kk)];
+      const long long co = wl.coloff(kk);
+      a = pa[co];
+      b = pb[co];
     }
     if (k == 0 || k == N / 2) {
       v[r] = cmake(a.x, b.x);
@@ -419,12 +423,15 @@ __global__ void __launch_bounds__(GroupCfg<NX>::THREADS, GroupCfg<NX>::MINB)
     block_fft_split<NX, FWD>(v, j, xb, tw);
     unpack_pair<NX>(v, j, xb, A, B);
     if (live) {
+      cplx* __restrict__ qa = a.P + a.pl.rowbase(layer, ya);
+      cplx* __restrict__ qb = a.P + a.pl.rowbase(layer, yb);
 #pragma unroll
       for (int r = 0; r < 9; ++r) {
         const int k = j + r * T;
         if ((r < 8 || j == 0) && k < a.kout) {
-          a.P[a.pl.off(layer, ya, k)] = A[r];
-          a.P[a.pl.off(layer, yb, k)] = B[r];
+          const long long co = a.pl.coloff(k);
+          qa[co] = A[r];
+          qb[co] = B[r];
         }
       }
     }
@@ -486,14 +493,16 @@ __global__ void __launch_bounds__(GroupCfg<NX>::THREADS, GroupCfg<NX>::MINB)
     block_fft_split<NX, FWD>(v, j, xb, tw);
     unpack_pair<NX>(v, j, xb, A, B);  // A = (uq)_h, B = (vq)_h
     if (live) {
-      const int fd = 2 * layer, fw = 2 * layer + 1;
+      cplx* __restrict__ qd = a.P + a.pl.rowbase(2 * layer, y);
+      cplx* __restrict__ qv = a.P + a.pl.rowbase(2 * layer + 1, y);
 #pragma unroll
       for (int r = 0; r < 9; ++r) {
         const int k = j + r * T;
         if ((r < 8 || j == 0) && k < a.kout) {
           const double kr = k * a.dkx;
-          a.P[a.pl.off(fd, y, k)] = cmake(kr * A[r].y, -kr * A[r].x);  // -i kr (uq)_h
-          a.P[a.pl.off(fw, y, k)] = B[r];
+          const long long co = a.pl.coloff(k);
+          qd[co] = cmake(kr * A[r].y, -kr * A[r].x);  // -i kr (uq)_h
+          qv[co] = B[r];
         }
       }
     }
@@ -509,8 +518,9 @@ __global__ void __launch_bounds__(GroupCfg<NX>::THREADS, GroupCfg<NX>::MINB)
       for (int r = 0; r < 9; ++r) {
         const int k = j + r * T;
         if ((r < 8 || j == 0) && k < a.kout) {
-          cplx& ea = a.P[a.pl.off(2 * layer, ya, k)];  // same thread wrote these in step 2
-          cplx& eb = a.P[a.pl.off(2 * layer, yb, k)];
+          const long long co = a.pl.coloff(k);
+          cplx& ea = a.P[a.pl.rowbase(2 * layer, ya) + co];  // same thread wrote these in step 2
+          cplx& eb = a.P[a.pl.rowbase(2 * layer, yb) + co];
           ea = csub(ea, A[r]);
           eb = csub(eb, B[r]);
         }
