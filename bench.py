@@ -159,6 +159,8 @@ def main():
     ap.add_argument("--workload", default="sqg4096")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: p2p = kernels store into peer memory over NVLink (fused exchange); nccl = all-to-all")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -184,7 +186,7 @@ def main():
     n = cfg["nx"]
     # N > 1: the SAME 4096^2 problem slab-sharded over the N GPUs (strong scaling): y-slabs in physical space,
     # round-robin kr column pairs in spectral space, one NCCL all-to-all per 2-D transform direction and stage
-    shard = (rank, world) if world > 1 else None
+    shard = (rank, world, None, args.transport) if world > 1 else None
     prob = pkg.SurfaceQG.Problem(dev, nx=n, Lx=cfg["Lx"], nu=cfg["nu"], nnu=cfg["nnu"], H=cfg["H"], dt=cfg["dt"],
                                  stepper=cfg["stepper"], shard=shard)
     bh0 = initial_bh(n)
@@ -253,7 +255,7 @@ def main():
     # all-to-all volume per GPU per step: W (3 fields) + P (2 fields) buffers, (P-1)/P of each leaves the GPU
     a2a_bytes = 0.0
     if world > 1:
-        a2a_bytes = 4 * 16.0 * (prob._wbuf[0].numel() + prob._pbuf[0].numel()) * (world - 1) / world
+        a2a_bytes = 4 * 16.0 * sum(prob._a2a_elems) * (world - 1) / world
     # ---- roofline of the dominant kernel ---------------------------------------------------------
     peak, peak_src = peaks()
     g = prob.grid
@@ -286,8 +288,9 @@ def main():
                    "initial_condition": "random-phase b_h ~ |k|(1+(|k|/6)^4)^-1/2, rms b = 0.1, numpy default_rng(0)",
                    "l2": "working set (>= 12 fields x %.0f MB) exceeds the 126 MB L2; no flush needed" % (16.0 * ny * nkr / 1e6),
                    "parallelism": "1 GPU" if world == 1 else
-                   "%d GPUs, one %d^2 problem: y-slabs / round-robin kr column pairs, 2 NCCL all-to-all per stage "
-                   "(%.0f MB sent per GPU per step)" % (world, n, a2a_bytes / 1e6),
+                   "%d GPUs, one %d^2 problem: y-slabs / round-robin kr column pairs, 2 exchanges per stage via %s "
+                   "(%.0f MB sent per GPU per step)" % (world, n, "P2P stores of K1/K2 into peer memory + flag barriers"
+                                                        if args.transport == "p2p" else "NCCL all-to-all", a2a_bytes / 1e6),
                    "state_finite": finite},
         "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": NCU_TRAFFIC.get(top), "peak_source": peak_src,
@@ -306,7 +309,7 @@ def main():
     if world > 1:
         # NVLink roofline of the sharded step: bytes that must leave each GPU / measured peer bandwidth (770 GB/s/dir)
         line["nvlink"] = {"a2a_bytes_per_gpu_per_step": a2a_bytes, "floor_ms_at_770GBs": a2a_bytes / 770e9 * 1e3,
-                          "collectives_per_step": 8, "note": "all-to-all not yet overlapped with the passes"}
+                          "exchanges_per_step": 8, "transport": args.transport}
     if world == 1 and not args.no_cpu_baseline:
         nsamp = 2 if n >= 4096 else 4
         per = cpu_steps(cfg, bh0, nsamp, 1)

@@ -36,7 +36,8 @@ EXPORTS = ["gfb_version", "gfb_last_error", "gfb_create", "gfb_destroy", "gfb_ge
            "gfb_rfft", "gfb_irfft", "gfb_dealias", "gfb_calcN", "gfb_step", "gfb_nstages", "gfb_stage", "gfb_diag",
            "gfb_streamfunction_from_pv", "gfb_pv_from_streamfunction", "gfb_updatevars", "gfb_device_bytes",
            "gfb_profile_begin", "gfb_profile_end", "gfb_shard_info", "gfb_state_import", "gfb_state_export",
-           "gfb_stage_pre", "gfb_stage_mid", "gfb_stage_post"]
+           "gfb_stage_pre", "gfb_stage_mid", "gfb_stage_post", "gfb_comm_create", "gfb_comm_connect",
+           "gfb_comm_connect_ptrs", "gfb_comm_status", "gfb_step_p2p"]
 
 
 class GfbError(RuntimeError):
@@ -71,6 +72,11 @@ def _prototype(lib):
     lib.gfb_stage_pre.argtypes = [vp, ip, vp, vp]
     lib.gfb_stage_mid.argtypes = [vp, vp, vp, ip, vp]
     lib.gfb_stage_post.argtypes = [vp, ip, vp, vp, vp, ip, vp]
+    lib.gfb_comm_create.argtypes = [vp, vp, C.POINTER(vp)]
+    lib.gfb_comm_connect.argtypes = [vp, vp]
+    lib.gfb_comm_connect_ptrs.argtypes = [vp, C.POINTER(vp)]
+    lib.gfb_comm_status.argtypes = [vp]
+    lib.gfb_step_p2p.argtypes = [vp, vp, ip, vp, vp, vp]
     lib.gfb_device_bytes.argtypes = [vp]
     lib.gfb_device_bytes.restype = C.c_longlong
     for name in EXPORTS:

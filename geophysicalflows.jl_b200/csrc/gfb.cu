@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "launch.h"
@@ -48,6 +49,14 @@ struct gfb_ctx {
   cplx *S0 = nullptr, *Fint = nullptr, *PV = nullptr, *Cin = nullptr, *Nint = nullptr;  // tiled copies of user arrays
   double *dpart = nullptr, *dout = nullptr;
   int dblocks = 0;
+  // "p2p" transport: one IPC-shareable buffer per rank = [flags | W receive | P receive]; peer[d] is rank d's
+  // buffer mapped into this process (peer[rank] = comm)
+  char* comm = nullptr;
+  size_t comm_w_off = 0, comm_p_off = 0, comm_bytes = 0;
+  char* peer[MAX_RANKS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool peer_ipc[MAX_RANKS] = {false, false, false, false, false, false, false, false};
+  bool connected = false;
+  unsigned long long epoch = 0;
   // optional per-kernel event timing
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev;   // pairs (start, stop)
@@ -196,6 +205,40 @@ static RowLayout row_layout(const gfb_ctx* c, int nf) {
   return r;
 }
 
+static int ilog2i(int n) {
+  int l = 0;
+  while ((1 << l) < n) ++l;
+  return l;
+}
+// destinations of the K1 / K2 stores (kernels.cuh PeerOut)
+static PeerOut out_local(cplx* p) {  // a ctx-owned array on one GPU
+  PeerOut o;
+  std::memset(&o, 0, sizeof o);
+  o.base[0] = p;
+  o.nranks = 1;
+  return o;
+}
+static PeerOut out_send(const gfb_ctx* c, cplx* send, int nf) {  // "nccl": chunk d of a local send buffer
+  PeerOut o;
+  std::memset(&o, 0, sizeof o);
+  o.chunk = row_layout(c, nf).chunk;
+  o.rank = c->g.rank;
+  o.nranks = c->g.nranks;
+  o.lg_rows = ilog2i(c->ny_loc);
+  for (int d = 0; d < o.nranks; ++d) o.base[d] = send + (long long)(d - o.rank) * o.chunk;
+  return o;
+}
+static PeerOut out_peers(const gfb_ctx* c, size_t byte_off, int nf) {  // "p2p": straight into rank d's receive buffer
+  PeerOut o;
+  std::memset(&o, 0, sizeof o);
+  o.chunk = row_layout(c, nf).chunk;
+  o.rank = c->g.rank;
+  o.nranks = c->g.nranks;
+  o.lg_rows = ilog2i(c->ny_loc);
+  for (int d = 0; d < o.nranks; ++d) o.base[d] = reinterpret_cast<cplx*>(c->peer[d] + byte_off);
+  return o;
+}
+
 extern "C" {
 
 const char* gfb_version(void) { return "gfb 0.2 (sm_100a)"; }
@@ -206,6 +249,10 @@ long long gfb_device_bytes(const gfb_ctx* ctx) { return ctx ? ctx->bytes : 0; }
 
 int gfb_destroy(gfb_ctx* c) {
   if (!c) return GFB_OK;
+#ifndef GFB_EMULATE
+  for (int d = 0; d < MAX_RANKS; ++d)
+    if (c->peer_ipc[d] && c->peer[d]) cudaIpcCloseMemHandle(c->peer[d]);
+#endif
   for (void* p : c->allocs) cudaFree(p);
   for (auto& e : c->prof_ev) cudaEventDestroy(e);
   delete c;
@@ -228,7 +275,7 @@ int gfb_create(gfb_ctx** out, const gfb_config* cfg) {
     return fail(nullptr, GFB_ERR_INVALID, "bad alias ranges");
   const int nranks = cfg->nranks > 0 ? cfg->nranks : 1;
   const int rank = cfg->nranks > 0 ? cfg->rank : 0;
-  if (rank < 0 || rank >= nranks || (nranks & (nranks - 1)) != 0 || cfg->ny % (8 * nranks) != 0)
+  if (rank < 0 || rank >= nranks || nranks > MAX_RANKS || (nranks & (nranks - 1)) != 0 || cfg->ny % (8 * nranks) != 0)
     return fail(nullptr, GFB_ERR_INVALID, "bad sharding: rank %d of %d (power of two, ny divisible by 8*nranks)", rank, nranks);
   gfb_ctx* c = new gfb_ctx();
   c->cfg = *cfg;
@@ -447,7 +494,7 @@ static int export_spec(gfb_ctx* c, void* user, const cplx* internal, cudaStream_
 
 // K1 on a stage input: fields u, v, q (+psi if nf == 4) for every layer of the LOCAL columns -> W
 // (tiled, row-block major, fields interleaved per row block: ld = nf*n*ldi, field stride = 8*ldi)
-static int run_col_inv_state(gfb_ctx* c, const Spec& sin, int nf, cplx* W, cudaStream_t st) {
+static int run_col_inv_state(gfb_ctx* c, const Spec& sin, int nf, const PeerOut& W, cudaStream_t st) {
   ColInvLaunch L;
   std::memset(&L, 0, sizeof L);
   L.g = c->g;
@@ -481,7 +528,7 @@ static int run_col_inv_state(gfb_ctx* c, const Spec& sin, int nf, cplx* W, cudaS
   return check_launch(c, launch_col_inv(c->g.ny, L), "k_col_inv");
 }
 
-static int run_row_product(gfb_ctx* c, const cplx* Wrecv, cplx* Psend, bool prune, cudaStream_t st) {
+static int run_row_product(gfb_ctx* c, const cplx* Wrecv, const PeerOut& Psend, bool prune, cudaStream_t st) {
   RowLaunch R;
   std::memset(&R, 0, sizeof R);
   R.mode = (c->kind == GFB_KIND_LAYERED) ? ROW_PRODUCT_Q : ROW_PRODUCT;
@@ -489,7 +536,7 @@ static int run_row_product(gfb_ctx* c, const cplx* Wrecv, cplx* Psend, bool prun
   R.a.wl = row_layout(c, 3 * c->nlayers);
   R.a.wstride = 3;
   R.a.kc = c->g.kcut;
-  R.a.P = Psend;
+  R.a.pout = Psend;
   R.a.pl = row_layout(c, 2 * c->nlayers);
   R.a.kout = prune ? c->g.kcut : c->g.nkr;
   R.a.eta = c->eta;
@@ -625,8 +672,8 @@ static int do_stage(gfb_ctx* c, int istage, bool forced, bool want_prevsol, int 
   EpiArgs e;
   int rc = plan_stage(c, istage, forced, want_prevsol, prune, sin, e);
   if (rc) return rc;
-  if ((rc = run_col_inv_state(c, sin, 3, c->W, st))) return rc;
-  if ((rc = run_row_product(c, c->W, c->P, e.prune != 0, st))) return rc;
+  if ((rc = run_col_inv_state(c, sin, 3, out_local(c->W), st))) return rc;
+  if ((rc = run_row_product(c, c->W, out_local(c->P), e.prune != 0, st))) return rc;
   if ((rc = run_col_fwd(c, e, c->P, st))) return rc;
   if (istage == nstages_of(c) - 1) {
     c->t += c->dt;
@@ -634,6 +681,180 @@ static int do_stage(gfb_ctx* c, int istage, bool forced, bool want_prevsol, int 
   }
   return 0;
 }
+
+// ---- "p2p" transport: the all-to-all is done by the kernels' own stores over NVLink -------------------------
+// Flags: slot [s] of rank r's buffer is written by rank s.  A barrier = every rank stores the epoch into its slot
+// on every peer (system-scope release after a system fence), then waits until all of its own slots carry it.
+struct PeerFlags {
+  unsigned long long* flags[MAX_RANKS];
+  int rank, nranks;
+};
+constexpr int FLAG_SLOTS = 32;       // 256 bytes: [0..7] epochs, [16] timeout marker
+constexpr int FLAG_TIMEOUT_SLOT = 16;
+
+__device__ __forceinline__ void flag_store_release(unsigned long long* p, unsigned long long v) {
+#ifdef GFB_EMULATE
+  __atomic_store_n(p, v, __ATOMIC_RELEASE);
+#else
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+#endif
+}
+__device__ __forceinline__ unsigned long long flag_load_acquire(const unsigned long long* p) {
+#ifdef GFB_EMULATE
+  return __atomic_load_n(p, __ATOMIC_ACQUIRE);
+#else
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+#endif
+}
+
+static __global__ void k_peer_barrier(const PeerFlags f, const unsigned long long epoch, const long long max_spins) {
+  const int d = threadIdx.x;
+  if (d >= f.nranks) return;
+#ifdef GFB_EMULATE
+  __atomic_thread_fence(__ATOMIC_SEQ_CST);
+#else
+  __threadfence_system();
+#endif
+  flag_store_release(f.flags[d] + f.rank, epoch);
+  const unsigned long long* mine = f.flags[f.rank] + d;
+  long long spins = 0;
+  while (flag_load_acquire(mine) < epoch) {
+#ifdef GFB_EMULATE
+    std::this_thread::yield();
+#else
+    __nanosleep(64);
+#endif
+    if (++spins > max_spins) {  // a peer died or never launched: give up instead of hanging the GPU
+      flag_store_release(f.flags[f.rank] + FLAG_TIMEOUT_SLOT, epoch);
+      break;
+    }
+  }
+}
+
+static int peer_barrier(gfb_ctx* c, cudaStream_t st) {
+  PeerFlags f;
+  std::memset(&f, 0, sizeof f);
+  f.rank = c->g.rank;
+  f.nranks = c->g.nranks;
+  for (int d = 0; d < f.nranks; ++d) f.flags[d] = reinterpret_cast<unsigned long long*>(c->peer[d]);
+  c->epoch += 1;
+  ProfScope ps(c, 3, st);
+  GFB_LAUNCH(k_peer_barrier, dim3(1), dim3(32), 0, st, f, c->epoch, (long long)40000000);
+  return check_launch(c, 0, "k_peer_barrier");
+}
+
+extern "C" {
+
+// Allocate this rank's exchange buffer.  handle64_out (may be null) receives the cudaIpcMemHandle_t other
+// PROCESSES open with gfb_comm_connect; local_ptr_out (may be null) the raw pointer for same-process peers.
+int gfb_comm_create(gfb_ctx* c, void* handle64_out, void** local_ptr_out) {
+  if (!c) return GFB_ERR_INVALID;
+  if (c->g.nranks < 2) return fail(c, GFB_ERR_INVALID, "gfb_comm_create: context is not sharded");
+  if (!c->comm) {
+    const size_t wb = (size_t)w_elems(c, 3 * c->nlayers) * sizeof(cplx), pb = (size_t)w_elems(c, 2 * c->nlayers) * sizeof(cplx);
+    c->comm_w_off = 256;
+    c->comm_p_off = c->comm_w_off + wb;
+    c->comm_bytes = c->comm_p_off + pb;
+    int rc = dev_alloc(c, &c->comm, c->comm_bytes);
+    if (rc) return rc;
+    GFB_CUDA(c, cudaMemset(c->comm, 0, c->comm_bytes));
+    GFB_CUDA(c, cudaDeviceSynchronize());
+  }
+  if (local_ptr_out) *local_ptr_out = c->comm;
+  if (handle64_out) {
+#ifdef GFB_EMULATE
+    std::memset(handle64_out, 0, 64);
+#else
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    GFB_CUDA(c, cudaIpcGetMemHandle(&h, c->comm));
+    std::memcpy(handle64_out, &h, 64);
+#endif
+  }
+  return GFB_OK;
+}
+
+// handles: nranks x 64 bytes, entry d = rank d's handle from gfb_comm_create (one process per GPU)
+int gfb_comm_connect(gfb_ctx* c, const void* handles) {
+  if (!c || !handles || !c->comm) return fail(c, GFB_ERR_INVALID, "gfb_comm_connect: bad argument (call gfb_comm_create first)");
+#ifdef GFB_EMULATE
+  return fail(c, GFB_ERR_UNSUPPORTED, "gfb_comm_connect: CUDA IPC only");
+#else
+  for (int d = 0; d < c->g.nranks; ++d) {
+    if (d == c->g.rank) {
+      c->peer[d] = c->comm;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, (const char*)handles + 64 * d, 64);
+    void* p = nullptr;
+    GFB_CUDA(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->peer[d] = (char*)p;
+    c->peer_ipc[d] = true;
+  }
+  c->connected = true;
+  return GFB_OK;
+#endif
+}
+
+// same-process variant (several contexts in one process, peer access already enabled by the caller)
+int gfb_comm_connect_ptrs(gfb_ctx* c, void* const* ptrs) {
+  if (!c || !ptrs || !c->comm) return fail(c, GFB_ERR_INVALID, "gfb_comm_connect_ptrs: bad argument (call gfb_comm_create first)");
+  for (int d = 0; d < c->g.nranks; ++d) c->peer[d] = (d == c->g.rank) ? c->comm : (char*)ptrs[d];
+  c->connected = true;
+  return GFB_OK;
+}
+
+// 0 = fine; GFB_ERR_CUDA if a barrier gave up waiting for a peer (synchronises the device)
+int gfb_comm_status(gfb_ctx* c) {
+  if (!c || !c->comm) return GFB_ERR_INVALID;
+  unsigned long long v = 0;
+  GFB_CUDA(c, cudaDeviceSynchronize());
+  GFB_CUDA(c, cudaMemcpy(&v, c->comm + 8 * FLAG_TIMEOUT_SLOT, 8, cudaMemcpyDeviceToHost));
+  if (v != 0) return fail(c, GFB_ERR_CUDA, "peer barrier timed out at epoch %llu", v);
+  return GFB_OK;
+}
+
+// stepforward! on a slab-sharded problem with the p2p transport: per stage
+//   K1 (stores W rows into their owners' buffers) -> barrier -> K2 (stores P column pairs into their owners'
+//   buffers) -> barrier -> K3.
+// One receive buffer each suffices: K1 of the next stage starts after this rank's K3, i.e. after the barrier that
+// proves every rank finished reading W; likewise for P.
+int gfb_step_p2p(gfb_ctx* c, void* sol_local, int nsteps, const void* Fh_local, void* prevsol_local, void* stream) {
+  if (!c || !sol_local || nsteps < 0) return fail(c, GFB_ERR_INVALID, "gfb_step_p2p: bad argument");
+  if (!c->connected) return fail(c, GFB_ERR_INVALID, "gfb_step_p2p: peers not connected");
+  if (nsteps == 0) return GFB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int ns = nstages_of(c), n = c->nlayers;
+  int rc = import_spec(c, c->S0, sol_local, st);
+  if (rc) return rc;
+  if (Fh_local && (rc = import_spec(c, c->Fint, Fh_local, st))) return rc;
+  const PeerOut wout = out_peers(c, c->comm_w_off, 3 * n), pout = out_peers(c, c->comm_p_off, 2 * n);
+  const cplx* wrecv = reinterpret_cast<const cplx*>(c->comm + c->comm_w_off);
+  const cplx* precv = reinterpret_cast<const cplx*>(c->comm + c->comm_p_off);
+  for (int s = 0; s < nsteps; ++s) {
+    const bool last = (s == nsteps - 1);
+    const int prune = (!last && !is_ab3(c)) ? 1 : 0;
+    for (int i = 0; i < ns; ++i) {
+      Spec sin;
+      EpiArgs e;
+      if ((rc = plan_stage(c, i, Fh_local != nullptr, last && prevsol_local != nullptr, prune, sin, e))) return rc;
+      if ((rc = run_col_inv_state(c, sin, 3, wout, st))) return rc;
+      if ((rc = peer_barrier(c, st))) return rc;
+      if ((rc = run_row_product(c, wrecv, pout, e.prune != 0, st))) return rc;
+      if ((rc = peer_barrier(c, st))) return rc;
+      if ((rc = run_col_fwd(c, e, precv, st))) return rc;
+    }
+    c->t += c->dt;
+    c->step += 1;
+  }
+  if (prevsol_local && (rc = export_spec(c, prevsol_local, c->PV, st))) return rc;
+  return export_spec(c, sol_local, c->S0, st);
+}
+
+}  // extern "C"
 
 template <int NL>
 static void launch_matvec(const gfb_ctx* c, cplx* y, const cplx* x, const double* M, cudaStream_t st) {
@@ -692,8 +913,8 @@ int gfb_calcN(gfb_ctx* c, void* N, void* sol, const void* Fh, void* stream) {
   e.out = int_spec(c, c->Nint);
   const Spec sin = int_spec(c, c->Cin);
   e.sin = sin;
-  if ((rc = run_col_inv_state(c, sin, 3, c->W, st))) return rc;
-  if ((rc = run_row_product(c, c->W, c->P, false, st))) return rc;
+  if ((rc = run_col_inv_state(c, sin, 3, out_local(c->W), st))) return rc;
+  if ((rc = run_row_product(c, c->W, out_local(c->P), false, st))) return rc;
   if ((rc = run_col_fwd(c, e, c->P, st))) return rc;
   return export_spec(c, N, c->Nint, st);
 }
@@ -746,11 +967,12 @@ int gfb_stage_pre(gfb_ctx* c, int istage, void* wsend, void* stream) {
   EpiArgs e;
   int rc = plan_stage(c, istage, false, false, 0, sin, e);
   if (rc) return rc;
-  return run_col_inv_state(c, sin, 3, (cplx*)wsend, (cudaStream_t)stream);
+  return run_col_inv_state(c, sin, 3, out_send(c, (cplx*)wsend, 3 * c->nlayers), (cudaStream_t)stream);
 }
 int gfb_stage_mid(gfb_ctx* c, const void* wrecv, void* psend, int prune, void* stream) {
   if (!c || !wrecv || !psend) return fail(c, GFB_ERR_INVALID, "gfb_stage_mid: null argument");
-  return run_row_product(c, (const cplx*)wrecv, (cplx*)psend, prune && c->g.kcut < c->g.nkr, (cudaStream_t)stream);
+  return run_row_product(c, (const cplx*)wrecv, out_send(c, (cplx*)psend, 2 * c->nlayers), prune && c->g.kcut < c->g.nkr,
+                         (cudaStream_t)stream);
 }
 int gfb_stage_post(gfb_ctx* c, int istage, const void* precv, const void* Fh_local, void* prevsol_local, int prune,
                    void* stream) {
@@ -785,7 +1007,7 @@ int gfb_irfft(gfb_ctx* c, double* out_phys, const void* in_spec, int batch, void
     L.pp.ld = c->g.nkr;
     L.pp.ls = (long long)c->g.ny * c->g.nkr;
     L.pp.scale = c->g.invN;
-    L.W = c->W;
+    L.W = out_local(c->W);
     L.ldw = nb * c->ldi;
     L.wfs = 8LL * c->ldi;
     L.ncols = c->g.nkr;
@@ -824,7 +1046,7 @@ int gfb_rfft(gfb_ctx* c, void* out_spec, const double* in_phys, int batch, void*
     RowLaunch R;
     std::memset(&R, 0, sizeof R);
     R.mode = ROW_R2C;
-    R.a.P = c->P;
+    R.a.pout = out_local(c->P);
     R.a.pl = row_layout(c, nb);
     R.a.kout = c->g.nkr;
     R.a.phys = const_cast<double*>(in_phys) + (long long)b0 * c->g.ny * c->g.nx;
@@ -864,7 +1086,7 @@ int gfb_updatevars(gfb_ctx* c, void* sol, double* q, double* psi, double* u, dou
   if (rc) return rc;
   const int nf = 4;
   if ((rc = import_spec(c, c->Cin, sol, st))) return rc;
-  rc = run_col_inv_state(c, int_spec(c, c->Cin), nf, c->W, st);
+  rc = run_col_inv_state(c, int_spec(c, c->Cin), nf, out_local(c->W), st);
   if (rc) return rc;
   double* outs[4] = {u, v, q, psi};
   for (int f = 0; f < 4; ++f) {

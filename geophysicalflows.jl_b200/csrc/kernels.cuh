@@ -73,6 +73,22 @@ struct SpecR {  // real-valued table with the same indexing
   __device__ __forceinline__ double at(int layer, int l, int kr) const { return p[layer * ls + toff(l, kr, ld)]; }
 };
 
+// Destination of the W (K1) and P (K2) stores.  On several GPUs both buffers are split into one chunk per
+// rank, and the chunk a store falls into names the rank that consumes it (K1: the owner of row y; K2: the owner
+// of column pair kp).  `base[d]` is where rank d's chunk lives, pre-biased by the host so that
+//     address = base[d] + rank*chunk + (offset inside the chunk)
+// holds for both transports: "nccl" -- base[d] = send buffer + (d - rank)*chunk, i.e. chunk d of the local send
+// buffer, exchanged afterwards by an all-to-all; "p2p" -- base[d] = rank d's RECEIVE buffer mapped into this
+// process (CUDA IPC over NVLink): the kernel's own stores are the all-to-all, no collective is launched.
+// One GPU: nranks = 1, base[0] = the ctx-owned array.
+constexpr int MAX_RANKS = 8;
+struct PeerOut {
+  cplx* base[MAX_RANKS];
+  long long chunk;  // elements per chunk
+  int rank, nranks;
+  int lg_rows;      // log2(rows per rank): K1 finds the destination of row y as y >> lg_rows
+};
+
 // One "FFT group" = T = N/16 threads transforming one length-N line at a time.  A CTA has G groups
 // (256 threads, or T when T > 256).  Shared memory per CTA: G split-exchange buffers of N(+pad) doubles
 // and thread-private stashes of PT complex per thread (`stash[r*THREADS + tid]`, conflict-free, no
@@ -209,7 +225,7 @@ struct PrepMulti {  // MultiLayerQG: psi_h = S^-1 q_h ; uh = -i l psi_h ; vh = i
 // ~200 bytes in flight per thread).
 template <int NY, class Prep>
 __global__ void __launch_bounds__(GroupCfg<NY>::THREADS, GroupCfg<NY>::MINB)
-    k_col_inv(const GridDesc g, const Prep prep, cplx* __restrict__ W, const int ldw, const long long wfs,
+    k_col_inv(const GridDesc g, const Prep prep, const __grid_constant__ PeerOut W, const int ldw, const long long wfs,
               const int ncols, const cplx* __restrict__ tw) {
   using GC = GroupCfg<NY>;
   constexpr int T = GC::T, THREADS = GC::THREADS;
@@ -262,10 +278,21 @@ __global__ void __launch_bounds__(GroupCfg<NY>::THREADS, GroupCfg<NY>::MINB)
   }
   block_fft_split<NY, INV>(v, j, xb, tw);
   if (liveA) {
-    cplx* out = W + field * wfs;
     const int ooff = toff(j, colA, ldw);
+    if (W.nranks == 1) {
+      cplx* out = W.base[0] + field * wfs;
 #pragma unroll
-    for (int r = 0; r < PT; ++r) stpair(out + toff_row<T>(ooff, j, r, colA, ldw), X[r * THREADS + tid], v[r]);
+      for (int r = 0; r < PT; ++r) stpair(out + toff_row<T>(ooff, j, r, colA, ldw), X[r * THREADS + tid], v[r]);
+    } else {
+      // row y belongs to rank d = y / (rows per rank): it lands in chunk `rank` of d's buffer, at the offset it
+      // has inside chunk d of a local send buffer
+#pragma unroll
+      for (int r = 0; r < PT; ++r) {
+        const int d = (j + r * T) >> W.lg_rows;
+        cplx* out = W.base[d] + (W.rank - d) * W.chunk + field * wfs;
+        stpair(out + toff_row<T>(ooff, j, r, colA, ldw), X[r * THREADS + tid], v[r]);
+      }
+    }
   }
 }
 
@@ -352,6 +379,14 @@ __device__ __forceinline__ void unpack_pair(const cplx (&v)[PT], const int j, do
   __syncthreads();
 }
 
+// address of P(row, k) given the row part of the offset: column pair kp belongs to rank kp % nranks
+__device__ __forceinline__ cplx* prow_ptr(const PeerOut& po, const long long rowbase, const int k) {
+  const int kp = k >> 1;
+  if (po.nranks == 1) return po.base[0] + rowbase + kp * 16 + (k & 1);
+  const int d = kp & (po.nranks - 1);
+  return po.base[d] + po.rank * po.chunk + rowbase + (kp / po.nranks) * 16 + (k & 1);
+}
+
 enum RowMode { ROW_PRODUCT = 0, ROW_C2R = 1, ROW_R2C = 2, ROW_PRODUCT_Q = 3 };
 
 struct RowArgs {
@@ -359,7 +394,7 @@ struct RowArgs {
   RowLayout wl;
   int kc;  // live input columns (kcut, or nkr for plain transforms)
   // outputs of the forward part: field = 2*layer + {d, v}
-  cplx* P;
+  PeerOut pout;  // P as the destination of the stores (see PeerOut)
   RowLayout pl;
   int kout;  // columns to write (nkr)
   // physical-space operands
@@ -376,7 +411,7 @@ struct RowArgs {
 
 template <int NX, int MODE>
 __global__ void __launch_bounds__(GroupCfg<NX>::THREADS, GroupCfg<NX>::MINB)
-    k_row(const RowArgs a, const cplx* __restrict__ tw) {
+    k_row(const __grid_constant__ RowArgs a, const cplx* __restrict__ tw) {
   using RC = GroupCfg<NX>;
   constexpr int T = RC::T, THREADS = RC::THREADS;
   GFB_DYN_SMEM(double, smd);
@@ -423,15 +458,13 @@ __global__ void __launch_bounds__(GroupCfg<NX>::THREADS, GroupCfg<NX>::MINB)
     block_fft_split<NX, FWD>(v, j, xb, tw);
     unpack_pair<NX>(v, j, xb, A, B);
     if (live) {
-      cplx* __restrict__ qa = a.P + a.pl.rowbase(layer, ya);
-      cplx* __restrict__ qb = a.P + a.pl.rowbase(layer, yb);
+      const long long ra = a.pl.rowbase(layer, ya), rb = a.pl.rowbase(layer, yb);
 #pragma unroll
       for (int r = 0; r < 9; ++r) {
         const int k = j + r * T;
         if ((r < 8 || j == 0) && k < a.kout) {
-          const long long co = a.pl.coloff(k);
-          qa[co] = A[r];
-          qb[co] = B[r];
+          *prow_ptr(a.pout, ra, k) = A[r];
+          *prow_ptr(a.pout, rb, k) = B[r];
         }
       }
     }
@@ -493,16 +526,15 @@ __global__ void __launch_bounds__(GroupCfg<NX>::THREADS, GroupCfg<NX>::MINB)
     block_fft_split<NX, FWD>(v, j, xb, tw);
     unpack_pair<NX>(v, j, xb, A, B);  // A = (uq)_h, B = (vq)_h
     if (live) {
-      cplx* __restrict__ qd = a.P + a.pl.rowbase(2 * layer, y);
-      cplx* __restrict__ qv = a.P + a.pl.rowbase(2 * layer + 1, y);
+      const long long rd = a.pl.rowbase(2 * layer, y), rv = a.pl.rowbase(2 * layer + 1, y);
 #pragma unroll
       for (int r = 0; r < 9; ++r) {
         const int k = j + r * T;
         if ((r < 8 || j == 0) && k < a.kout) {
           const double kr = k * a.dkx;
-          const long long co = a.pl.coloff(k);
-          qd[co] = cmake(kr * A[r].y, -kr * A[r].x);  // -i kr (uq)_h
-          qv[co] = B[r];
+          cplx* qd = prow_ptr(a.pout, rd, k);
+          qd[0] = cmake(kr * A[r].y, -kr * A[r].x);  // -i kr (uq)_h
+          qd[rv - rd] = B[r];                         // same row block, next field
         }
       }
     }
@@ -518,9 +550,8 @@ __global__ void __launch_bounds__(GroupCfg<NX>::THREADS, GroupCfg<NX>::MINB)
       for (int r = 0; r < 9; ++r) {
         const int k = j + r * T;
         if ((r < 8 || j == 0) && k < a.kout) {
-          const long long co = a.pl.coloff(k);
-          cplx& ea = a.P[a.pl.rowbase(2 * layer, ya) + co];  // same thread wrote these in step 2
-          cplx& eb = a.P[a.pl.rowbase(2 * layer, yb) + co];
+          cplx& ea = *prow_ptr(a.pout, a.pl.rowbase(2 * layer, ya), k);  // same thread wrote these in step 2
+          cplx& eb = *prow_ptr(a.pout, a.pl.rowbase(2 * layer, yb), k);
           ea = csub(ea, A[r]);
           eb = csub(eb, B[r]);
         }

@@ -14,7 +14,7 @@ struct ColInvLaunch {
   PrepSingle ps;
   PrepMulti pm;
   int nl;              // layers (PREP_MULTI template argument)
-  cplx* W;
+  PeerOut W;
   int ldw;
   long long wfs;
   int ncols;

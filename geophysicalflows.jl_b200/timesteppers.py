@@ -77,8 +77,11 @@ class Shard:
     """Slab decomposition of one Problem over `nranks` GPUs: spectral column PAIRS are dealt
     round-robin (local pair p = global pair p*nranks + rank), physical rows are contiguous slabs."""
 
-    def __init__(self, rank, nranks, grid, group=None):
-        self.rank, self.nranks, self.group = int(rank), int(nranks), group
+    def __init__(self, rank, nranks, grid, group=None, transport="nccl"):
+        self.rank, self.nranks, self.group, self.transport = int(rank), int(nranks), group, transport
+        # "p2p-manual": the caller wires the peers itself (gfb_comm_connect_ptrs; several ranks in one process)
+        if transport not in ("nccl", "p2p", "p2p-manual"):
+            raise ValueError("unknown shard transport %r" % (transport,))
         nkp = (grid.nkr + 1) // 2
         self.nkpl = -(-nkp // nranks)
         cols = []
@@ -164,9 +167,13 @@ class Problem:
             info = (C.c_longlong * 8)()
             self._check(self.lib.gfb_shard_info(ctx, info), "gfb_shard_info")
             assert info[2] == shard.nkl and info[4] == shard.ny_loc
-            # all-to-all buffers: P equal contiguous chunks each, exactly what the kernels read and write
-            self._wbuf = [self.dev.zeros((int(info[5]),), torch.complex128) for _ in range(2)]
-            self._pbuf = [self.dev.zeros((int(info[6]),), torch.complex128) for _ in range(2)]
+            self._a2a_elems = (int(info[5]), int(info[6]))
+            if shard.transport == "p2p":
+                self._connect_p2p()
+            elif shard.transport == "nccl":
+                # all-to-all buffers: P equal contiguous chunks each, exactly what the kernels read and write
+                self._wbuf = [self.dev.zeros((int(info[5]),), torch.complex128) for _ in range(2)]
+                self._pbuf = [self.dev.zeros((int(info[6]),), torch.complex128) for _ in range(2)]
         if params is not None:
             params._prob = self
         grid._prob = self
@@ -190,8 +197,22 @@ class Problem:
         assert t.is_contiguous() and t.device == self.sol.device
         return t.data_ptr()
 
+    def _connect_p2p(self):
+        """Exchange the CUDA IPC handles of the per-rank receive buffers (one process per GPU) and map the peers."""
+        import torch.distributed as dist
+        handle = (C.c_ubyte * 64)()
+        self._check(self.lib.gfb_comm_create(self.ctx, handle, None), "gfb_comm_create")
+        handles = [None] * self.shard.nranks
+        dist.all_gather_object(handles, bytes(handle), group=self.shard.group)
+        blob = b"".join(handles)
+        self._check(self.lib.gfb_comm_connect(self.ctx, C.c_char_p(blob)), "gfb_comm_connect")
+        dist.barrier(group=self.shard.group)  # nobody stores into a buffer before everyone has mapped it
+
     def step_lib(self, nsteps, Fh=None, prevsol=None):
         if self.shard is not None and self.shard.nranks > 1:
+            if self.shard.transport != "nccl":
+                return self._check(self.lib.gfb_step_p2p(self.ctx, self._p(self.sol), int(nsteps), self._p(Fh),
+                                                         self._p(prevsol), self.dev.stream_ptr()), "gfb_step_p2p")
             return self._step_sharded(nsteps, Fh, prevsol)
         self._check(self.lib.gfb_step(self.ctx, self._p(self.sol), int(nsteps), self._p(Fh), self._p(prevsol),
                                       self.dev.stream_ptr()), "gfb_step")

@@ -25,10 +25,12 @@ def Problem(dev=None, nx=256, ny=None, Lx=2 * np.pi, Ly=None, nu=0.0, nnu=1, mu=
 
 
 def _make_shard(shard, grid):
-    """shard = None | Shard | (rank, nranks[, process_group])"""
+    """shard = None | Shard | (rank, nranks[, process_group[, transport]]); transport = "nccl" (all-to-all through
+    torch.distributed, any backend) or "p2p" (the kernels store straight into the peers' buffers over NVLink)"""
     if shard is None or isinstance(shard, Shard):
         return shard
-    return Shard(shard[0], shard[1], grid, shard[2] if len(shard) > 2 else None)
+    return Shard(shard[0], shard[1], grid, shard[2] if len(shard) > 2 else None,
+                 shard[3] if len(shard) > 3 and shard[3] else "nccl")
 
 
 def Equation_(params, grid):

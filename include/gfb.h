@@ -181,6 +181,20 @@ int gfb_stage_mid(gfb_ctx* ctx, const void* wrecv, void* psend, int prune, void*
 int gfb_stage_post(gfb_ctx* ctx, int istage, const void* precv, const void* Fh_local, void* prevsol_local, int prune,
                    void* stream);
 
+/* "p2p" transport of a sharded context: instead of handing send buffers to an all-to-all, K1 and K2 store every
+ * row / column pair straight into the buffer of the rank that consumes it (peer memory over NVLink), and a
+ * flag barrier in peer memory separates the passes -- the exchange is fused into the kernels.
+ *   gfb_comm_create   allocates this rank's receive buffer; handle64_out gets its 64-byte cudaIpcMemHandle_t
+ *   gfb_comm_connect  opens the other ranks' buffers: `handles` = nranks x 64 bytes, entry d from rank d
+ *   gfb_comm_connect_ptrs  same for contexts living in ONE process (raw pointers from gfb_comm_create)
+ *   gfb_step_p2p      the sharded stepforward! (same arguments as gfb_step, local arrays); every rank must call it
+ *   gfb_comm_status   synchronises and reports a barrier that gave up on a missing peer */
+int gfb_comm_create(gfb_ctx* ctx, void* handle64_out, void** local_ptr_out);
+int gfb_comm_connect(gfb_ctx* ctx, const void* handles);
+int gfb_comm_connect_ptrs(gfb_ctx* ctx, void* const* ptrs);
+int gfb_comm_status(gfb_ctx* ctx);
+int gfb_step_p2p(gfb_ctx* ctx, void* sol_local, int nsteps, const void* Fh_local, void* prevsol_local, void* stream);
+
 /* Per-kernel device timing (CUDA events on the caller's stream around every launch), for the roofline
  * report of bench.py.  Classes: 0 = k_col_inv (K1), 1 = k_row (K2), 2 = k_col_fwd (K3), 3 = other.
  * gfb_profile_end synchronises the recorded events and returns summed milliseconds and launch counts. */

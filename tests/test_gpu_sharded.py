@@ -1,0 +1,117 @@
+"""The slab-sharded path on real GPUs (`-m gpu`, needs >= 2 devices; skipped on a 1-GPU box): one process per
+GPU over NCCL, the CUDA library through the C ABI, gathered state and all-reduced diagnostics against the
+oracle on the same seeded input (north_star tolerance 1e-10; measured ~1e-14)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, case, transport, out_q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import gfb_loader
+        import refcases as R
+        gf = gfb_loader.load()
+        from oracle import gfo
+        gfo.set_workers(max(1, (os.cpu_count() or 2) // world))
+        module, kw, nsteps, nlayers = case
+        M, O = getattr(gf, module), getattr(gfo, module)
+        dev = gf.GPU(rank)
+        rng = np.random.default_rng(7)
+        extra = dict(shard=(rank, world, None, transport))
+        if nlayers:
+            po = O.Problem(nlayers, **kw)
+            pg = M.Problem(nlayers, dev, **extra, **kw)
+            shape = (nlayers, kw["ny"], kw["nx"])
+        else:
+            po = O.Problem(**kw)
+            pg = M.Problem(dev, **extra, **kw)
+            shape = (kw["ny"], kw["nx"])
+        s0 = np.fft.rfft2(rng.standard_normal(shape)) * 8 / (kw["nx"] * kw["ny"])
+        po.sol[...] = s0
+        pg.sol.copy_(torch.from_numpy(pg.shard.spec_local(s0)))
+        gf.stepforward_(pg, nsteps)
+        gf.stepforward_(pg, 1)  # a second call: buffers and epochs must survive re-entry
+        torch.cuda.synchronize()
+        loc = pg.sol.cpu().numpy()
+        if module == "surfaceqg":
+            dg = M.kinetic_energy(pg)
+        elif module == "twodnavierstokes":
+            dg = M.enstrophy(pg)
+        else:
+            dg = np.concatenate(M.energies(pg))
+        parts = [None] * world
+        dist.all_gather_object(parts, (pg.shard.cols, loc))
+        if rank == 0:
+            gfo.stepforward_(po, nsteps + 1)
+            full = np.zeros_like(po.sol)
+            for cols, a in parts:
+                full[..., cols] = a
+            if module == "surfaceqg":
+                do = O.kinetic_energy(po)
+            elif module == "twodnavierstokes":
+                do = O.enstrophy(po)
+            else:
+                do = np.concatenate(O.energies(po))
+            derr = float(np.max(np.abs(np.asarray(dg) / np.asarray(do) - 1)))
+            out_q.put((R.relerr(full, po.sol), derr))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+CASES = {
+    "sqg_etdrk4_512": ("surfaceqg", dict(nx=512, ny=512, Lx=2 * np.pi, nu=1e-8, nnu=2, dt=1e-3, stepper="FilteredETDRK4"), 5, 0),
+    "twodns_rk4_rect": ("twodnavierstokes", dict(nx=1024, ny=256, Lx=2 * np.pi, Ly=3.0, nu=1e-5, nnu=1, mu=0.01, nmu=0,
+                                                 dt=5e-4, stepper="RK4"), 4, 0),
+    "mqg3_frk4": ("multilayerqg", dict(nx=128, ny=256, Lx=2 * np.pi, f0=1.0, beta=0.5, mu=0.05, nu=1e-5,
+                                        H=[0.25, 0.25, 0.5], b=[-1.0, -1.2, -1.4], U=[0.3, 0.1, 0.0], dt=1e-3,
+                                        stepper="FilteredRK4"), 3, 3),
+}
+
+
+def _run(case, world, transport):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, CASES[case], transport, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=600)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    return q.get(timeout=5)
+
+
+@pytest.mark.parametrize("transport", ["nccl", "p2p"])
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_sharded_gpus_match_oracle(case, transport):
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    world = 4 if ngpu >= 4 and case == "sqg_etdrk4_512" else 2
+    err, derr = _run(case, world, transport)
+    assert err < 1e-10, err
+    assert derr < 1e-10, derr

@@ -99,3 +99,58 @@ def test_sharded_matches_oracle(case, world):
     assert err < 1e-13, err       # full state incl. the aliased band, gathered from all ranks
     assert derr < 1e-12, derr     # all-reduced diagnostics
     assert dt == 0.0
+
+
+# ---- "p2p" transport: the kernels store straight into the peers' receive buffers ---------------------------------
+# On the GPUs the peers are other processes (CUDA IPC, tests/test_gpu_sharded.py); here the ranks are threads of one
+# process connected by raw pointers (gfb_comm_connect_ptrs), the flag barrier spins for real between them.
+@pytest.mark.parametrize("world", [2, 4])
+def test_p2p_transport_matches_oracle(world):
+    import ctypes as C
+    import threading
+    sys.path.insert(0, HERE)
+    os.environ["GFB_EMU_THREADS"] = "1"
+    import backends
+    import refcases as R
+    from oracle import gfo
+    B = backends.emu_backend()
+    gf = B.pkg
+    gfo.set_workers(1)
+    kw = dict(nx=64, ny=64, Lx=2 * np.pi, nu=1e-6, nnu=2, dt=2e-3, stepper="FilteredETDRK4")
+    po = gfo.surfaceqg.Problem(**kw)
+    rng = np.random.default_rng(3)
+    s0 = np.fft.rfft2(rng.standard_normal((64, 64))) * 8 / 4096
+    po.sol[...] = s0
+    probs = []
+    for r in range(world):
+        sh = gf.timesteppers.Shard(r, world, gf.TwoDGrid(B.device, 64, 2 * np.pi), transport="p2p-manual")
+        probs.append(gf.surfaceqg.Problem(B.device, shard=sh, **kw))
+    ptrs = (C.c_void_p * world)()
+    for r, p in enumerate(probs):
+        loc = C.c_void_p()
+        p._check(p.lib.gfb_comm_create(p.ctx, None, C.byref(loc)), "gfb_comm_create")
+        ptrs[r] = loc.value
+    for p in probs:
+        p._check(p.lib.gfb_comm_connect_ptrs(p.ctx, ptrs), "gfb_comm_connect_ptrs")
+        p.sol.copy_(torch.from_numpy(p.shard.spec_local(s0)))
+    nsteps = 3
+    errs = []
+
+    def run(p):
+        try:
+            for n in (nsteps - 1, 1):  # two calls: epochs and buffers survive re-entry
+                p._check(p.lib.gfb_step_p2p(p.ctx, p._p(p.sol), n, None, None, None), "gfb_step_p2p")
+            p._check(p.lib.gfb_comm_status(p.ctx), "gfb_comm_status")
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+    th = [threading.Thread(target=run, args=(p,)) for p in probs]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=600)
+    assert not errs, errs
+    gfo.stepforward_(po, nsteps)
+    full = np.zeros_like(po.sol)
+    for p in probs:
+        full[..., p.shard.cols] = p.sol.numpy()
+    assert R.relerr(full, po.sol) < 1e-13
