@@ -232,8 +232,11 @@ __global__ void __launch_bounds__(GroupCfg<NY>::THREADS, GroupCfg<NY>::MINB)
   GFB_DYN_SMEM(double, smd);
   const int tid = threadIdx.x;
   const int gi = tid / T, j = tid % T;
-  const int colA = 2 * (blockIdx.x * GC::G + gi), colB = colA + 1;
-  const int field = blockIdx.y;
+  // the CTAs of one column pair (one per field) are neighbours in launch order: they run at the same time, so
+  // the state columns they all read come from DRAM once and from L2 afterwards
+  const int nfields = gridDim.y, lin = blockIdx.y * gridDim.x + blockIdx.x;
+  const int field = lin % nfields;
+  const int colA = 2 * ((lin / nfields) * GC::G + gi), colB = colA + 1;
   const bool liveA = colA < ncols, liveB = colB < ncols;
   double* xb = smd + gi * GC::GSD;
   cplx* X = reinterpret_cast<cplx*>(smd + GC::XB_DOUBLES);
@@ -558,6 +561,203 @@ __global__ void __launch_bounds__(GroupCfg<NX>::THREADS, GroupCfg<NX>::MINB)
       }
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2, product modes (the hot path): persistent, software-pipelined.
+//
+// A CTA loops over row pairs.  Every row pair has three input phases -- (q_a, q_b), (u_a, v_a), (u_b, v_b) -- and the
+// two half-spectra rows of the NEXT phase are fetched with cp.async into a shared-memory line buffer while the
+// transforms of the current phase run (the last phase of a pair prefetches the first phase of the CTA's next
+// pair), so no thread ever waits on a global load in steady state.  q of both rows (and the (u+U)Qx + vQy
+// accumulator) is parked in the thread's TMEM slot instead of shared memory, which is what makes room for the
+// line buffer with two CTAs per SM.
+// ------------------------------------------------------------------------------------------------
+template <int N>
+struct RowPipeCfg {
+  using RC = GroupCfg<N>;
+  static constexpr int TM_PER_WG(bool withq) { return withq ? 128 : 64; }               // TMEM columns per thread slot set
+  static constexpr int TM_COLS(bool withq) { return (RC::THREADS / 128) * TM_PER_WG(withq); }  // 128 / 256 (256 / 512 at 512 threads)
+};
+
+// fetch the two half-spectrum rows of one phase into the group's line buffer: lb[0..kc) = A, lb[kcp..kcp+kc) = B
+template <int T>
+__device__ __forceinline__ void row_prefetch(cplx* __restrict__ lb, const int kcp, const cplx* __restrict__ W, const RowLayout& wl,
+                                             const int fA, const int rowA, const int fB, const int rowB, const int kc, const int j) {
+  const cplx* __restrict__ pa = W + wl.rowbase(fA, rowA);
+  const cplx* __restrict__ pb = W + wl.rowbase(fB, rowB);
+  for (int k = j; k < kc; k += T) {
+    const long long co = wl.coloff(k);
+    cp_async16(lb + k, pa + co);
+    cp_async16(lb + kcp + k, pb + co);
+  }
+}
+
+// Z[k] = A[k] + i B[k] with Hermitian extension, from the line buffer (same semantics as load_hermitian)
+template <int N>
+__device__ __forceinline__ void assemble_hermitian(cplx (&v)[PT], const int j, const cplx* __restrict__ lb, const int kcp, const int kc) {
+  constexpr int T = N / PT;
+#pragma unroll
+  for (int r = 0; r < PT; ++r) {
+    const int k = j + r * T;
+    const int kk = (k <= N / 2) ? k : N - k;
+    cplx a = cmake(0.0, 0.0), b = cmake(0.0, 0.0);
+    if (kk < kc) {
+      a = lb[kk];
+      b = lb[kcp + kk];
+    }
+    if (k == 0 || k == N / 2) {
+      v[r] = cmake(a.x, b.x);
+    } else if (k < N / 2) {
+      v[r] = cmake(a.x - b.y, a.y + b.x);
+    } else {
+      v[r] = cmake(a.x + b.y, b.x - a.y);
+    }
+  }
+}
+
+template <int NX, bool WITHQ>
+__global__ void __launch_bounds__(GroupCfg<NX>::THREADS, GroupCfg<NX>::MINB)
+    k_row_product(const __grid_constant__ RowArgs a, const cplx* __restrict__ tw, const int nunits, const int nlayers, const int kcp) {
+  using RC = GroupCfg<NX>;
+  constexpr int T = RC::T, G = RC::G;
+  GFB_DYN_SMEM(double, smd);
+  const int tid = threadIdx.x;
+  const int gi = tid / T, j = tid % T;
+  double* xb = smd + gi * RC::GSD;
+  cplx* lb = reinterpret_cast<cplx*>(smd + RC::XB_DOUBLES) + 1 + (size_t)gi * 2 * kcp;  // [0] holds the TMEM base word
+  const int tmcols = RowPipeCfg<NX>::TM_COLS(WITHQ);
+  const uint32_t tbase = tmem_setup(reinterpret_cast<uint32_t*>(smd + RC::XB_DOUBLES), tmcols);
+  const uint32_t tq = tmem_thread_base(tbase, RowPipeCfg<NX>::TM_PER_WG(WITHQ));
+  const uint32_t tg = tq + 64;
+  const int npairs = a.ny / 2;  // row pairs per layer
+  const int niter = (nunits + (int)gridDim.x * G - 1) / ((int)gridDim.x * G);
+  cplx v[PT];
+  cplx A[9], B[9];
+
+  // unit -> (layer, first row); phase -> (fields, rows)
+  auto unit_of = [&](int it) { return (it * (int)gridDim.x + (int)blockIdx.x) * G + gi; };
+  auto prefetch = [&](int unit, int ph) {
+    if (unit >= nunits) return;
+    const int layer = unit / npairs, ya = 2 * (unit - layer * npairs);
+    const int fu = a.wstride * layer, fv = fu + 1, fq = fu + 2;
+    if (ph == 0) row_prefetch<T>(lb, kcp, a.W, a.wl, fq, ya, fq, ya + 1, a.kc, j);
+    else row_prefetch<T>(lb, kcp, a.W, a.wl, fu, ya + ph - 1, fv, ya + ph - 1, a.kc, j);
+  };
+  prefetch(unit_of(0), 0);
+#pragma unroll 1
+  for (int it = 0; it < niter; ++it) {
+    const int unit = unit_of(it);
+    const bool live = unit < nunits;
+    const int layer = live ? unit / npairs : 0;
+    const int ya = live ? 2 * (unit - layer * npairs) : 0;
+#pragma unroll 1
+    for (int ph = 0; ph < 3; ++ph) {
+      cp_async_wait_all();
+      __syncthreads();  // the line buffer is complete and visible
+      if (live) assemble_hermitian<NX>(v, j, lb, kcp, a.kc);
+      else {
+#pragma unroll
+        for (int r = 0; r < PT; ++r) v[r] = cmake(0.0, 0.0);
+      }
+      __syncthreads();  // everyone has consumed the line buffer: refill it behind the transforms
+      if (ph < 2) prefetch(unit, ph + 1);
+      else if (it + 1 < niter) prefetch(unit_of(it + 1), 0);
+      block_fft_split<NX, INV>(v, j, xb, tw);
+      if (ph == 0) {  // q of both rows (+ eta) -> TMEM
+        if (a.eta != nullptr && live) {
+          const double* ea = a.eta + (long long)ya * NX;
+          const double* eb = ea + NX;
+#pragma unroll
+          for (int r = 0; r < PT; ++r) {
+            v[r].x += ea[j + r * T];
+            v[r].y += eb[j + r * T];
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < PT; ++r) tmem_store(tq + 4 * r, v[r]);
+        tmem_wait_st();
+        continue;
+      }
+      const int h = ph - 1, y = ya + h;
+      if (WITHQ) {  // (u + U) Qx + v Qy of this row -> its half of the TMEM accumulator
+        const double Uy = (a.U && live) ? a.U[(long long)layer * a.ny + y] : 0.0;
+        const double* qx = a.Qx + ((long long)layer * a.ny + y) * NX;
+        const double* qy = a.Qy + ((long long)layer * a.ny + y) * NX;
+#pragma unroll
+        for (int c0 = 0; c0 < PT; c0 += 4) {
+          cplx gs[4];
+          if (h == 1) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) gs[q] = tmem_load(tg + 4 * (c0 + q));
+            tmem_wait_ld();
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int r = c0 + q;
+            v[r].x += Uy;
+            const double gq = live ? v[r].x * qx[j + r * T] + v[r].y * qy[j + r * T] : 0.0;
+            if (h == 0) gs[q] = cmake(gq, 0.0);
+            else gs[q].y = gq;
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) tmem_store(tg + 4 * (c0 + q), gs[q]);
+        }
+        tmem_wait_st();
+      }
+#pragma unroll
+      for (int c0 = 0; c0 < PT; c0 += 4) {
+        cplx q2[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) q2[q] = tmem_load(tq + 4 * (c0 + q));
+        tmem_wait_ld();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const double qq = (h == 0) ? q2[q].x : q2[q].y;
+          v[c0 + q].x *= qq;
+          v[c0 + q].y *= qq;
+        }
+      }
+      block_fft_split<NX, FWD>(v, j, xb, tw);
+      unpack_pair<NX>(v, j, xb, A, B);  // A = (uq)_h, B = (vq)_h
+      if (live) {
+        const long long rd = a.pl.rowbase(2 * layer, y), rv = a.pl.rowbase(2 * layer + 1, y);
+#pragma unroll
+        for (int r = 0; r < 9; ++r) {
+          const int k = j + r * T;
+          if ((r < 8 || j == 0) && k < a.kout) {
+            const double kr = k * a.dkx;
+            cplx* qd = prow_ptr(a.pout, rd, k);
+            qd[0] = cmake(kr * A[r].y, -kr * A[r].x);  // -i kr (uq)_h
+            qd[rv - rd] = B[r];                         // same row block, next field
+          }
+        }
+      }
+    }
+    if (WITHQ) {  // the Q-gradient term of both rows with one more transform: d -= ((u+U) Qx + v Qy)_h
+#pragma unroll
+      for (int c0 = 0; c0 < PT; c0 += 4) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[c0 + q] = tmem_load(tg + 4 * (c0 + q));
+        tmem_wait_ld();
+      }
+      block_fft_split<NX, FWD>(v, j, xb, tw);
+      unpack_pair<NX>(v, j, xb, A, B);
+      if (live) {
+#pragma unroll
+        for (int r = 0; r < 9; ++r) {
+          const int k = j + r * T;
+          if ((r < 8 || j == 0) && k < a.kout) {
+            cplx& ea = *prow_ptr(a.pout, a.pl.rowbase(2 * layer, ya), k);  // same thread wrote these above
+            cplx& eb = *prow_ptr(a.pout, a.pl.rowbase(2 * layer, ya + 1), k);
+            ea = csub(ea, A[r]);
+            eb = csub(eb, B[r]);
+          }
+        }
+      }
+    }
+  }
+  tmem_release(tbase, tmcols);
 }
 
 // ------------------------------------------------------------------------------------------------

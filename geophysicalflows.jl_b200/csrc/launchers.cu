@@ -60,12 +60,42 @@ static int do_row(const RowLaunch& L) {
   return 0;
 }
 
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, dev) == cudaSuccess) n = p.multiProcessorCount;
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// the persistent, software-pipelined product pass (k_row_product)
+template <bool WITHQ>
+static int do_row_product(const RowLaunch& L) {
+  using RC = GroupCfg<GFB_N>;
+  const int kcp = (L.a.kc + 1) & ~1;  // line buffer rows stay 32-byte aligned
+  const size_t smem = (size_t)RC::XB_DOUBLES * sizeof(double) + 16 + (size_t)RC::G * 2 * kcp * sizeof(cplx);
+  static size_t attr = 0;
+  if (smem > attr) {
+    if (set_smem(k_row_product<GFB_N, WITHQ>, smem)) return -2;
+    attr = smem;
+  }
+  const int nunits = (L.a.ny / 2) * L.nlayers;
+  const int want = (nunits + RC::G - 1) / RC::G, cap = sm_count() * RC::MINB;
+  dim3 grid(want < cap ? want : cap);
+  GFB_LAUNCH((k_row_product<GFB_N, WITHQ>), grid, dim3(RC::THREADS), smem, L.st, L.a, L.tw, nunits, L.nlayers, kcp);
+  return 0;
+}
+
 int GFB_CAT(launch_row_, GFB_N)(const RowLaunch& L) {
   switch (L.mode) {
-    case ROW_PRODUCT: return do_row<ROW_PRODUCT>(L);
+    case ROW_PRODUCT: return do_row_product<false>(L);
+    case ROW_PRODUCT_Q: return do_row_product<true>(L);
     case ROW_C2R: return do_row<ROW_C2R>(L);
     case ROW_R2C: return do_row<ROW_R2C>(L);
-    case ROW_PRODUCT_Q: return do_row<ROW_PRODUCT_Q>(L);
   }
   return -1;
 }
