@@ -30,6 +30,14 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
 #endif
 }
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+#ifdef GFB_EMULATE
+  *reinterpret_cast<double*>(smem_dst) = *reinterpret_cast<const double*>(gmem_src);
+#else
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gmem_src) : "memory");
+#endif
+}
 // Two adjacent complex values (a column pair of one row) = one 32-byte sector.  On sm_100a this is a
 // single LDG.E.256 / STG.E.256; `p` must be 32-byte aligned (all ctx-owned arrays have an even leading
 // dimension, so a pair starting at an even column always is).

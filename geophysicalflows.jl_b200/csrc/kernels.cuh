@@ -299,6 +299,129 @@ __global__ void __launch_bounds__(GroupCfg<NY>::THREADS, GroupCfg<NY>::MINB)
   }
 }
 
+// K1 for the single-layer modules (the hot path): persistent and software-pipelined.  A CTA group walks over
+// (column pair, field) units; the raw state column it transforms NEXT (and the matching column of G) is always
+// in flight behind the transform it is doing NOW:
+//     FFT(A_u) | park A_u in TMEM | take B_u from the slots, refill them with A_{u+1} | FFT(B_u) | store the pair
+//     | take A_{u+1}, refill with B_{u+1} | ...
+// The slots are thread-private shared memory filled by cp.async (no registers, no barrier -- a thread only reads
+// what it copied itself) and hold only the rows that survive the dealias mask (<= 11 of a thread's 16 rows with
+// the 2/3 rule), which is what lets state + G slots fit beside the exchange buffer with two CTAs per SM.
+// rows r of thread j (l = j + r*T) that survive dealias!, as a bit mask; recomputed where it is used (a handful of
+// integer compares) instead of being carried across the transforms in a register
+template <int T>
+__device__ __forceinline__ unsigned k1_live_mask(const GridDesc& g, const int j) {
+  unsigned m = 0;
+#pragma unroll
+  for (int r = 0; r < PT; ++r)
+    if (!l_aliased(g, j + r * T)) m |= 1u << r;
+  return m;
+}
+
+// start fetching column `which` (0 = A, 1 = B) of the unit's pair into the slots.  S / SG: [slot][tid]
+template <int T, int THREADS>
+__device__ __forceinline__ void k1_issue(cplx* __restrict__ S, double* __restrict__ SG, const PrepSingle& prep, const GridDesc& g,
+                                         const int unit, const int which, const int nunits, const int nfields, const int ncols,
+                                         const int j, const int tid) {
+  if (unit >= nunits) return;
+  const int field = unit % nfields, colA = 2 * (unit / nfields);
+  if (colA + which >= ncols) return;
+  const unsigned lmask = k1_live_mask<T>(g, j);
+  const int off0 = toff(j, colA, prep.ld) + which;
+  int slot = tid;
+#pragma unroll
+  for (int r = 0; r < PT; ++r)
+    if (lmask >> r & 1) {
+      const int off = (T % 8 == 0) ? off0 + r * T * prep.ld : toff(j + r * T, colA, prep.ld) + which;
+      cp_async16(&S[slot], prep.sol + off);
+      if (field != 2) cp_async8(&SG[slot], prep.G + off);
+      slot += THREADS;
+      compiler_fence();  // addresses are formed one row at a time: v[] is live here
+    }
+}
+
+// v <- the prepared column (zeros for dead units / columns / rows); branch-free: dead rows read a valid slot
+template <int T, int THREADS>
+__device__ __forceinline__ void k1_take(cplx (&v)[PT], const cplx* __restrict__ S, const double* __restrict__ SG, const PrepSingle& prep,
+                                        const GridDesc& g, const int unit, const int which, const int nunits, const int nfields,
+                                        const int ncols, const int nslots, const int j, const int tid) {
+  const bool ok = unit < nunits && 2 * (unit / nfields) + which < ncols;
+  const int field = ok ? unit % nfields : 2, col = ok ? 2 * (unit / nfields) + which : 0;
+  const double kr = wav_kr(g, col);
+  const unsigned lmask = k1_live_mask<T>(g, j);
+  const unsigned m = ok ? lmask : 0u;
+  const int last = (nslots - 1) * THREADS + tid;
+  int slot = tid;
+#pragma unroll
+  for (int r = 0; r < PT; ++r) {
+    const int sl = slot < last ? slot : last;
+    const double gg = (field != 2) ? SG[sl] : 0.0;
+    const cplx t = prep.apply(g, field, wav_l(g, j + r * T), kr, gg, S[sl]);
+    const bool on = (m >> r) & 1u;
+    v[r] = cmake(on ? t.x : 0.0, on ? t.y : 0.0);
+    if (lmask >> r & 1) slot += THREADS;
+    if ((r & 3) == 3) compiler_fence();
+  }
+}
+
+template <int NY>
+__global__ void __launch_bounds__(GroupCfg<NY>::THREADS, GroupCfg<NY>::MINB)
+    k_col_inv_single(const __grid_constant__ GridDesc g, const __grid_constant__ PrepSingle prep, const __grid_constant__ PeerOut W,
+                     const int ldw, const long long wfs, const int ncols, const int nfields, const int nslots, const int nunits,
+                     const cplx* __restrict__ tw) {
+  using GC = GroupCfg<NY>;
+  constexpr int T = GC::T, THREADS = GC::THREADS, G = GC::G;
+  GFB_DYN_SMEM(double, smd);
+  const int tid = threadIdx.x;
+  const int gi = tid / T, j = tid % T;
+  double* xb = smd + gi * GC::GSD;
+  cplx* S = reinterpret_cast<cplx*>(smd + GC::XB_DOUBLES) + 1;  // element [0] of the region = TMEM base word
+  double* SG = reinterpret_cast<double*>(S + (size_t)nslots * THREADS);
+  constexpr int tmcols = (THREADS / 128) * 64;
+  const uint32_t tbase = tmem_setup(reinterpret_cast<uint32_t*>(smd + GC::XB_DOUBLES), tmcols);
+  const uint32_t tA = tmem_thread_base(tbase, 64);
+  const int stride = (int)gridDim.x * G, unit0 = (int)blockIdx.x * G + gi;
+  const int ncolumns = 2 * ((nunits - (int)blockIdx.x * G + stride - 1) / stride);  // same for every group of the CTA
+  cplx v[PT];
+
+  // column ci of this group's stream = column (ci & 1) of unit unit0 + (ci >> 1) * stride
+  k1_issue<T, THREADS>(S, SG, prep, g, unit0, 0, nunits, nfields, ncols, j, tid);
+  cp_async_wait_all();
+  k1_take<T, THREADS>(v, S, SG, prep, g, unit0, 0, nunits, nfields, ncols, nslots, j, tid);
+  k1_issue<T, THREADS>(S, SG, prep, g, unit0, 1, nunits, nfields, ncols, j, tid);
+#pragma unroll 1
+  for (int ci = 0; ci < ncolumns; ++ci) {
+    const int unit = unit0 + (ci >> 1) * stride, which = ci & 1;
+    block_fft_split<NY, INV>(v, j, xb, tw);
+    if (which == 0) {  // column A waits in TMEM for its partner
+#pragma unroll
+      for (int r = 0; r < PT; ++r) tmem_store(tA + 4 * r, v[r]);
+      tmem_wait_st();
+    } else if (unit < nunits) {
+      const int field = unit % nfields, colA = 2 * (unit / nfields);
+      const int ooff = toff(j, colA, ldw);
+#pragma unroll
+      for (int c0 = 0; c0 < PT; c0 += 4) {
+        cplx ra[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) ra[q] = tmem_load(tA + 4 * (c0 + q));
+        tmem_wait_ld();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int r = c0 + q;
+          const int d = (W.nranks == 1) ? 0 : (j + r * T) >> W.lg_rows;
+          cplx* out = W.base[d] + (W.rank - d) * W.chunk + field * wfs;
+          stpair(out + toff_row<T>(ooff, j, r, colA, ldw), ra[q], v[r]);
+        }
+      }
+    }
+    cp_async_wait_all();
+    k1_take<T, THREADS>(v, S, SG, prep, g, unit0 + ((ci + 1) >> 1) * stride, (ci + 1) & 1, nunits, nfields, ncols, nslots, j, tid);
+    k1_issue<T, THREADS>(S, SG, prep, g, unit0 + ((ci + 2) >> 1) * stride, ci & 1, nunits, nfields, ncols, j, tid);
+  }
+  tmem_release(tbase, tmcols);
+}
+
 // ------------------------------------------------------------------------------------------------
 // K2 row pass
 // ------------------------------------------------------------------------------------------------

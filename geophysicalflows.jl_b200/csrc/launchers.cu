@@ -35,10 +35,49 @@ static int do_col_inv(const ColInvLaunch& L, const Prep& prep) {
   return 0;
 }
 
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, dev) == cudaSuccess) n = p.multiProcessorCount;
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// the persistent, software-pipelined pre-pass of the single-layer modules (k_col_inv_single)
+static int do_col_inv_single(const ColInvLaunch& L) {
+  using GC = GroupCfg<GFB_N>;
+  // most rows any thread keeps after the dealias mask (thread j owns rows j + r*T)
+  int nslots = 1;
+  for (int j = 0; j < GC::T; ++j) {
+    int n = 0;
+    for (int r = 0; r < PT; ++r) {
+      const int l = j + r * GC::T;
+      if (!(l >= L.g.la0 && l < L.g.la1)) ++n;
+    }
+    if (n > nslots) nslots = n;
+  }
+  const size_t smem = (size_t)GC::XB_DOUBLES * sizeof(double) + 16 + (size_t)nslots * GC::THREADS * (sizeof(cplx) + sizeof(double));
+  static size_t attr = 0;
+  if (smem > attr) {
+    if (set_smem(k_col_inv_single<GFB_N>, smem)) return -2;
+    attr = smem;
+  }
+  const int nunits = ((L.ncols + 1) / 2) * L.nfields;
+  const int want = (nunits + GC::G - 1) / GC::G, cap = sm_count() * GC::MINB;
+  dim3 grid(want < cap ? want : cap);
+  GFB_LAUNCH((k_col_inv_single<GFB_N>), grid, dim3(GC::THREADS), smem, L.st, L.g, L.ps, L.W, L.ldw, L.wfs, L.ncols, L.nfields,
+             nslots, nunits, L.tw);
+  return 0;
+}
+
 int GFB_CAT(launch_col_inv_, GFB_N)(const ColInvLaunch& L) {
   switch (L.prep) {
     case PREP_PLAIN: return do_col_inv(L, L.pp);
-    case PREP_SINGLE: return do_col_inv(L, L.ps);
+    case PREP_SINGLE: return do_col_inv_single(L);
     case PREP_MULTI: return do_col_inv(L, L.pm);
   }
   return -1;
@@ -58,18 +97,6 @@ static int do_row(const RowLaunch& L) {
   dim3 grid((nunits + RC::G - 1) / RC::G, L.nlayers);
   GFB_LAUNCH((k_row<GFB_N, MODE>), grid, dim3(RC::THREADS), smem, L.st, L.a, L.tw);
   return 0;
-}
-
-static int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceProp p;
-    if (cudaGetDeviceProperties(&p, dev) == cudaSuccess) n = p.multiProcessorCount;
-    if (n <= 0) n = 148;
-  }
-  return n;
 }
 
 // the persistent, software-pipelined product pass (k_row_product)

@@ -294,6 +294,7 @@ static inline T __shfl_down_sync(unsigned, T v, int delta) {
 }
 template <class T>
 static inline T __shfl_sync(unsigned, T v, int src) { return emu::shfl_idx(v, src); }
+static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
 
