@@ -1206,6 +1206,21 @@ struct TmemCfg {
   static constexpr int COLS = (GroupCfg<NY>::THREADS / 128) * PER_WG;  // 256 (512 for 512-thread CTAs)
 };
 
+// start fetching one column (16 B per row) of a tiled P field into the thread-private stash
+template <int NY>
+__device__ __forceinline__ void k3_issue(cplx* __restrict__ X, const cplx* __restrict__ p, const int ldp, const int colA, const int which,
+                                         const int j, const int tid) {
+  using GC = GroupCfg<NY>;
+  constexpr int T = GC::T, THREADS = GC::THREADS;
+  const int off0 = toff(j, colA, ldp);
+#pragma unroll
+  for (int r = 0; r < PT; ++r) cp_async16(&X[r * THREADS + tid], p + toff_row<T>(off0, j, r, colA, ldp) + which);
+}
+
+// ONE transform call site in a loop over the columns (four inlined copies of the transform made ptxas spill
+// kilobytes): ci = 0, 1 are the v-field columns A, B (their -i l weighted transforms wait in TMEM), ci = 2, 3 the
+// d-field columns.  Every column arrives by cp.async in the thread-private stash X while the previous one is
+// being transformed.
 template <int NY, bool TWO>
 __global__ void __launch_bounds__(GroupCfg<NY>::THREADS, GroupCfg<NY>::MINB)
     k_col_fwd(const __grid_constant__ GridDesc g, const cplx* __restrict__ P, const int ldp, const long long pfs,
@@ -1221,53 +1236,56 @@ __global__ void __launch_bounds__(GroupCfg<NY>::THREADS, GroupCfg<NY>::MINB)
   const int colA = 2 * (blockIdx.x * GC::G + gi);
   const bool liveA = colA < ncols;
   const cplx* pd = P + (TWO ? 2 * layer : layer) * pfs;
+  const cplx* pv = P + (2 * layer + 1) * pfs;  // TWO only
   cplx v[PT];
   uint32_t tbase = 0, tA = 0, tB = 0;
   if (TWO) {
     tbase = tmem_setup(reinterpret_cast<uint32_t*>(X + GC::STASH), TmemCfg<NY>::COLS);
     tA = tmem_thread_base(tbase, TmemCfg<NY>::PER_WG);
     tB = tA + 64;
-    // ---- phase V: -i l FFTy(Pv) of both columns -> TMEM
-    const cplx* pv = P + (2 * layer + 1) * pfs;
-    load_pair_column<NY>(v, X, pv, ldp, colA, liveA, j, tid);
-    block_fft_split<NY, FWD>(v, j, xb, tw);
-    cp_async_wait_all();
-#pragma unroll
-    for (int r = 0; r < PT; ++r) {
-      const double ll = wav_l(g, j + r * T);
-      tmem_store(tA + 4 * r, cmake(ll * v[r].y, -ll * v[r].x));  // -i l (vq)_h, column A
-      v[r] = X[r * THREADS + tid];
-    }
-    block_fft_split<NY, FWD>(v, j, xb, tw);
-#pragma unroll
-    for (int r = 0; r < PT; ++r) {
-      const double ll = wav_l(g, j + r * T);
-      tmem_store(tB + 4 * r, cmake(ll * v[r].y, -ll * v[r].x));  // column B
-    }
-    tmem_wait_st();
   }
-  // ---- phase D: FFTy(Pd) of both columns (+ the parked phase-V results)
-  load_pair_column<NY>(v, X, pd, ldp, colA, liveA, j, tid);
-  block_fft_split<NY, FWD>(v, j, xb, tw);
+  constexpr int NCI = TWO ? 4 : 2;
+  if (liveA) k3_issue<NY>(X, TWO ? pv : pd, ldp, colA, 0, j, tid);
   cp_async_wait_all();
-  if (TWO) {
 #pragma unroll
-    for (int c0 = 0; c0 < PT; c0 += 4) {
-      cplx a[4];
+  for (int r = 0; r < PT; ++r) v[r] = liveA ? X[r * THREADS + tid] : cmake(0.0, 0.0);
+  if (liveA) k3_issue<NY>(X, TWO ? pv : pd, ldp, colA, 1, j, tid);
+#pragma unroll 1
+  for (int ci = 0; ci < NCI; ++ci) {
+    block_fft_split<NY, FWD>(v, j, xb, tw);
+    if (TWO && ci < 2) {
+      // -i l (vq)_h of column A / B -> TMEM, then take the next column and start fetching the one after it
+      const uint32_t tdst = (ci == 0) ? tA : tB;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) a[q] = tmem_load(tA + 4 * (c0 + q));
-      tmem_wait_ld();
+      for (int r = 0; r < PT; ++r) {
+        const double ll = wav_l(g, j + r * T);
+        tmem_store(tdst + 4 * r, cmake(ll * v[r].y, -ll * v[r].x));
+      }
+      cp_async_wait_all();
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const cplx t = X[(c0 + q) * THREADS + tid];
-        X[(c0 + q) * THREADS + tid] = cadd(v[c0 + q], a[q]);
-        v[c0 + q] = t;
+      for (int r = 0; r < PT; ++r) v[r] = liveA ? X[r * THREADS + tid] : cmake(0.0, 0.0);
+      if (liveA) k3_issue<NY>(X, pd, ldp, colA, ci, j, tid);
+      tmem_wait_st();
+    } else if (ci == NCI - 2) {
+      // first column of the d field: N_A = FFTy(d_A) (+ its parked v partner) goes to the stash, column B comes out
+      cp_async_wait_all();
+#pragma unroll
+      for (int c0 = 0; c0 < PT; c0 += 4) {
+        cplx a[4];
+        if (TWO) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) a[q] = tmem_load(tA + 4 * (c0 + q));
+          tmem_wait_ld();
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const cplx t = liveA ? X[(c0 + q) * THREADS + tid] : cmake(0.0, 0.0);
+          X[(c0 + q) * THREADS + tid] = TWO ? cadd(v[c0 + q], a[q]) : v[c0 + q];
+          v[c0 + q] = t;
+        }
       }
     }
-  } else {
-    swap_stash(v, X, tid, THREADS);
   }
-  block_fft_split<NY, FWD>(v, j, xb, tw);
   if constexpr (!TWO) {
     if (liveA) {
 #pragma unroll
