@@ -30,6 +30,15 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
 #endif
 }
+// same, L2 only (no L1 allocation): for streams that are read exactly once by this SM
+__device__ __forceinline__ void cp_async16_cg(void* smem_dst, const void* gmem_src) {
+#ifdef GFB_EMULATE
+  *reinterpret_cast<double2*>(smem_dst) = *reinterpret_cast<const double2*>(gmem_src);
+#else
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+#endif
+}
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
 #ifdef GFB_EMULATE
   *reinterpret_cast<double*>(smem_dst) = *reinterpret_cast<const double*>(gmem_src);

@@ -333,7 +333,7 @@ __device__ __forceinline__ void k1_issue(cplx* __restrict__ S, double* __restric
   for (int r = 0; r < PT; ++r)
     if (lmask >> r & 1) {
       const int off = (T % 8 == 0) ? off0 + r * T * prep.ld : toff(j + r * T, colA, prep.ld) + which;
-      cp_async16(&S[slot], prep.sol + off);
+      cp_async16_cg(&S[slot], prep.sol + off);
       if (field != 2) cp_async8(&SG[slot], prep.G + off);
       slot += THREADS;
       compiler_fence();  // addresses are formed one row at a time: v[] is live here
@@ -707,12 +707,37 @@ struct RowPipeCfg {
 template <int T>
 __device__ __forceinline__ void row_prefetch(cplx* __restrict__ lb, const int kcp, const cplx* __restrict__ W, const RowLayout& wl,
                                              const int fA, const int rowA, const int fB, const int rowB, const int kc, const int j) {
+  // fully unrolled with one base address per row and immediate offsets: an LDGSTS holds its address registers until
+  // the LSU has taken it, so a rolled loop that bumps them stalls on every iteration
+  if (wl.nranks == 1) {
+    const cplx* __restrict__ pa = W + wl.rowbase(fA, rowA) + (j >> 1) * 16 + (j & 1);
+    const cplx* __restrict__ pb = W + wl.rowbase(fB, rowB) + (j >> 1) * 16 + (j & 1);
+    cplx* __restrict__ da = lb + j;
+    cplx* __restrict__ db = lb + kcp + j;
+#pragma unroll
+    for (int i = 0; i <= PT / 2; ++i)  // kc <= N/2 + 1 = 8 T + 1
+      if (j + i * T < kc) {
+        if (T % 2 == 0) {
+          cp_async16_cg(da + i * T, pa + i * (T / 2) * 16);
+          cp_async16_cg(db + i * T, pb + i * (T / 2) * 16);
+        } else {
+          const int k = j + i * T;
+          cp_async16_cg(da + i * T, pa - ((j >> 1) * 16 + (j & 1)) + (k >> 1) * 16 + (k & 1));
+          cp_async16_cg(db + i * T, pb - ((j >> 1) * 16 + (j & 1)) + (k >> 1) * 16 + (k & 1));
+        }
+      }
+    return;
+  }
   const cplx* __restrict__ pa = W + wl.rowbase(fA, rowA);
   const cplx* __restrict__ pb = W + wl.rowbase(fB, rowB);
-  for (int k = j; k < kc; k += T) {
-    const long long co = wl.coloff(k);
-    cp_async16(lb + k, pa + co);
-    cp_async16(lb + kcp + k, pb + co);
+#pragma unroll
+  for (int i = 0; i <= PT / 2; ++i) {  // kc <= N/2 + 1 = 8 T + 1
+    const int k = j + i * T;
+    if (k < kc) {
+      const long long co = wl.coloff(k);
+      cp_async16_cg(lb + k, pa + co);
+      cp_async16_cg(lb + kcp + k, pb + co);
+    }
   }
 }
 
@@ -1106,7 +1131,9 @@ __device__ __forceinline__ void epilogue_tile(const GridDesc& g, const EpiArgs& 
                                               const int tid) {
   using GC = GroupCfg<NY>;
   constexpr int T = GC::T, THREADS = GC::THREADS;
-  constexpr int CH = 4;  // rows fetched before anything is stored: ~4 x (3..5) independent 128/256-bit loads in flight
+  // rows fetched before anything is stored.  Four rows of the kinds that read five or six arrays per wavenumber do not
+  // fit the register file next to N (ptxas spilled ~2 KB per thread): those take two rows at a time.
+  constexpr int CH = (KIND == EPI_STORE || KIND == EPI_RK_LAST || KIND == EPI_RK_ONLY || KIND == EPI_ETD_4) ? 4 : 2;
   const int off0 = toff(j, colA, e.out.ld);  // every ctx-owned array shares this leading dimension
   if (e.Nconst.p || e.F.p || (e.mu != 0.0 && layer == e.nlayers - 1)) {
 #pragma unroll 1
@@ -1214,7 +1241,7 @@ __device__ __forceinline__ void k3_issue(cplx* __restrict__ X, const cplx* __res
   constexpr int T = GC::T, THREADS = GC::THREADS;
   const int off0 = toff(j, colA, ldp);
 #pragma unroll
-  for (int r = 0; r < PT; ++r) cp_async16(&X[r * THREADS + tid], p + toff_row<T>(off0, j, r, colA, ldp) + which);
+  for (int r = 0; r < PT; ++r) cp_async16_cg(&X[r * THREADS + tid], p + toff_row<T>(off0, j, r, colA, ldp) + which);
 }
 
 // ONE transform call site in a loop over the columns (four inlined copies of the transform made ptxas spill
