@@ -59,7 +59,7 @@ __device__ __forceinline__ cpair ldpair(const double2* p) {
   r.a = p[0];
   r.b = p[1];
 #else
-  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.a.x), "=d"(r.a.y), "=d"(r.b.x), "=d"(r.b.y) : "l"(p));
+  asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.a.x), "=d"(r.a.y), "=d"(r.b.x), "=d"(r.b.y) : "l"(p));
 #endif
   return r;
 }
@@ -72,7 +72,13 @@ __device__ __forceinline__ void stpair(double2* p, double2 a, double2 b) {
 #endif
 }
 __device__ __forceinline__ double2 ldpair_d(const double* p) {  // two adjacent doubles, 16-byte aligned
+#ifdef GFB_EMULATE
   return *reinterpret_cast<const double2*>(p);
+#else
+  double2 r;
+  asm volatile("ld.global.cg.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+#endif
 }
 __device__ __forceinline__ void compiler_fence() { asm volatile("" ::: "memory"); }
 
