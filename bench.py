@@ -32,9 +32,36 @@ NCU_TRAFFIC = {}
 
 
 def workload(name):
-    n = {"sqg4096": 4096, "sqg2048": 2048, "sqg1024": 1024, "sqg512": 512}[name]
-    return dict(module="SurfaceQG", nx=n, ny=n, Lx=2 * np.pi, nu=1e-19 * (256 / n) ** 8, nnu=4, H=np.inf,
-                dt=0.03 * 256 / n, stepper="ETDRK4")
+    """sqgN: BASELINE.json configs[3] (SurfaceQG decaying, ETDRK4; examples/surfaceqg_decaying.jl scaled to N).
+    twodnsN: configs[4] scaled to N (TwoDNavierStokes stochastically forced, ETDRK4;
+    examples/twodnavierstokes_stochasticforcing.jl: nu = 2e-7, nnu = 2, mu = 0.1, k_f = 14, eps = 0.1 at 256^2)."""
+    kind, n = ("twodns", int(name[6:])) if name.startswith("twodns") else ("sqg", int(name[3:]))
+    if kind == "sqg":
+        return dict(module="SurfaceQG", nx=n, ny=n, Lx=2 * np.pi, nu=1e-19 * (256 / n) ** 8, nnu=4, H=np.inf,
+                    dt=0.03 * 256 / n, stepper="ETDRK4")
+    return dict(module="TwoDNavierStokes", nx=n, ny=n, Lx=2 * np.pi, nu=2e-7 * (256 / n) ** 4, nnu=2, mu=0.1, nmu=0,
+                dt=0.005 * 256 / n, stepper="ETDRK4", kf=14.0, dkf=1.5, eps=0.1)
+
+
+def forcing_fh(cfg, seed=1):
+    """One realisation of the reference example's white-in-time ring forcing, F_h = sqrt(spectrum) e^{i theta} / sqrt(dt),
+    spectrum ~ exp(-(|k| - k_f)^2 / (2 dk^2)) normalised to the energy input rate eps; frozen over the timed steps."""
+    n, dt = cfg["nx"], cfg["dt"]
+    rng = np.random.default_rng(seed)
+    kr = np.arange(n // 2 + 1)[None, :]
+    l = np.fft.fftfreq(n, 1 / n)[:, None]
+    K2 = (kr**2 + l**2).astype(np.float64)
+    K = np.sqrt(K2)
+    spec = np.exp(-(K - cfg["kf"]) ** 2 / (2 * cfg["dkf"] ** 2))
+    spec[K < 2] = 0
+    spec[K > 20] = 0
+    with np.errstate(divide="ignore", invalid="ignore"):
+        e0 = np.sum(np.where(K2 > 0, spec / K2, 0.0)) / (n * n) ** 2 * 2  # ~ parsevalsum(spec * invKrsq / 2) per unit area
+    spec *= cfg["eps"] / e0
+    th = rng.uniform(0, 2 * np.pi, K.shape)
+    Fh = np.sqrt(spec) * np.exp(1j * th) / np.sqrt(dt)
+    Fh[0, 0] = 0
+    return Fh
 
 
 def initial_bh(n, seed=0):
@@ -100,9 +127,24 @@ class ClockSampler(threading.Thread):
 def oracle_problem(cfg):
     from oracle import gfo
     gfo.set_workers(os.cpu_count() or 1)
-    po = gfo.surfaceqg.Problem(nx=cfg["nx"], Lx=cfg["Lx"], nu=cfg["nu"], nnu=cfg["nnu"], H=cfg["H"], dt=cfg["dt"],
-                               stepper=cfg["stepper"])
+    if cfg["module"] == "SurfaceQG":
+        po = gfo.surfaceqg.Problem(nx=cfg["nx"], Lx=cfg["Lx"], nu=cfg["nu"], nnu=cfg["nnu"], H=cfg["H"], dt=cfg["dt"],
+                                   stepper=cfg["stepper"])
+    else:
+        Fh = forcing_fh(cfg)
+
+        def calcF(F, sol, t, clock, vars, params, grid):
+            F[...] = Fh
+        po = gfo.twodnavierstokes.Problem(nx=cfg["nx"], Lx=cfg["Lx"], nu=cfg["nu"], nnu=cfg["nnu"], mu=cfg["mu"], nmu=cfg["nmu"],
+                                          dt=cfg["dt"], stepper=cfg["stepper"], calcF=calcF, stochastic=True)
     return gfo, po
+
+
+def workload_name(cfg):
+    n = cfg["nx"]
+    if cfg["module"] == "SurfaceQG":
+        return "SurfaceQG decaying %d^2 ETDRK4 Float64 (BASELINE.json configs[3])" % n
+    return "TwoDNavierStokes stochastically forced %d^2 ETDRK4 Float64 (BASELINE.json configs[4] at the largest supported size)" % n
 
 
 def cpu_steps(cfg, bh0, nsteps, warmup):
@@ -142,7 +184,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "SurfaceQG decaying %d^2 ETDRK4 Float64 (BASELINE.json configs[3])" % n,
+            "config": {"workload": workload_name(cfg),
                        "impl": "oracle port of the reference CPU path: numpy broadcast + scipy.fft(pocketfft) workers=%d; "
                                "the Julia/FFTW reference itself cannot run here (no Julia, FourierFlows.jl not vendored)" % cores},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
@@ -187,8 +229,21 @@ def main():
     # N > 1: the SAME 4096^2 problem slab-sharded over the N GPUs (strong scaling): y-slabs in physical space,
     # round-robin kr column pairs in spectral space, one NCCL all-to-all per 2-D transform direction and stage
     shard = (rank, world, None, args.transport) if world > 1 else None
-    prob = pkg.SurfaceQG.Problem(dev, nx=n, Lx=cfg["Lx"], nu=cfg["nu"], nnu=cfg["nnu"], H=cfg["H"], dt=cfg["dt"],
-                                 stepper=cfg["stepper"], shard=shard)
+    forced = cfg["module"] != "SurfaceQG"
+    if not forced:
+        prob = pkg.SurfaceQG.Problem(dev, nx=n, Lx=cfg["Lx"], nu=cfg["nu"], nnu=cfg["nnu"], H=cfg["H"], dt=cfg["dt"],
+                                     stepper=cfg["stepper"], shard=shard)
+        diag = pkg.SurfaceQG.kinetic_energy
+    else:
+        fh_dev = []
+
+        def calcF(F, sol, t, clock, vars, params, grid):  # the realisation is frozen: same work per step as a fresh draw
+            F.copy_(fh_dev[0], non_blocking=True)
+        prob = pkg.TwoDNavierStokes.Problem(dev, nx=n, Lx=cfg["Lx"], nu=cfg["nu"], nnu=cfg["nnu"], mu=cfg["mu"], nmu=cfg["nmu"],
+                                            dt=cfg["dt"], stepper=cfg["stepper"], calcF=calcF, stochastic=True, shard=shard)
+        fh = forcing_fh(cfg)
+        fh_dev.append(dev.array(prob.shard.spec_local(fh) if world > 1 else fh, torch.complex128))
+        diag = pkg.TwoDNavierStokes.energy
     bh0 = initial_bh(n)
     bh0[0, 0] = 0
     if world > 1:
@@ -239,7 +294,7 @@ def main():
         prob.sol.copy_(host_sol, non_blocking=True)
         pkg.stepforward_(prob, 1)
         out_host.copy_(prob.sol, non_blocking=True)
-        ke = pkg.SurfaceQG.kinetic_energy(prob)  # device->host scalar (synchronises the stream)
+        ke = diag(prob)  # device->host scalar (synchronises the stream)
     barrier()
     e2e_s = (time.perf_counter() - t0) / args.e2e_steps
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
@@ -267,7 +322,11 @@ def main():
 
     def k3_bytes(ncols, nout):
         return 2 * 16.0 * ny * ncols + sum(epi) / 4.0 * nout
-    wfull = 1.0 / float(args.steps)                     # one full (un-pruned) step per stepforward! call,
+    if forced:                                          # + F_h in every stage, prevsol written in stage 1
+        epi = [e + 16 for e in epi]
+        epi[0] += 16
+    # one full (un-pruned) step per stepforward! call; the forced problem steps one call at a time (calcF! per step)
+    wfull = 1.0 if forced else 1.0 / float(args.steps)
     kbytes = {                                          # the others skip the aliased band of N
         "k_col_inv": (16.0 + 8.0) * band + 3 * 16.0 * ny * kcut,
         "k_row": 3 * 16.0 * ny * kcut + 2 * 16.0 * ny * (wfull * nkr + (1 - wfull) * kcut),
@@ -283,9 +342,10 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "SurfaceQG decaying %d^2 ETDRK4 Float64 (BASELINE.json configs[3])" % n,
+        "config": {"workload": workload_name(cfg),
                    "grid": [n, n], "stepper": cfg["stepper"], "dt": cfg["dt"],
-                   "initial_condition": "random-phase b_h ~ |k|(1+(|k|/6)^4)^-1/2, rms b = 0.1, numpy default_rng(0)",
+                   "initial_condition": "random-phase field_h ~ |k|(1+(|k|/6)^4)^-1/2, rms = 0.1, numpy default_rng(0)"
+                   + ("; ring forcing k_f = 14, one frozen realisation re-applied by calcF! every step" if forced else ""),
                    "l2": "working set (>= 12 fields x %.0f MB) exceeds the 126 MB L2; no flush needed" % (16.0 * ny * nkr / 1e6),
                    "parallelism": "1 GPU" if world == 1 else
                    "%d GPUs, one %d^2 problem: y-slabs / round-robin kr column pairs, 2 exchanges per stage via %s "
@@ -303,7 +363,7 @@ def main():
         "kernels": {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps} for k, v in prof.items()},
         "gpu_launches": launches,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_s * 1e3, "what": "per step: pinned-host sol -> device, stepforward!(prob, 1), sol + kinetic_energy -> host"},
+                "ms_per_step": e2e_s * 1e3, "what": "per step: pinned-host sol -> device, stepforward!(prob, 1), sol + energy diagnostic -> host"},
         "clocks": sampler.summary(),
     }
     if world > 1:
