@@ -28,7 +28,8 @@ UNIT = "grid-point-steps/s"
 ALGO_BYTES_PER_POINT_STEP = 480.0  # 60 field passes x 8 B (Float64), RK4/ETDRK4 families
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the same
 # command (profiles/): full-mode (un-pruned) launches of the 4096^2 workload
-NCU_TRAFFIC = {}
+NCU_TRAFFIC = {"k_row": 268.84e6 + 143.42e6}  # k_row_product<4096,false>, pruned stage (profiles/r1_ncu_key_metrics_pipelined.txt)
+KERNEL_FUNCTION = {"k_col_inv": "k_col_inv_single<4096>", "k_row": "k_row_product<4096,false>", "k_col_fwd": "k_col_fwd<4096,true>"}
 
 
 def workload(name):
@@ -90,38 +91,61 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons DURING the timed region (B200_PROFILING.md recipe).  NVML is polled every few
+    milliseconds (the timed region of the default run is a fraction of a second); nvidia-smi is the fallback."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index=0):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+        self.index, self.stop_flag = index, threading.Event()
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml = pynvml
+            self.mx.append(float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)))
+        except Exception:
+            self.nvml = None
+
+    def _poll_nvml(self):
+        n = self.nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for nm, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40)):
+            if r & bit:
+                self.reasons.add(nm)
+
+    def _poll_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout
+        r = [c.strip() for c in out.strip().split(",")]
+        self.sm.append(float(r[0]))
+        self.mx.append(float(r[1]))
+        for nm, v in zip(self.NAMES, r[3:7]):
+            if v.lower().startswith("active"):
+                self.reasons.add(nm)
 
     def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([c.strip() for c in out.strip().split(",")])
+                if self.nvml is not None:
+                    self._poll_nvml()
+                else:
+                    self._poll_smi()
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.003 if self.nvml is not None else 0.2)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-                for nm, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
-            except Exception:
-                continue
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def oracle_problem(cfg):
@@ -195,7 +219,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="sqg4096")
@@ -336,7 +360,7 @@ def main():
     top = max(("k_col_inv", "k_row", "k_col_fwd"), key=lambda k: prof[k]["ms"])
     avg_ms = prof[top]["ms"] / max(prof[top]["launches"], 1)
     achieved = kbytes[top] / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else None
-    step_gbs = ALGO_BYTES_PER_POINT_STEP * n * n / (ms_per_step * 1e-3) / 1e9
+    step_gbs = ALGO_BYTES_PER_POINT_STEP * n * n / world / (ms_per_step * 1e-3) / 1e9  # per GPU
     launches = sum(v["launches"] for v in prof.values())
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -352,13 +376,14 @@ def main():
                    "(%.0f MB sent per GPU per step)" % (world, n, "P2P stores of K1/K2 into peer memory + flag barriers"
                                                         if args.transport == "p2p" else "NCCL all-to-all", a2a_bytes / 1e6),
                    "state_finite": finite},
-        "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": NCU_TRAFFIC.get(top), "peak_source": peak_src,
+        "roofline": {"bound": "hbm", "kernel": top, "kernel_function": KERNEL_FUNCTION[top].replace("4096", str(n)), "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None,
+                     "traffic": NCU_TRAFFIC.get(top) if (world == 1 and n == 4096 and not forced) else None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": kbytes[top], "avg_launch_ms": avg_ms,
                      "all_kernels": {k: {"achieved_gbs": kbytes[k] / (prof[k]["ms"] / max(prof[k]["launches"], 1) * 1e-3) / 1e9
                                          if prof[k]["ms"] > 0 else None,
                                          "algorithmic_bytes_per_launch": kbytes[k]} for k in kbytes}},
-        "step_roofline": {"algorithmic_bytes_per_step": ALGO_BYTES_PER_POINT_STEP * n * n, "achieved_gbs": step_gbs,
+        "step_roofline": {"algorithmic_bytes_per_step": ALGO_BYTES_PER_POINT_STEP * n * n, "achieved_gbs_per_gpu": step_gbs,
                           "frac_of_measured_peak": step_gbs / peak, "frac_of_8tbs_nominal": step_gbs / 8000.0},
         "kernels": {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps} for k, v in prof.items()},
         "gpu_launches": launches,
