@@ -374,7 +374,7 @@ def main():
                    "parallelism": "1 GPU" if world == 1 else
                    "%d GPUs, one %d^2 problem: y-slabs / round-robin kr column pairs, 2 exchanges per stage via %s "
                    "(%.0f MB sent per GPU per step)" % (world, n, "P2P stores of K1/K2 into peer memory + flag barriers"
-                                                        if args.transport == "p2p" else "NCCL all-to-all", a2a_bytes / 1e6),
+                                                        if prob.shard.transport == "p2p" else "NCCL all-to-all", a2a_bytes / 1e6),
                    "state_finite": finite},
         "roofline": {"bound": "hbm", "kernel": top, "kernel_function": KERNEL_FUNCTION[top].replace("4096", str(n)), "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None,
@@ -394,7 +394,7 @@ def main():
     if world > 1:
         # NVLink roofline of the sharded step: bytes that must leave each GPU / measured peer bandwidth (770 GB/s/dir)
         line["nvlink"] = {"a2a_bytes_per_gpu_per_step": a2a_bytes, "floor_ms_at_770GBs": a2a_bytes / 770e9 * 1e3,
-                          "exchanges_per_step": 8, "transport": args.transport}
+                          "exchanges_per_step": 8, "transport": prob.shard.transport}
     if world == 1 and not args.no_cpu_baseline:
         nsamp = 2 if n >= 4096 else 4
         per = cpu_steps(cfg, bh0, nsamp, 1)

@@ -37,7 +37,7 @@ EXPORTS = ["gfb_version", "gfb_last_error", "gfb_create", "gfb_destroy", "gfb_ge
            "gfb_streamfunction_from_pv", "gfb_pv_from_streamfunction", "gfb_updatevars", "gfb_device_bytes",
            "gfb_profile_begin", "gfb_profile_end", "gfb_shard_info", "gfb_state_import", "gfb_state_export",
            "gfb_stage_pre", "gfb_stage_mid", "gfb_stage_post", "gfb_comm_create", "gfb_comm_connect",
-           "gfb_comm_connect_ptrs", "gfb_comm_status", "gfb_step_p2p"]
+           "gfb_comm_connect_ptrs", "gfb_comm_status", "gfb_step_p2p", "gfb_set_defer_alias_band"]
 
 
 class GfbError(RuntimeError):
@@ -77,6 +77,7 @@ def _prototype(lib):
     lib.gfb_comm_connect_ptrs.argtypes = [vp, C.POINTER(vp)]
     lib.gfb_comm_status.argtypes = [vp]
     lib.gfb_step_p2p.argtypes = [vp, vp, ip, vp, vp, vp]
+    lib.gfb_set_defer_alias_band.argtypes = [vp, ip]
     lib.gfb_device_bytes.argtypes = [vp]
     lib.gfb_device_bytes.restype = C.c_longlong
     for name in EXPORTS:

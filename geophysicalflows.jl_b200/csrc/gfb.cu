@@ -57,6 +57,7 @@ struct gfb_ctx {
   bool peer_ipc[MAX_RANKS] = {false, false, false, false, false, false, false, false};
   bool connected = false;
   unsigned long long epoch = 0;
+  bool defer_alias = false;  // gfb_set_defer_alias_band
   // optional per-kernel event timing
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev;   // pairs (start, stop)
@@ -836,7 +837,7 @@ int gfb_step_p2p(gfb_ctx* c, void* sol_local, int nsteps, const void* Fh_local, 
   const cplx* precv = reinterpret_cast<const cplx*>(c->comm + c->comm_p_off);
   for (int s = 0; s < nsteps; ++s) {
     const bool last = (s == nsteps - 1);
-    const int prune = (!last && !is_ab3(c)) ? 1 : 0;
+    const int prune = ((!last || c->defer_alias) && !is_ab3(c)) ? 1 : 0;
     for (int i = 0; i < ns; ++i) {
       Spec sin;
       EpiArgs e;
@@ -921,6 +922,12 @@ int gfb_calcN(gfb_ctx* c, void* N, void* sol, const void* Fh, void* stream) {
 
 int gfb_nstages(const gfb_ctx* c) { return c ? nstages_of(c) : GFB_ERR_INVALID; }
 
+int gfb_set_defer_alias_band(gfb_ctx* c, int on) {
+  if (!c) return GFB_ERR_INVALID;
+  c->defer_alias = on != 0;
+  return GFB_OK;
+}
+
 int gfb_stage(gfb_ctx* c, void* sol, int istage, const void* Fh, void* prevsol, void* stream) {
   if (!c || !sol) return fail(c, GFB_ERR_INVALID, "gfb_stage: null argument");
   NEED_SINGLE_GPU(c, "gfb_stage");
@@ -946,7 +953,7 @@ int gfb_step(gfb_ctx* c, void* sol, int nsteps, const void* Fh, void* prevsol, v
   for (int s = 0; s < nsteps; ++s) {
     const bool last = (s == nsteps - 1);
     for (int i = 0; i < ns; ++i)
-      if ((rc = do_stage(c, i, Fh != nullptr, last && prevsol != nullptr, (!last && !is_ab3(c)) ? 1 : 0, st))) return rc;
+      if ((rc = do_stage(c, i, Fh != nullptr, last && prevsol != nullptr, ((!last || c->defer_alias) && !is_ab3(c)) ? 1 : 0, st))) return rc;
   }
   if (prevsol && (rc = export_spec(c, prevsol, c->PV, st))) return rc;
   return export_spec(c, sol, c->S0, st);

@@ -198,15 +198,29 @@ class Problem:
         return t.data_ptr()
 
     def _connect_p2p(self):
-        """Exchange the CUDA IPC handles of the per-rank receive buffers (one process per GPU) and map the peers."""
+        """Exchange the CUDA IPC handles of the per-rank receive buffers (one process per GPU) and map the peers.
+        If any rank cannot create or map a buffer (no peer access between the devices, IPC disabled in the
+        container), EVERY rank falls back to the all-to-all transport -- announced, never silent."""
+        import warnings
         import torch.distributed as dist
         handle = (C.c_ubyte * 64)()
-        self._check(self.lib.gfb_comm_create(self.ctx, handle, None), "gfb_comm_create")
-        handles = [None] * self.shard.nranks
-        dist.all_gather_object(handles, bytes(handle), group=self.shard.group)
-        blob = b"".join(handles)
-        self._check(self.lib.gfb_comm_connect(self.ctx, C.c_char_p(blob)), "gfb_comm_connect")
-        dist.barrier(group=self.shard.group)  # nobody stores into a buffer before everyone has mapped it
+        ok = self.lib.gfb_comm_create(self.ctx, handle, None) == 0
+        msgs = [None] * self.shard.nranks
+        dist.all_gather_object(msgs, (ok, bytes(handle)), group=self.shard.group)
+        if all(m[0] for m in msgs):
+            blob = b"".join(m[1] for m in msgs)
+            ok = self.lib.gfb_comm_connect(self.ctx, C.c_char_p(blob)) == 0
+        else:
+            ok = False
+        oks = [None] * self.shard.nranks
+        dist.all_gather_object(oks, ok, group=self.shard.group)  # also: nobody stores before everyone has mapped
+        if all(oks):
+            return
+        why = self.lib.gfb_last_error(self.ctx).decode()
+        warnings.warn("geophysicalflows.jl_b200: p2p transport unavailable (%s); using the all-to-all transport" % why)
+        self.shard.transport = "nccl"
+        self._wbuf = [self.dev.zeros((self._a2a_elems[0],), torch.complex128) for _ in range(2)]
+        self._pbuf = [self.dev.zeros((self._a2a_elems[1],), torch.complex128) for _ in range(2)]
 
     def step_lib(self, nsteps, Fh=None, prevsol=None):
         if self.shard is not None and self.shard.nranks > 1:
@@ -231,7 +245,7 @@ class Problem:
         self._check(lib.gfb_state_import(ctx, self._p(self.sol), sp), "gfb_state_import")
         for s in range(int(nsteps)):
             last = s == nsteps - 1
-            prune = 0 if (last or ab3) else 1
+            prune = 0 if ((last and not getattr(self, "_defer_alias", False)) or ab3) else 1
             for i in range(nst):
                 self._check(lib.gfb_stage_pre(ctx, i, self._p(ws), sp), "gfb_stage_pre")
                 self._all_to_all(wr, ws)
@@ -240,6 +254,11 @@ class Problem:
                 self._check(lib.gfb_stage_post(ctx, i, self._p(pr), self._p(Fh), self._p(prevsol) if last else None,
                                                prune, sp), "gfb_stage_post")
         self._check(lib.gfb_state_export(ctx, self._p(self.sol), sp), "gfb_state_export")
+
+    def set_defer_alias_band(self, on):
+        """gfb_set_defer_alias_band: while on, the aliased band of the state a step returns is left unspecified."""
+        self._defer_alias = bool(on)
+        self._check(self.lib.gfb_set_defer_alias_band(self.ctx, 1 if on else 0), "gfb_set_defer_alias_band")
 
     def stage_lib(self, istage, Fh=None, prevsol=None):
         self._check(self.lib.gfb_stage(self.ctx, self._p(self.sol), int(istage), self._p(Fh), self._p(prevsol),
@@ -327,11 +346,18 @@ def stepforward_(prob, nsteps=1, diags=()):
             advance(nsteps)
         return
     if v.stochastic:
-        # addforcing!: forcing drawn once per step at t == clock.t on the dealiased state, prevsol kept
-        for _ in range(nsteps):
+        # addforcing!: forcing drawn once per step at t == clock.t on the dealiased state, prevsol kept.
+        # The aliased band of the state is only computed when somebody can look at it: after the last step of this
+        # call, or when a diagnostic fires (they read the raw sol); otherwise the next dealias! wipes it unseen.
+        for i in range(nsteps):
             prob.dealias_lib(prob.sol)
             calcF(Fh, prob.sol, c.t, c, v, p, prob.grid)
-            prob.step_lib(1, Fh, v.prevsol)
+            observed = i == nsteps - 1 or any((c.step + 1) % d.freq == 0 for d in diags)
+            prob.set_defer_alias_band(not observed)
+            try:
+                prob.step_lib(1, Fh, v.prevsol)
+            finally:
+                prob.set_defer_alias_band(False)
             advance(1)
         return
     # deterministic forcing: re-evaluated at every stage time (src/twodnavierstokes.jl:304-310)

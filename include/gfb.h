@@ -181,6 +181,14 @@ int gfb_stage_mid(gfb_ctx* ctx, const void* wrecv, void* psend, int prune, void*
 int gfb_stage_post(gfb_ctx* ctx, int istage, const void* precv, const void* Fh_local, void* prevsol_local, int prune,
                    void* stream);
 
+/* Lazy alias band for callers that step one call at a time (stochastic forcing: calcF! runs between the steps).
+ * gfb_step / gfb_step_p2p always compute the aliased band of N -- which lands only in the aliased band of the
+ * returned state and is wiped by the next dealias! -- in the LAST step of a call, so that everything a caller can
+ * observe is exact.  While this switch is on the last step skips it too: the aliased band of the returned `sol` is
+ * then unspecified.  Legal whenever the next thing that touches `sol` is dealias! (the reference's calcN! starts
+ * with it, src/twodnavierstokes.jl:287); switch it off for the step after which diagnostics or output read `sol`. */
+int gfb_set_defer_alias_band(gfb_ctx* ctx, int on);
+
 /* "p2p" transport of a sharded context: instead of handing send buffers to an all-to-all, K1 and K2 store every
  * row / column pair straight into the buffer of the rank that consumes it (peer memory over NVLink), and a
  * flag barrier in peer memory separates the passes -- the exchange is fused into the kernels.
