@@ -120,7 +120,6 @@ __device__ __forceinline__ void swap_stash(cplx (&v)[PT], cplx* __restrict__ X, 
 // load_pair(g, field, l, colA, liveB, a, b): values of `field` at (l, colA) and (l, colA+1), ready for the
 // inverse y-FFT.  Sources that are ctx-owned (kAligned) are read with one 256-bit access per row.
 struct PrepPlain {  // irfft of arbitrary (user, dense) spectra: field = batch index
-  static constexpr bool kAsync = false;
   const cplx* in;
   int ld;  // dense (user) leading dimension; offsets are computed inside
   long long ls;
@@ -133,18 +132,6 @@ struct PrepPlain {  // irfft of arbitrary (user, dense) spectra: field = batch i
 };
 
 struct PrepSingle {  // single-layer modules: psi_h = -G*sol ; uh = i l G sol ; vh = -i kr G sol ; qh = sol
-  static constexpr bool kAsync = true;  // column B: raw value by cp.async into the stash, prepared when swapped in
-  __device__ __forceinline__ bool live(const GridDesc& g, int l) const { return !l_aliased(g, l); }
-  __device__ __forceinline__ const cplx* src(int, int off) const { return sol + off; }
-  __device__ __forceinline__ cplx prepare(const GridDesc& g, int field, int l, int col, int off, cplx raw) const {
-    double gg = 0.0;
-    if (field != 2) gg = G[off];
-    return apply(g, field, wav_l(g, l), wav_kr(g, col), gg, raw);
-  }
-  __device__ __forceinline__ cplx load_one(const GridDesc& g, int field, int l, int col, int off) const {
-    if (l_aliased(g, l)) return cmake(0.0, 0.0);
-    return prepare(g, field, l, col, off, sol[off]);
-  }
   const cplx* sol;   // ctx-owned, ld even
   int ld;
   const double* G;   // ctx-owned, ld = ldg even
@@ -171,7 +158,6 @@ struct PrepSingle {  // single-layer modules: psi_h = -G*sol ; uh = i l G sol ; 
 };
 
 struct PrepMulti {  // MultiLayerQG: psi_h = S^-1 q_h ; uh = -i l psi_h ; vh = i kr psi_h ; field = nf*layer + {u,v,q[,psi]}
-  static constexpr bool kAsync = false;
   const cplx* sol;     // ctx-owned, ld even
   int ld;
   long long ls;
@@ -219,7 +205,8 @@ struct PrepMulti {  // MultiLayerQG: psi_h = S^-1 q_h ; uh = -i l psi_h ; vh = i
   }
 };
 
-// K1.  Each group takes a PAIR of adjacent kr columns: one 256-bit access per row on the spectral side and
+// K1 (generic: MultiLayerQG pre-pass and plain transforms; the single-layer hot path is k_col_inv_single below).
+// Each group takes a PAIR of adjacent kr columns: one 256-bit access per row on the spectral side and
 // on the W side.  The two columns are transformed one after the other in the same registers; the other
 // column waits in the thread-private stash.  Loads are issued four rows at a time (bounded registers,
 // ~200 bytes in flight per thread).
@@ -242,44 +229,24 @@ __global__ void __launch_bounds__(GroupCfg<NY>::THREADS, GroupCfg<NY>::MINB)
   cplx* X = reinterpret_cast<cplx*>(smd + GC::XB_DOUBLES);
   cplx v[PT];
   const int inoff = toff(j, colA, prep.ld);
-  if constexpr (Prep::kAsync) {
-    if (liveA) {
 #pragma unroll
-      for (int r = 0; r < PT; ++r)
-        if (prep.live(g, j + r * T)) cp_async16(&X[r * THREADS + tid], prep.src(field, toff_row<T>(inoff, j, r, colA, prep.ld) + 1));
+  for (int c0 = 0; c0 < PT; c0 += 4) {
+    cplx bb[4];
 #pragma unroll
-      for (int r = 0; r < PT; ++r) v[r] = prep.load_one(g, field, j + r * T, colA, toff_row<T>(inoff, j, r, colA, prep.ld));
-    } else {
-#pragma unroll
-      for (int r = 0; r < PT; ++r) v[r] = cmake(0.0, 0.0);
+    for (int q = 0; q < 4; ++q) {
+      if (liveA) prep.load_pair(g, field, j + (c0 + q) * T, colA, liveB, toff_row<T>(inoff, j, c0 + q, colA, prep.ld), v[c0 + q], bb[q]);
+      else v[c0 + q] = bb[q] = cmake(0.0, 0.0);
     }
-    block_fft_split<NY, INV>(v, j, xb, tw);
-    cp_async_wait_all();
 #pragma unroll
-    for (int r = 0; r < PT; ++r) {
-      const int l = j + r * T;
-      cplx t = cmake(0.0, 0.0);
-      if (liveA && prep.live(g, l)) t = prep.prepare(g, field, l, colB, toff_row<T>(inoff, j, r, colA, prep.ld) + 1, X[r * THREADS + tid]);
-      X[r * THREADS + tid] = v[r];
-      v[r] = t;
-    }
-  } else {
-#pragma unroll
-    for (int c0 = 0; c0 < PT; c0 += 4) {
-      cplx bb[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (liveA) prep.load_pair(g, field, j + (c0 + q) * T, colA, liveB, toff_row<T>(inoff, j, c0 + q, colA, prep.ld), v[c0 + q], bb[q]);
-        else v[c0 + q] = bb[q] = cmake(0.0, 0.0);
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) X[(c0 + q) * THREADS + tid] = bb[q];
-      compiler_fence();
-    }
-    block_fft_split<NY, INV>(v, j, xb, tw);
-    swap_stash(v, X, tid, THREADS);
+    for (int q = 0; q < 4; ++q) X[(c0 + q) * THREADS + tid] = bb[q];
+    compiler_fence();
   }
-  block_fft_split<NY, INV>(v, j, xb, tw);
+  // one transform call site for both columns (two inlined copies made ptxas spill ~0.5 KB per thread)
+#pragma unroll 1
+  for (int c = 0; c < 2; ++c) {
+    block_fft_split<NY, INV>(v, j, xb, tw);
+    if (c == 0) swap_stash(v, X, tid, THREADS);
+  }
   if (liveA) {
     const int ooff = toff(j, colA, ldw);
     if (W.nranks == 1) {
@@ -597,93 +564,7 @@ __global__ void __launch_bounds__(GroupCfg<NX>::THREADS, GroupCfg<NX>::MINB)
     return;
   }
 
-  // ---- ROW_PRODUCT (+_Q: extra (u+U)*Qx + v*Qy term, MultiLayerQG / SingleLayerQG with U(y)) ----
-  const bool withQ = (MODE == ROW_PRODUCT_Q);
-  const int fu = a.wstride * layer + 0, fv = a.wstride * layer + 1, fq = a.wstride * layer + 2;
-  // 1. q of both rows: one complex transform gives q_a + i q_b
-  if (live) load_hermitian<NX>(v, j, a.W, a.wl, fq, ya, fq, yb, a.kc);
-  else {
-#pragma unroll
-    for (int r = 0; r < PT; ++r) v[r] = cmake(0.0, 0.0);
-  }
-  block_fft_split<NX, INV>(v, j, xb, tw);
-  if (a.eta != nullptr && live) {
-    const double* ea = a.eta + (long long)ya * NX;
-    const double* eb = ea + NX;
-#pragma unroll
-    for (int r = 0; r < PT; ++r) {
-      v[r].x += ea[j + r * T];
-      v[r].y += eb[j + r * T];
-    }
-  }
-#pragma unroll
-  for (int r = 0; r < PT; ++r) stash[r * THREADS + tid] = v[r];
-  cplx* gst = stash + PT * THREADS;  // second thread-private stash (ROW_PRODUCT_Q only)
-
-  // 2. per row: (u + i v) -> times q -> forward -> split into uq_h, vq_h
-#pragma unroll 1
-  for (int h = 0; h < 2; ++h) {
-    const int y = ya + h;
-    if (live) load_hermitian<NX>(v, j, a.W, a.wl, fu, y, fv, y, a.kc);
-    else {
-#pragma unroll
-      for (int r = 0; r < PT; ++r) v[r] = cmake(0.0, 0.0);
-    }
-    block_fft_split<NX, INV>(v, j, xb, tw);
-    if (withQ && live) {
-      const double Uy = a.U ? a.U[(long long)layer * a.ny + y] : 0.0;
-      const double* qx = a.Qx + ((long long)layer * a.ny + y) * NX;
-      const double* qy = a.Qy + ((long long)layer * a.ny + y) * NX;
-#pragma unroll
-      for (int r = 0; r < PT; ++r) {
-        v[r].x += Uy;
-        const double gq = v[r].x * qx[j + r * T] + v[r].y * qy[j + r * T];
-        cplx& gs = gst[r * THREADS + tid];
-        if (h == 0) gs.x = gq; else gs.y = gq;
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < PT; ++r) {
-      const cplx q2 = stash[r * THREADS + tid];
-      const double q = (h == 0) ? q2.x : q2.y;
-      v[r].x *= q;
-      v[r].y *= q;
-    }
-    block_fft_split<NX, FWD>(v, j, xb, tw);
-    unpack_pair<NX>(v, j, xb, A, B);  // A = (uq)_h, B = (vq)_h
-    if (live) {
-      const long long rd = a.pl.rowbase(2 * layer, y), rv = a.pl.rowbase(2 * layer + 1, y);
-#pragma unroll
-      for (int r = 0; r < 9; ++r) {
-        const int k = j + r * T;
-        if ((r < 8 || j == 0) && k < a.kout) {
-          const double kr = k * a.dkx;
-          cplx* qd = prow_ptr(a.pout, rd, k);
-          qd[0] = cmake(kr * A[r].y, -kr * A[r].x);  // -i kr (uq)_h
-          qd[rv - rd] = B[r];                         // same row block, next field
-        }
-      }
-    }
-  }
-  // 3. the Q-gradient term of both rows with one more transform: d -= ((u+U) Qx + v Qy)_h
-  if (withQ) {
-#pragma unroll
-    for (int r = 0; r < PT; ++r) v[r] = live ? gst[r * THREADS + tid] : cmake(0.0, 0.0);
-    block_fft_split<NX, FWD>(v, j, xb, tw);
-    unpack_pair<NX>(v, j, xb, A, B);
-    if (live) {
-#pragma unroll
-      for (int r = 0; r < 9; ++r) {
-        const int k = j + r * T;
-        if ((r < 8 || j == 0) && k < a.kout) {
-          cplx& ea = *prow_ptr(a.pout, a.pl.rowbase(2 * layer, ya), k);  // same thread wrote these in step 2
-          cplx& eb = *prow_ptr(a.pout, a.pl.rowbase(2 * layer, yb), k);
-          ea = csub(ea, A[r]);
-          eb = csub(eb, B[r]);
-        }
-      }
-    }
-  }
+  // the product modes (ROW_PRODUCT, ROW_PRODUCT_Q) live in k_row_product below
 }
 
 // ------------------------------------------------------------------------------------------------
