@@ -5,10 +5,10 @@
 //   V2 split, one CTA-wide + one warp-local exchange (fft4096_nat2tr / tr2nat)
 //   V3 un-split, one CTA-wide + one warp-local exchange
 // Also checks V2/V3 against V0 element by element.
-// build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -I geophysicalflows.jl_b200/csrc tools/fft_bench.cu -o tools/fft_bench
+// build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a --expt-relaxed-constexpr -I geophysicalflows.jl_b200/csrc -I tools tools/fft_bench.cu -o tools/fft_bench
 #include <cstdio>
 #include <vector>
-#include "fft_core.cuh"
+#include "fft_variants.cuh"
 using namespace gfb;
 
 template <int VAR>
