@@ -95,13 +95,17 @@ function stepforward!(prob::FourierFlows.Problem{<:Any, <:Any, <:B200TimeStepper
     for _ in 1:nsteps; c.t += c.dt; c.step += 1; end
   elseif prevsol !== nothing                       # stochastic: F drawn once per step at t == clock.t
     calcF! = hasproperty(prob.params, :calcF!) ? prob.params.calcF! : prob.params.calcFq!
-    for _ in 1:nsteps
+    for i in 1:nsteps
       dealias!(prob.sol, prob.grid)
       calcF!(Fh, prob.sol, c.t, c, v, prob.params, prob.grid)
+      # the aliased band of the returned state is only needed when somebody can look at it (last step of this call;
+      # the diagnostics variant of stepforward! switches it on whenever a diagnostic is due)
+      ccall((:gfb_set_defer_alias_band, libgfb), Cint, (Ptr{Cvoid}, Cint), ts.ctx, i < nsteps ? 1 : 0)
       check(ccall((:gfb_step, libgfb), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
                   ts.ctx, dptr(prob.sol), 1, dptr(Fh), dptr(prevsol), stream()), ts.ctx)
       c.t += c.dt; c.step += 1
     end
+    ccall((:gfb_set_defer_alias_band, libgfb), Cint, (Ptr{Cvoid}, Cint), ts.ctx, 0)
   else                                             # deterministic forcing: re-evaluated at every stage time
     calcF! = hasproperty(prob.params, :calcF!) ? prob.params.calcF! : prob.params.calcFq!
     nst = ccall((:gfb_nstages, libgfb), Cint, (Ptr{Cvoid},), ts.ctx)

@@ -193,3 +193,19 @@ def test_stochastic_forcing_defers_alias_band_only_when_unobserved(emu, oracle_b
     assert seen[0::2] == [True, False, True, False, True, False]
     assert R.relerr(emu.host(pb.sol), po.sol) < 1e-13          # full state incl. the aliased band
     assert np.allclose(db.data, zo, rtol=1e-12)                # enstrophy reads the raw sol (aliased band included)
+
+
+@pytest.mark.parametrize("nx,ny,stepper", [(4096, 32, "FilteredETDRK4"), (32, 4096, "ETDRK4"), (8192, 32, "RK4"), (32, 8192, "FilteredRK4"),
+                                           (512, 32, "FilteredETDRK4"), (32, 1024, "RK4"), (64, 2048, "FilteredRK4")])
+def test_hot_path_instantiations(emu, oracle_backend, nx, ny, stepper):
+    """The transform lengths of the BASELINE configurations (256-thread groups at 4096, 512-thread CTAs at 8192, several
+    groups per CTA below): persistent K1/K2 loops, TMEM slot mapping and the lazy alias band on elongated grids."""
+    kw = dict(nx=nx, ny=ny, Lx=2 * np.pi, Ly=3.0, nu=1e-4, nnu=1, mu=0.02, nmu=0, dt=1e-3, stepper=stepper)
+    po = oracle_backend.twodnavierstokes.Problem(**kw)
+    pb = emu.twodnavierstokes.Problem(**kw)
+    s0 = np.fft.rfft2(np.random.default_rng(nx + ny).standard_normal((ny, nx))) * 300 / (nx * ny)
+    po.sol[...] = s0
+    pb.sol.copy_(emu.dev(s0))
+    oracle_backend.stepforward_(po, 2)
+    emu.stepforward_(pb, 2)
+    assert R.relerr(emu.host(pb.sol), po.sol) < 1e-13
