@@ -34,6 +34,7 @@ struct gfb_ctx {
   int nkpl = 0;     // column pairs per rank (ldi = 2 * nkpl)
   // tables
   cplx *tw_x = nullptr, *tw_y = nullptr;
+  cplx* tw_x2 = nullptr;  // nx = 16384: W_nx^i for the half-length row scheme (tw_x then holds W_{nx/2}^i)
   double* G = nullptr;
   double *Sinv = nullptr, *S = nullptr;
   double *eta = nullptr, *U = nullptr, *Qx = nullptr, *Qy = nullptr;
@@ -167,6 +168,7 @@ int launch_col_inv(int NY, const ColInvLaunch& L) {
   return -1;
 }
 int launch_row(int NX, const RowLaunch& L) {
+  if (NX == 16384) return launch_row_half_8192(L);
   switch (NX) {
 #define GFB_CASE(N) case N: return launch_row_##N(L);
     GFB_CASE(32) GFB_CASE(64) GFB_CASE(128) GFB_CASE(256) GFB_CASE(512) GFB_CASE(1024) GFB_CASE(2048) GFB_CASE(4096) GFB_CASE(8192)
@@ -263,8 +265,12 @@ int gfb_destroy(gfb_ctx* c) {
 int gfb_create(gfb_ctx** out, const gfb_config* cfg) {
   if (!out || !cfg) return fail(nullptr, GFB_ERR_INVALID, "null argument");
   *out = nullptr;
-  if (!pow2_ok(cfg->nx) || !pow2_ok(cfg->ny))
-    return fail(nullptr, GFB_ERR_UNSUPPORTED, "nx=%d, ny=%d: sizes must be powers of two in [32, 8192]", cfg->nx, cfg->ny);
+  // nx = 16384 runs its rows as 8192-point half-length transforms (single-layer modules, stepping only)
+  const bool half_rows = cfg->nx == 16384;
+  if (!(pow2_ok(cfg->nx) || half_rows) || !pow2_ok(cfg->ny))
+    return fail(nullptr, GFB_ERR_UNSUPPORTED, "nx=%d, ny=%d: sizes must be powers of two, nx in [32, 16384], ny in [32, 8192]", cfg->nx,
+                cfg->ny);
+  if (half_rows && cfg->kind != GFB_KIND_SINGLE) return fail(nullptr, GFB_ERR_UNSUPPORTED, "nx=16384 is available for the single-layer modules only");
   if (cfg->nlayers < 1 || cfg->nlayers > MAX_LAYERS) return fail(nullptr, GFB_ERR_UNSUPPORTED, "nlayers=%d not in [1, %d]", cfg->nlayers, MAX_LAYERS);
   if (cfg->kind == GFB_KIND_SINGLE && cfg->nlayers != 1) return fail(nullptr, GFB_ERR_INVALID, "GFB_KIND_SINGLE needs nlayers == 1");
   if (cfg->kind != GFB_KIND_SINGLE && cfg->kind != GFB_KIND_LAYERED) return fail(nullptr, GFB_ERR_INVALID, "unknown kind %d", cfg->kind);
@@ -316,7 +322,8 @@ int gfb_create(gfb_ctx** out, const gfb_config* cfg) {
       return rc;           \
     }                      \
   } while (0)
-  TRY(make_twiddles(c, &c->tw_x, g.nx));
+  TRY(make_twiddles(c, &c->tw_x, half_rows ? g.nx / 2 : g.nx));
+  if (half_rows) TRY(make_twiddles(c, &c->tw_x2, g.nx));
   TRY(make_twiddles(c, &c->tw_y, g.ny));
   const size_t nspec = (size_t)nl * g.nkl, nphys = (size_t)c->ny_loc * g.nx;
   if (cfg->G) {
@@ -548,6 +555,7 @@ static int run_row_product(gfb_ctx* c, const cplx* Wrecv, const PeerOut& Psend, 
   R.a.ny = c->ny_loc;
   R.nlayers = c->nlayers;
   R.tw = c->tw_x;
+  R.tw2 = c->tw_x2;
   R.st = st;
   ProfScope ps(c, 1, st);
   return check_launch(c, launch_row(c->g.nx, R), "k_row");

@@ -28,6 +28,7 @@ struct RowLaunch {
   RowArgs a;
   int nlayers;         // grid.y
   const cplx* tw;
+  const cplx* tw2;     // W_{nx}^i when the row transforms run at half length (nx = 16384), else unused
   cudaStream_t st;
 };
 
@@ -61,6 +62,8 @@ GFB_DECL_SIZE(2048)
 GFB_DECL_SIZE(4096)
 GFB_DECL_SIZE(8192)
 #undef GFB_DECL_SIZE
+
+int launch_row_half_8192(const RowLaunch& L);  // rows of 16384 points as 8192-point half-length transforms
 
 int launch_col_inv(int NY, const ColInvLaunch& L);
 int launch_row(int NX, const RowLaunch& L);

@@ -127,6 +127,26 @@ int GFB_CAT(launch_row_, GFB_N)(const RowLaunch& L) {
   return -1;
 }
 
+#if GFB_N == 8192
+// nx = 16384: the row pass at half length (k_row_product_half); product mode of the single-layer modules only
+int launch_row_half_8192(const RowLaunch& L) {
+  using RC = GroupCfg<8192>;
+  if (L.mode != ROW_PRODUCT) return -1;
+  const int kcp = (L.a.kc + 1) & ~1;
+  const size_t smem = (size_t)RC::XB_DOUBLES * sizeof(double) + 16 + (size_t)RC::G * kcp * sizeof(cplx);
+  static size_t attr = 0;
+  if (smem > attr) {
+    if (set_smem(k_row_product_half<8192>, smem)) return -2;
+    attr = smem;
+  }
+  const int nunits = L.a.ny * L.nlayers;
+  const int want = (nunits + RC::G - 1) / RC::G, cap = sm_count() * RC::MINB;
+  dim3 grid(want < cap ? want : cap);
+  GFB_LAUNCH((k_row_product_half<8192>), grid, dim3(RC::THREADS), smem, L.st, L.a, L.tw, L.tw2, nunits, kcp);
+  return 0;
+}
+#endif
+
 template <bool TWO>
 static int do_col_fwd(const ColFwdLaunch& L) {
   using GC = GroupCfg<GFB_N>;

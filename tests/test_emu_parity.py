@@ -209,3 +209,41 @@ def test_hot_path_instantiations(emu, oracle_backend, nx, ny, stepper):
     oracle_backend.stepforward_(po, 2)
     emu.stepforward_(pb, 2)
     assert R.relerr(emu.host(pb.sol), po.sol) < 1e-13
+
+
+@pytest.mark.parametrize("module,stepper", [("twodnavierstokes", "FilteredETDRK4"), ("twodnavierstokes", "FilteredAB3"),
+                                            ("surfaceqg", "ETDRK4"), ("singlelayerqg", "FilteredRK4")])
+def test_rows_of_16384_points(emu, oracle_backend, module, stepper):
+    """nx = 16384: every real row is one 8192-point half-length complex transform (k_row_product_half)."""
+    nx, ny = 16384, 32
+    kw = dict(nx=nx, ny=ny, Lx=2 * np.pi, Ly=3.0, dt=1e-3, stepper=stepper)
+    amp = 300.0
+    if module == "twodnavierstokes":
+        kw.update(nu=1e-4, nnu=1, mu=0.02, nmu=0)
+    elif module == "surfaceqg":
+        kw.update(nu=1e-12, nnu=2)
+        amp = 3.0
+    else:
+        eta = 0.1 * np.random.default_rng(3).standard_normal((ny, nx))
+        kw.update(beta=1.5, deformation_radius=1.1, U=0.2, mu=0.01, nu=1e-9, nnu=1, eta=eta)
+    po = getattr(oracle_backend, module).Problem(**kw)
+    pb = getattr(emu, module).Problem(**kw)
+    s0 = np.fft.rfft2(np.random.default_rng(16384).standard_normal((ny, nx))) * amp / (nx * ny)
+    po.sol[...] = s0
+    pb.sol.copy_(emu.dev(s0))
+    oracle_backend.stepforward_(po, 3)
+    emu.stepforward_(pb, 3)
+    assert np.isfinite(po.sol).all()
+    assert R.relerr(emu.host(pb.sol), po.sol) < 1e-13  # incl. the aliased band left by the last step
+
+
+def test_16384_is_limited_to_what_is_built(emu):
+    """Loud, specific failures for what the 16384-point support does not cover yet."""
+    with pytest.raises(emu.pkg.GfbError, match="ny in"):
+        emu.twodnavierstokes.Problem(nx=64, ny=16384, Lx=2 * np.pi, stepper="RK4")
+    with pytest.raises(emu.pkg.GfbError, match="single-layer"):
+        emu.multilayerqg.Problem(2, nx=16384, ny=32, Lx=2 * np.pi, f0=1.0, beta=0.0, H=[0.5, 0.5], b=[-1.0, -1.2], U=[0.0, 0.0],
+                                 stepper="RK4")
+    prob = emu.twodnavierstokes.Problem(nx=16384, ny=32, Lx=2 * np.pi, stepper="RK4")
+    with pytest.raises(emu.pkg.GfbError, match="unsupported"):
+        prob.irfft(prob.sol)
