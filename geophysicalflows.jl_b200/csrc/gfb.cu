@@ -34,7 +34,7 @@ struct gfb_ctx {
   int nkpl = 0;     // column pairs per rank (ldi = 2 * nkpl)
   // tables
   cplx *tw_x = nullptr, *tw_y = nullptr;
-  cplx* tw_x2 = nullptr;  // nx = 16384: W_nx^i for the half-length row scheme (tw_x then holds W_{nx/2}^i)
+  cplx *tw_x2 = nullptr, *tw_y2 = nullptr;  // nx = 16384: W_nx^i for the half-length row scheme (tw_x then holds W_{nx/2}^i); ny = 16384: W_ny^i (tw_y holds W_{ny/4}^i)
   double* G = nullptr;
   double *Sinv = nullptr, *S = nullptr;
   double *eta = nullptr, *U = nullptr, *Qx = nullptr, *Qy = nullptr;
@@ -160,6 +160,7 @@ static int make_twiddles(gfb_ctx* c, cplx** out, int N) {
 
 namespace gfb {
 int launch_col_inv(int NY, const ColInvLaunch& L) {
+  if (NY == 16384) return launch_col_inv_16384(L);
   switch (NY) {
 #define GFB_CASE(N) case N: return launch_col_inv_##N(L);
     GFB_CASE(32) GFB_CASE(64) GFB_CASE(128) GFB_CASE(256) GFB_CASE(512) GFB_CASE(1024) GFB_CASE(2048) GFB_CASE(4096) GFB_CASE(8192)
@@ -177,6 +178,7 @@ int launch_row(int NX, const RowLaunch& L) {
   return -1;
 }
 int launch_col_fwd(int NY, const ColFwdLaunch& L) {
+  if (NY == 16384) return launch_col_fwd_16384(L);
   switch (NY) {
 #define GFB_CASE(N) case N: return launch_col_fwd_##N(L);
     GFB_CASE(32) GFB_CASE(64) GFB_CASE(128) GFB_CASE(256) GFB_CASE(512) GFB_CASE(1024) GFB_CASE(2048) GFB_CASE(4096) GFB_CASE(8192)
@@ -266,11 +268,12 @@ int gfb_create(gfb_ctx** out, const gfb_config* cfg) {
   if (!out || !cfg) return fail(nullptr, GFB_ERR_INVALID, "null argument");
   *out = nullptr;
   // nx = 16384 runs its rows as 8192-point half-length transforms (single-layer modules, stepping only)
-  const bool half_rows = cfg->nx == 16384;
-  if (!(pow2_ok(cfg->nx) || half_rows) || !pow2_ok(cfg->ny))
-    return fail(nullptr, GFB_ERR_UNSUPPORTED, "nx=%d, ny=%d: sizes must be powers of two, nx in [32, 16384], ny in [32, 8192]", cfg->nx,
-                cfg->ny);
-  if (half_rows && cfg->kind != GFB_KIND_SINGLE) return fail(nullptr, GFB_ERR_UNSUPPORTED, "nx=16384 is available for the single-layer modules only");
+  // 16384-point lines: rows as 8192-point half-length transforms, columns as 4 x 4096 (single-layer modules, stepping only)
+  const bool half_rows = cfg->nx == 16384, quad_cols = cfg->ny == 16384;
+  if (!(pow2_ok(cfg->nx) || half_rows) || !(pow2_ok(cfg->ny) || quad_cols))
+    return fail(nullptr, GFB_ERR_UNSUPPORTED, "nx=%d, ny=%d: sizes must be powers of two in [32, 16384]", cfg->nx, cfg->ny);
+  if ((half_rows || quad_cols) && cfg->kind != GFB_KIND_SINGLE)
+    return fail(nullptr, GFB_ERR_UNSUPPORTED, "16384-point lines are available for the single-layer modules only");
   if (cfg->nlayers < 1 || cfg->nlayers > MAX_LAYERS) return fail(nullptr, GFB_ERR_UNSUPPORTED, "nlayers=%d not in [1, %d]", cfg->nlayers, MAX_LAYERS);
   if (cfg->kind == GFB_KIND_SINGLE && cfg->nlayers != 1) return fail(nullptr, GFB_ERR_INVALID, "GFB_KIND_SINGLE needs nlayers == 1");
   if (cfg->kind != GFB_KIND_SINGLE && cfg->kind != GFB_KIND_LAYERED) return fail(nullptr, GFB_ERR_INVALID, "unknown kind %d", cfg->kind);
@@ -324,7 +327,8 @@ int gfb_create(gfb_ctx** out, const gfb_config* cfg) {
   } while (0)
   TRY(make_twiddles(c, &c->tw_x, half_rows ? g.nx / 2 : g.nx));
   if (half_rows) TRY(make_twiddles(c, &c->tw_x2, g.nx));
-  TRY(make_twiddles(c, &c->tw_y, g.ny));
+  TRY(make_twiddles(c, &c->tw_y, quad_cols ? g.ny / 4 : g.ny));
+  if (quad_cols) TRY(make_twiddles(c, &c->tw_y2, g.ny));
   const size_t nspec = (size_t)nl * g.nkl, nphys = (size_t)c->ny_loc * g.nx;
   if (cfg->G) {
     void* gp = nullptr;
@@ -511,6 +515,7 @@ static int run_col_inv_state(gfb_ctx* c, const Spec& sin, int nf, const PeerOut&
   L.wfs = 8LL * c->ldi;
   L.ncols = local_cols_below(c, c->g.kcut);
   L.tw = c->tw_y;
+  L.tw2 = c->tw_y2;
   L.st = st;
   L.nl = c->nlayers;
   if (L.ncols == 0) return 0;
@@ -574,6 +579,7 @@ static int run_col_fwd(gfb_ctx* c, const EpiArgs& e, const cplx* Precv, cudaStre
   F.nl = c->nlayers;
   F.two = true;
   F.tw = c->tw_y;
+  F.tw2 = c->tw_y2;
   F.st = st;
   if (F.ncols == 0) return 0;
   ProfScope ps(c, 2, st);

@@ -20,6 +20,7 @@ struct ColInvLaunch {
   int ncols;
   int nfields;         // grid.y
   const cplx* tw;
+  const cplx* tw2;     // W_{ny}^i when the columns are cut 4 x (ny/4) (ny = 16384), else unused
   cudaStream_t st;
 };
 
@@ -43,6 +44,7 @@ struct ColFwdLaunch {
   int nl;              // template NL (layers coupled in the epilogue)
   bool two;
   const cplx* tw;
+  const cplx* tw2;     // as in ColInvLaunch
   cudaStream_t st;
 };
 
@@ -63,7 +65,9 @@ GFB_DECL_SIZE(4096)
 GFB_DECL_SIZE(8192)
 #undef GFB_DECL_SIZE
 
-int launch_row_half_8192(const RowLaunch& L);  // rows of 16384 points as 8192-point half-length transforms
+int launch_row_half_8192(const RowLaunch& L);
+int launch_col_inv_16384(const ColInvLaunch& L);  // columns of 16384 points as 4 x 4096 (radix-4 DIF while loading)
+int launch_col_fwd_16384(const ColFwdLaunch& L);  // rows of 16384 points as 8192-point half-length transforms
 
 int launch_col_inv(int NY, const ColInvLaunch& L);
 int launch_row(int NX, const RowLaunch& L);

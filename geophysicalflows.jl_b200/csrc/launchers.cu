@@ -127,6 +127,38 @@ int GFB_CAT(launch_row_, GFB_N)(const RowLaunch& L) {
   return -1;
 }
 
+#if GFB_N == 4096
+// ny = 16384: column passes as 4 x 4096 (k_col_inv16k / k_col_fwd16k); stepping of the single-layer modules only
+int launch_col_inv_16384(const ColInvLaunch& L) {
+  using GC = GroupCfg<4096>;
+  if (L.prep != PREP_SINGLE) return -1;
+  const size_t smem = (size_t)GC::XB_DOUBLES * sizeof(double) + (size_t)GC::STASH * sizeof(cplx);
+  static bool attr = false;
+  if (!attr) {
+    if (set_smem(k_col_inv16k<4096>, smem)) return -2;
+    attr = true;
+  }
+  const int npairs = (L.ncols + 1) / 2;
+  dim3 grid(npairs * L.nfields * 4);
+  GFB_LAUNCH((k_col_inv16k<4096>), grid, dim3(GC::THREADS), smem, L.st, L.g, L.ps, L.W, L.ldw, L.wfs, L.ncols, L.nfields, L.tw, L.tw2);
+  return 0;
+}
+
+int launch_col_fwd_16384(const ColFwdLaunch& L) {
+  using GC = GroupCfg<4096>;
+  if (!L.two) return -1;
+  const size_t smem = (size_t)GC::XB_DOUBLES * sizeof(double) + (size_t)GC::STASH * sizeof(cplx) + 16;
+  static bool attr = false;
+  if (!attr) {
+    if (set_smem(k_col_fwd16k<4096>, smem)) return -2;
+    attr = true;
+  }
+  dim3 grid(((L.ncols + 1) / 2) * 4, L.nlayers);
+  GFB_LAUNCH((k_col_fwd16k<4096>), grid, dim3(GC::THREADS), smem, L.st, L.g, L.P, L.ldp, L.pfs, L.e, L.ncols, L.tw, L.tw2);
+  return 0;
+}
+#endif
+
 #if GFB_N == 8192
 // nx = 16384: the row pass at half length (k_row_product_half); product mode of the single-layer modules only
 int launch_row_half_8192(const RowLaunch& L) {

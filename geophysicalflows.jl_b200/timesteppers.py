@@ -31,17 +31,24 @@ def makefilter(grid, order=4, innerK=2 / 3, outerK=1, tol=1e-15):
 
 
 def getetdcoeffs(dt, L, ncirc=32, rcirc=1):
-    """ETDRK4 coefficients by the 32-point contour mean (Kassam & Trefethen)."""
+    """ETDRK4 coefficients by the 32-point contour mean (Kassam & Trefethen).  Evaluated in slabs along the first axis so
+    that the (.., 32) work array of a 16384^2 grid stays at a few hundred MB instead of 70 GB."""
     pts = rcirc * np.exp(2j * np.pi * (np.arange(ncirc) + 0.5) / ncirc)
-    z = dt * L[..., None] + pts
-    ez, ezh = np.exp(z), np.exp(z / 2)
-    out = [dt * np.mean((ezh - 1) / z, axis=-1),
-           dt * np.mean((-4 - z + ez * (4 - 3 * z + z**2)) / z**3, axis=-1),
-           dt * np.mean((2 + z + ez * (z - 2)) / z**3, axis=-1),
-           dt * np.mean((-4 - 3 * z - z**2 + ez * (4 - z)) / z**3, axis=-1)]
-    if not np.iscomplexobj(L):
-        out = [o.real for o in out]
-    return out
+    L = np.asarray(L)
+    real = not np.iscomplexobj(L)
+    flat = L.reshape(-1, L.shape[-1]) if L.ndim > 1 else L.reshape(1, -1)
+    out = [np.empty(flat.shape, dtype=np.float64 if real else np.complex128) for _ in range(4)]
+    rows = max(1, (1 << 22) // max(1, flat.shape[1]))
+    for i in range(0, flat.shape[0], rows):
+        z = dt * flat[i:i + rows, :, None] + pts
+        ez, ezh = np.exp(z), np.exp(z / 2)
+        vals = (dt * np.mean((ezh - 1) / z, axis=-1),
+                dt * np.mean((-4 - z + ez * (4 - 3 * z + z**2)) / z**3, axis=-1),
+                dt * np.mean((2 + z + ez * (z - 2)) / z**3, axis=-1),
+                dt * np.mean((-4 - 3 * z - z**2 + ez * (4 - z)) / z**3, axis=-1))
+        for o, val in zip(out, vals):
+            o[i:i + rows] = val.real if real else val
+    return [o.reshape(L.shape) for o in out]
 
 
 class TimeStepper:

@@ -77,6 +77,8 @@ CASES = {
                                                  dt=1e-3, stepper="RK4"), 3, 0),
     "twodns_16384_rows": ("twodnavierstokes", dict(nx=16384, ny=32, Lx=2 * np.pi, Ly=3.0, nu=1e-4, nnu=1, mu=0.01, nmu=0,
                                                    dt=1e-3, stepper="ETDRK4"), 2, 0),
+    "twodns_16384_cols": ("twodnavierstokes", dict(nx=32, ny=16384, Lx=2 * np.pi, Ly=3.0, nu=1e-4, nnu=1, mu=0.01, nmu=0,
+                                                   dt=1e-3, stepper="FilteredRK4"), 2, 0),
     "mqg3_frk4": ("multilayerqg", dict(nx=32, ny=64, Lx=2 * np.pi, f0=1.0, beta=0.5, mu=0.05, nu=1e-4,
                                         H=[0.25, 0.25, 0.5], b=[-1.0, -1.2, -1.4], U=[0.3, 0.1, 0.0], dt=2e-3,
                                         stepper="FilteredRK4"), 3, 3),
