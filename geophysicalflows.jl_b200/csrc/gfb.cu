@@ -1034,6 +1034,7 @@ int gfb_irfft(gfb_ctx* c, double* out_phys, const void* in_spec, int batch, void
     L.ncols = c->g.nkr;
     L.nfields = nb;
     L.tw = c->tw_y;
+    L.tw2 = c->tw_y2;
     L.st = st;
     L.nl = 1;
     int rc = check_launch(c, launch_col_inv(c->g.ny, L), "k_col_inv(plain)");
@@ -1050,6 +1051,7 @@ int gfb_irfft(gfb_ctx* c, double* out_phys, const void* in_spec, int batch, void
     R.a.ny = c->g.ny;
     R.nlayers = nb;
     R.tw = c->tw_x;
+    R.tw2 = c->tw_x2;
     R.st = st;
     rc = check_launch(c, launch_row(c->g.nx, R), "k_row(c2r)");
     if (rc) return rc;
@@ -1074,6 +1076,7 @@ int gfb_rfft(gfb_ctx* c, void* out_spec, const double* in_phys, int batch, void*
     R.a.ny = c->g.ny;
     R.nlayers = nb;
     R.tw = c->tw_x;
+    R.tw2 = c->tw_x2;
     R.st = st;
     int rc = check_launch(c, launch_row(c->g.nx, R), "k_row(r2c)");
     if (rc) return rc;
@@ -1092,6 +1095,7 @@ int gfb_rfft(gfb_ctx* c, void* out_spec, const double* in_phys, int batch, void*
     F.nl = 1;
     F.two = false;
     F.tw = c->tw_y;
+    F.tw2 = c->tw_y2;
     F.st = st;
     rc = check_launch(c, launch_col_fwd(c->g.ny, F), "k_col_fwd(plain)");
     if (rc) return rc;
@@ -1124,6 +1128,7 @@ int gfb_updatevars(gfb_ctx* c, void* sol, double* q, double* psi, double* u, dou
     R.a.ny = c->g.ny;
     R.nlayers = c->nlayers;
     R.tw = c->tw_x;
+    R.tw2 = c->tw_x2;
     R.st = st;
     rc = check_launch(c, launch_row(c->g.nx, R), "k_row(c2r,updatevars)");
     if (rc) return rc;

@@ -1365,10 +1365,10 @@ __device__ __forceinline__ cplx dif4(const cplx x0, const cplx x1, const cplx x2
   return q == 1 ? cadd(o, h) : csub(o, h);
 }
 
-// K1 for ny = 4*NS, single-layer modules: unit = (column pair, field, q)
-template <int NS>
+// K1 for ny = 4*NS (single-layer pre-pass or plain inverse transform): unit = (column pair, field, q)
+template <int NS, class Prep>
 __global__ void __launch_bounds__(GroupCfg<NS>::THREADS, GroupCfg<NS>::MINB)
-    k_col_inv16k(const GridDesc g, const PrepSingle prep, const __grid_constant__ PeerOut W, const int ldw, const long long wfs,
+    k_col_inv16k(const GridDesc g, const Prep prep, const __grid_constant__ PeerOut W, const int ldw, const long long wfs,
                  const int ncols, const int nfields, const cplx* __restrict__ tw, const cplx* __restrict__ tw2) {
   using GC = GroupCfg<NS>;
   constexpr int T = GC::T, THREADS = GC::THREADS;
@@ -1495,6 +1495,81 @@ __global__ void __launch_bounds__(GroupCfg<NS>::THREADS, GroupCfg<NS>::MINB)
   if (e.cplxL) epilogue_dispatch<NS, true, 4 * T>(g, e, layer, colA, liveA, X, tA, l0, tid);
   else epilogue_dispatch<NS, false, 4 * T>(g, e, layer, colA, liveA, X, tA, l0, tid);
   tmem_release(tbase, TmemCfg<NS>::COLS);
+}
+
+// plain forward transform of one tiled field along 4*NS-point columns -> dense user array (the mul! seam at ny = 16384)
+template <int NS>
+__global__ void __launch_bounds__(GroupCfg<NS>::THREADS, GroupCfg<NS>::MINB)
+    k_col_fwd16k_plain(const GridDesc g, const cplx* __restrict__ P, const int ldp, const long long pfs, cplx* __restrict__ out,
+                       const int ldo, const long long los, const int ncols, const cplx* __restrict__ tw, const cplx* __restrict__ tw2) {
+  using GC = GroupCfg<NS>;
+  constexpr int T = GC::T, THREADS = GC::THREADS;
+  GFB_DYN_SMEM(double, smd);
+  const int tid = threadIdx.x, j = tid;
+  const int q = blockIdx.x & 3, colA = 2 * (blockIdx.x >> 2);
+  const int field = blockIdx.y;
+  const bool liveA = colA < ncols;
+  double* xb = smd;
+  cplx* X = reinterpret_cast<cplx*>(smd + GC::XB_DOUBLES);
+  cplx v[PT];
+  k3_load16k<NS>(v, X, P + field * pfs, ldp, colA, liveA, q, j, tid, tw2);
+#pragma unroll 1
+  for (int c = 0; c < 2; ++c) {
+    block_fft_split<NS, FWD>(v, j, xb, tw);
+    if (c == 0) swap_stash(v, X, tid, THREADS);
+  }
+  if (liveA) {
+#pragma unroll
+    for (int r = 0; r < PT; ++r) {
+      const int l = 4 * (j + r * T) + q;
+      cplx* o = out + field * los + (long long)l * ldo + colA;
+      o[0] = X[r * THREADS + tid];
+      if (colA + 1 < g.nkl) o[1] = v[r];
+    }
+  }
+}
+
+// plain real transforms of rows of 2*NH points at half length (the ldiv! / mul! seams at nx = 16384); one row per CTA
+// group; MODE = ROW_C2R or ROW_R2C, arguments as for k_row
+template <int NH, int MODE>
+__global__ void __launch_bounds__(GroupCfg<NH>::THREADS, GroupCfg<NH>::MINB)
+    k_row_half(const __grid_constant__ RowArgs a, const cplx* __restrict__ tw, const cplx* __restrict__ tw2, const int kcp) {
+  using RC = GroupCfg<NH>;
+  constexpr int T = RC::T;
+  static_assert(RC::G == 1, "one group per CTA");
+  GFB_DYN_SMEM(double, smd);
+  const int j = threadIdx.x;
+  const int y = blockIdx.x, layer = blockIdx.y;
+  double* xb = smd;
+  cplx v[PT];
+  if (MODE == ROW_C2R) {
+    cplx* lb = reinterpret_cast<cplx*>(smd + RC::XB_DOUBLES);
+    row_prefetch1<T>(lb, a.W, a.wl, a.wstride * layer + a.fsel, y, a.kc, j);
+    cp_async_wait_all();
+    __syncthreads();
+    assemble_half<NH>(v, j, lb, a.kc, tw2);
+    block_fft_split<NH, INV>(v, j, xb, tw);
+    double* o = a.phys + ((long long)layer * a.ny + y) * (2 * NH);
+#pragma unroll
+    for (int r = 0; r < PT; ++r) *reinterpret_cast<double2*>(o + 2 * (j + r * T)) = v[r];
+    return;
+  }
+  const double* in = a.phys + ((long long)layer * a.ny + y) * (2 * NH);
+#pragma unroll
+  for (int r = 0; r < PT; ++r) v[r] = *reinterpret_cast<const double2*>(in + 2 * (j + r * T));
+  block_fft_split<NH, FWD>(v, j, xb, tw);
+  cplx A[9], B[9];
+  unpack_pair<NH>(v, j, xb, A, B);
+  const long long rb = a.pl.rowbase(layer, y);
+#pragma unroll
+  for (int r = 0; r < 9; ++r) {
+    const int k = j + r * T, km = NH - k;
+    if (r < 8 || j == 0) {
+      const cplx t = cmul(__ldg(&tw2[k]), B[r]);
+      if (k < a.kout) *prow_ptr(a.pout, rb, k) = cadd(A[r], t);
+      if (km != k && km < a.kout) *prow_ptr(a.pout, rb, km) = cconj(csub(A[r], t));
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -129,31 +129,50 @@ int GFB_CAT(launch_row_, GFB_N)(const RowLaunch& L) {
 
 #if GFB_N == 4096
 // ny = 16384: column passes as 4 x 4096 (k_col_inv16k / k_col_fwd16k); stepping of the single-layer modules only
-int launch_col_inv_16384(const ColInvLaunch& L) {
+template <class Prep>
+static int do_col_inv_16384(const ColInvLaunch& L, const Prep& prep) {
   using GC = GroupCfg<4096>;
-  if (L.prep != PREP_SINGLE) return -1;
   const size_t smem = (size_t)GC::XB_DOUBLES * sizeof(double) + (size_t)GC::STASH * sizeof(cplx);
   static bool attr = false;
   if (!attr) {
-    if (set_smem(k_col_inv16k<4096>, smem)) return -2;
+    if (set_smem(k_col_inv16k<4096, Prep>, smem)) return -2;
     attr = true;
   }
   const int npairs = (L.ncols + 1) / 2;
   dim3 grid(npairs * L.nfields * 4);
-  GFB_LAUNCH((k_col_inv16k<4096>), grid, dim3(GC::THREADS), smem, L.st, L.g, L.ps, L.W, L.ldw, L.wfs, L.ncols, L.nfields, L.tw, L.tw2);
+  GFB_LAUNCH((k_col_inv16k<4096, Prep>), grid, dim3(GC::THREADS), smem, L.st, L.g, prep, L.W, L.ldw, L.wfs, L.ncols, L.nfields, L.tw,
+             L.tw2);
   return 0;
+}
+
+int launch_col_inv_16384(const ColInvLaunch& L) {
+  switch (L.prep) {
+    case PREP_PLAIN: return do_col_inv_16384(L, L.pp);
+    case PREP_SINGLE: return do_col_inv_16384(L, L.ps);
+  }
+  return -1;  // MultiLayerQG: not at 16384 points per column
 }
 
 int launch_col_fwd_16384(const ColFwdLaunch& L) {
   using GC = GroupCfg<4096>;
-  if (!L.two) return -1;
-  const size_t smem = (size_t)GC::XB_DOUBLES * sizeof(double) + (size_t)GC::STASH * sizeof(cplx) + 16;
-  static bool attr = false;
-  if (!attr) {
-    if (set_smem(k_col_fwd16k<4096>, smem)) return -2;
-    attr = true;
+  const dim3 grid(((L.ncols + 1) / 2) * 4, L.nlayers);
+  if (!L.two) {  // plain forward transform -> dense user array
+    const size_t smem = (size_t)GC::XB_DOUBLES * sizeof(double) + (size_t)GC::STASH * sizeof(cplx);
+    static bool attr = false;
+    if (!attr) {
+      if (set_smem(k_col_fwd16k_plain<4096>, smem)) return -2;
+      attr = true;
+    }
+    GFB_LAUNCH((k_col_fwd16k_plain<4096>), grid, dim3(GC::THREADS), smem, L.st, L.g, L.P, L.ldp, L.pfs, L.e.out.p, L.e.out.ld, L.e.out.ls,
+               L.ncols, L.tw, L.tw2);
+    return 0;
   }
-  dim3 grid(((L.ncols + 1) / 2) * 4, L.nlayers);
+  const size_t smem = (size_t)GC::XB_DOUBLES * sizeof(double) + (size_t)GC::STASH * sizeof(cplx) + 16;
+  static bool attr2 = false;
+  if (!attr2) {
+    if (set_smem(k_col_fwd16k<4096>, smem)) return -2;
+    attr2 = true;
+  }
   GFB_LAUNCH((k_col_fwd16k<4096>), grid, dim3(GC::THREADS), smem, L.st, L.g, L.P, L.ldp, L.pfs, L.e, L.ncols, L.tw, L.tw2);
   return 0;
 }
@@ -161,9 +180,25 @@ int launch_col_fwd_16384(const ColFwdLaunch& L) {
 
 #if GFB_N == 8192
 // nx = 16384: the row pass at half length (k_row_product_half); product mode of the single-layer modules only
+template <int MODE>
+static int do_row_half_plain(const RowLaunch& L) {
+  using RC = GroupCfg<8192>;
+  const int kcp = (L.a.kc + 1) & ~1;
+  const size_t smem = (size_t)RC::XB_DOUBLES * sizeof(double) + (MODE == ROW_C2R ? (size_t)kcp * sizeof(cplx) : 0);
+  static size_t attr = 0;
+  if (smem > attr) {
+    if (set_smem(k_row_half<8192, MODE>, smem)) return -2;
+    attr = smem;
+  }
+  GFB_LAUNCH((k_row_half<8192, MODE>), dim3(L.a.ny, L.nlayers), dim3(RC::THREADS), smem, L.st, L.a, L.tw, L.tw2, kcp);
+  return 0;
+}
+
 int launch_row_half_8192(const RowLaunch& L) {
   using RC = GroupCfg<8192>;
-  if (L.mode != ROW_PRODUCT) return -1;
+  if (L.mode == ROW_C2R) return do_row_half_plain<ROW_C2R>(L);
+  if (L.mode == ROW_R2C) return do_row_half_plain<ROW_R2C>(L);
+  if (L.mode != ROW_PRODUCT) return -1;  // MultiLayerQG: not at 16384 points per row
   const int kcp = (L.a.kc + 1) & ~1;
   const size_t smem = (size_t)RC::XB_DOUBLES * sizeof(double) + 16 + (size_t)RC::G * kcp * sizeof(cplx);
   static size_t attr = 0;

@@ -261,6 +261,24 @@ def test_16384_is_limited_to_what_is_built(emu):
     with pytest.raises(emu.pkg.GfbError, match="single-layer"):
         emu.multilayerqg.Problem(2, nx=16384, ny=32, Lx=2 * np.pi, f0=1.0, beta=0.0, H=[0.5, 0.5], b=[-1.0, -1.2], U=[0.0, 0.0],
                                  stepper="RK4")
-    prob = emu.twodnavierstokes.Problem(nx=16384, ny=32, Lx=2 * np.pi, stepper="RK4")
-    with pytest.raises(emu.pkg.GfbError, match="unsupported"):
-        prob.irfft(prob.sol)
+
+
+@pytest.mark.parametrize("nx,ny", [(16384, 32), (32, 16384)])
+def test_plain_transforms_and_updatevars_16384(emu, oracle_backend, nx, ny):
+    """mul! / ldiv! seams, set_zeta! and updatevars! with 16384 points along x or y."""
+    prob = emu.twodnavierstokes.Problem(nx=nx, ny=ny, Lx=2 * np.pi, Ly=3.0, stepper="ForwardEuler")
+    rng = np.random.default_rng(nx + ny)
+    a = rng.standard_normal((2, ny, nx))
+    ah = prob.rfft(emu.dev(a))
+    assert R.relerr(emu.host(ah), np.fft.rfft2(a)) < 1e-14
+    assert R.relerr(emu.host(prob.irfft(ah)), a) < 1e-14
+    bh = np.fft.rfft2(a)
+    bh[:, :, 0] += 1j * rng.standard_normal((2, ny))
+    bh[:, :, -1] += 1j * rng.standard_normal((2, ny))
+    assert R.relerr(emu.host(prob.irfft(emu.dev(bh))), np.fft.irfft2(bh, s=(ny, nx))) < 1e-14
+    po = oracle_backend.twodnavierstokes.Problem(nx=nx, ny=ny, Lx=2 * np.pi, Ly=3.0, stepper="ForwardEuler")
+    z0 = rng.standard_normal((ny, nx))
+    emu.twodnavierstokes.set_zeta_(prob, emu.dev(z0))
+    oracle_backend.twodnavierstokes.set_zeta_(po, z0)
+    for f in ("zeta", "u", "v"):
+        assert R.relerr(emu.host(getattr(prob.vars, f)), getattr(po.vars, f)) < 1e-13

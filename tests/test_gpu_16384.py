@@ -32,3 +32,12 @@ def test_16384_lines_vs_oracle(gpu, oracle_backend, nx, ny):
     assert R.relerr(gpu.host(pg.sol), po.sol) < 1e-10
     O, M = oracle_backend.twodnavierstokes, gpu.twodnavierstokes
     assert abs(M.enstrophy(pg) / O.enstrophy(po) - 1) < 1e-10
+
+
+@pytest.mark.parametrize("nx,ny", [(16384, 64), (64, 16384)])
+def test_16384_plain_transforms(gpu, nx, ny):
+    prob = gpu.twodnavierstokes.Problem(nx=nx, ny=ny, Lx=2 * np.pi, Ly=3.0, stepper="ForwardEuler")
+    a = np.random.default_rng(nx + ny).standard_normal((2, ny, nx))
+    ah = prob.rfft(gpu.dev(a))
+    assert R.relerr(gpu.host(ah), np.fft.rfft2(a)) < 1e-14
+    assert R.relerr(gpu.host(prob.irfft(ah)), a) < 1e-14
