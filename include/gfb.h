@@ -45,7 +45,7 @@ enum gfb_status {
   GFB_ERR_INVALID = -1,     /* bad argument / unsupported configuration */
   GFB_ERR_CUDA = -2,        /* CUDA runtime error (message has the CUDA string) */
   GFB_ERR_ALLOC = -3,
-  GFB_ERR_UNSUPPORTED = -4  /* e.g. grid size that is not a power of two in [16, 8192] */
+  GFB_ERR_UNSUPPORTED = -4  /* e.g. grid size that is not a power of two in [32, 16384] */
 };
 
 /* which calcN! family */
@@ -69,7 +69,7 @@ enum gfb_stepper {
 /* All pointers in the config are HOST pointers, read (copied to the device) during gfb_create. */
 typedef struct gfb_config {
   int kind;               /* gfb_kind */
-  int nx, ny, nlayers;    /* nx, ny powers of two in [32, 8192] */
+  int nx, ny, nlayers;    /* nx, ny powers of two in [32, 16384]; 16384: GFB_KIND_SINGLE only */
   double Lx, Ly;
   /* dealias! index ranges, 0-based half-open ([FF] getaliasedwavenumbers): columns [kr_alias0, nkr) and
    * rows [l_alias0, l_alias1) are zeroed.  kr_alias0 = nkr and l_alias0 = l_alias1 disables. */
