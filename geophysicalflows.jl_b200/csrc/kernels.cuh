@@ -1,11 +1,18 @@
 // kernels.cuh -- the three fused passes of one calcN! + stage update, and the plain 2-D transforms.
 //
-//   K1  k_col_inv   : spectral pre-pass (dealias mask on load, psi inversion / S^-1 matvec, i*k
-//                     derivatives, 1/(nx*ny)) fused with the inverse FFT along y (columns)
-//   K2  k_row       : Hermitian c2r along x of (u, v) and q, physical products, r2c along x --
-//                     physical fields never touch HBM
-//   K3  k_col_fwd   : forward FFT along y of the two product fields fused with the divergence
-//                     (-i kr, -i l), forcing and the time-stepper stage update
+//   K1  spectral pre-pass (dealias mask on load, psi inversion / S^-1 matvec, i*k derivatives, 1/(nx*ny)) fused
+//       with the inverse FFT along y (columns)
+//         k_col_inv_single   single-layer modules, the hot path: persistent, rolling cp.async prefetch, TMEM stash
+//         k_col_inv          MultiLayerQG pre-pass and plain inverse transforms
+//         k_col_inv16k       ny = 16384: 4 x 4096 by a radix-4 DIF step while loading
+//   K2  Hermitian c2r along x of (u, v) and q, physical products, r2c along x -- physical fields never touch HBM
+//         k_row_product      the hot path: persistent, line-buffer prefetch of the next phase, q parked in TMEM
+//         k_row              plain c2r / r2c (ldiv! / mul! seams, updatevars!)
+//         k_row_product_half / k_row_half   nx = 16384: every real row as one 8192-point half-length transform
+//   K3  forward FFT along y of the two product fields fused with the divergence (-i kr, -i l), forcing and the
+//       time-stepper stage update
+//         k_col_fwd          one transform call site over the four columns, TMEM-parked partners, fused epilogue
+//         k_col_fwd16k (+ _plain)   ny = 16384
 //
 // Reference sequence being replaced: calcN_advection! /root/reference/src/twodnavierstokes.jl:253-275,
 // src/surfaceqg.jl:257-278, src/singlelayerqg.jl:356-432, src/multilayerqg.jl:695-731; dealias!
