@@ -1013,25 +1013,31 @@ int gfb_stage_post(gfb_ctx* c, int istage, const void* precv, const void* Fh_loc
   return GFB_OK;
 }
 
+// Sharded context (p2p transport connected): in_spec is the LOCAL dense [batch][nl][nkl] slice, out_phys the LOCAL rows
+// [batch][ny_loc][nx]; K1's stores are the exchange, a flag barrier before K2 and one after it (the receive buffer is
+// shared with the stepping passes).
 int gfb_irfft(gfb_ctx* c, double* out_phys, const void* in_spec, int batch, void* stream) {
   if (!c || !out_phys || !in_spec || batch < 1) return fail(c, GFB_ERR_INVALID, "gfb_irfft: bad argument");
-  NEED_SINGLE_GPU(c, "gfb_irfft");
+  const bool sharded = c->g.nranks != 1;
+  if (sharded && !c->connected)
+    return fail(c, GFB_ERR_UNSUPPORTED, "gfb_irfft on a sharded context needs the p2p transport (gfb_comm_create / gfb_comm_connect)");
   cudaStream_t st = (cudaStream_t)stream;
-  const int maxb = 4 * c->nlayers;
+  const int maxb = (sharded ? 3 : 4) * c->nlayers;
+  const long long spec_ls = (long long)c->g.ny * c->g.nkl, phys_ls = (long long)c->ny_loc * c->g.nx;
   for (int b0 = 0; b0 < batch; b0 += maxb) {
     const int nb = (batch - b0 < maxb) ? batch - b0 : maxb;
     ColInvLaunch L;
     std::memset(&L, 0, sizeof L);
     L.g = c->g;
     L.prep = PREP_PLAIN;
-    L.pp.in = (const cplx*)in_spec + (long long)b0 * c->g.ny * c->g.nkr;
-    L.pp.ld = c->g.nkr;
-    L.pp.ls = (long long)c->g.ny * c->g.nkr;
+    L.pp.in = (const cplx*)in_spec + (long long)b0 * spec_ls;
+    L.pp.ld = c->g.nkl;
+    L.pp.ls = spec_ls;
     L.pp.scale = c->g.invN;
-    L.W = out_local(c->W);
+    L.W = sharded ? out_peers(c, c->comm_w_off, nb) : out_local(c->W);
     L.ldw = nb * c->ldi;
     L.wfs = 8LL * c->ldi;
-    L.ncols = c->g.nkr;
+    L.ncols = c->g.nkl;
     L.nfields = nb;
     L.tw = c->tw_y;
     L.tw2 = c->tw_y2;
@@ -1039,58 +1045,65 @@ int gfb_irfft(gfb_ctx* c, double* out_phys, const void* in_spec, int batch, void
     L.nl = 1;
     int rc = check_launch(c, launch_col_inv(c->g.ny, L), "k_col_inv(plain)");
     if (rc) return rc;
+    if (sharded && (rc = peer_barrier(c, st))) return rc;
     RowLaunch R;
     std::memset(&R, 0, sizeof R);
     R.mode = ROW_C2R;
-    R.a.W = c->W;
+    R.a.W = sharded ? reinterpret_cast<const cplx*>(c->comm + c->comm_w_off) : c->W;
     R.a.wl = row_layout(c, nb);
     R.a.wstride = 1;
     R.a.fsel = 0;
     R.a.kc = c->g.nkr;
-    R.a.phys = out_phys + (long long)b0 * c->g.ny * c->g.nx;
-    R.a.ny = c->g.ny;
+    R.a.phys = out_phys + (long long)b0 * phys_ls;
+    R.a.ny = c->ny_loc;
     R.nlayers = nb;
     R.tw = c->tw_x;
     R.tw2 = c->tw_x2;
     R.st = st;
     rc = check_launch(c, launch_row(c->g.nx, R), "k_row(c2r)");
     if (rc) return rc;
+    if (sharded && (rc = peer_barrier(c, st))) return rc;
   }
   return GFB_OK;
 }
 
+// Sharded context: in_phys is the LOCAL rows [batch][ny_loc][nx], out_spec the LOCAL dense [batch][nl][nkl] slice.
 int gfb_rfft(gfb_ctx* c, void* out_spec, const double* in_phys, int batch, void* stream) {
   if (!c || !out_spec || !in_phys || batch < 1) return fail(c, GFB_ERR_INVALID, "gfb_rfft: bad argument");
-  NEED_SINGLE_GPU(c, "gfb_rfft");
+  const bool sharded = c->g.nranks != 1;
+  if (sharded && !c->connected)
+    return fail(c, GFB_ERR_UNSUPPORTED, "gfb_rfft on a sharded context needs the p2p transport (gfb_comm_create / gfb_comm_connect)");
   cudaStream_t st = (cudaStream_t)stream;
   const int maxb = 2 * c->nlayers;
+  const long long spec_ls = (long long)c->g.ny * c->g.nkl, phys_ls = (long long)c->ny_loc * c->g.nx;
   for (int b0 = 0; b0 < batch; b0 += maxb) {
     const int nb = (batch - b0 < maxb) ? batch - b0 : maxb;
     RowLaunch R;
     std::memset(&R, 0, sizeof R);
     R.mode = ROW_R2C;
-    R.a.pout = out_local(c->P);
+    R.a.pout = sharded ? out_peers(c, c->comm_p_off, nb) : out_local(c->P);
     R.a.pl = row_layout(c, nb);
     R.a.kout = c->g.nkr;
-    R.a.phys = const_cast<double*>(in_phys) + (long long)b0 * c->g.ny * c->g.nx;
-    R.a.ny = c->g.ny;
+    R.a.phys = const_cast<double*>(in_phys) + (long long)b0 * phys_ls;
+    R.a.ny = c->ny_loc;
     R.nlayers = nb;
     R.tw = c->tw_x;
     R.tw2 = c->tw_x2;
     R.st = st;
     int rc = check_launch(c, launch_row(c->g.nx, R), "k_row(r2c)");
     if (rc) return rc;
+    if (sharded && (rc = peer_barrier(c, st))) return rc;
     ColFwdLaunch F;
     std::memset(&F, 0, sizeof F);
     F.g = c->g;
-    F.P = c->P;
+    F.P = sharded ? reinterpret_cast<const cplx*>(c->comm + c->comm_p_off) : c->P;
     F.ldp = nb * c->ldi;
     F.pfs = 8LL * c->ldi;
     F.e.kind = EPI_PLAIN;
-    F.e.out.p = (cplx*)out_spec + (long long)b0 * c->g.ny * c->g.nkr;
-    F.e.out.ld = c->g.nkr;
-    F.e.out.ls = (long long)c->g.ny * c->g.nkr;
-    F.ncols = c->g.nkr;
+    F.e.out.p = (cplx*)out_spec + (long long)b0 * spec_ls;
+    F.e.out.ld = c->g.nkl;
+    F.e.out.ls = spec_ls;
+    F.ncols = c->g.nkl;
     F.nlayers = nb;
     F.nl = 1;
     F.two = false;
@@ -1099,6 +1112,7 @@ int gfb_rfft(gfb_ctx* c, void* out_spec, const double* in_phys, int batch, void*
     F.st = st;
     rc = check_launch(c, launch_col_fwd(c->g.ny, F), "k_col_fwd(plain)");
     if (rc) return rc;
+    if (sharded && (rc = peer_barrier(c, st))) return rc;
   }
   return GFB_OK;
 }

@@ -12,7 +12,7 @@ from . import _lib
 from .device import GPU
 from .grid import TwoDGrid
 from .timesteppers import Equation, Problem as _Problem
-from .twodnavierstokes import _vars, _ps, _spectral_vars, _make_shard, calcN_ as _calcN_common
+from .twodnavierstokes import _vars, _ps, _spectral_vars, _make_shard, _sharded, calcN_ as _calcN_common
 
 
 def Problem(dev=None, nx=256, ny=None, Lx=2 * np.pi, Ly=None, beta=0.0, deformation_radius=np.inf, U=0.0,
@@ -102,6 +102,9 @@ def updatevars_(prob):
 
 def set_q_(prob, q):
     """src/singlelayerqg.jl:525-534 (the domain mean is NOT removed)."""
+    if _sharded(prob):  # `q` = this rank's rows
+        prob.rfft(prob.dev.array(q, torch.float64), out=prob.sol)
+        return
     prob.rfft(prob.dev.array(q, torch.float64), out=prob.vars.qh)
     prob.sol.copy_(prob.vars.qh)
     updatevars_(prob)

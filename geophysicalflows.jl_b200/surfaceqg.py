@@ -8,7 +8,7 @@ from . import _lib
 from .device import GPU
 from .grid import TwoDGrid
 from .timesteppers import Equation, Problem as _Problem
-from .twodnavierstokes import _vars, _ps, _make_shard
+from .twodnavierstokes import _vars, _ps, _make_shard, _sharded
 
 
 def psihfrombh(H, grid):
@@ -52,6 +52,10 @@ def updatevars_(prob):
 def set_b_(prob, b):
     """src/surfaceqg.jl:357-365."""
     prob.rfft(prob.dev.array(b, torch.float64), out=prob.sol)
+    if _sharded(prob):  # `b` = this rank's rows
+        if prob.shard.rank == 0:
+            prob.sol[0, 0] = 0
+        return
     prob.sol[0, 0] = 0
     updatevars_(prob)
 

@@ -277,21 +277,29 @@ class Problem:
     def dealias_lib(self, a):
         self._check(self.lib.gfb_dealias(self.ctx, self._p(a), self.dev.stream_ptr()), "gfb_dealias")
 
+    def _local_shapes(self):
+        """(rows, spectral columns) this context holds: everything on one GPU, a y-slab / the local kr pairs when sharded"""
+        sharded = self.shard is not None and self.shard.nranks > 1
+        return (self.shard.ny_loc if sharded else self.grid.ny), (self.shard.nkl if sharded else self.grid.nkr)
+
     def rfft(self, a, out=None):
-        """mul!(out, grid.rfftplan, a) for a [.., ny, nx] real tensor."""
+        """mul!(out, grid.rfftplan, a) for a [.., ny, nx] real tensor (sharded: [.., ny_loc, nx] -> [.., nl, nkl], p2p
+        transport; every rank must call it)."""
         a = a.contiguous()
-        batch = int(a.numel() // (self.grid.ny * self.grid.nx))
+        rows, cols = self._local_shapes()
+        batch = int(a.numel() // (rows * self.grid.nx))
         if out is None:
-            out = self.dev.zeros(tuple(a.shape[:-2]) + (self.grid.nl, self.grid.nkr), torch.complex128)
+            out = self.dev.zeros(tuple(a.shape[:-2]) + (self.grid.nl, cols), torch.complex128)
         self._check(self.lib.gfb_rfft(self.ctx, self._p(out), self._p(a), batch, self.dev.stream_ptr()), "gfb_rfft")
         return out
 
     def irfft(self, ah, out=None):
-        """ldiv!(out, grid.rfftplan, ah); `ah` is left intact."""
+        """ldiv!(out, grid.rfftplan, ah); `ah` is left intact (sharded: local spectral slice -> local rows)."""
         ah = ah.contiguous()
-        batch = int(ah.numel() // (self.grid.nl * self.grid.nkr))
+        rows, cols = self._local_shapes()
+        batch = int(ah.numel() // (self.grid.nl * cols))
         if out is None:
-            out = self.dev.zeros(tuple(ah.shape[:-2]) + (self.grid.ny, self.grid.nx), torch.float64)
+            out = self.dev.zeros(tuple(ah.shape[:-2]) + (rows, self.grid.nx), torch.float64)
         self._check(self.lib.gfb_irfft(self.ctx, self._p(out), self._p(ah), batch, self.dev.stream_ptr()), "gfb_irfft")
         return out
 

@@ -95,8 +95,16 @@ def _spectral_vars(prob, qh_out, G):
 def set_zeta_(prob, zeta):
     """src/twodnavierstokes.jl:352-360."""
     prob.rfft(prob.dev.array(zeta, torch.float64), out=prob.sol)
+    if _sharded(prob):  # `zeta` = this rank's rows; the zero mode lives in the first local column of rank 0
+        if prob.shard.rank == 0:
+            prob.sol[0, 0] = 0
+        return
     prob.sol[0, 0] = 0
     updatevars_(prob)
+
+
+def _sharded(prob):
+    return prob.shard is not None and prob.shard.nranks > 1
 
 
 def _ps(prob, kind, scale, **kw):

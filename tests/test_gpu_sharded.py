@@ -115,3 +115,54 @@ def test_sharded_gpus_match_oracle(case, transport):
     err, derr = _run(case, world, transport)
     assert err < 1e-10, err
     assert derr < 1e-10, derr
+
+
+def _transform_worker(rank, world, port, out_q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import gfb_loader
+        import refcases as R
+        gf = gfb_loader.load()
+        nx, ny = 512, 256
+        dev = gf.GPU(rank)
+        p = gf.twodnavierstokes.Problem(dev, nx=nx, ny=ny, Lx=2 * np.pi, Ly=3.0, stepper="RK4", shard=(rank, world, None, "p2p"))
+        a = np.random.default_rng(3).standard_normal((2, ny, nx))
+        ah = np.fft.rfft2(a)
+        loc = dev.array(np.ascontiguousarray(a[:, p.shard.rows, :]))
+        spec = p.rfft(loc)
+        back = p.irfft(spec)
+        gf.twodnavierstokes.set_zeta_(p, loc[0])
+        torch.cuda.synchronize()
+        z = ah[0].copy()
+        z[0, 0] = 0
+        errs = (R.relerr(spec.cpu().numpy(), ah[..., p.shard.cols]), R.relerr(back.cpu().numpy(), a[:, p.shard.rows, :]),
+                R.relerr(p.sol.cpu().numpy(), z[..., p.shard.cols]))
+        allerrs = [None] * world
+        dist.all_gather_object(allerrs, errs)
+        if rank == 0:
+            out_q.put(max(max(e) for e in allerrs))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_plain_transforms_p2p():
+    """mul! / ldiv! / set_zeta! on a sharded context: local rows <-> local kr column pairs through peer memory."""
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_transform_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=600)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    assert q.get(timeout=5) < 1e-13
