@@ -109,11 +109,11 @@ def test_sharded_matches_oracle(case, world):
 # On the GPUs the peers are other processes (CUDA IPC, tests/test_gpu_sharded.py); here the ranks are threads of one
 # process connected by raw pointers (gfb_comm_connect_ptrs), the flag barrier spins for real between them.
 @pytest.mark.parametrize("world", [2, 4])
-def test_p2p_transport_matches_oracle(world):
+def test_p2p_transport_matches_oracle(world, monkeypatch):
     import ctypes as C
     import threading
     sys.path.insert(0, HERE)
-    os.environ["GFB_EMU_THREADS"] = "1"
+    monkeypatch.setenv("GFB_EMU_THREADS", "1")  # one emulation worker per rank thread
     import backends
     import refcases as R
     from oracle import gfo
@@ -161,12 +161,12 @@ def test_p2p_transport_matches_oracle(world):
 
 
 @pytest.mark.parametrize("nx,ny", [(64, 64), (32, 16384)])
-def test_p2p_plain_transforms(nx, ny):
+def test_p2p_plain_transforms(nx, ny, monkeypatch):
     """mul! / ldiv! on a slab-sharded context: local rows <-> local kr column pairs, exchange fused into the kernels."""
     import ctypes as C
     import threading
     sys.path.insert(0, HERE)
-    os.environ["GFB_EMU_THREADS"] = "1"
+    monkeypatch.setenv("GFB_EMU_THREADS", "1")
     import backends
     import refcases as R
     B = backends.emu_backend()
