@@ -54,7 +54,7 @@ def getetdcoeffs(dt, L, ncirc=32, rcirc=1):
 class TimeStepper:
     """Field names follow the reference's steppers where the library exposes them."""
 
-    def __init__(self, name, eqn, dt):
+    def __init__(self, name, eqn, dt, shard=None):
         if name not in _lib.STEPPERS:
             raise ValueError("unknown stepper %r" % name)
         self.name = name
@@ -62,8 +62,10 @@ class TimeStepper:
         self.etd = "ETDRK4" in name
         grid = eqn.grid
         self.filter = makefilter(grid) if self.filtered else None
+        self.local_tables = shard is not None and shard.nranks > 1
         if self.etd:
-            L = eqn.L
+            # on a sharded problem every rank evaluates the (32-point contour) coefficients of ITS kr columns only
+            L = shard.cut("L", eqn.L) if self.local_tables else eqn.L
             self.expLdt = np.exp(dt * L)
             self.exphalfLdt = np.exp(dt * L / 2)
             self.zeta, self.alpha, self.beta, self.Gamma = getetdcoeffs(dt, L)
@@ -120,7 +122,7 @@ class Problem:
     def __init__(self, eqn, stepper, dt, grid, vars, params, kind, tables, shard=None):
         self.eqn, self.grid, self.vars, self.params = eqn, grid, vars, params
         self.clock = Clock(dt)
-        self.timestepper = TimeStepper(stepper, eqn, dt)
+        self.timestepper = TimeStepper(stepper, eqn, dt, shard)
         self.dev = grid.device
         self.lib = self.dev.lib
         self.nlayers = eqn.dims[0] if len(eqn.dims) == 3 else 1
@@ -143,11 +145,13 @@ class Problem:
         if shard is not None:
             cfg.rank, cfg.nranks = shard.rank, shard.nranks
 
-        def table(key, a, dtype=ldt, shape=full):
+        def table(key, a, dtype=ldt, shape=full, local=False):
             if a is None:
                 return None
+            if local:  # already cut to this rank's columns
+                shape = tuple(shape[:-1]) + (shard.nkl,)
             b = np.broadcast_to(np.asarray(a, dtype=dtype).reshape(shape if np.ndim(a) == len(shape) else np.shape(a)), shape)
-            if shard is not None:
+            if shard is not None and not local:
                 b = shard.cut(key, b)
             b = np.ascontiguousarray(b, dtype=dtype)
             self._keep.append(b)
@@ -158,7 +162,7 @@ class Problem:
         if ts.etd:
             for key, arr in (("expLdt", ts.expLdt), ("exphalfLdt", ts.exphalfLdt), ("zeta", ts.zeta),
                              ("alpha", ts.alpha), ("beta", ts.beta), ("Gamma", ts.Gamma)):
-                setattr(cfg, key, _ptr(table(key, arr)))
+                setattr(cfg, key, _ptr(table(key, arr, local=ts.local_tables)))
         for key, (arr, dtype, shape) in tables.items():
             if key == "mu":
                 cfg.mu = float(arr)
