@@ -215,7 +215,7 @@ static int ilog2i(int n) {
   while ((1 << l) < n) ++l;
   return l;
 }
-// destinations of the K1 / K2 stores (kernels.cuh PeerOut)
+// destinations of the K1 / K2 stores (layout.cuh PeerOut)
 static PeerOut out_local(cplx* p) {  // a ctx-owned array on one GPU
   PeerOut o;
   std::memset(&o, 0, sizeof o);
