@@ -768,7 +768,8 @@ int gfb_comm_create(gfb_ctx* c, void* handle64_out, void** local_ptr_out) {
   if (!c) return GFB_ERR_INVALID;
   if (c->g.nranks < 2) return fail(c, GFB_ERR_INVALID, "gfb_comm_create: context is not sharded");
   if (!c->comm) {
-    const size_t wb = (size_t)w_elems(c, 3 * c->nlayers) * sizeof(cplx), pb = (size_t)w_elems(c, 2 * c->nlayers) * sizeof(cplx);
+    // W: u, v, q (+ psi for updatevars!) ; P: d, v
+    const size_t wb = (size_t)w_elems(c, 4 * c->nlayers) * sizeof(cplx), pb = (size_t)w_elems(c, 2 * c->nlayers) * sizeof(cplx);
     c->comm_w_off = 256;
     c->comm_p_off = c->comm_w_off + wb;
     c->comm_bytes = c->comm_p_off + pb;
@@ -1117,29 +1118,33 @@ int gfb_rfft(gfb_ctx* c, void* out_spec, const double* in_phys, int batch, void*
   return GFB_OK;
 }
 
+// Sharded context (p2p transport connected): `sol` is the local spectral slice, the outputs are this rank's rows.
 int gfb_updatevars(gfb_ctx* c, void* sol, double* q, double* psi, double* u, double* v, void* stream) {
   if (!c || !sol) return fail(c, GFB_ERR_INVALID, "gfb_updatevars: null argument");
-  NEED_SINGLE_GPU(c, "gfb_updatevars");
+  const bool sharded = c->g.nranks != 1;
+  if (sharded && !c->connected)
+    return fail(c, GFB_ERR_UNSUPPORTED, "gfb_updatevars on a sharded context needs the p2p transport (gfb_comm_create / gfb_comm_connect)");
   cudaStream_t st = (cudaStream_t)stream;
   int rc = gfb_dealias(c, sol, stream);
   if (rc) return rc;
   const int nf = 4;
   if ((rc = import_spec(c, c->Cin, sol, st))) return rc;
-  rc = run_col_inv_state(c, int_spec(c, c->Cin), nf, out_local(c->W), st);
+  rc = run_col_inv_state(c, int_spec(c, c->Cin), nf, sharded ? out_peers(c, c->comm_w_off, nf * c->nlayers) : out_local(c->W), st);
   if (rc) return rc;
+  if (sharded && (rc = peer_barrier(c, st))) return rc;
   double* outs[4] = {u, v, q, psi};
   for (int f = 0; f < 4; ++f) {
     if (!outs[f]) continue;
     RowLaunch R;
     std::memset(&R, 0, sizeof R);
     R.mode = ROW_C2R;
-    R.a.W = c->W;
+    R.a.W = sharded ? reinterpret_cast<const cplx*>(c->comm + c->comm_w_off) : c->W;
     R.a.wl = row_layout(c, nf * c->nlayers);
     R.a.wstride = nf;
     R.a.fsel = f;
     R.a.kc = c->g.kcut;
     R.a.phys = outs[f];
-    R.a.ny = c->g.ny;
+    R.a.ny = c->ny_loc;
     R.nlayers = c->nlayers;
     R.tw = c->tw_x;
     R.tw2 = c->tw_x2;
@@ -1147,6 +1152,7 @@ int gfb_updatevars(gfb_ctx* c, void* sol, double* q, double* psi, double* u, dou
     rc = check_launch(c, launch_row(c->g.nx, R), "k_row(c2r,updatevars)");
     if (rc) return rc;
   }
+  if (sharded && (rc = peer_barrier(c, st))) return rc;
   return GFB_OK;
 }
 

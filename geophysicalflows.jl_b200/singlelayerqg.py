@@ -102,9 +102,6 @@ def updatevars_(prob):
 
 def set_q_(prob, q):
     """src/singlelayerqg.jl:525-534 (the domain mean is NOT removed)."""
-    if _sharded(prob):  # `q` = this rank's rows
-        prob.rfft(prob.dev.array(q, torch.float64), out=prob.sol)
-        return
     prob.rfft(prob.dev.array(q, torch.float64), out=prob.vars.qh)
     prob.sol.copy_(prob.vars.qh)
     updatevars_(prob)

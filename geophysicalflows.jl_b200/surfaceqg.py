@@ -52,11 +52,8 @@ def updatevars_(prob):
 def set_b_(prob, b):
     """src/surfaceqg.jl:357-365."""
     prob.rfft(prob.dev.array(b, torch.float64), out=prob.sol)
-    if _sharded(prob):  # `b` = this rank's rows
-        if prob.shard.rank == 0:
-            prob.sol[0, 0] = 0
-        return
-    prob.sol[0, 0] = 0
+    if not _sharded(prob) or prob.shard.rank == 0:  # sharded: `b` = this rank's rows, the zero mode lives on rank 0
+        prob.sol[0, 0] = 0
     updatevars_(prob)
 
 

@@ -43,14 +43,14 @@ def Equation_(params, grid):
 
 def _vars(dev, grid, forced, stochastic, phys=("zeta", "u", "v"), spec=("zetah", "uh", "vh"), shard=None):
     """DecayingVars / ForcedVars / StochasticForcedVars (src/twodnavierstokes.jl:170-236).  On a sharded
-    problem only the local spectral slices of Fh / prevsol exist (updatevars! needs a gathered state)."""
+    problem every array is the local piece: this rank's rows of the physical fields, its kr columns of the spectra."""
     v = SimpleNamespace(forced=forced, stochastic=stochastic, Fh=None, prevsol=None)
     nkl = grid.nkr if shard is None else shard.nkl
-    if shard is None or shard.nranks == 1:
-        for n in phys:
-            setattr(v, n, dev.zeros((grid.ny, grid.nx), torch.float64))
-        for n in spec:
-            setattr(v, n, dev.zeros((grid.nl, grid.nkr), torch.complex128))
+    rows = grid.ny if shard is None else shard.ny_loc
+    for n in phys:
+        setattr(v, n, dev.zeros((rows, grid.nx), torch.float64))
+    for n in spec:
+        setattr(v, n, dev.zeros((grid.nl, nkl), torch.complex128))
     if forced:
         v.Fh = dev.zeros((grid.nl, nkl), torch.complex128)
         if stochastic:
@@ -85,9 +85,12 @@ def _spectral_vars(prob, qh_out, G):
     psi_h = -G sol, uh = -i l psi_h, vh = i kr psi_h."""
     g, v, dev = prob.grid, prob.vars, prob.dev
     qh_out.copy_(prob.sol)
+    kr = g.kr
+    if _sharded(prob):  # this rank's kr columns
+        G, kr = prob.shard.spec_local(G), np.take(kr, prob.shard.cols, axis=-1)
     GG = dev.array(G)
     v.uh.copy_(1j * dev.array(g.l) * GG * prob.sol)
-    v.vh.copy_(-1j * dev.array(g.kr) * GG * prob.sol)
+    v.vh.copy_(-1j * dev.array(kr) * GG * prob.sol)
     if hasattr(v, "psih"):
         v.psih.copy_(-GG * prob.sol)
 
@@ -95,11 +98,8 @@ def _spectral_vars(prob, qh_out, G):
 def set_zeta_(prob, zeta):
     """src/twodnavierstokes.jl:352-360."""
     prob.rfft(prob.dev.array(zeta, torch.float64), out=prob.sol)
-    if _sharded(prob):  # `zeta` = this rank's rows; the zero mode lives in the first local column of rank 0
-        if prob.shard.rank == 0:
-            prob.sol[0, 0] = 0
-        return
-    prob.sol[0, 0] = 0
+    if not _sharded(prob) or prob.shard.rank == 0:  # sharded: `zeta` = this rank's rows, the zero mode lives on rank 0
+        prob.sol[0, 0] = 0
     updatevars_(prob)
 
 

@@ -138,10 +138,12 @@ def _transform_worker(rank, world, port, out_q):
         back = p.irfft(spec)
         gf.twodnavierstokes.set_zeta_(p, loc[0])
         torch.cuda.synchronize()
-        z = ah[0].copy()
-        z[0, 0] = 0
+        from oracle import gfo
+        ref = gfo.twodnavierstokes.Problem(nx=nx, ny=ny, Lx=2 * np.pi, Ly=3.0, stepper="RK4")
+        gfo.twodnavierstokes.set_zeta_(ref, a[0])  # zero mode removed, dealiased, updatevars!
         errs = (R.relerr(spec.cpu().numpy(), ah[..., p.shard.cols]), R.relerr(back.cpu().numpy(), a[:, p.shard.rows, :]),
-                R.relerr(p.sol.cpu().numpy(), z[..., p.shard.cols]))
+                R.relerr(p.sol.cpu().numpy(), ref.sol[..., p.shard.cols]),
+                R.relerr(p.vars.u.cpu().numpy(), ref.vars.u[p.shard.rows]), R.relerr(p.vars.zeta.cpu().numpy(), ref.vars.zeta[p.shard.rows]))
         allerrs = [None] * world
         dist.all_gather_object(allerrs, errs)
         if rank == 0:

@@ -203,10 +203,16 @@ def test_p2p_plain_transforms(nx, ny, monkeypatch):
     for t in th:
         t.join(timeout=900)
     assert not errs, errs
+    from oracle import gfo
+    ref = gfo.twodnavierstokes.Problem(nx=nx, ny=ny, Lx=2 * np.pi, Ly=3.0, stepper="RK4")
+    gfo.twodnavierstokes.set_zeta_(ref, a[0])
     for p in probs:
         spec, back = res[p.shard.rank]
         assert R.relerr(spec, ah[..., p.shard.cols]) < 1e-14
         assert R.relerr(back, a[:, p.shard.rows, :]) < 1e-14
-        z = ah[0].copy()
-        z[0, 0] = 0
-        assert R.relerr(p.sol.numpy(), z[..., p.shard.cols]) < 1e-14
+        assert R.relerr(p.sol.numpy(), ref.sol[..., p.shard.cols]) < 1e-14  # set_zeta!: zero mode removed, dealiased
+        # updatevars! (called by set_zeta!): this rank's rows of zeta, u, v from the dealiased state
+        assert R.relerr(p.vars.zeta.numpy(), ref.vars.zeta[p.shard.rows]) < 1e-13
+        assert R.relerr(p.vars.u.numpy(), ref.vars.u[p.shard.rows]) < 1e-13
+        assert R.relerr(p.vars.v.numpy(), ref.vars.v[p.shard.rows]) < 1e-13
+        assert R.relerr(p.vars.uh.numpy(), ref.vars.uh[..., p.shard.cols]) < 1e-13
