@@ -267,13 +267,11 @@ int gfb_destroy(gfb_ctx* c) {
 int gfb_create(gfb_ctx** out, const gfb_config* cfg) {
   if (!out || !cfg) return fail(nullptr, GFB_ERR_INVALID, "null argument");
   *out = nullptr;
-  // nx = 16384 runs its rows as 8192-point half-length transforms (single-layer modules, stepping only)
-  // 16384-point lines: rows as 8192-point half-length transforms, columns as 4 x 4096 (single-layer modules, stepping only)
+  // nx = 16384 runs its rows as 8192-point half-length transforms 
+  // 16384-point lines: rows as 8192-point half-length transforms, columns as 4 x 4096 
   const bool half_rows = cfg->nx == 16384, quad_cols = cfg->ny == 16384;
   if (!(pow2_ok(cfg->nx) || half_rows) || !(pow2_ok(cfg->ny) || quad_cols))
     return fail(nullptr, GFB_ERR_UNSUPPORTED, "nx=%d, ny=%d: sizes must be powers of two in [32, 16384]", cfg->nx, cfg->ny);
-  if ((half_rows || quad_cols) && cfg->kind != GFB_KIND_SINGLE)
-    return fail(nullptr, GFB_ERR_UNSUPPORTED, "16384-point lines are available for the single-layer modules only");
   if (cfg->nlayers < 1 || cfg->nlayers > MAX_LAYERS) return fail(nullptr, GFB_ERR_UNSUPPORTED, "nlayers=%d not in [1, %d]", cfg->nlayers, MAX_LAYERS);
   if (cfg->kind == GFB_KIND_SINGLE && cfg->nlayers != 1) return fail(nullptr, GFB_ERR_INVALID, "GFB_KIND_SINGLE needs nlayers == 1");
   if (cfg->kind != GFB_KIND_SINGLE && cfg->kind != GFB_KIND_LAYERED) return fail(nullptr, GFB_ERR_INVALID, "unknown kind %d", cfg->kind);

@@ -59,7 +59,7 @@ __device__ __forceinline__ void assemble_half(cplx (&v)[PT], const int j, const 
   }
 }
 
-template <int NH>
+template <int NH, bool WITHQ>
 __global__ void __launch_bounds__(GroupCfg<NH>::THREADS, GroupCfg<NH>::MINB)
     k_row_product_half(const __grid_constant__ RowArgs a, const cplx* __restrict__ tw, const cplx* __restrict__ tw2, const int nunits,
                        const int kcp) {
@@ -70,9 +70,10 @@ __global__ void __launch_bounds__(GroupCfg<NH>::THREADS, GroupCfg<NH>::MINB)
   const int gi = tid / T, j = tid % T;
   double* xb = smd + gi * RC::GSD;
   cplx* lb = reinterpret_cast<cplx*>(smd + RC::XB_DOUBLES) + 1 + (size_t)gi * kcp;  // [0] holds the TMEM base word
-  constexpr int tmcols = (RC::THREADS / 128) * 64;
+  constexpr int tmcols = (RC::THREADS / 128) * (WITHQ ? 128 : 64);
   const uint32_t tbase = tmem_setup(reinterpret_cast<uint32_t*>(smd + RC::XB_DOUBLES), tmcols);
-  const uint32_t tq = tmem_thread_base(tbase, 64);
+  const uint32_t tq = tmem_thread_base(tbase, WITHQ ? 128 : 64);
+  const uint32_t tg = tq + 64;  // WITHQ: (u + U) Qx + v Qy of this row at the thread's even / odd points
   const int stride = (int)gridDim.x * G, unit0 = (int)blockIdx.x * G + gi;
   const int niter = (nunits - (int)blockIdx.x * G + stride - 1) / stride;  // same for every group of the CTA
   cplx v[PT];
@@ -113,6 +114,32 @@ __global__ void __launch_bounds__(GroupCfg<NH>::THREADS, GroupCfg<NH>::MINB)
         tmem_wait_st();
         continue;
       }
+      if (WITHQ) {  // u += U(y); accumulate (u + U) Qx (phase u) + v Qy (phase v) in TMEM
+        const double Uy = (ph == 1 && a.U && live) ? a.U[(long long)layer * a.ny + y] : 0.0;
+        const double* qg = (ph == 1 ? a.Qx : a.Qy) + ((long long)layer * a.ny + y) * (2 * NH);
+#pragma unroll
+        for (int c0 = 0; c0 < PT; c0 += 4) {
+          cplx gs[4];
+          if (ph == 2) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) gs[q] = tmem_load(tg + 4 * (c0 + q));
+            tmem_wait_ld();
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int r = c0 + q;
+            v[r].x += Uy;
+            v[r].y += Uy;
+            double2 g2 = make_double2(0.0, 0.0);
+            if (live) g2 = *reinterpret_cast<const double2*>(qg + 2 * (j + r * T));
+            if (ph == 1) gs[q] = cmake(v[r].x * g2.x, v[r].y * g2.y);
+            else gs[q] = cmake(gs[q].x + v[r].x * g2.x, gs[q].y + v[r].y * g2.y);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) tmem_store(tg + 4 * (c0 + q), gs[q]);
+        }
+        tmem_wait_st();
+      }
 #pragma unroll
       for (int c0 = 0; c0 < PT; c0 += 4) {
         cplx q2[4];
@@ -144,6 +171,34 @@ __global__ void __launch_bounds__(GroupCfg<NH>::THREADS, GroupCfg<NH>::MINB)
             if (km != k && km < a.kout) *prow_ptr(a.pout, rb, km) = Xm;
           }
           compiler_fence();  // one wavenumber pair at a time: bounded registers
+        }
+      }
+    }
+    if (WITHQ) {  // d -= ((u + U) Qx + v Qy)_h : one more half-length transform of the accumulated row
+#pragma unroll
+      for (int c0 = 0; c0 < PT; c0 += 4) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[c0 + q] = tmem_load(tg + 4 * (c0 + q));
+        tmem_wait_ld();
+      }
+      block_fft_split<NH, FWD>(v, j, xb, tw);
+      unpack_pair<NH>(v, j, xb, A, B);
+      if (live) {
+        const long long rb = a.pl.rowbase(2 * layer, y);
+#pragma unroll
+        for (int r = 0; r < 9; ++r) {
+          const int k = j + r * T, km = NH - k;
+          if (r < 8 || j == 0) {
+            const cplx t = cmul(__ldg(&tw2[k]), B[r]);
+            if (k < a.kout) {
+              cplx& e = *prow_ptr(a.pout, rb, k);  // same thread wrote it in the u phase
+              e = csub(e, cadd(A[r], t));
+            }
+            if (km != k && km < a.kout) {
+              cplx& e = *prow_ptr(a.pout, rb, km);
+              e = csub(e, cconj(csub(A[r], t)));
+            }
+          }
         }
       }
     }

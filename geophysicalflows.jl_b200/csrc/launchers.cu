@@ -149,8 +149,9 @@ int launch_col_inv_16384(const ColInvLaunch& L) {
   switch (L.prep) {
     case PREP_PLAIN: return do_col_inv_16384(L, L.pp);
     case PREP_SINGLE: return do_col_inv_16384(L, L.ps);
+    case PREP_MULTI: return do_col_inv_16384(L, L.pm);
   }
-  return -1;  // MultiLayerQG: not at 16384 points per column
+  return -1;
 }
 
 int launch_col_fwd_16384(const ColFwdLaunch& L) {
@@ -194,23 +195,31 @@ static int do_row_half_plain(const RowLaunch& L) {
   return 0;
 }
 
-int launch_row_half_8192(const RowLaunch& L) {
+template <bool WITHQ>
+static int do_row_half_product(const RowLaunch& L) {
   using RC = GroupCfg<8192>;
-  if (L.mode == ROW_C2R) return do_row_half_plain<ROW_C2R>(L);
-  if (L.mode == ROW_R2C) return do_row_half_plain<ROW_R2C>(L);
-  if (L.mode != ROW_PRODUCT) return -1;  // MultiLayerQG: not at 16384 points per row
   const int kcp = (L.a.kc + 1) & ~1;
   const size_t smem = (size_t)RC::XB_DOUBLES * sizeof(double) + 16 + (size_t)RC::G * kcp * sizeof(cplx);
   static size_t attr = 0;
   if (smem > attr) {
-    if (set_smem(k_row_product_half<8192>, smem)) return -2;
+    if (set_smem(k_row_product_half<8192, WITHQ>, smem)) return -2;
     attr = smem;
   }
   const int nunits = L.a.ny * L.nlayers;
   const int want = (nunits + RC::G - 1) / RC::G, cap = sm_count() * RC::MINB;
   dim3 grid(want < cap ? want : cap);
-  GFB_LAUNCH((k_row_product_half<8192>), grid, dim3(RC::THREADS), smem, L.st, L.a, L.tw, L.tw2, nunits, kcp);
+  GFB_LAUNCH((k_row_product_half<8192, WITHQ>), grid, dim3(RC::THREADS), smem, L.st, L.a, L.tw, L.tw2, nunits, kcp);
   return 0;
+}
+
+int launch_row_half_8192(const RowLaunch& L) {
+  switch (L.mode) {
+    case ROW_C2R: return do_row_half_plain<ROW_C2R>(L);
+    case ROW_R2C: return do_row_half_plain<ROW_R2C>(L);
+    case ROW_PRODUCT: return do_row_half_product<false>(L);
+    case ROW_PRODUCT_Q: return do_row_half_product<true>(L);
+  }
+  return -1;
 }
 #endif
 

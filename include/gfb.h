@@ -69,7 +69,7 @@ enum gfb_stepper {
 /* All pointers in the config are HOST pointers, read (copied to the device) during gfb_create. */
 typedef struct gfb_config {
   int kind;               /* gfb_kind */
-  int nx, ny, nlayers;    /* nx, ny powers of two in [32, 16384]; 16384: GFB_KIND_SINGLE only */
+  int nx, ny, nlayers;    /* nx, ny powers of two in [32, 16384] */
   double Lx, Ly;
   /* dealias! index ranges, 0-based half-open ([FF] getaliasedwavenumbers): columns [kr_alias0, nkr) and
    * rows [l_alias0, l_alias1) are zeroed.  kr_alias0 = nkr and l_alias0 = l_alias1 disables. */

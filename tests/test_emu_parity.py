@@ -258,9 +258,6 @@ def test_16384_is_limited_to_what_is_built(emu):
     """Loud, specific failures for what the 16384-point support does not cover yet."""
     with pytest.raises(emu.pkg.GfbError, match="powers of two"):
         emu.twodnavierstokes.Problem(nx=64, ny=32768, Lx=2 * np.pi, stepper="RK4")
-    with pytest.raises(emu.pkg.GfbError, match="single-layer"):
-        emu.multilayerqg.Problem(2, nx=16384, ny=32, Lx=2 * np.pi, f0=1.0, beta=0.0, H=[0.5, 0.5], b=[-1.0, -1.2], U=[0.0, 0.0],
-                                 stepper="RK4")
 
 
 @pytest.mark.parametrize("nx,ny", [(16384, 32), (32, 16384)])
@@ -282,3 +279,25 @@ def test_plain_transforms_and_updatevars_16384(emu, oracle_backend, nx, ny):
     oracle_backend.twodnavierstokes.set_zeta_(po, z0)
     for f in ("zeta", "u", "v"):
         assert R.relerr(emu.host(getattr(prob.vars, f)), getattr(po.vars, f)) < 1e-13
+
+
+@pytest.mark.parametrize("nx,ny", [(16384, 32), (32, 16384)])
+def test_mqg_16384(emu, oracle_backend, nx, ny):
+    """MultiLayerQG with 16384 points along x (half-length rows incl. the (u+U)Qx + vQy transform) or along y."""
+    rng = np.random.default_rng(11)
+    y = np.linspace(-np.pi, np.pi, ny, endpoint=False)
+    U = np.stack([0.1 * (j + 1) * np.cos(y) for j in range(2)], axis=1)
+    eta = 0.3 * rng.standard_normal((ny, nx))
+    kw = dict(nx=nx, ny=ny, Lx=2 * np.pi, Ly=2 * np.pi, f0=1.0, beta=0.5, U=U, eta=eta, mu=0.05, nu=1e-9, H=[0.3, 0.7], b=[-1.0, -1.2],
+              topographic_pv_gradient=(0.01, 0.02), dt=1e-3, stepper="FilteredRK4")
+    po = oracle_backend.multilayerqg.Problem(2, **kw)
+    pb = emu.multilayerqg.Problem(2, **kw)
+    s0 = np.fft.rfft2(rng.standard_normal((2, ny, nx))) * 30 / (nx * ny)
+    po.sol[...] = s0
+    pb.sol.copy_(emu.dev(s0))
+    oracle_backend.stepforward_(po, 2)
+    emu.stepforward_(pb, 2)
+    assert R.relerr(emu.host(pb.sol), po.sol) < 1e-13
+    KEo, PEo = oracle_backend.multilayerqg.energies(po)
+    KEb, PEb = emu.multilayerqg.energies(pb)
+    assert np.allclose(KEb, KEo, rtol=1e-12) and np.allclose(PEb, PEo, rtol=1e-12)
