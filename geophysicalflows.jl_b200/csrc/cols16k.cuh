@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(GroupCfg<NS>::THREADS, GroupCfg<NS>::MINB)
   for (int r = 0; r < PT; ++r) {
     const int d = (W.nranks == 1) ? 0 : (y0 + 4 * T * r) >> W.lg_rows;
     cplx* out = W.base[d] + (W.rank - d) * W.chunk + field * wfs;
-    stpair(out + ooff + r * (4 * T) * ldw, X[r * THREADS + tid], v[r]);
+    stpair(out + ooff + (long long)r * (4 * T) * ldw, X[r * THREADS + tid], v[r]);  // 64-bit: 5 layers x 16384^2 exceed 2^31 elements
   }
 }
 
