@@ -103,14 +103,20 @@ __device__ __forceinline__ uint32_t* emu_tmem_cell(uint32_t taddr) {
   const int col = (int)(taddr & 0xffffu);
   return emu::tmem_storage() + (size_t)lane * 512 + col;
 }
-__device__ __forceinline__ void tmem_store(uint32_t taddr, double2 v) { std::memcpy(emu_tmem_cell(taddr), &v, 16); }
+// every emulated TMEM operation is logged (emu::tmem_note): the emulation aborts when the lanes of a warp disagree on
+// the sequence of these warp-collective operations, i.e. when one of them sits under divergent control flow
+__device__ __forceinline__ void tmem_store(uint32_t taddr, double2 v) {
+  emu::tmem_note(1, taddr & 0xffffu);
+  std::memcpy(emu_tmem_cell(taddr), &v, 16);
+}
 __device__ __forceinline__ double2 tmem_load(uint32_t taddr) {
+  emu::tmem_note(2, taddr & 0xffffu);
   double2 v;
   std::memcpy(&v, emu_tmem_cell(taddr), 16);
   return v;
 }
-__device__ __forceinline__ void tmem_wait_st() {}
-__device__ __forceinline__ void tmem_wait_ld() {}
+__device__ __forceinline__ void tmem_wait_st() { emu::tmem_note(3, 0); }
+__device__ __forceinline__ void tmem_wait_ld() { emu::tmem_note(4, 0); }
 #else
 // all threads of the CTA call this; warp 0 allocates `cols` (power of two >= 32) columns
 __device__ __forceinline__ uint32_t tmem_setup(uint32_t* smem_word, int cols) {

@@ -255,8 +255,12 @@ __global__ void __launch_bounds__(GroupCfg<NY>::THREADS, GroupCfg<NY>::MINB)
 #pragma unroll
       for (int r = 0; r < PT; ++r) tmem_store(tA + 4 * r, v[r]);
       tmem_wait_st();
-    } else if (unit < nunits) {
-      const int field = unit % nfields, colA = 2 * (unit / nfields);
+    } else {
+      // `unit` depends on the group index and, for NY < 512 (T < 32), one warp spans several groups: the
+      // warp-collective TMEM reads are therefore issued by EVERY thread (the slot is always valid) and only the
+      // global stores are predicated on the unit being live (gfb_platform.h: no tcgen05 under divergence)
+      const bool live = unit < nunits;
+      const int field = live ? unit % nfields : 0, colA = live ? 2 * (unit / nfields) : 0;
       const int ooff = toff(j, colA, ldw);
 #pragma unroll
       for (int c0 = 0; c0 < PT; c0 += 4) {
@@ -264,12 +268,14 @@ __global__ void __launch_bounds__(GroupCfg<NY>::THREADS, GroupCfg<NY>::MINB)
 #pragma unroll
         for (int q = 0; q < 4; ++q) ra[q] = tmem_load(tA + 4 * (c0 + q));
         tmem_wait_ld();
+        if (live) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int r = c0 + q;
-          const int d = (W.nranks == 1) ? 0 : (j + r * T) >> W.lg_rows;
-          cplx* out = W.base[d] + (W.rank - d) * W.chunk + field * wfs;
-          stpair(out + toff_row<T>(ooff, j, r, colA, ldw), ra[q], v[r]);
+          for (int q = 0; q < 4; ++q) {
+            const int r = c0 + q;
+            const int d = (W.nranks == 1) ? 0 : (j + r * T) >> W.lg_rows;
+            cplx* out = W.base[d] + (W.rank - d) * W.chunk + field * wfs;
+            stpair(out + toff_row<T>(ooff, j, r, colA, ldw), ra[q], v[r]);
+          }
         }
       }
     }

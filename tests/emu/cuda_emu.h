@@ -131,6 +131,10 @@ struct BlockState {
   char* smem = nullptr;
   size_t smem_cap = 0;
   uint32_t* tmem = nullptr;  // emulated tensor memory: 128 lanes x 512 columns
+  // tcgen05.* are warp-collective (.sync.aligned): every lane of a warp must execute the same sequence of them.  Each
+  // fiber keeps a running hash of its TMEM operations; the hashes of a warp are compared whenever the CTA barrier
+  // completes and when the CTA ends, so a TMEM access under divergent control flow aborts the emulated kernel.
+  std::vector<uint64_t> tm_hash;
   ~BlockState() {
     for (char* s : stacks) std::free(s);
     std::free(smem);
@@ -170,7 +174,34 @@ inline void barrier_drop(Barrier& bar) {  // a thread exits: it no longer partic
   }
 }
 
-inline void sync_block() { barrier_wait(tl_block->block_bar); }
+inline void tmem_note(unsigned kind, unsigned column) {
+  BlockState* b = tl_block;
+  uint64_t& h = b->tm_hash[b->current];
+  h = (h ^ (((uint64_t)kind << 32) | column)) * 0x100000001b3ull + 0x9e3779b97f4a7c15ull;
+}
+inline void tmem_check_uniform(const char* where) {
+  BlockState* b = tl_block;
+  const size_t nt = b->tm_hash.size();
+  for (size_t w = 0; w * 32 < nt; ++w) {
+    bool have = false;
+    uint64_t ref = 0;
+    for (size_t t = w * 32; t < nt && t < (w + 1) * 32; ++t) {
+      if (b->fibers[t].done) continue;
+      if (!have) { ref = b->tm_hash[t]; have = true; }
+      else if (b->tm_hash[t] != ref) {
+        std::fprintf(stderr, "cuda_emu: warp %zu of CTA (%u,%u) executed tcgen05 (TMEM) operations under divergent control flow "
+                             "(detected at %s): lanes disagree on the sequence of warp-collective operations\n",
+                     w, tl_blockIdx.x, tl_blockIdx.y, where);
+        std::abort();
+      }
+    }
+  }
+}
+inline void sync_block() {
+  Barrier& bar = tl_block->block_bar;
+  if (bar.count + 1 >= bar.expected) tmem_check_uniform("__syncthreads");  // last arrival: everybody else is waiting here
+  barrier_wait(bar);
+}
 inline void sync_warp() { barrier_wait(tl_block->warp_bar[tl_block->current / 32]); }
 
 template <class T>
@@ -221,6 +252,7 @@ inline void run_block(BlockState& b, dim3 grid, dim3 block, uint3 bidx, size_t s
   b.warp_bar.assign((nt + 31) / 32, Barrier());
   for (unsigned w = 0; w < b.warp_bar.size(); ++w) b.warp_bar[w].expected = (int)std::min(32u, nt - 32 * w);
   b.shfl_slot.assign(nt, 0);
+  b.tm_hash.assign(nt, 0);
   for (unsigned t = 0; t < nt; ++t) {
     Fiber& f = b.fibers[t];
     f.done = false;
@@ -242,6 +274,8 @@ inline void run_block(BlockState& b, dim3 grid, dim3 block, uint3 bidx, size_t s
       if (f.done) --alive;
     }
   }
+  for (unsigned t = 0; t < nt; ++t) b.fibers[t].done = false;  // compare the final TMEM histories of all lanes
+  tmem_check_uniform("kernel exit");
   b.current = -1;
 }
 

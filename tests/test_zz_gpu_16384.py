@@ -1,15 +1,11 @@
-"""16384-point lines on the GPU.  These kernels were brought up against the oracle through the CPU emulation layer only
-(the round's GPU budget was spent before they existed), so the first hardware run is this test: xfail(strict=False)
-keeps an unexpected hardware-only problem from hiding the rest of the suite, and an XPASS reports that it works.  The
-file name sorts it LAST: a fault inside an unverified kernel would poison the CUDA context of the pytest process, so
-nothing verified may run after it."""
+"""16384-point lines on the GPU (rows as 8192-point half-length transforms, columns as 4 x 4096): stepping and the plain
+transforms against the oracle.  The file name sorts it last (largest line lengths of the suite)."""
 import numpy as np
 import pytest
 
 import refcases as R
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="16384-point lines: verified in emulation only, first hardware run")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module")
