@@ -18,6 +18,7 @@ STEPPERS = {"ForwardEuler": 0, "FilteredForwardEuler": 1, "RK4": 2, "FilteredRK4
 
 class GfbConfig(C.Structure):
     _fields_ = [
+        ("struct_size", C.c_int),
         ("kind", C.c_int), ("nx", C.c_int), ("ny", C.c_int), ("nlayers", C.c_int),
         ("Lx", C.c_double), ("Ly", C.c_double),
         ("kr_alias0", C.c_int), ("l_alias0", C.c_int), ("l_alias1", C.c_int),
@@ -32,16 +33,23 @@ class GfbConfig(C.Structure):
     ]
 
 
-EXPORTS = ["gfb_version", "gfb_last_error", "gfb_create", "gfb_destroy", "gfb_get_clock", "gfb_set_clock",
+EXPORTS = ["gfb_version", "gfb_config_size", "gfb_last_error", "gfb_create", "gfb_destroy", "gfb_get_clock", "gfb_set_clock",
            "gfb_rfft", "gfb_irfft", "gfb_dealias", "gfb_calcN", "gfb_step", "gfb_nstages", "gfb_stage", "gfb_diag",
            "gfb_streamfunction_from_pv", "gfb_pv_from_streamfunction", "gfb_updatevars", "gfb_device_bytes",
            "gfb_profile_begin", "gfb_profile_end", "gfb_shard_info", "gfb_state_import", "gfb_state_export",
            "gfb_stage_pre", "gfb_stage_mid", "gfb_stage_post", "gfb_comm_create", "gfb_comm_connect",
-           "gfb_comm_connect_ptrs", "gfb_comm_status", "gfb_step_p2p", "gfb_set_defer_alias_band"]
+           "gfb_comm_connect_ptrs", "gfb_comm_status", "gfb_step_p2p", "gfb_set_defer_alias_band", "gfb_path_info"]
 
 
 class GfbError(RuntimeError):
     pass
+
+
+def new_config():
+    """A zeroed gfb_config with struct_size filled in (gfb_create checks it)."""
+    cfg = GfbConfig()
+    cfg.struct_size = C.sizeof(GfbConfig)
+    return cfg
 
 
 def _prototype(lib):
@@ -78,6 +86,7 @@ def _prototype(lib):
     lib.gfb_comm_status.argtypes = [vp]
     lib.gfb_step_p2p.argtypes = [vp, vp, ip, vp, vp, vp]
     lib.gfb_set_defer_alias_band.argtypes = [vp, ip]
+    lib.gfb_path_info.argtypes = [vp, C.POINTER(C.c_longlong)]
     lib.gfb_device_bytes.argtypes = [vp]
     lib.gfb_device_bytes.restype = C.c_longlong
     for name in EXPORTS:
@@ -101,5 +110,9 @@ def load(path=None):
     for name in EXPORTS:
         if not hasattr(lib, name):
             raise GfbError("%s does not export %s" % (path, name))
-    _cached[path] = _prototype(lib)
+    _prototype(lib)
+    if lib.gfb_config_size() != C.sizeof(GfbConfig):
+        raise GfbError("%s: struct gfb_config is %d bytes in the library, %d in this binding" %
+                       (path, lib.gfb_config_size(), C.sizeof(GfbConfig)))
+    _cached[path] = lib
     return _cached[path]

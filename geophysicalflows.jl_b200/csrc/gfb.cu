@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -59,6 +60,10 @@ struct gfb_ctx {
   bool connected = false;
   unsigned long long epoch = 0;
   bool defer_alias = false;  // gfb_set_defer_alias_band
+  // TMA-staged row pass (single GPU, single-layer kinds, nx = 4096 / 8192): tensor maps of W and P
+  bool row_tma = false;
+  long long row_tma_launches = 0;
+  RowTma rt_pruned, rt_full;  // output boxes sized for kout = kcut / nkr
   // optional per-kernel event timing
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev;   // pairs (start, stop)
@@ -158,6 +163,68 @@ static int make_twiddles(gfb_ctx* c, cplx** out, int N) {
   return dev_upload(c, out, h.data(), (size_t)N);
 }
 
+// ---- TMA tensor maps ---------------------------------------------------------------------------------------
+// W / P as the row kernel sees them (k2_row.cuh RowLayout, one GPU): element (field, y, k) at
+//   (y/8)*rbs + field*fstr + (k/2)*16 + (y%8)*2 + k%2   complex elements, rbs = 8*nf*ld, fstr = 8*ld,
+// i.e. a 5-D tensor of doubles [y/8][field][k/2][y%8][4] (slowest first).  A box of {4, 1, boxp, 1, 1} is one row's
+// run of boxp column pairs: boxp 32-byte pieces 256 bytes apart in global memory, dense in shared memory.
+#ifndef GFB_EMULATE
+#include <cuda.h>
+typedef CUresult (*gfb_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+#endif
+static int make_tma_5d(gfb_ctx* c, TmaDesc* out, void* base, const unsigned long long dims[5], const unsigned long long strides_bytes[5],
+                       const unsigned box[5]) {
+#ifdef GFB_EMULATE
+  out->base = (char*)base;
+  out->rank = 5;
+  out->esize = 8;
+  for (int i = 0; i < 5; ++i) {
+    out->dims[i] = dims[i];
+    out->strides[i] = strides_bytes[i];
+    out->box[i] = box[i];
+  }
+  return 0;
+#else
+  static gfb_encode_fn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn ||
+        q != cudaDriverEntryPointSuccess)
+      return fail(c, GFB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    encode = (gfb_encode_fn)fn;
+  }
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5] = {1, 1, 1, 1, 1};
+  for (int i = 0; i < 5; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    if (i > 0) gs[i - 1] = strides_bytes[i];
+  }
+  static_assert(sizeof(TmaDesc) == sizeof(CUtensorMap), "TmaDesc is the opaque CUtensorMap");
+  const CUresult r = encode(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, base, gd, gs, bx, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(c, GFB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+#endif
+}
+// boxes per row and column pairs per box (a multiple of 4 = 128 bytes) covering ncols columns
+static void row_boxes(int ncols, int* nbox, int* boxp) {
+  const int npairs = (ncols + 1) / 2;
+  *nbox = (npairs + 255) / 256;
+  *boxp = (((npairs + *nbox - 1) / *nbox) + 3) & ~3;
+}
+static int make_row_tensor(gfb_ctx* c, TmaDesc* out, cplx* base, int nf, int boxp) {
+  const unsigned long long ld = (unsigned long long)c->ldi;
+  const unsigned long long dims[5] = {4, 8, ld / 2, (unsigned long long)nf, (unsigned long long)(c->ny_loc / 8)};
+  const unsigned long long strides[5] = {8, 32, 256, 8 * ld * 16, 8 * (unsigned long long)nf * ld * 16};
+  const unsigned box[5] = {4, 1, (unsigned)boxp, 1, 1};
+  return make_tma_5d(c, out, base, dims, strides, box);
+}
+
 namespace gfb {
 int launch_col_inv(int NY, const ColInvLaunch& L) {
   if (NY == 16384) return launch_col_inv_16384(L);
@@ -246,7 +313,9 @@ static PeerOut out_peers(const gfb_ctx* c, size_t byte_off, int nf) {  // "p2p":
 
 extern "C" {
 
-const char* gfb_version(void) { return "gfb 0.2 (sm_100a)"; }
+const char* gfb_version(void) { return "gfb 0.3 (sm_100a)"; }
+
+int gfb_config_size(void) { return (int)sizeof(gfb_config); }
 
 const char* gfb_last_error(const gfb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
@@ -267,7 +336,9 @@ int gfb_destroy(gfb_ctx* c) {
 int gfb_create(gfb_ctx** out, const gfb_config* cfg) {
   if (!out || !cfg) return fail(nullptr, GFB_ERR_INVALID, "null argument");
   *out = nullptr;
-  // nx = 16384 runs its rows as 8192-point half-length transforms 
+  if (cfg->struct_size != (int)sizeof(gfb_config))
+    return fail(nullptr, GFB_ERR_INVALID, "gfb_config.struct_size = %d, the library expects %d: the binding's struct mirror does not match include/gfb.h",
+                cfg->struct_size, (int)sizeof(gfb_config));
   // 16384-point lines: rows as 8192-point half-length transforms, columns as 4 x 4096 
   const bool half_rows = cfg->nx == 16384, quad_cols = cfg->ny == 16384;
   if (!(pow2_ok(cfg->nx) || half_rows) || !(pow2_ok(cfg->ny) || quad_cols))
@@ -373,6 +444,23 @@ int gfb_create(gfb_ctx** out, const gfb_config* cfg) {
     TRY(dev_alloc(c, &c->W, (size_t)w_elems(c, 4 * n)));
     TRY(dev_alloc(c, &c->P, (size_t)w_elems(c, 2 * n)));
   }
+  if (nranks == 1 && c->kind == GFB_KIND_SINGLE && (g.nx == 4096 || g.nx == 8192) && (g.ny % 8) == 0) {
+    // TMA-staged row pass: tensor maps of W (3 fields) and P (2 fields); the output boxes come in two sizes
+    int nbi, bpi, nbo, bpo;
+    row_boxes(g.kcut, &nbi, &bpi);
+    for (int full = 0; full < 2; ++full) {
+      RowTma& rt = full ? c->rt_full : c->rt_pruned;
+      row_boxes(full ? g.nkr : g.kcut, &nbo, &bpo);
+      rt.nbox_in = nbi;
+      rt.boxp_in = bpi;
+      rt.nbox_out = nbo;
+      rt.boxp_out = bpo;
+      TRY(make_row_tensor(c, &rt.w, c->W, 3 * n, bpi));
+      TRY(make_row_tensor(c, &rt.p, c->P, 2 * n, bpo));
+    }
+    const char* off = getenv("GFB_NO_ROW_TMA");
+    c->row_tma = !(off && off[0] == '1');
+  }
   int nstate = 0;
   switch (cfg->stepper) {
     case GFB_FORWARD_EULER: case GFB_FILTERED_FORWARD_EULER: nstate = 0; break;
@@ -444,6 +532,14 @@ int gfb_profile_end(gfb_ctx* c, double* ms4, long long* launches4) {
     ms4[k] = timed[k] ? ms[k] * (double)c->prof_launches[k] / (double)timed[k] : 0.0;
     launches4[k] = c->prof_launches[k];
   }
+  return GFB_OK;
+}
+
+int gfb_path_info(const gfb_ctx* c, long long* info4) {
+  if (!c || !info4) return GFB_ERR_INVALID;
+  info4[0] = c->row_tma ? 1 : 0;
+  info4[1] = c->row_tma_launches;
+  info4[2] = info4[3] = 0;
   return GFB_OK;
 }
 
@@ -560,6 +656,11 @@ static int run_row_product(gfb_ctx* c, const cplx* Wrecv, const PeerOut& Psend, 
   R.tw = c->tw_x;
   R.tw2 = c->tw_x2;
   R.st = st;
+  // the TMA-staged kernel reads the ctx-owned W and writes the ctx-owned P (the tensor maps are bound to them)
+  if (c->row_tma && Wrecv == c->W && Psend.nranks == 1 && Psend.base[0] == c->P) {
+    R.tma = prune ? &c->rt_pruned : &c->rt_full;
+    c->row_tma_launches += 1;
+  }
   ProfScope ps(c, 1, st);
   return check_launch(c, launch_row(c->g.nx, R), "k_row");
 }

@@ -179,3 +179,143 @@ __device__ __forceinline__ cplx cfma(cplx a, cplx b, cplx c) { return cadd(cmul(
 __device__ __forceinline__ double cabs2(cplx a) { return a.x * a.x + a.y * a.y; }
 
 }  // namespace gfb
+
+// ---- TMA (tensor memory accelerator) + mbarrier ------------------------------------------------------------
+// Bulk asynchronous tensor copies between global and shared memory (cp.async.bulk.tensor, SASS UTMALDG / UTMASTG):
+// ONE instruction of ONE thread moves a whole box of a <= 5-D tensor; the LSU never sees the individual sectors.
+// The row kernel uses them to gather a row out of the 8-row tiled work arrays (a train of 32-byte pieces 256 bytes
+// apart) into a dense line buffer and to scatter result rows back.  Completion of loads is signalled on an mbarrier
+// in shared memory (transaction bytes), of stores through bulk async-groups.
+//
+// TmaDesc is the 128-byte CUtensorMap on the device; the emulation build carries the tensor geometry in the clear and
+// copies synchronously.
+namespace gfb {
+
+constexpr int TMA_MAXRANK = 5;
+
+#ifdef GFB_EMULATE
+struct TmaDesc {
+  char* base;
+  int rank, esize;
+  unsigned long long dims[TMA_MAXRANK];     // elements, fastest first
+  unsigned long long strides[TMA_MAXRANK];  // bytes; strides[0] = esize
+  unsigned box[TMA_MAXRANK];
+};
+struct Mbar {
+  int arrivals_left, arrivals_init;
+  long long tx;
+  unsigned phase;
+};
+__device__ __forceinline__ void mbar_init(Mbar* b, int count) {
+  b->arrivals_left = b->arrivals_init = count;
+  b->tx = 0;
+  b->phase = 0;
+}
+__device__ __forceinline__ void mbar_fence_init() {}
+__device__ __forceinline__ void emu_mbar_check(Mbar* b) {
+  if (b->arrivals_left == 0 && b->tx == 0) {
+    b->arrivals_left = b->arrivals_init;
+    b->phase ^= 1u;
+  }
+}
+__device__ __forceinline__ void mbar_expect_tx(Mbar* b, unsigned bytes) {  // arrive + expect_tx
+  b->tx += bytes;
+  b->arrivals_left -= 1;
+  emu_mbar_check(b);
+}
+__device__ __forceinline__ void mbar_wait(Mbar* b, unsigned parity) {
+  while ((b->phase & 1u) == (parity & 1u)) emu::yield_to_sched();
+}
+// copy one box; dir = 0: global -> smem (out-of-bounds elements read as zero), 1: smem -> global (dropped)
+__device__ __forceinline__ void emu_tma_copy(const TmaDesc& d, char* smem, const int* c, int dir) {
+  unsigned idx[TMA_MAXRANK] = {0, 0, 0, 0, 0};
+  unsigned long long total = 1;
+  for (int i = 0; i < d.rank; ++i) total *= d.box[i];
+  for (unsigned long long n = 0; n < total; ++n) {
+    bool inb = true;
+    unsigned long long off = 0;
+    for (int i = 0; i < d.rank; ++i) {
+      const long long g = (long long)c[i] + idx[i];
+      if (g < 0 || (unsigned long long)g >= d.dims[i]) inb = false;
+      off += (unsigned long long)g * d.strides[i];
+    }
+    char* s = smem + n * d.esize;
+    if (dir == 0) {
+      if (inb) std::memcpy(s, d.base + off, d.esize);
+      else std::memset(s, 0, d.esize);
+    } else if (inb) {
+      std::memcpy(d.base + off, s, d.esize);
+    }
+    for (int i = 0; i < d.rank; ++i) {
+      if (++idx[i] < d.box[i]) break;
+      idx[i] = 0;
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_5d(void* dst, const TmaDesc* d, Mbar* bar, int c0, int c1, int c2, int c3, int c4) {
+  const int c[5] = {c0, c1, c2, c3, c4};
+  emu_tma_copy(*d, (char*)dst, c, 0);
+  unsigned long long bytes = d->esize;
+  for (int i = 0; i < d->rank; ++i) bytes *= d->box[i];
+  bar->tx -= (long long)bytes;
+  emu_mbar_check(bar);
+}
+__device__ __forceinline__ void tma_store_5d(const TmaDesc* d, const void* src, int c0, int c1, int c2, int c3, int c4) {
+  const int c[5] = {c0, c1, c2, c3, c4};
+  emu_tma_copy(*d, (char*)const_cast<void*>(src), c, 1);
+}
+__device__ __forceinline__ void tma_commit() {}
+template <int N>
+__device__ __forceinline__ void tma_wait_read() {}
+template <int N>
+__device__ __forceinline__ void tma_wait_all() {}
+__device__ __forceinline__ void fence_proxy_async() {}
+#else
+struct alignas(64) TmaDesc {
+  unsigned char opaque[128];
+};
+typedef unsigned long long Mbar;
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(Mbar* b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(Mbar* b, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(Mbar* b, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(smem_addr(b)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_5d(void* dst, const TmaDesc* d, Mbar* bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
+          smem_addr(dst)),
+      "l"(d), "r"(smem_addr(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const TmaDesc* d, const void* src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(d),
+               "r"(smem_addr(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_wait_read() {  // the sources of all but the N youngest store groups have been read
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_wait_all() {  // all but the N youngest store groups are complete (globally visible)
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+// generic-proxy writes to shared memory -> visible to the async proxy (TMA store) that reads them next
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#endif
+
+}  // namespace gfb

@@ -406,3 +406,144 @@ __global__ void __launch_bounds__(GroupCfg<NX>::THREADS, GroupCfg<NX>::MINB)
 }
 
 }  // namespace gfb
+
+namespace gfb {
+
+// ------------------------------------------------------------------------------------------------
+// K2, product mode of the single-layer modules, TMA-staged (single GPU, one group per CTA: NX >= 4096).
+//
+// Same arithmetic and phase structure as k_row_product, but no thread ever issues a global load or store for the
+// spectral rows:
+//   * the two half-spectrum rows of the next phase are gathered out of the 8-row tiled W by TMA tensor loads
+//     (cp.async.bulk.tensor.5d, box = 1 row x <= 256 column pairs of 32 bytes) issued by ONE thread and signalled on
+//     an mbarrier -- instead of 22 LDGSTS per thread and phase, each of which cost the LSU 16 sector wavefronts;
+//   * the two result rows of a phase are assembled densely in shared memory (the d row in the FFT exchange buffer,
+//     which is idle between the unpack and the next transform; the v row behind the line buffer) and scattered into
+//     the tiled P by TMA tensor stores -- instead of 18 STG.128 per thread and phase hitting 16 lines each.
+// Geometry of a staged row: nbox boxes of boxp column pairs (boxp a multiple of 4, so every box starts 128-byte
+// aligned in shared memory); columns beyond the live ones inside the last box are real (aliased) columns of the
+// tensor or out of bounds (zero-filled on load, dropped on store) and never used.
+// ------------------------------------------------------------------------------------------------
+struct RowTma {
+  TmaDesc w, p;            // tensor maps of W (3 fields per layer) and P (2 fields per layer); gfb.cu make_row_tma
+  int nbox_in, boxp_in;    // input rows: boxes per row, column pairs per box
+  int nbox_out, boxp_out;  // output rows (depends on kout)
+};
+
+template <int NX>
+__global__ void __launch_bounds__(GroupCfg<NX>::THREADS, GroupCfg<NX>::MINB)
+    k_row_product_tma(const __grid_constant__ RowArgs a, const __grid_constant__ RowTma tm, const cplx* __restrict__ tw, const int nunits) {
+  using RC = GroupCfg<NX>;
+  constexpr int T = RC::T;
+  static_assert(RC::G == 1, "one FFT group per CTA");
+  GFB_DYN_SMEM(double, smd);
+  const int j = threadIdx.x;
+  double* xb = smd;
+  const int kcp = 2 * tm.nbox_in * tm.boxp_in;  // complex elements per staged input row
+  const int kop = 2 * tm.nbox_out * tm.boxp_out;
+  // [xb | 128 B: TMEM base word, mbarrier | line buffer: 2 input rows | v row staging]
+  unsigned char* ctl = reinterpret_cast<unsigned char*>(smd + RC::XB_DOUBLES);
+  Mbar* full = reinterpret_cast<Mbar*>(ctl + 16);
+  cplx* lb = reinterpret_cast<cplx*>(ctl + 128);
+  cplx* vst = lb + 2 * (size_t)kcp;
+  cplx* dst = reinterpret_cast<cplx*>(xb);  // d row staging: kop complex <= XB_DOUBLES / 2 (checked by the launcher)
+  (void)kop;
+  const int tmcols = RowPipeCfg<NX>::TM_COLS(false);
+  if (j == 0) {
+    mbar_init(full, 1);
+    mbar_fence_init();
+  }
+  const uint32_t tbase = tmem_setup(reinterpret_cast<uint32_t*>(ctl), tmcols);  // contains the __syncthreads
+  const uint32_t tq = tmem_thread_base(tbase, RowPipeCfg<NX>::TM_PER_WG(false));
+  const int npairs = a.ny / 2;  // row pairs per layer
+  const int niter = (nunits - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  cplx v[PT];
+  cplx A[9], B[9];
+  unsigned parity = 0;
+
+  // one elected thread gathers the two rows of a phase out of W into the line buffer
+  auto prefetch = [&](int unit, int ph) {
+    if (j != 0) return;
+    const int layer = unit / npairs, ya = 2 * (unit - layer * npairs);
+    const int fu = a.wstride * layer, fv = fu + 1, fq = fu + 2;
+    const int fA = ph == 0 ? fq : fu, fB = ph == 0 ? fq : fv;
+    const int rowA = ph == 0 ? ya : ya + ph - 1, rowB = ph == 0 ? ya + 1 : ya + ph - 1;
+    mbar_expect_tx(full, (unsigned)(2 * kcp * sizeof(cplx)));
+    for (int b = 0; b < tm.nbox_in; ++b) {
+      tma_load_5d(lb + 2 * b * tm.boxp_in, &tm.w, full, 0, rowA & 7, b * tm.boxp_in, fA, rowA >> 3);
+      tma_load_5d(lb + kcp + 2 * b * tm.boxp_in, &tm.w, full, 0, rowB & 7, b * tm.boxp_in, fB, rowB >> 3);
+    }
+  };
+  if (niter > 0) prefetch((int)blockIdx.x, 0);
+#pragma unroll 1
+  for (int it = 0; it < niter; ++it) {
+    const int unit = (int)blockIdx.x + it * (int)gridDim.x;
+    const int layer = unit / npairs;
+    const int ya = 2 * (unit - layer * npairs);
+#pragma unroll 1
+    for (int ph = 0; ph < 3; ++ph) {
+      mbar_wait(full, parity);  // the line buffer holds this phase's two rows
+      parity ^= 1u;
+      assemble_hermitian<NX>(v, j, lb, kcp, a.kc);
+      if (j == 0) tma_wait_read<0>();  // the result rows of the previous phase have left the staging buffers (xb is one)
+      __syncthreads();                 // everyone has consumed the line buffer: refill it behind the transforms
+      if (ph < 2) prefetch(unit, ph + 1);
+      else if (it + 1 < niter) prefetch(unit + (int)gridDim.x, 0);
+      block_fft_split<NX, INV>(v, j, xb, tw);
+      if (ph == 0) {  // q of both rows (+ eta) -> TMEM
+        if (a.eta != nullptr) {
+          const double* ea = a.eta + (long long)ya * NX;
+          const double* eb = ea + NX;
+#pragma unroll
+          for (int r = 0; r < PT; ++r) {
+            v[r].x += ea[j + r * T];
+            v[r].y += eb[j + r * T];
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < PT; ++r) tmem_store(tq + 4 * r, v[r]);
+        tmem_wait_st();
+        continue;
+      }
+      const int h = ph - 1, y = ya + h;
+#pragma unroll
+      for (int c0 = 0; c0 < PT; c0 += 4) {
+        cplx q2[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) q2[q] = tmem_load(tq + 4 * (c0 + q));
+        tmem_wait_ld();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const double qq = (h == 0) ? q2[q].x : q2[q].y;
+          v[c0 + q].x *= qq;
+          v[c0 + q].y *= qq;
+        }
+      }
+      block_fft_split<NX, FWD>(v, j, xb, tw);
+      unpack_pair<NX>(v, j, xb, A, B);  // A = (uq)_h, B = (vq)_h ; ends with a barrier: xb is free
+      // result rows, dense, into the staging buffers: d = -i kr (uq)_h in xb, v = (vq)_h behind the line buffer
+#pragma unroll
+      for (int r = 0; r < 9; ++r) {
+        const int k = j + r * T;
+        if ((r < 8 || j == 0) && k < a.kout) {
+          const double kr = k * a.dkx;
+          dst[k] = cmake(kr * A[r].y, -kr * A[r].x);
+          vst[k] = B[r];
+        }
+      }
+      fence_proxy_async();  // generic-proxy writes above -> visible to the TMA engine
+      __syncthreads();
+      if (j == 0) {
+        for (int b = 0; b < tm.nbox_out; ++b) {
+          tma_store_5d(&tm.p, dst + 2 * b * tm.boxp_out, 0, y & 7, b * tm.boxp_out, 2 * layer, y >> 3);
+          tma_store_5d(&tm.p, vst + 2 * b * tm.boxp_out, 0, y & 7, b * tm.boxp_out, 2 * layer + 1, y >> 3);
+        }
+        tma_commit();
+      }
+    }
+  }
+  if (j == 0) tma_wait_all<0>();  // every result row is in P before the CTA (and its shared memory) goes away
+  tmem_release(tbase, tmcols);
+}
+
+}  // namespace gfb

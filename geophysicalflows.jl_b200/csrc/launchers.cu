@@ -10,6 +10,19 @@ namespace gfb {
 #define GFB_CAT2(a, b) a##b
 #define GFB_CAT(a, b) GFB_CAT2(a, b)
 
+// cudaFuncSetAttribute and the SM count are PER DEVICE: the "already configured" caches below are indexed by the
+// current device, so several contexts on different devices of one process (gfb_comm_connect_ptrs) each opt in
+constexpr int MAX_DEVICES = 64;
+static inline int cur_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) dev = 0;
+  return dev;
+}
+struct AttrCache {
+  size_t bytes[MAX_DEVICES] = {};
+  bool done[MAX_DEVICES] = {};
+};
+
 template <class K>
 static inline int set_smem(K kernel, size_t bytes) {
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -24,10 +37,10 @@ template <class Prep>
 static int do_col_inv(const ColInvLaunch& L, const Prep& prep) {
   using GC = GroupCfg<GFB_N>;
   const size_t smem = (size_t)GC::XB_DOUBLES * sizeof(double) + (size_t)GC::STASH * sizeof(cplx);
-  static bool attr = false;
-  if (!attr) {
+  static AttrCache attr;
+  if (!attr.done[cur_device()]) {
     if (set_smem(k_col_inv<GFB_N, Prep>, smem)) return -2;
-    attr = true;
+    attr.done[cur_device()] = true;
   }
   const int npairs = (L.ncols + 1) / 2;
   dim3 grid((npairs + GC::G - 1) / GC::G, L.nfields);
@@ -36,15 +49,14 @@ static int do_col_inv(const ColInvLaunch& L, const Prep& prep) {
 }
 
 static int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceProp p;
-    if (cudaGetDeviceProperties(&p, dev) == cudaSuccess) n = p.multiProcessorCount;
-    if (n <= 0) n = 148;
+  static int n[MAX_DEVICES] = {};
+  const int dev = cur_device();
+  if (n[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess) n[dev] = v;
+    if (n[dev] <= 0) n[dev] = 148;
   }
-  return n;
+  return n[dev];
 }
 
 // the persistent, software-pipelined pre-pass of the single-layer modules (k_col_inv_single)
@@ -61,10 +73,10 @@ static int do_col_inv_single(const ColInvLaunch& L) {
     if (n > nslots) nslots = n;
   }
   const size_t smem = (size_t)GC::XB_DOUBLES * sizeof(double) + 16 + (size_t)nslots * GC::THREADS * (sizeof(cplx) + sizeof(double));
-  static size_t attr = 0;
-  if (smem > attr) {
+  static AttrCache attr;
+  if (smem > attr.bytes[cur_device()]) {
     if (set_smem(k_col_inv_single<GFB_N>, smem)) return -2;
-    attr = smem;
+    attr.bytes[cur_device()] = smem;
   }
   const int nunits = ((L.ncols + 1) / 2) * L.nfields;
   const int want = (nunits + GC::G - 1) / GC::G, cap = sm_count() * GC::MINB;
@@ -88,10 +100,10 @@ static int do_row(const RowLaunch& L) {
   using RC = GroupCfg<GFB_N>;
   const int nst = (MODE == ROW_PRODUCT) ? 1 : (MODE == ROW_PRODUCT_Q ? 2 : 0);
   const size_t smem = (size_t)RC::XB_DOUBLES * sizeof(double) + (size_t)nst * RC::STASH * sizeof(cplx);
-  static bool attr = false;
-  if (!attr) {
+  static AttrCache attr;
+  if (!attr.done[cur_device()]) {
     if (set_smem(k_row<GFB_N, MODE>, smem)) return -2;
-    attr = true;
+    attr.done[cur_device()] = true;
   }
   const int nunits = L.a.ny / 2;
   dim3 grid((nunits + RC::G - 1) / RC::G, L.nlayers);
@@ -105,10 +117,10 @@ static int do_row_product(const RowLaunch& L) {
   using RC = GroupCfg<GFB_N>;
   const int kcp = (L.a.kc + 1) & ~1;  // line buffer rows stay 32-byte aligned
   const size_t smem = (size_t)RC::XB_DOUBLES * sizeof(double) + 16 + (size_t)RC::G * 2 * kcp * sizeof(cplx);
-  static size_t attr = 0;
-  if (smem > attr) {
+  static AttrCache attr;
+  if (smem > attr.bytes[cur_device()]) {
     if (set_smem(k_row_product<GFB_N, WITHQ>, smem)) return -2;
-    attr = smem;
+    attr.bytes[cur_device()] = smem;
   }
   const int nunits = (L.a.ny / 2) * L.nlayers;
   const int want = (nunits + RC::G - 1) / RC::G, cap = sm_count() * RC::MINB;
@@ -117,7 +129,31 @@ static int do_row_product(const RowLaunch& L) {
   return 0;
 }
 
+#if GFB_N >= 4096
+// the TMA-staged product pass (k_row_product_tma): rows gathered / scattered by cp.async.bulk.tensor
+static int do_row_product_tma(const RowLaunch& L) {
+  using RC = GroupCfg<GFB_N>;
+  const RowTma& t = *L.tma;
+  const size_t in_row = (size_t)2 * t.nbox_in * t.boxp_in * sizeof(cplx), out_row = (size_t)2 * t.nbox_out * t.boxp_out * sizeof(cplx);
+  if (out_row > (size_t)RC::XB_DOUBLES * sizeof(double)) return -1;  // the d row is staged in the exchange buffer
+  const size_t smem = (size_t)RC::XB_DOUBLES * sizeof(double) + 128 + 2 * in_row + out_row;
+  static AttrCache attr;
+  if (smem > attr.bytes[cur_device()]) {
+    if (set_smem(k_row_product_tma<GFB_N>, smem)) return -2;
+    attr.bytes[cur_device()] = smem;
+  }
+  const int nunits = (L.a.ny / 2) * L.nlayers;
+  const int cap = sm_count() * RC::MINB;
+  dim3 grid(nunits < cap ? nunits : cap);
+  GFB_LAUNCH((k_row_product_tma<GFB_N>), grid, dim3(RC::THREADS), smem, L.st, L.a, t, L.tw, nunits);
+  return 0;
+}
+#endif
+
 int GFB_CAT(launch_row_, GFB_N)(const RowLaunch& L) {
+#if GFB_N >= 4096
+  if (L.mode == ROW_PRODUCT && L.tma != nullptr) return do_row_product_tma(L);
+#endif
   switch (L.mode) {
     case ROW_PRODUCT: return do_row_product<false>(L);
     case ROW_PRODUCT_Q: return do_row_product<true>(L);
@@ -133,10 +169,10 @@ template <class Prep>
 static int do_col_inv_16384(const ColInvLaunch& L, const Prep& prep) {
   using GC = GroupCfg<4096>;
   const size_t smem = (size_t)GC::XB_DOUBLES * sizeof(double) + (size_t)GC::STASH * sizeof(cplx);
-  static bool attr = false;
-  if (!attr) {
+  static AttrCache attr;
+  if (!attr.done[cur_device()]) {
     if (set_smem(k_col_inv16k<4096, Prep>, smem)) return -2;
-    attr = true;
+    attr.done[cur_device()] = true;
   }
   const int npairs = (L.ncols + 1) / 2;
   dim3 grid(npairs * L.nfields * 4);
@@ -159,20 +195,20 @@ int launch_col_fwd_16384(const ColFwdLaunch& L) {
   const dim3 grid(((L.ncols + 1) / 2) * 4, L.nlayers);
   if (!L.two) {  // plain forward transform -> dense user array
     const size_t smem = (size_t)GC::XB_DOUBLES * sizeof(double) + (size_t)GC::STASH * sizeof(cplx);
-    static bool attr = false;
-    if (!attr) {
+    static AttrCache attr;
+    if (!attr.done[cur_device()]) {
       if (set_smem(k_col_fwd16k_plain<4096>, smem)) return -2;
-      attr = true;
+      attr.done[cur_device()] = true;
     }
     GFB_LAUNCH((k_col_fwd16k_plain<4096>), grid, dim3(GC::THREADS), smem, L.st, L.g, L.P, L.ldp, L.pfs, L.e.out.p, L.e.out.ld, L.e.out.ls,
                L.ncols, L.tw, L.tw2);
     return 0;
   }
   const size_t smem = (size_t)GC::XB_DOUBLES * sizeof(double) + (size_t)GC::STASH * sizeof(cplx) + 16;
-  static bool attr2 = false;
-  if (!attr2) {
+  static AttrCache attr2;
+  if (!attr2.done[cur_device()]) {
     if (set_smem(k_col_fwd16k<4096>, smem)) return -2;
-    attr2 = true;
+    attr2.done[cur_device()] = true;
   }
   GFB_LAUNCH((k_col_fwd16k<4096>), grid, dim3(GC::THREADS), smem, L.st, L.g, L.P, L.ldp, L.pfs, L.e, L.ncols, L.tw, L.tw2);
   return 0;
@@ -186,10 +222,10 @@ static int do_row_half_plain(const RowLaunch& L) {
   using RC = GroupCfg<8192>;
   const int kcp = (L.a.kc + 1) & ~1;
   const size_t smem = (size_t)RC::XB_DOUBLES * sizeof(double) + (MODE == ROW_C2R ? (size_t)kcp * sizeof(cplx) : 0);
-  static size_t attr = 0;
-  if (smem > attr) {
+  static AttrCache attr;
+  if (smem > attr.bytes[cur_device()]) {
     if (set_smem(k_row_half<8192, MODE>, smem)) return -2;
-    attr = smem;
+    attr.bytes[cur_device()] = smem;
   }
   GFB_LAUNCH((k_row_half<8192, MODE>), dim3(L.a.ny, L.nlayers), dim3(RC::THREADS), smem, L.st, L.a, L.tw, L.tw2, kcp);
   return 0;
@@ -200,10 +236,10 @@ static int do_row_half_product(const RowLaunch& L) {
   using RC = GroupCfg<8192>;
   const int kcp = (L.a.kc + 1) & ~1;
   const size_t smem = (size_t)RC::XB_DOUBLES * sizeof(double) + 16 + (size_t)RC::G * kcp * sizeof(cplx);
-  static size_t attr = 0;
-  if (smem > attr) {
+  static AttrCache attr;
+  if (smem > attr.bytes[cur_device()]) {
     if (set_smem(k_row_product_half<8192, WITHQ>, smem)) return -2;
-    attr = smem;
+    attr.bytes[cur_device()] = smem;
   }
   const int nunits = L.a.ny * L.nlayers;
   const int want = (nunits + RC::G - 1) / RC::G, cap = sm_count() * RC::MINB;
@@ -227,10 +263,10 @@ template <bool TWO>
 static int do_col_fwd(const ColFwdLaunch& L) {
   using GC = GroupCfg<GFB_N>;
   const size_t smem = (size_t)GC::XB_DOUBLES * sizeof(double) + (size_t)GC::STASH * sizeof(cplx) + 16;  // + TMEM base word
-  static bool attr = false;
-  if (!attr) {
+  static AttrCache attr;
+  if (!attr.done[cur_device()]) {
     if (set_smem(k_col_fwd<GFB_N, TWO>, smem)) return -2;
-    attr = true;
+    attr.done[cur_device()] = true;
   }
   const int ntiles = ((L.ncols + 1) / 2 + GC::G - 1) / GC::G;
   dim3 grid(ntiles, L.nlayers);

@@ -22,6 +22,7 @@ const STEPPERS = Dict("ForwardEuler" => 0, "FilteredForwardEuler" => 1, "RK4" =>
 
 # mirrors `struct gfb_config` field for field (include/gfb.h)
 Base.@kwdef mutable struct GfbConfig
+  struct_size::Cint = 0   # filled by `create` with sizeof(GfbConfig); gfb_create rejects a mismatch
   kind::Cint = 0;  nx::Cint = 0;  ny::Cint = 0;  nlayers::Cint = 1
   Lx::Cdouble = 2π; Ly::Cdouble = 2π
   kr_alias0::Cint = 0; l_alias0::Cint = 0; l_alias1::Cint = 0
@@ -34,6 +35,13 @@ Base.@kwdef mutable struct GfbConfig
   Sinv::Ptr{Cdouble} = C_NULL; S::Ptr{Cdouble} = C_NULL; U::Ptr{Cdouble} = C_NULL
   Qx::Ptr{Cdouble} = C_NULL; Qy::Ptr{Cdouble} = C_NULL
   mu::Cdouble = 0.0; no_dealias_in_calcN::Cint = 0
+  rank::Cint = 0; nranks::Cint = 0   # single GPU; a sharded driver sets both (include/gfb.h)
+end
+
+# the mirror above must be byte-identical to the C struct: checked once against the library itself
+function check_config_layout()
+  n = ccall((:gfb_config_size, libgfb), Cint, ())
+  n == sizeof(GfbConfig) || error("libgfb: struct gfb_config is $n bytes in the library, $(sizeof(GfbConfig)) in GfbConfig")
 end
 
 mutable struct B200TimeStepper{T} <: FourierFlows.AbstractTimeStepper{T}
@@ -57,7 +65,8 @@ function B200TimeStepper(stepper::String, eqn, dt, grid; kind, G=nothing, eta=no
   L = Array(eqn.L)
   filtered = startswith(stepper, "Filtered")
   filter = filtered ? Array(FourierFlows.makefilter(eqn))[:, :, 1] : nothing
-  cfg = GfbConfig(kind=kind, nx=grid.nx, ny=grid.ny, nlayers=size(L, 3), Lx=grid.Lx, Ly=grid.Ly,
+  check_config_layout()
+  cfg = GfbConfig(struct_size=sizeof(GfbConfig), kind=kind, nx=grid.nx, ny=grid.ny, nlayers=size(L, 3), Lx=grid.Lx, Ly=grid.Ly,
                   kr_alias0=first(grid.kralias) - 1, l_alias0=first(grid.lalias) - 1, l_alias1=last(grid.lalias),
                   stepper=STEPPERS[stepper], dt=dt, L_is_complex=eltype(L) <: Complex, mu=μ)
   keep = Any[L]

@@ -130,7 +130,7 @@ class Problem:
         nkl = grid.nkr if shard is None else shard.nkl
         self.sol = self.dev.zeros(tuple(eqn.dims[:-1]) + (nkl,), torch.complex128)
         self._keep = []  # host arrays referenced by the config during gfb_create
-        cfg = _lib.GfbConfig()
+        cfg = _lib.new_config()
         cfg.kind = kind
         cfg.nx, cfg.ny, cfg.nlayers = grid.nx, grid.ny, self.nlayers
         cfg.Lx, cfg.Ly = grid.Lx, grid.Ly
@@ -323,6 +323,11 @@ class Problem:
             dist.all_reduce(t, group=self.shard.group)
             vals = [float(x) for x in t.cpu()]
         return vals
+
+    def path_info(self):
+        info = (C.c_longlong * 4)()
+        self._check(self.lib.gfb_path_info(self.ctx, info), "gfb_path_info")
+        return {"row_tma": bool(info[0]), "row_tma_launches": int(info[1])}
 
     def profile_begin(self):
         self._check(self.lib.gfb_profile_begin(self.ctx), "gfb_profile_begin")

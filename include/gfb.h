@@ -68,6 +68,8 @@ enum gfb_stepper {
 
 /* All pointers in the config are HOST pointers, read (copied to the device) during gfb_create. */
 typedef struct gfb_config {
+  int struct_size;        /* = sizeof(gfb_config) of the header the CALLER was built against; gfb_create rejects a
+                             mismatch (a binding whose struct mirror has drifted) instead of reading past the struct */
   int kind;               /* gfb_kind */
   int nx, ny, nlayers;    /* nx, ny powers of two in [32, 16384] */
   double Lx, Ly;
@@ -107,6 +109,7 @@ typedef struct gfb_config {
 } gfb_config;
 
 const char* gfb_version(void);
+int gfb_config_size(void); /* sizeof(gfb_config) of the LIBRARY: every binding asserts its own mirror against it */
 const char* gfb_last_error(const gfb_ctx* ctx); /* ctx may be NULL: error of the last failed gfb_create */
 
 int gfb_create(gfb_ctx** out, const gfb_config* cfg);
@@ -208,6 +211,11 @@ int gfb_step_p2p(gfb_ctx* ctx, void* sol_local, int nsteps, const void* Fh_local
  * gfb_profile_end synchronises the recorded events and returns summed milliseconds and launch counts. */
 int gfb_profile_begin(gfb_ctx* ctx);
 int gfb_profile_end(gfb_ctx* ctx, double* ms4, long long* launches4);
+
+/* Which kernel variants the context dispatches to (for tests and the bench line):
+ *   info[0] = 1: the row pass of the stepping path is the TMA-staged kernel (k_row_product_tma)
+ *   info[1] = launches of it so far, info[2..3] reserved */
+int gfb_path_info(const gfb_ctx* ctx, long long* info4);
 
 /* bytes of device memory owned by the context */
 long long gfb_device_bytes(const gfb_ctx* ctx);

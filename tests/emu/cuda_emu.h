@@ -96,6 +96,11 @@ static inline cudaError_t cudaGetDevice(int* d) {
   *d = 0;
   return cudaSuccess;
 }
+enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16 };
+static inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) {
+  *v = 148;
+  return cudaSuccess;
+}
 struct cudaDeviceProp {
   int multiProcessorCount;
   size_t sharedMemPerBlockOptin;

@@ -50,9 +50,62 @@ def test_config_struct_matches_header(pkg):
     assert names == [f[0] for f in pkg._lib.GfbConfig._fields_]
 
 
+def test_julia_binding_mirrors_header():
+    """The Julia stub's GfbConfig (source only: no Julia here) lists the same fields in the same order as gfb.h."""
+    jl = open(os.path.join(ROOT, "geophysicalflows.jl_b200", "julia", "GeophysicalFlowsB200.jl")).read()
+    body = jl[jl.index("mutable struct GfbConfig"):]
+    body = body[:body.index("\nend")]
+    body = re.sub(r"#.*", "", body)
+    jnames = re.findall(r"([A-Za-z_0-9]+)::C?[A-Za-z{}]+", body)
+    hdr = open(os.path.join(ROOT, "include", "gfb.h")).read()
+    hb = hdr[hdr.index("typedef struct gfb_config {"):hdr.index("} gfb_config;")]
+    hb = re.sub(r"/\*.*?\*/", "", hb, flags=re.S)
+    hnames = []
+    for stmt in hb.split(";"):
+        stmt = stmt.replace("typedef struct gfb_config {", "").strip()
+        if stmt:
+            for part in stmt.split(","):
+                hnames.append(re.findall(r"([A-Za-z_0-9]+)\s*$", part.replace("*", " ").strip())[0])
+    assert jnames == hnames
+    assert "gfb_config_size" in jl and "struct_size=sizeof(GfbConfig)" in jl
+
+
+def test_c_program_through_the_header(tmp_path):
+    """A plain C translation unit includes include/gfb.h, fills gfb_config and calls the library: the header is valid C
+    and the struct the C compiler lays out is the one the library reads (tests/abi_c/test_abi.c)."""
+    import subprocess
+    exe = str(tmp_path / "test_abi")
+    libdir = os.path.join(ROOT, "geophysicalflows.jl_b200")
+    subprocess.run(["gcc", "-std=gnu99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "abi_c", "test_abi.c"), "-o", exe, "-L", libdir, "-l:libgfb.so",
+                    "-Wl,-rpath," + libdir, "-lm", "-ldl"], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "abi ok" in r.stdout
+
+
+@pytest.mark.gpu
+def test_c_program_steps_on_the_gpu(tmp_path):
+    """The same C program with --gpu: gfb_create / gfb_step / gfb_get_clock through the header on the device."""
+    import subprocess
+    exe = str(tmp_path / "test_abi")
+    libdir = os.path.join(ROOT, "geophysicalflows.jl_b200")
+    subprocess.run(["gcc", "-std=gnu99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "abi_c", "test_abi.c"), "-o", exe, "-L", libdir, "-l:libgfb.so",
+                    "-Wl,-rpath," + libdir, "-lm", "-ldl"], check=True)
+    r = subprocess.run([exe, "--gpu"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "abi ok (gpu)" in r.stdout
+
+
 def test_create_errors_are_codes_not_crashes(lib, pkg):
     cfg = pkg._lib.GfbConfig()
     ctx = C.c_void_p()
+    cfg.nx, cfg.ny, cfg.nlayers = 64, 64, 1
+    rc = lib.gfb_create(C.byref(ctx), C.byref(cfg))  # struct_size not filled in: a drifted binding is refused
+    assert rc == -1 and b"struct_size" in lib.gfb_last_error(None)
+    cfg = pkg._lib.new_config()
+    assert cfg.struct_size == lib.gfb_config_size() == C.sizeof(pkg._lib.GfbConfig)
     cfg.nx, cfg.ny, cfg.nlayers = 100, 64, 1  # not a power of two
     rc = lib.gfb_create(C.byref(ctx), C.byref(cfg))
     assert rc == -4 and b"powers of two" in lib.gfb_last_error(None)

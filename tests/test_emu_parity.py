@@ -209,6 +209,9 @@ def test_hot_path_instantiations(emu, oracle_backend, nx, ny, stepper):
     oracle_backend.stepforward_(po, 2)
     emu.stepforward_(pb, 2)
     assert R.relerr(emu.host(pb.sol), po.sol) < 1e-13
+    # rows of 4096 / 8192 points go through the TMA-staged row kernel (pruned first step, full last step)
+    info = pb.path_info()
+    assert info["row_tma"] == (nx >= 4096) and (info["row_tma_launches"] > 0) == (nx >= 4096)
 
 
 @pytest.mark.parametrize("module,stepper", [("twodnavierstokes", "FilteredETDRK4"), ("twodnavierstokes", "FilteredAB3"),
