@@ -178,10 +178,19 @@ __device__ __forceinline__ void twiddle_apply(cplx* x, const cplx w1) {
   }
 }
 
+// Barrier between the exchange phases of a transform: BAR = 0 -> __syncthreads() (the whole CTA takes part in the
+// transform), BAR = k > 0 -> named barrier k over the N/16 threads of the group (warp-specialised kernels: the other
+// warps of the CTA are busy moving data and never join).
+template <int BAR, int T>
+__device__ __forceinline__ void fft_sync() {
+  if (BAR == 0) __syncthreads();
+  else bar_sync(BAR, T);
+}
+
 // One Stockham pass of radix R with Ns = product of earlier radices.
 //   tw: W_N^i (forward sign), i < N.   xb: this group's exchange buffer (xbuf_elems(N) cplx),
 // LAST pass leaves the result in registers in natural strided layout; other passes exchange.
-template <int N, int DIR, int R, int Ns, bool LAST>
+template <int N, int DIR, int R, int Ns, bool LAST, int BAR = 0>
 __device__ __forceinline__ void fft_pass(cplx (&v)[PT], const int j, cplx* __restrict__ xb,
                                          const cplx* __restrict__ tw) {
   constexpr int T = N / PT;
@@ -211,16 +220,16 @@ __device__ __forceinline__ void fft_pass(cplx (&v)[PT], const int j, cplx* __res
     }
   }
   if (!LAST) {
-    __syncthreads();
+    fft_sync<BAR, T>();
 #pragma unroll
     for (int r = 0; r < PT; ++r) v[r] = xb[xpad(j + r * T)];
-    __syncthreads();
+    fft_sync<BAR, T>();
   }
 }
 
 // Full length-N transform of the group's registers.  All threads of the CTA must call it together
 // (it contains __syncthreads); idle groups simply transform garbage in their own buffer.
-template <int N, int DIR>
+template <int N, int DIR, int BAR = 0>
 __device__ __forceinline__ void block_fft(cplx (&v)[PT], const int j, cplx* __restrict__ xb,
                                           const cplx* __restrict__ tw) {
   using P = Plan<N>;
@@ -228,27 +237,27 @@ __device__ __forceinline__ void block_fft(cplx (&v)[PT], const int j, cplx* __re
   constexpr int RR = rem > 1 ? rem : 2;
   if constexpr (P::n16 == 1) {
     if constexpr (rem == 1) {
-      fft_pass<N, DIR, 16, 1, true>(v, j, xb, tw);
+      fft_pass<N, DIR, 16, 1, true, BAR>(v, j, xb, tw);
     } else {
-      fft_pass<N, DIR, 16, 1, false>(v, j, xb, tw);
-      fft_pass<N, DIR, RR, 16, true>(v, j, xb, tw);
+      fft_pass<N, DIR, 16, 1, false, BAR>(v, j, xb, tw);
+      fft_pass<N, DIR, RR, 16, true, BAR>(v, j, xb, tw);
     }
   } else if constexpr (P::n16 == 2) {
-    fft_pass<N, DIR, 16, 1, false>(v, j, xb, tw);
+    fft_pass<N, DIR, 16, 1, false, BAR>(v, j, xb, tw);
     if constexpr (rem == 1) {
-      fft_pass<N, DIR, 16, 16, true>(v, j, xb, tw);
+      fft_pass<N, DIR, 16, 16, true, BAR>(v, j, xb, tw);
     } else {
-      fft_pass<N, DIR, 16, 16, false>(v, j, xb, tw);
-      fft_pass<N, DIR, RR, 256, true>(v, j, xb, tw);
+      fft_pass<N, DIR, 16, 16, false, BAR>(v, j, xb, tw);
+      fft_pass<N, DIR, RR, 256, true, BAR>(v, j, xb, tw);
     }
   } else {  // n16 == 3
-    fft_pass<N, DIR, 16, 1, false>(v, j, xb, tw);
-    fft_pass<N, DIR, 16, 16, false>(v, j, xb, tw);
+    fft_pass<N, DIR, 16, 1, false, BAR>(v, j, xb, tw);
+    fft_pass<N, DIR, 16, 16, false, BAR>(v, j, xb, tw);
     if constexpr (rem == 1) {
-      fft_pass<N, DIR, 16, 256, true>(v, j, xb, tw);
+      fft_pass<N, DIR, 16, 256, true, BAR>(v, j, xb, tw);
     } else {
-      fft_pass<N, DIR, 16, 256, false>(v, j, xb, tw);
-      fft_pass<N, DIR, RR, 4096, true>(v, j, xb, tw);
+      fft_pass<N, DIR, 16, 256, false, BAR>(v, j, xb, tw);
+      fft_pass<N, DIR, RR, 4096, true, BAR>(v, j, xb, tw);
     }
   }
 }

@@ -63,6 +63,8 @@ struct gfb_ctx {
   // TMA-staged row pass (single GPU, single-layer kinds, nx = 4096 / 8192): tensor maps of W and P
   bool row_tma = false;
   long long row_tma_launches = 0;
+  bool col_ws = false;  // warp-specialised column kernels (ny = 4096, single-layer kinds)
+  long long col_ws_launches = 0;
   RowTma rt_pruned, rt_full;  // output boxes sized for kout = kcut / nkr
   // optional per-kernel event timing
   bool prof_on = false;
@@ -461,6 +463,10 @@ int gfb_create(gfb_ctx** out, const gfb_config* cfg) {
     const char* off = getenv("GFB_NO_ROW_TMA");
     c->row_tma = !(off && off[0] == '1');
   }
+  {
+    const char* off = getenv("GFB_NO_COL_WS");
+    c->col_ws = c->kind == GFB_KIND_SINGLE && g.ny == 4096 && !(off && off[0] == '1');
+  }
   int nstate = 0;
   switch (cfg->stepper) {
     case GFB_FORWARD_EULER: case GFB_FILTERED_FORWARD_EULER: nstate = 0; break;
@@ -539,7 +545,8 @@ int gfb_path_info(const gfb_ctx* c, long long* info4) {
   if (!c || !info4) return GFB_ERR_INVALID;
   info4[0] = c->row_tma ? 1 : 0;
   info4[1] = c->row_tma_launches;
-  info4[2] = info4[3] = 0;
+  info4[2] = c->col_ws ? 1 : 0;
+  info4[3] = c->col_ws_launches;
   return GFB_OK;
 }
 
@@ -620,6 +627,8 @@ static int run_col_inv_state(gfb_ctx* c, const Spec& sin, int nf, const PeerOut&
     L.ps.G = c->G;
     L.ps.ldg = c->ldi;
     L.nfields = nf;
+    L.ws = c->col_ws;
+    if (L.ws) c->col_ws_launches += 1;
   } else {
     L.prep = PREP_MULTI;
     L.pm.sol = sin.p;

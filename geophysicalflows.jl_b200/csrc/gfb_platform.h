@@ -159,6 +159,24 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 #endif
 
+// ---- named barriers: synchronise a SUBSET of the CTA's warps (bar.sync / bar.arrive id, count) ----------------
+// The warp-specialised kernels split a CTA into an FFT group and a helper group: the FFT group's internal exchanges use
+// bar_sync(id, 256) instead of __syncthreads(), and the two groups hand buffers to each other with the classic
+// producer/consumer pair: the producer bar_arrive()s (does not wait), the consumer bar_sync()s; `count` is the total of
+// both.  id 0 is __syncthreads' barrier: ids 1..15 are free.
+#ifdef GFB_EMULATE
+__device__ __forceinline__ void bar_sync(int id, int count) { emu::named_bar(id, count, true); }
+__device__ __forceinline__ void bar_arrive(int id, int count) { emu::named_bar(id, count, false); }
+__device__ __forceinline__ void tmem_fence_before_sync() {}
+__device__ __forceinline__ void tmem_fence_after_sync() {}
+#else
+__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+// order this thread's TMEM accesses with a following / preceding thread synchronisation (hand-off to other warps)
+__device__ __forceinline__ void tmem_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+#endif
+
 __device__ __forceinline__ void cp_async_wait_all() {
 #ifndef GFB_EMULATE
   asm volatile("cp.async.wait_all;\n" ::: "memory");

@@ -2,7 +2,9 @@
 //
 //   K1  spectral pre-pass (dealias mask on load, psi inversion / S^-1 matvec, i*k derivatives, 1/(nx*ny)) fused
 //       with the inverse FFT along y (columns)
-//         k_col_inv_single   single-layer modules, the hot path: persistent, rolling cp.async prefetch, TMEM stash
+//         k_col_inv_ws       single-layer modules at ny = 4096 (the headline): warp-specialised, one CTA per SM = an FFT
+//                            group + a helper group that loads / prepares ahead, hand-off through TMEM
+//         k_col_inv_single   single-layer modules, other sizes: persistent, rolling cp.async prefetch, TMEM stash
 //         k_col_inv          MultiLayerQG pre-pass and plain inverse transforms
 //         k_col_inv16k       ny = 16384: 4 x 4096 by a radix-4 DIF step while loading
 //   K2  Hermitian c2r along x of (u, v) and q, physical products, r2c along x -- physical fields never touch HBM
@@ -25,6 +27,7 @@
 #pragma once
 #include "layout.cuh"
 #include "k1_col_inv.cuh"
+#include "k1_col_inv_ws.cuh"
 #include "k2_row.cuh"
 #include "k2_row_half.cuh"
 #include "k3_col_fwd.cuh"

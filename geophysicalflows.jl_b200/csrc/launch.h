@@ -19,6 +19,7 @@ struct ColInvLaunch {
   long long wfs;
   int ncols;
   int nfields;         // grid.y
+  bool ws;             // PREP_SINGLE at ny = 4096: the warp-specialised kernel (k_col_inv_ws)
   const cplx* tw;
   const cplx* tw2;     // W_{ny}^i when the columns are cut 4 x (ny/4) (ny = 16384), else unused
   cudaStream_t st;

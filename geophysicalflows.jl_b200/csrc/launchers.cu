@@ -86,7 +86,27 @@ static int do_col_inv_single(const ColInvLaunch& L) {
   return 0;
 }
 
+#if GFB_N == 4096
+// the warp-specialised pre-pass (k_col_inv_ws): one 512-thread CTA per SM
+static int do_col_inv_ws(const ColInvLaunch& L) {
+  const size_t smem = (size_t)xbuf_elems(GFB_N) * sizeof(cplx) + 128;
+  static AttrCache attr;
+  if (!attr.done[cur_device()]) {
+    if (set_smem(k_col_inv_ws<GFB_N>, smem)) return -2;
+    attr.done[cur_device()] = true;
+  }
+  const int nunits = ((L.ncols + 1) / 2) * L.nfields;
+  const int cap = sm_count();
+  dim3 grid(nunits < cap ? nunits : cap);
+  GFB_LAUNCH((k_col_inv_ws<GFB_N>), grid, dim3(WS_THREADS), smem, L.st, L.g, L.ps, L.W, L.ldw, L.wfs, L.ncols, L.nfields, nunits, L.tw);
+  return 0;
+}
+#endif
+
 int GFB_CAT(launch_col_inv_, GFB_N)(const ColInvLaunch& L) {
+#if GFB_N == 4096
+  if (L.prep == PREP_SINGLE && L.ws) return do_col_inv_ws(L);
+#endif
   switch (L.prep) {
     case PREP_PLAIN: return do_col_inv(L, L.pp);
     case PREP_SINGLE: return do_col_inv_single(L);

@@ -327,7 +327,8 @@ class Problem:
     def path_info(self):
         info = (C.c_longlong * 4)()
         self._check(self.lib.gfb_path_info(self.ctx, info), "gfb_path_info")
-        return {"row_tma": bool(info[0]), "row_tma_launches": int(info[1])}
+        return {"row_tma": bool(info[0]), "row_tma_launches": int(info[1]), "col_ws": bool(info[2]),
+                "col_ws_launches": int(info[3])}
 
     def profile_begin(self):
         self._check(self.lib.gfb_profile_begin(self.ctx), "gfb_profile_begin")

@@ -214,7 +214,8 @@ int gfb_profile_end(gfb_ctx* ctx, double* ms4, long long* launches4);
 
 /* Which kernel variants the context dispatches to (for tests and the bench line):
  *   info[0] = 1: the row pass of the stepping path is the TMA-staged kernel (k_row_product_tma)
- *   info[1] = launches of it so far, info[2..3] reserved */
+ *   info[1] = launches of it so far
+ *   info[2] = 1: the column pre-pass is the warp-specialised kernel (k_col_inv_ws), info[3] = its launches so far */
 int gfb_path_info(const gfb_ctx* ctx, long long* info4);
 
 /* bytes of device memory owned by the context */

@@ -130,6 +130,7 @@ struct BlockState {
   ucontext_t sched;
   Barrier block_bar;
   std::vector<Barrier> warp_bar;
+  Barrier named_bar[16];  // bar.sync / bar.arrive id, count
   std::vector<uint64_t> shfl_slot;
   int current = -1;
   const std::function<void()>* body = nullptr;
@@ -207,6 +208,17 @@ inline void sync_block() {
   if (bar.count + 1 >= bar.expected) tmem_check_uniform("__syncthreads");  // last arrival: everybody else is waiting here
   barrier_wait(bar);
 }
+// bar.sync (wait = true) / bar.arrive (wait = false) on named barrier `id` expecting `count` threads in total
+inline void named_bar(int id, int count, bool wait) {
+  Barrier& bar = tl_block->named_bar[id & 15];
+  const unsigned gen = bar.generation;
+  if (++bar.count >= count) {
+    bar.count = 0;
+    bar.generation++;
+  } else if (wait) {
+    while (bar.generation == gen) yield_to_sched();
+  }
+}
 inline void sync_warp() { barrier_wait(tl_block->warp_bar[tl_block->current / 32]); }
 
 template <class T>
@@ -253,6 +265,7 @@ inline void run_block(BlockState& b, dim3 grid, dim3 block, uint3 bidx, size_t s
   if (b.fibers.size() < nt) b.fibers.resize(nt);
   while (b.stacks.size() < nt) b.stacks.push_back((char*)std::malloc(kStack));
   b.block_bar = Barrier();
+  for (auto& nb : b.named_bar) nb = Barrier();
   b.block_bar.expected = (int)nt;
   b.warp_bar.assign((nt + 31) / 32, Barrier());
   for (unsigned w = 0; w < b.warp_bar.size(); ++w) b.warp_bar[w].expected = (int)std::min(32u, nt - 32 * w);

@@ -212,6 +212,8 @@ def test_hot_path_instantiations(emu, oracle_backend, nx, ny, stepper):
     # rows of 4096 / 8192 points go through the TMA-staged row kernel (pruned first step, full last step)
     info = pb.path_info()
     assert info["row_tma"] == (nx >= 4096) and (info["row_tma_launches"] > 0) == (nx >= 4096)
+    # columns of 4096 points go through the warp-specialised pre-pass (FFT group + helper group, TMEM hand-off)
+    assert info["col_ws"] == (ny == 4096) and (info["col_ws_launches"] > 0) == (ny == 4096)
 
 
 @pytest.mark.parametrize("module,stepper", [("twodnavierstokes", "FilteredETDRK4"), ("twodnavierstokes", "FilteredAB3"),
