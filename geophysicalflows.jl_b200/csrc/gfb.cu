@@ -63,7 +63,8 @@ struct gfb_ctx {
   // TMA-staged row pass (single GPU, single-layer kinds, nx = 4096 / 8192): tensor maps of W and P
   bool row_tma = false;
   long long row_tma_launches = 0;
-  bool col_ws = false;  // warp-specialised column kernels (ny = 4096, single-layer kinds)
+  bool col_ws = false;  // warp-specialised column pre-pass (ny = 4096, single-layer kinds)
+  bool col_ws3 = false; // warp-specialised forward column pass + epilogue (ny = 4096, any kind)
   long long col_ws_launches = 0;
   RowTma rt_pruned, rt_full;  // output boxes sized for kout = kcut / nkr
   // optional per-kernel event timing
@@ -466,6 +467,8 @@ int gfb_create(gfb_ctx** out, const gfb_config* cfg) {
   {
     const char* off = getenv("GFB_NO_COL_WS");
     c->col_ws = c->kind == GFB_KIND_SINGLE && g.ny == 4096 && !(off && off[0] == '1');
+    const char* off3 = getenv("GFB_NO_COL_WS3");
+    c->col_ws3 = g.ny == 4096 && !(off3 && off3[0] == '1');
   }
   int nstate = 0;
   switch (cfg->stepper) {
@@ -686,6 +689,7 @@ static int run_col_fwd(gfb_ctx* c, const EpiArgs& e, const cplx* Precv, cudaStre
   F.nlayers = c->nlayers;
   F.nl = c->nlayers;
   F.two = true;
+  F.ws = c->col_ws3;
   F.tw = c->tw_y;
   F.tw2 = c->tw_y2;
   F.st = st;

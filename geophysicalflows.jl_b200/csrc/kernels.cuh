@@ -13,7 +13,9 @@
 //         k_row_product_half / k_row_half   nx = 16384: every real row as one 8192-point half-length transform
 //   K3  forward FFT along y of the two product fields fused with the divergence (-i kr, -i l), forcing and the
 //       time-stepper stage update
-//         k_col_fwd          one transform call site over the four columns, TMEM-parked partners, fused epilogue
+//         k_col_fwd_ws       ny = 4096 (the headline): warp-specialised -- the FFT group transforms while the helper group
+//                            streams the next columns in and runs the previous pair's epilogue out of TMEM
+//         k_col_fwd          other sizes: one transform call site over the four columns, TMEM-parked partners, fused epilogue
 //         k_col_fwd16k (+ _plain)   ny = 16384
 //
 // Reference sequence being replaced: calcN_advection! /root/reference/src/twodnavierstokes.jl:253-275,
@@ -31,5 +33,6 @@
 #include "k2_row.cuh"
 #include "k2_row_half.cuh"
 #include "k3_col_fwd.cuh"
+#include "k3_col_fwd_ws.cuh"
 #include "cols16k.cuh"
 #include "aux_kernels.cuh"

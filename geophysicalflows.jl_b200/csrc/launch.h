@@ -45,6 +45,7 @@ struct ColFwdLaunch {
   int nlayers;         // grid.y
   int nl;              // template NL (layers coupled in the epilogue)
   bool two;
+  bool ws;             // ny = 4096, two = true: the warp-specialised kernel (k_col_fwd_ws)
   const cplx* tw;
   const cplx* tw2;     // as in ColInvLaunch
   cudaStream_t st;

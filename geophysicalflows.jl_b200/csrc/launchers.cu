@@ -294,7 +294,27 @@ static int do_col_fwd(const ColFwdLaunch& L) {
   return 0;
 }
 
+#if GFB_N == 4096
+// the warp-specialised forward column pass + epilogue (k_col_fwd_ws): one 512-thread CTA per SM
+static int do_col_fwd_ws(const ColFwdLaunch& L) {
+  const size_t smem = (size_t)xbuf_elems(GFB_N) * sizeof(cplx) + (size_t)2 * PT * WS_FFT_THREADS * sizeof(cplx) + 128;
+  static AttrCache attr;
+  if (!attr.done[cur_device()]) {
+    if (set_smem(k_col_fwd_ws<GFB_N>, smem)) return -2;
+    attr.done[cur_device()] = true;
+  }
+  const int npairs = (L.ncols + 1) / 2, nunits = npairs * L.nlayers;
+  const int cap = sm_count();
+  dim3 grid(nunits < cap ? nunits : cap);
+  GFB_LAUNCH((k_col_fwd_ws<GFB_N>), grid, dim3(WS_THREADS), smem, L.st, L.g, L.P, L.ldp, L.pfs, L.e, npairs, nunits, L.tw);
+  return 0;
+}
+#endif
+
 int GFB_CAT(launch_col_fwd_, GFB_N)(const ColFwdLaunch& L) {
+#if GFB_N == 4096
+  if (L.two && L.ws) return do_col_fwd_ws(L);
+#endif
   return L.two ? do_col_fwd<true>(L) : do_col_fwd<false>(L);
 }
 

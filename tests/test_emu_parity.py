@@ -216,6 +216,59 @@ def test_hot_path_instantiations(emu, oracle_backend, nx, ny, stepper):
     assert info["col_ws"] == (ny == 4096) and (info["col_ws_launches"] > 0) == (ny == 4096)
 
 
+@pytest.mark.parametrize("case", ["twodns_forced_rk4", "twodns_fab3", "slqg_feuler", "mqg2_frk4", "sqg_fetdrk4"])
+def test_columns_of_4096_points_warp_specialised(emu, oracle_backend, case):
+    """ny = 4096: the warp-specialised column kernels (k_col_inv_ws: FFT group + loader group; k_col_fwd_ws: FFT group +
+    epilogue group; hand-off through TMEM, named barriers) for every epilogue family: explicit RK with stochastic
+    forcing + prevsol, AB3 histories, ForwardEuler with topography (Nconst, eta), MultiLayerQG bottom drag, ETDRK4 tables."""
+    nx, ny, nsteps = 32, 4096, 3
+    rng = np.random.default_rng(4096)
+    if case.startswith("twodns"):
+        stepper = "RK4" if case == "twodns_forced_rk4" else "FilteredAB3"
+        kw = dict(nx=nx, ny=ny, Lx=2 * np.pi, Ly=3.0, nu=1e-4, nnu=1, mu=0.02, nmu=0, dt=1e-3, stepper=stepper)
+        O, M = oracle_backend.twodnavierstokes, emu.twodnavierstokes
+        if case == "twodns_forced_rk4":
+            draws = [np.fft.rfft2(rng.standard_normal((ny, nx))) * 1e-3 for _ in range(nsteps)]
+
+            def mk(B):
+                it = iter(draws)
+
+                def calcF(Fh, sol, t, clock, vars, params, grid):
+                    B.assign(Fh, B.dev(next(it)))
+                return calcF
+            po, pb = O.Problem(calcF=mk(oracle_backend), stochastic=True, **kw), M.Problem(calcF=mk(emu), stochastic=True, **kw)
+        else:
+            po, pb = O.Problem(**kw), M.Problem(**kw)
+        amp = 300.0
+    elif case == "slqg_feuler":
+        eta = 0.1 * rng.standard_normal((ny, nx))
+        kw = dict(nx=nx, ny=ny, Lx=2 * np.pi, Ly=3.0, beta=1.5, deformation_radius=1.1, U=0.2, mu=0.01, nu=1e-9, nnu=1, eta=eta,
+                  dt=1e-4, stepper="ForwardEuler")
+        po, pb = oracle_backend.singlelayerqg.Problem(**kw), emu.singlelayerqg.Problem(**kw)
+        amp = 300.0
+    elif case == "mqg2_frk4":
+        kw = dict(nx=nx, ny=ny, Lx=2 * np.pi, Ly=3.0, f0=1.0, beta=5.0, mu=5e-2, H=[0.2, 0.8], b=[-1.0, -1.2], U=[1.0, 0.0],
+                  dt=2e-4, stepper="FilteredRK4")
+        po, pb = oracle_backend.multilayerqg.Problem(2, **kw), emu.multilayerqg.Problem(2, **kw)
+        amp = 3.0
+    else:
+        kw = dict(nx=nx, ny=ny, Lx=2 * np.pi, Ly=3.0, nu=1e-12, nnu=2, dt=1e-3, stepper="FilteredETDRK4")
+        po, pb = oracle_backend.surfaceqg.Problem(**kw), emu.surfaceqg.Problem(**kw)
+        amp = 3.0
+    shape = po.sol.shape
+    s0 = np.fft.rfft2(rng.standard_normal(shape[:-2] + (ny, nx))) * amp / (nx * ny)
+    po.sol[...] = s0
+    pb.sol.copy_(emu.dev(s0))
+    oracle_backend.stepforward_(po, nsteps)
+    emu.stepforward_(pb, nsteps)
+    assert np.isfinite(po.sol).all() and np.linalg.norm(po.sol) > 0
+    assert R.relerr(emu.host(pb.sol), po.sol) < 1e-13
+    if case == "twodns_forced_rk4":
+        assert R.relerr(emu.host(pb.vars.prevsol), po.vars.prevsol) < 1e-13
+    info = pb.path_info()
+    assert info["col_ws_launches"] > 0 or case == "mqg2_frk4"  # the layered pre-pass keeps its own kernel
+
+
 @pytest.mark.parametrize("module,stepper", [("twodnavierstokes", "FilteredETDRK4"), ("twodnavierstokes", "FilteredAB3"),
                                             ("surfaceqg", "ETDRK4"), ("singlelayerqg", "FilteredRK4")])
 def test_rows_of_16384_points(emu, oracle_backend, module, stepper):
