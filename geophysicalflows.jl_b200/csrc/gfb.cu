@@ -62,6 +62,7 @@ struct gfb_ctx {
   bool defer_alias = false;  // gfb_set_defer_alias_band
   // TMA-staged row pass (single GPU, single-layer kinds, nx = 4096 / 8192): tensor maps of W and P
   bool row_tma = false;
+  bool row_ws = false;  // nx = 4096: the warp-specialised row kernel on top of the TMA staging
   long long row_tma_launches = 0;
   bool col_ws = false;  // warp-specialised column pre-pass (ny = 4096, single-layer kinds)
   bool col_ws3 = false; // warp-specialised forward column pass + epilogue (ny = 4096, any kind)
@@ -463,6 +464,8 @@ int gfb_create(gfb_ctx** out, const gfb_config* cfg) {
     }
     const char* off = getenv("GFB_NO_ROW_TMA");
     c->row_tma = !(off && off[0] == '1');
+    const char* offw = getenv("GFB_NO_ROW_WS");
+    c->row_ws = c->row_tma && g.nx == 4096 && !(offw && offw[0] == '1');
   }
   {
     const char* off = getenv("GFB_NO_COL_WS");
@@ -671,6 +674,7 @@ static int run_row_product(gfb_ctx* c, const cplx* Wrecv, const PeerOut& Psend, 
   // the TMA-staged kernel reads the ctx-owned W and writes the ctx-owned P (the tensor maps are bound to them)
   if (c->row_tma && Wrecv == c->W && Psend.nranks == 1 && Psend.base[0] == c->P) {
     R.tma = prune ? &c->rt_pruned : &c->rt_full;
+    R.ws = c->row_ws;
     c->row_tma_launches += 1;
   }
   ProfScope ps(c, 1, st);

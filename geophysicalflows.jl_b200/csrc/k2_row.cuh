@@ -60,23 +60,23 @@ __device__ __forceinline__ void load_hermitian(cplx (&v)[PT], const int j, const
 // After a forward FFT of z = a + i b (a, b real rows): thread holds Z[k], k = j + r*T.  Exchanges
 // through shared memory (re then im) to fetch Z[N-k] and returns A[k], B[k] for r = 0..8 (r = 8 only valid
 // for j == 0, k = N/2).
-template <int N>
+template <int N, int BAR = 0>
 __device__ __forceinline__ void unpack_pair(const cplx (&v)[PT], const int j, double* __restrict__ xb,
                                             cplx (&A)[9], cplx (&B)[9]) {
   constexpr int T = N / PT;
   double wre[9];
 #pragma unroll
   for (int r = 0; r < PT; ++r) xb[xpad(j + r * T)] = v[r].x;
-  __syncthreads();
+  fft_sync<BAR, T>();
 #pragma unroll
   for (int r = 0; r < 9; ++r) {
     const int m = (N - (j + r * T)) & (N - 1);
     wre[r] = (r < 8 || j == 0) ? xb[xpad(m)] : v[r].x;
   }
-  __syncthreads();
+  fft_sync<BAR, T>();
 #pragma unroll
   for (int r = 0; r < PT; ++r) xb[xpad(j + r * T)] = v[r].y;
-  __syncthreads();
+  fft_sync<BAR, T>();
 #pragma unroll
   for (int r = 0; r < 9; ++r) {
     const int m = (N - (j + r * T)) & (N - 1);
@@ -85,7 +85,7 @@ __device__ __forceinline__ void unpack_pair(const cplx (&v)[PT], const int j, do
     A[r] = cmake(0.5 * (o.x + wre[r]), 0.5 * (o.y - wim));
     B[r] = cmake(0.5 * (o.y + wim), -0.5 * (o.x - wre[r]));
   }
-  __syncthreads();
+  fft_sync<BAR, T>();
 }
 
 // address of P(row, k) given the row part of the offset: column pair kp belongs to rank kp % nranks

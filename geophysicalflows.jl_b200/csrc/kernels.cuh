@@ -8,7 +8,11 @@
 //         k_col_inv          MultiLayerQG pre-pass and plain inverse transforms
 //         k_col_inv16k       ny = 16384: 4 x 4096 by a radix-4 DIF step while loading
 //   K2  Hermitian c2r along x of (u, v) and q, physical products, r2c along x -- physical fields never touch HBM
-//         k_row_product      the hot path: persistent, line-buffer prefetch of the next phase, q parked in TMEM
+//         k_row_product_ws   nx = 4096, single-layer modules (the headline): warp-specialised -- the FFT group does the five
+//                            transforms of a row pair; the helper group gathers rows by TMA, assembles the Hermitian input,
+//                            separates the output spectra and scatters the result rows by TMA; hand-off through TMEM
+//         k_row_product_tma  nx = 8192: as k_row_product with TMA row gathers / scatters
+//         k_row_product      other sizes / layered: persistent, line-buffer prefetch of the next phase, q parked in TMEM
 //         k_row              plain c2r / r2c (ldiv! / mul! seams, updatevars!)
 //         k_row_product_half / k_row_half   nx = 16384: every real row as one 8192-point half-length transform
 //   K3  forward FFT along y of the two product fields fused with the divergence (-i kr, -i l), forcing and the
@@ -31,6 +35,7 @@
 #include "k1_col_inv.cuh"
 #include "k1_col_inv_ws.cuh"
 #include "k2_row.cuh"
+#include "k2_row_ws.cuh"
 #include "k2_row_half.cuh"
 #include "k3_col_fwd.cuh"
 #include "k3_col_fwd_ws.cuh"

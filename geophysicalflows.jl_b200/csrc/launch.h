@@ -29,6 +29,7 @@ struct RowLaunch {
   int mode;            // RowMode
   RowArgs a;
   const RowTma* tma;   // non-null: TMA-staged product kernel (single GPU, single-layer kinds, NX >= 4096)
+  bool ws;             // with tma at nx = 4096: the warp-specialised kernel (k_row_product_ws)
   int nlayers;         // grid.y
   const cplx* tw;
   const cplx* tw2;     // W_{nx}^i when the row transforms run at half length (nx = 16384), else unused

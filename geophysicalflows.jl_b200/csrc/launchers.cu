@@ -170,7 +170,30 @@ static int do_row_product_tma(const RowLaunch& L) {
 }
 #endif
 
+#if GFB_N == 4096
+// the warp-specialised product pass (k_row_product_ws): one 512-thread CTA per SM
+static int do_row_product_ws(const RowLaunch& L) {
+  const RowTma& t = *L.tma;
+  const size_t in_row = (size_t)2 * t.nbox_in * t.boxp_in * sizeof(cplx), out_row = (size_t)2 * t.nbox_out * t.boxp_out * sizeof(cplx);
+  const size_t smem = (size_t)xbuf_elems(GFB_N) * sizeof(cplx) + 128 + 4 * in_row + 2 * out_row;
+  if (2 * out_row < (size_t)xbuf_elems(GFB_N) * sizeof(double) || smem > 227 * 1024) return do_row_product_tma(L);
+  static AttrCache attr;
+  if (smem > attr.bytes[cur_device()]) {
+    if (set_smem(k_row_product_ws<GFB_N>, smem)) return -2;
+    attr.bytes[cur_device()] = smem;
+  }
+  const int nunits = (L.a.ny / 2) * L.nlayers;
+  const int cap = sm_count();
+  dim3 grid(nunits < cap ? nunits : cap);
+  GFB_LAUNCH((k_row_product_ws<GFB_N>), grid, dim3(WS_THREADS), smem, L.st, L.a, t, L.tw, nunits);
+  return 0;
+}
+#endif
+
 int GFB_CAT(launch_row_, GFB_N)(const RowLaunch& L) {
+#if GFB_N == 4096
+  if (L.mode == ROW_PRODUCT && L.tma != nullptr && L.ws) return do_row_product_ws(L);
+#endif
 #if GFB_N >= 4096
   if (L.mode == ROW_PRODUCT && L.tma != nullptr) return do_row_product_tma(L);
 #endif

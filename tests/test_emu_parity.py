@@ -269,6 +269,31 @@ def test_columns_of_4096_points_warp_specialised(emu, oracle_backend, case):
     assert info["col_ws_launches"] > 0 or case == "mqg2_frk4"  # the layered pre-pass keeps its own kernel
 
 
+@pytest.mark.parametrize("module,stepper", [("surfaceqg", "ETDRK4"), ("singlelayerqg", "FilteredRK4")])
+def test_rows_of_4096_points_warp_specialised(emu, oracle_backend, module, stepper):
+    """nx = 4096: the warp-specialised row kernel (k_row_product_ws: FFT group + helper group that gathers rows by TMA,
+    assembles the Hermitian input, separates the spectra and scatters rows by TMA), incl. the q + eta path."""
+    nx, ny = 4096, 32
+    kw = dict(nx=nx, ny=ny, Lx=2 * np.pi, Ly=3.0, dt=1e-3, stepper=stepper)
+    if module == "surfaceqg":
+        kw.update(nu=1e-12, nnu=2)
+        amp = 3.0
+    else:
+        eta = 0.1 * np.random.default_rng(3).standard_normal((ny, nx))
+        kw.update(beta=1.5, deformation_radius=1.1, U=0.2, mu=0.01, nu=1e-9, nnu=1, eta=eta)
+        amp = 300.0
+    po = getattr(oracle_backend, module).Problem(**kw)
+    pb = getattr(emu, module).Problem(**kw)
+    s0 = np.fft.rfft2(np.random.default_rng(40).standard_normal((ny, nx))) * amp / (nx * ny)
+    po.sol[...] = s0
+    pb.sol.copy_(emu.dev(s0))
+    oracle_backend.stepforward_(po, 3)
+    emu.stepforward_(pb, 3)
+    assert np.isfinite(po.sol).all()
+    assert R.relerr(emu.host(pb.sol), po.sol) < 1e-13
+    assert pb.path_info()["row_tma_launches"] > 0
+
+
 @pytest.mark.parametrize("module,stepper", [("twodnavierstokes", "FilteredETDRK4"), ("twodnavierstokes", "FilteredAB3"),
                                             ("surfaceqg", "ETDRK4"), ("singlelayerqg", "FilteredRK4")])
 def test_rows_of_16384_points(emu, oracle_backend, module, stepper):
