@@ -262,6 +262,53 @@ __device__ __forceinline__ void block_fft(cplx (&v)[PT], const int j, cplx* __re
   }
 }
 
+// Register-resident twiddles (N = 16^3 = 4096): with one radix-16 butterfly per thread and pass, the twiddle base of a
+// thread is the same for every transform it ever does -- W_N^{16 (j & 15)} in pass 2, W_N^{j} in pass 3 -- so it is
+// loaded ONCE per kernel instead of once per pass.  (The per-pass __ldg sat on the critical path of every pass: with
+// ~200 KB of the SM's 256 KB carved out as shared memory the 64 KB table does not stay in L1, and the load -- an L2
+// round trip -- was the top stall of the warp-specialised kernels' FFT group.)
+struct Tw4096 {
+  cplx w2, w3;  // forward sign
+};
+__device__ __forceinline__ Tw4096 load_tw4096(const int j, const cplx* __restrict__ tw) {
+  Tw4096 t;
+  t.w2 = __ldg(&tw[(j & 15) * 16]);
+  t.w3 = __ldg(&tw[j & 255]);
+  return t;
+}
+template <int DIR, int Ns, bool LAST, int BAR>
+__device__ __forceinline__ void fft_pass4096(cplx (&v)[PT], const int j, cplx* __restrict__ xb, cplx w1) {
+  constexpr int N = 4096, T = N / PT, R = 16;
+  cplx x[R];
+#pragma unroll
+  for (int s = 0; s < R; ++s) x[s] = v[s];
+  if (Ns > 1) {
+    if (DIR == INV) w1.y = -w1.y;
+    twiddle_apply<R>(x, w1);
+  }
+  Dft<DIR, R>::run(x);
+  if (LAST) {
+#pragma unroll
+    for (int s = 0; s < R; ++s) v[s] = x[s];
+  } else {
+    const int k = j & (Ns - 1);
+    const int base = (j - k) * R + k;
+#pragma unroll
+    for (int s = 0; s < R; ++s) xb[xpad(base + s * Ns)] = x[s];
+    fft_sync<BAR, T>();
+#pragma unroll
+    for (int r = 0; r < PT; ++r) v[r] = xb[xpad(j + r * T)];
+    fft_sync<BAR, T>();
+  }
+}
+// 4096-point transform of the group's registers, un-split exchange, twiddles from registers
+template <int DIR, int BAR>
+__device__ __forceinline__ void block_fft4096(cplx (&v)[PT], const int j, cplx* __restrict__ xb, const Tw4096& t) {
+  fft_pass4096<DIR, 1, false, BAR>(v, j, xb, t.w2);
+  fft_pass4096<DIR, 16, false, BAR>(v, j, xb, t.w2);
+  fft_pass4096<DIR, 256, true, BAR>(v, j, xb, t.w3);
+}
+
 // Split (re / im) exchange variant: the exchange buffer holds N doubles (+pad) instead of N complex, so it
 // costs half the shared memory (two CTAs of a 4096-point kernel fit one SM) for twice the barriers.
 template <int N, int DIR, int R, int Ns, bool LAST>

@@ -177,6 +177,18 @@ __device__ __forceinline__ void tmem_fence_before_sync() { asm volatile("tcgen05
 __device__ __forceinline__ void tmem_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 #endif
 
+// Bulk L2 prefetch (cp.async.bulk.prefetch.L2, issued through the TMA unit): `bytes` contiguous bytes (a multiple of 16,
+// 16-byte aligned) start moving from DRAM into L2; costs no register and nothing waits on it.  The helper groups of the
+// warp-specialised kernels use it to turn the DRAM latency of the NEXT block of rows into an L2 hit.
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, unsigned bytes) {
+#ifndef GFB_EMULATE
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+#else
+  (void)p;
+  (void)bytes;
+#endif
+}
+
 __device__ __forceinline__ void cp_async_wait_all() {
 #ifndef GFB_EMULATE
   asm volatile("cp.async.wait_all;\n" ::: "memory");
@@ -336,4 +348,65 @@ __device__ __forceinline__ void tma_wait_all() {  // all but the N youngest stor
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 #endif
 
+}  // namespace gfb
+
+// ---- wide TMEM transfers: a thread's 16 (or 4) complex values in ONE tcgen05 instruction ---------------------------
+// tcgen05.ld / .st are issued per warp and carry a fixed cost per instruction; the .x64 shape moves 64 columns (16
+// complex doubles) of the thread's lane at once, the .x16 shape 4 complex values.
+namespace gfb {
+#ifdef GFB_EMULATE
+__device__ __forceinline__ void tmem_store16(uint32_t taddr, const cplx (&v)[16]) {
+  emu::tmem_note(5, taddr & 0xffffu);
+  for (int r = 0; r < 16; ++r) std::memcpy(emu_tmem_cell(taddr + 4 * r), &v[r], 16);
+}
+__device__ __forceinline__ void tmem_load16(uint32_t taddr, cplx (&v)[16]) {
+  emu::tmem_note(6, taddr & 0xffffu);
+  for (int r = 0; r < 16; ++r) std::memcpy(&v[r], emu_tmem_cell(taddr + 4 * r), 16);
+}
+__device__ __forceinline__ void tmem_load4(uint32_t taddr, cplx (&v)[4]) {
+  emu::tmem_note(7, taddr & 0xffffu);
+  for (int r = 0; r < 4; ++r) std::memcpy(&v[r], emu_tmem_cell(taddr + 4 * r), 16);
+}
+__device__ __forceinline__ void tmem_store4(uint32_t taddr, const cplx (&v)[4]) {
+  emu::tmem_note(8, taddr & 0xffffu);
+  for (int r = 0; r < 4; ++r) std::memcpy(emu_tmem_cell(taddr + 4 * r), &v[r], 16);
+}
+#else
+__device__ __forceinline__ void tmem_store16(uint32_t taddr, const cplx (&v)[16]) {
+  uint32_t w[64];
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    w[4 * r + 0] = (uint32_t)__double2loint(v[r].x);
+    w[4 * r + 1] = (uint32_t)__double2hiint(v[r].x);
+    w[4 * r + 2] = (uint32_t)__double2loint(v[r].y);
+    w[4 * r + 3] = (uint32_t)__double2hiint(v[r].y);
+  }
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x64.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63, %64};" ::"r"(taddr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]), "r"(w[8]), "r"(w[9]), "r"(w[10]), "r"(w[11]), "r"(w[12]), "r"(w[13]), "r"(w[14]), "r"(w[15]), "r"(w[16]), "r"(w[17]), "r"(w[18]), "r"(w[19]), "r"(w[20]), "r"(w[21]), "r"(w[22]), "r"(w[23]), "r"(w[24]), "r"(w[25]), "r"(w[26]), "r"(w[27]), "r"(w[28]), "r"(w[29]), "r"(w[30]), "r"(w[31]), "r"(w[32]), "r"(w[33]), "r"(w[34]), "r"(w[35]), "r"(w[36]), "r"(w[37]), "r"(w[38]), "r"(w[39]), "r"(w[40]), "r"(w[41]), "r"(w[42]), "r"(w[43]), "r"(w[44]), "r"(w[45]), "r"(w[46]), "r"(w[47]), "r"(w[48]), "r"(w[49]), "r"(w[50]), "r"(w[51]), "r"(w[52]), "r"(w[53]), "r"(w[54]), "r"(w[55]), "r"(w[56]), "r"(w[57]), "r"(w[58]), "r"(w[59]), "r"(w[60]), "r"(w[61]), "r"(w[62]), "r"(w[63]) : "memory");
+}
+__device__ __forceinline__ void tmem_load16(uint32_t taddr, cplx (&v)[16]) {  // valid after tmem_wait_ld()
+  uint32_t w[64];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]), "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15]), "=r"(w[16]), "=r"(w[17]), "=r"(w[18]), "=r"(w[19]), "=r"(w[20]), "=r"(w[21]), "=r"(w[22]), "=r"(w[23]), "=r"(w[24]), "=r"(w[25]), "=r"(w[26]), "=r"(w[27]), "=r"(w[28]), "=r"(w[29]), "=r"(w[30]), "=r"(w[31]), "=r"(w[32]), "=r"(w[33]), "=r"(w[34]), "=r"(w[35]), "=r"(w[36]), "=r"(w[37]), "=r"(w[38]), "=r"(w[39]), "=r"(w[40]), "=r"(w[41]), "=r"(w[42]), "=r"(w[43]), "=r"(w[44]), "=r"(w[45]), "=r"(w[46]), "=r"(w[47]), "=r"(w[48]), "=r"(w[49]), "=r"(w[50]), "=r"(w[51]), "=r"(w[52]), "=r"(w[53]), "=r"(w[54]), "=r"(w[55]), "=r"(w[56]), "=r"(w[57]), "=r"(w[58]), "=r"(w[59]), "=r"(w[60]), "=r"(w[61]), "=r"(w[62]), "=r"(w[63]) : "r"(taddr) : "memory");
+#pragma unroll
+  for (int r = 0; r < 16; ++r)
+    v[r] = make_double2(__hiloint2double((int)w[4 * r + 1], (int)w[4 * r + 0]), __hiloint2double((int)w[4 * r + 3], (int)w[4 * r + 2]));
+}
+__device__ __forceinline__ void tmem_store4(uint32_t taddr, const cplx (&v)[4]) {
+  uint32_t w[16];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    w[4 * r + 0] = (uint32_t)__double2loint(v[r].x);
+    w[4 * r + 1] = (uint32_t)__double2hiint(v[r].x);
+    w[4 * r + 2] = (uint32_t)__double2loint(v[r].y);
+    w[4 * r + 3] = (uint32_t)__double2hiint(v[r].y);
+  }
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]), "r"(w[8]), "r"(w[9]), "r"(w[10]), "r"(w[11]), "r"(w[12]), "r"(w[13]), "r"(w[14]), "r"(w[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_load4(uint32_t taddr, cplx (&v)[4]) {  // valid after tmem_wait_ld()
+  uint32_t w[16];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]), "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15]) : "r"(taddr) : "memory");
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+    v[r] = make_double2(__hiloint2double((int)w[4 * r + 1], (int)w[4 * r + 0]), __hiloint2double((int)w[4 * r + 3], (int)w[4 * r + 2]));
+}
+#endif
 }  // namespace gfb

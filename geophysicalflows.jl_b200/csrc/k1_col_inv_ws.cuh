@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
   const int j = is_fft ? tid : tid - WS_FFT_THREADS;
   const uint32_t tbase = tmem_setup(tmem_word, 512);
   const uint32_t tm = ws_tmem_base(tbase);
-  const uint32_t t_in[2] = {tm, tm + 64};
+  const uint32_t t_in[2] = {tm, tm + 64};  // (indexed with b = n & 1)
   const uint32_t t_park = tm + 128;
   // unit u = (column pair, field); this CTA transforms units blockIdx.x + i * gridDim.x, two columns each
   const int nmine = (nunits - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -65,33 +65,42 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
       const bool live_col = col < ncols;
       const double kr = wav_kr(g, col);
       const int off0 = toff(j, colA, prep.ld) + which;
+      // the NEXT unit's column pair (state + G tiles of this thread's live rows) starts moving DRAM -> L2 now: one
+      // thread in eight issues, for the 256-byte tile its row shares with its seven neighbours
+      if (which == 0 && (n >> 1) + 1 < nmine && (j & 7) == 0) {
+        const int un = unit + (int)gridDim.x, fn = un % nfields, cn = 2 * (un / nfields);
+        const int pf0 = toff(j, cn, prep.ld);
+#pragma unroll
+        for (int r = 0; r < PT; ++r) {
+          if (!l_aliased(g, j + r * T) || !l_aliased(g, j + r * T + 7)) {
+            prefetch_l2_bulk(prep.sol + pf0 + r * T * prep.ld, 256);
+            if (fn != 2) prefetch_l2_bulk(prep.G + pf0 + r * T * prep.ld, 128);
+          }
+        }
+      }
+      // all 16 rows in one batch: 16 x (16 + 8) bytes in flight per thread, one memory round trip per column
       cplx val[PT];
+      double gg[PT];
 #pragma unroll
-      for (int h = 0; h < PT; h += 8) {  // two batches of eight rows: 8 x (16 + 8) bytes in flight per thread
-        cplx raw[8];
-        double gg[8];
+      for (int r = 0; r < PT; ++r) {
+        const bool on = live_col && !l_aliased(g, j + r * T);
+        const int off = off0 + r * T * prep.ld;  // T % 8 == 0: the tiled layout is affine in r
+        val[r] = on ? prep.sol[off] : cmake(0.0, 0.0);
+        gg[r] = (on && field != 2) ? prep.G[off] : 0.0;
+      }
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int r = h + q, l = j + r * T;
-          const bool on = live_col && !l_aliased(g, l);
-          const int off = off0 + r * T * prep.ld;  // T % 8 == 0: the tiled layout is affine in r
-          raw[q] = on ? prep.sol[off] : cmake(0.0, 0.0);
-          gg[q] = (on && field != 2) ? prep.G[off] : 0.0;
-        }
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int r = h + q, l = j + r * T;
-          const bool on = live_col && !l_aliased(g, l);
-          const cplx t = prep.apply(g, field, wav_l(g, l), kr, gg[q], raw[q]);
-          val[r] = cmake(on ? t.x : 0.0, on ? t.y : 0.0);
-        }
+      for (int r = 0; r < PT; ++r) {
+        const int l = j + r * T;
+        const bool on = live_col && !l_aliased(g, l);
+        const cplx t = prep.apply(g, field, wav_l(g, l), kr, gg[r], val[r]);
+        val[r] = cmake(on ? t.x : 0.0, on ? t.y : 0.0);
       }
       if (n >= 2) {  // the FFT group has taken column n - 2 out of this slot
         bar_sync(WS_BAR_EMPTY + b, WS_THREADS);
         tmem_fence_after_sync();
       }
 #pragma unroll
-      for (int r = 0; r < PT; ++r) tmem_store(t_in[b] + 4 * r, val[r]);
+      for (int r = 0; r < PT; ++r) tmem_store(t_in[b] + 4 * r, val[r]);  // 16 x .x4: one .x64 store is 5x slower (tools/tmem_bench)
       tmem_wait_st();
       tmem_fence_before_sync();
       bar_arrive(WS_BAR_FULL + b, WS_THREADS);
@@ -99,19 +108,19 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
   } else {
     // ---------------- FFT group: slot -> registers -> transform -> park (column A) / store the pair (column B) --------
     cplx v[PT];
+    const Tw4096 twr = load_tw4096(j, tw);
 #pragma unroll 1
     for (int n = 0; n < ncolumns; ++n) {
       const int unit = (int)blockIdx.x + (n >> 1) * (int)gridDim.x, which = n & 1, b = n & 1;
       bar_sync(WS_BAR_FULL + b, WS_THREADS);
       tmem_fence_after_sync();
-#pragma unroll
-      for (int r = 0; r < PT; ++r) v[r] = tmem_load(t_in[b] + 4 * r);
+      tmem_load16(t_in[b], v);
       tmem_wait_ld();
       if (n + 2 < ncolumns) {  // hand the slot back (only if somebody will wait for it)
         tmem_fence_before_sync();
         bar_arrive(WS_BAR_EMPTY + b, WS_THREADS);
       }
-      block_fft<NY, INV, WS_BAR_FFT>(v, j, xb, tw);
+      block_fft4096<INV, WS_BAR_FFT>(v, j, xb, twr);
       if (which == 0) {  // column A waits in TMEM for its partner
 #pragma unroll
         for (int r = 0; r < PT; ++r) tmem_store(t_park + 4 * r, v[r]);
@@ -122,8 +131,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
 #pragma unroll
         for (int c0 = 0; c0 < PT; c0 += 4) {
           cplx ra[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) ra[q] = tmem_load(t_park + 4 * (c0 + q));
+          tmem_load4(t_park + 4 * c0, ra);
           tmem_wait_ld();
 #pragma unroll
           for (int q = 0; q < 4; ++q) {

@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
           tmem_fence_after_sync();
         }
 #pragma unroll
-        for (int r = 0; r < PT; ++r) tmem_store(tmb + 64 * s + 4 * r, v[r]);
+        for (int r = 0; r < PT; ++r) tmem_store(tmb + 64 * s + 4 * r, v[r]);  // 16 x .x4: one .x64 store is 5x slower (tools/tmem_bench)
         tmem_wait_st();
         tmem_fence_before_sync();
         bar_arrive(WS_BAR_FULL + s, WS_THREADS);
@@ -106,8 +106,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
         const int layer = unit / npairs, y = 2 * (unit - layer * npairs) + h;
         bar_sync(WS_BAR_OUT_FULL, WS_THREADS);
         tmem_fence_after_sync();
-#pragma unroll
-        for (int r = 0; r < PT; ++r) v[r] = tmem_load(t_out + 4 * r);
+        tmem_load16(t_out, v);
         tmem_wait_ld();
         if (mo + 1 < nphases) {  // another output follows (phase mo + 1 or mo + 2): hand the out-slot back
           tmem_fence_before_sync();
@@ -142,20 +141,20 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
   } else {
     // ------------------------------------------ FFT group ------------------------------------------------------------
     cplx v[PT];
+    const Tw4096 twr = load_tw4096(j, tw);
     int nout = 0;
 #pragma unroll 1
     for (int m = 0; m < nphases; ++m) {
       const int s = m & 1, ph = m % 3;
       bar_sync(WS_BAR_FULL + s, WS_THREADS);
       tmem_fence_after_sync();
-#pragma unroll
-      for (int r = 0; r < PT; ++r) v[r] = tmem_load(tmb + 64 * s + 4 * r);
+      tmem_load16(tmb + 64 * s, v);
       tmem_wait_ld();
       if (m + 2 < nphases) {
         tmem_fence_before_sync();
         bar_arrive(WS_BAR_EMPTY + s, WS_THREADS);
       }
-      block_fft<NX, INV, WS_BAR_FFT>(v, j, xb, tw);
+      block_fft4096<INV, WS_BAR_FFT>(v, j, xb, twr);
       if (ph == 0) {  // q of both rows (+ eta) -> TMEM
         if (a.eta != nullptr) {
           const int unit = (int)blockIdx.x + (m / 3) * (int)gridDim.x;
@@ -176,8 +175,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
 #pragma unroll
       for (int c0 = 0; c0 < PT; c0 += 4) {
         cplx q2[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) q2[q] = tmem_load(t_q + 4 * (c0 + q));
+        tmem_load4(t_q + 4 * c0, q2);
         tmem_wait_ld();
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -186,7 +184,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
           v[c0 + q].y *= qq;
         }
       }
-      block_fft<NX, FWD, WS_BAR_FFT>(v, j, xb, tw);
+      block_fft4096<FWD, WS_BAR_FFT>(v, j, xb, twr);
       if (nout > 0) {  // the helper group has taken the previous spectrum out of the out-slot
         bar_sync(WS_BAR_OUT_EMPTY, WS_THREADS);
         tmem_fence_after_sync();

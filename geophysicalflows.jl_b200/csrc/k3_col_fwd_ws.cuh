@@ -32,10 +32,59 @@ namespace gfb {
 constexpr int WS_BAR_NFULL = 6;
 constexpr int WS_BAR_NEMPTY = 8;
 
-// rows r_begin .. r_begin + 3 of this thread's 16 rows of the column pair, N of both columns in TMEM (ta, tb)
+// Start moving one 8-row tile (rows l .. l + 7 of the column pair at colA) of every array the epilogue of this kind READS
+// from DRAM into L2 (same selection as epi_fetch; the masks of masked_pair are honoured so nothing useless moves).
+template <int KIND, bool CL>
+__device__ __forceinline__ void epi_prefetch_tile(const GridDesc& g, const EpiArgs& e, const int layer, const int colA, const int off) {
+  auto pc = [&](const Spec& a) {
+    if (a.p) prefetch_l2_bulk(a.p + layer * a.ls + off, 256);
+  };
+  auto pk = [&](const Coef& t) {
+    if (CL) prefetch_l2_bulk(t.c + layer * t.ls + off, 256);
+    else prefetch_l2_bulk(t.r + layer * t.ls + off, 128);
+  };
+  const bool live_col = gcol(g, colA) < g.kcut;
+  if (KIND == EPI_RK_LAST || KIND == EPI_RK_ONLY || KIND == EPI_ETD_4 || KIND == EPI_AB3) {
+    if (e.filter.p) prefetch_l2_bulk(e.filter.p + off, 128);
+  }
+  if ((KIND == EPI_RK_FIRST || KIND == EPI_RK_MID || KIND == EPI_RK_ONLY || KIND == EPI_ETD_1 || KIND == EPI_ETD_2 || KIND == EPI_ETD_3 ||
+       KIND == EPI_AB3) && live_col)
+    pc(e.sol);
+  if ((KIND == EPI_RK_MID || KIND == EPI_RK_LAST) && live_col) pc(e.sin);
+  if (KIND == EPI_RK_FIRST || KIND == EPI_RK_MID || KIND == EPI_RK_LAST || KIND == EPI_RK_ONLY || KIND == EPI_AB3) pk(e.L);
+  if (KIND == EPI_RK_MID || KIND == EPI_RK_LAST || KIND == EPI_ETD_2 || KIND == EPI_ETD_3 || KIND == EPI_ETD_4) pc(e.acc);
+  if (KIND == EPI_AB3 && (e.b != 0.0 || e.d != 0.0)) {
+    pc(e.acc);
+    pc(e.n1);
+  }
+  if (KIND == EPI_ETD_3) pc(e.n1);
+  if (KIND == EPI_ETD_1 || KIND == EPI_ETD_2 || KIND == EPI_ETD_3) {
+    pk(e.c1);
+    pk(e.c2);
+  }
+  if (KIND == EPI_ETD_1) pk(e.c3);
+  if (KIND == EPI_ETD_1 || KIND == EPI_ETD_2 || KIND == EPI_ETD_3 || KIND == EPI_ETD_4) pk(e.c4);
+  pc(e.Nconst);
+  pc(e.F);
+}
+
+// rows r_begin .. r_begin + 3 of this thread's 16 rows of the column pair, N of both columns in TMEM (ta, tb).
+// (nlayer, ncolA, nr_begin): the slice this thread works on NEXT (nr_begin < 0: none) -- its tiles are prefetched into
+// L2 first, by one thread in eight (a tile = the rows of eight neighbouring threads), so that the one-row-at-a-time loop
+// below waits for an L2 hit instead of a DRAM round trip per row.
 template <int T, int KIND, bool CL>
 __device__ __forceinline__ void epilogue_rows_ws(const GridDesc& g, const EpiArgs& e, const int layer, const int colA,
-                                                 const uint32_t ta, const uint32_t tb, const int j, const int r_begin) {
+                                                 const uint32_t ta, const uint32_t tb, const int j, const int r_begin,
+                                                 const int nlayer, const int ncolA, const int nr_begin) {
+  if (nr_begin >= 0 && (j & 7) == 0) {
+    const int poff = toff(j, ncolA, e.out.ld);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int l = j + (nr_begin + q) * T;
+      if (!(e.prune && l_aliased(g, l) && l_aliased(g, l + 7)))
+        epi_prefetch_tile<KIND, CL>(g, e, nlayer, ncolA, toff_row<T>(poff, j, nr_begin + q, ncolA, e.out.ld));
+    }
+  }
   // one row (two wavenumbers) per iteration: the helper group shares the 128-register budget of the FFT group's
   // transform, and two rows of the six-array kinds spill; 256 threads x ~6 x 32 bytes in flight still cover the latency
   constexpr int CH = 1;
@@ -72,9 +121,9 @@ __device__ __forceinline__ void epilogue_rows_ws(const GridDesc& g, const EpiArg
 
 template <int T, bool CL>
 __device__ __forceinline__ void epilogue_rows_ws_dispatch(const GridDesc& g, const EpiArgs& e, int layer, int colA, uint32_t ta,
-                                                          uint32_t tb, int j, int r_begin) {
+                                                          uint32_t tb, int j, int r_begin, int nlayer, int ncolA, int nr_begin) {
   switch (e.kind) {
-#define GFB_EPI_CASE(K) case K: epilogue_rows_ws<T, K, CL>(g, e, layer, colA, ta, tb, j, r_begin); break;
+#define GFB_EPI_CASE(K) case K: epilogue_rows_ws<T, K, CL>(g, e, layer, colA, ta, tb, j, r_begin, nlayer, ncolA, nr_begin); break;
     GFB_EPI_CASE(EPI_STORE)
     GFB_EPI_CASE(EPI_RK_FIRST)
     GFB_EPI_CASE(EPI_RK_MID)
@@ -139,8 +188,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
           tmem_fence_after_sync();
         }
         const uint32_t ta = tm + 128 * nb, tb = ta + 64;
-        if (e.cplxL) epilogue_rows_ws_dispatch<T, true>(g, e, layer, colA, ta, tb, j, 4 * slice);
-        else epilogue_rows_ws_dispatch<T, false>(g, e, layer, colA, ta, tb, j, 4 * slice);
+        // the slice after this one: same unit, or the first slice of this CTA's next unit
+        int nlayer = layer, ncolA = colA, nr_begin = 4 * (slice + 1);
+        if (slice == 3) {
+          nr_begin = (i + 1 < nmine) ? 0 : -1;
+          if (nr_begin == 0) unit_of(i + 1, nlayer, ncolA);
+        }
+        if (e.cplxL) epilogue_rows_ws_dispatch<T, true>(g, e, layer, colA, ta, tb, j, 4 * slice, nlayer, ncolA, nr_begin);
+        else epilogue_rows_ws_dispatch<T, false>(g, e, layer, colA, ta, tb, j, 4 * slice, nlayer, ncolA, nr_begin);
         if (slice == 3 && i + 2 < nmine) {  // the FFT group may overwrite this buffer with unit i + 2
           tmem_fence_before_sync();
           bar_arrive(WS_BAR_NEMPTY + nb, WS_THREADS);
@@ -154,6 +209,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
   } else {
     // ------------------------------------------ FFT group ------------------------------------------------------------
     cplx v[PT];
+    const Tw4096 twr = load_tw4096(j, tw);
 #pragma unroll 1
     for (int n = 0; n < ncolumns; ++n) {
       const int s = n & 1, i = n >> 2, ci = n & 3, nb = i & 1;
@@ -164,7 +220,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
         for (int r = 0; r < PT; ++r) v[r] = src[r * T];
       }
       if (n + 2 < ncolumns) bar_arrive(WS_BAR_EMPTY + s, WS_THREADS);
-      block_fft<NY, FWD, WS_BAR_FFT>(v, j, xb, tw);
+      block_fft4096<FWD, WS_BAR_FFT>(v, j, xb, twr);
       const uint32_t tdst = tm + 128 * nb + 64 * (ci & 1);
       if (ci < 2) {
         if (ci == 0 && i >= 2) {  // the epilogue of unit i - 2 has read this buffer
@@ -174,18 +230,21 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
 #pragma unroll
         for (int r = 0; r < PT; ++r) {
           const double ll = wav_l(g, j + r * T);
-          tmem_store(tdst + 4 * r, cmake(ll * v[r].y, -ll * v[r].x));  // -i l (vq)_h
+          v[r] = cmake(ll * v[r].y, -ll * v[r].x);  // -i l (vq)_h
         }
+#pragma unroll
+        for (int r = 0; r < PT; ++r) tmem_store(tdst + 4 * r, v[r]);  // 16 x .x4: one .x64 store is 5x slower (tools/tmem_bench)
         tmem_wait_st();
       } else {
 #pragma unroll
         for (int c0 = 0; c0 < PT; c0 += 4) {
           cplx a[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) a[q] = tmem_load(tdst + 4 * (c0 + q));
+          tmem_load4(tdst + 4 * c0, a);
           tmem_wait_ld();
 #pragma unroll
-          for (int q = 0; q < 4; ++q) tmem_store(tdst + 4 * (c0 + q), cadd(v[c0 + q], a[q]));
+          for (int q = 0; q < 4; ++q) a[q] = cadd(v[c0 + q], a[q]);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) tmem_store(tdst + 4 * (c0 + q), a[q]);
         }
         tmem_wait_st();
         if (ci == 3) {
