@@ -26,10 +26,26 @@ sys.path.insert(0, ROOT)
 METRIC = "grid-point-steps/sec"
 UNIT = "grid-point-steps/s"
 ALGO_BYTES_PER_POINT_STEP = 480.0  # 60 field passes x 8 B (Float64), RK4/ETDRK4 families
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the same
-# command (profiles/): full-mode (un-pruned) launches of the 4096^2 workload
-NCU_TRAFFIC = {"k_row": 268.84e6 + 143.42e6}  # k_row_product<4096,false>, pruned stage (profiles/r1_ncu_key_metrics_pipelined.txt)
-KERNEL_FUNCTION = {"k_col_inv": "k_col_inv_single<4096>", "k_row": "k_row_product<4096,false>", "k_col_fwd": "k_col_fwd<4096,true>"}
+# roofline.traffic = dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from an `ncu --set full`
+# capture of THIS command; it cannot be measured inside a timed run, so it is read from profiles/ncu_traffic.json, which
+# tools/ncu_traffic.py writes from the .ncu-rep of the same build (keyed by kernel function; null when no entry matches)
+NCU_TRAFFIC_FILE = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+
+
+def kernel_functions(n, info):
+    """which kernel serves each class for this context (gfb_path_info); spelled as ncu prints the instantiation, which is
+    the key of profiles/ncu_traffic.json"""
+    ws_r, ws_c = info.get("row_ws"), info.get("col_ws")
+    return {"k_col_inv": ("k_col_inv_ws<%d,%d>" % (n, int(os.environ.get("GFB_K1WS_VAR", "0")))) if ws_c else "k_col_inv_single<%d>" % n,
+            "k_row": ("k_row_product_ws<%d>" % n) if ws_r else (("k_row_product_tma<%d>" % n) if info.get("row_tma") else "k_row_product<%d,0>" % n),
+            "k_col_fwd": ("k_col_fwd_ws<%d>" if info.get("col_ws3") else "k_col_fwd<%d,1>") % n}
+
+
+def ncu_traffic(function):
+    try:
+        return json.load(open(NCU_TRAFFIC_FILE)).get(function, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
 
 
 def workload(name):
@@ -78,6 +94,60 @@ def initial_bh(n, seed=0):
     b = np.fft.irfft2(bh, s=(n, n))
     b *= 0.1 / np.sqrt(np.mean(b * b))  # rms b = 0.1: CFL = max|u| dt/dx stays < 1 at dt = 0.03*256/n
     return np.fft.rfft2(b)
+
+
+def local_spectral_columns(cfg, cols, seed, what):
+    """Columns `cols` (global kr indices) of the synthetic spectra of the forced workload, generated WITHOUT ever forming
+    the global array (a 16384^2 spectrum is 2 GB; every rank builds only its own columns).  what = "ic": random-phase
+    state A(|k|) e^{i theta}, A ~ |k| (1 + (|k|/6)^4)^-1/2, un-normalised (the caller scales to rms 0.1 from the exact
+    Parseval sum of A^2); "forcing": the ring forcing of forcing_fh (same spectrum, normalised on the kr <= 21 sub-grid
+    that holds the whole ring).  Phases come from one generator per global column (seed, column), so the field does not
+    depend on how the columns are dealt to ranks; the kr = 0 and kr = nx/2 columns are made Hermitian in l."""
+    n = cfg["nx"]
+    l = np.fft.fftfreq(n, 1 / n)[:, None]
+    out = np.empty((n, len(cols)), dtype=np.complex128)
+    if what == "forcing":
+        krs = np.arange(0, 22)[None, :]
+        K2s = krs**2 + l**2
+        Ks = np.sqrt(K2s)
+        specs = np.exp(-(Ks - cfg["kf"]) ** 2 / (2 * cfg["dkf"] ** 2))
+        specs[(Ks < 2) | (Ks > 20)] = 0
+        with np.errstate(divide="ignore", invalid="ignore"):
+            e0 = np.sum(np.where(K2s > 0, specs / K2s, 0.0)) / (n * n) ** 2 * 2
+    for i, c in enumerate(cols):
+        K = np.sqrt(float(c) ** 2 + l[:, 0] ** 2)
+        th = np.random.default_rng([seed, int(c)]).uniform(0, 2 * np.pi, n)
+        if what == "ic":
+            a = K / np.sqrt(1 + (K / 6) ** 4)
+        else:
+            a = np.exp(-(K - cfg["kf"]) ** 2 / (2 * cfg["dkf"] ** 2))
+            a[(K < 2) | (K > 20)] = 0
+            a = np.sqrt(a * cfg["eps"] / e0) / np.sqrt(cfg["dt"])
+        col = a * np.exp(1j * th)
+        if c == 0 or c == n // 2:  # a real field: a(-l) = conj a(l), a(0) and a(ny/2) real
+            col[n // 2 + 1:] = np.conj(col[1:n // 2][::-1])
+            col[0] = col[0].real
+            col[n // 2] = col[n // 2].real
+        out[:, i] = col
+    if what == "ic" or True:
+        z = np.nonzero(np.asarray(cols) == 0)[0]
+        if len(z):
+            out[0, z[0]] = 0
+    return out
+
+
+def ic_parseval_sumsq(n):
+    """sum over the FULL spectrum of |A|^2 for the "ic" amplitude: mean(b^2) = this / n^4 (Parseval), evaluated column by
+    column in float64 without a global array"""
+    l2 = np.fft.fftfreq(n, 1 / n) ** 2
+    tot = 0.0
+    for c in range(n // 2 + 1):
+        K2 = float(c) ** 2 + l2
+        a2 = K2 / (1 + (K2 / 36.0) ** 2)
+        if c == 0:
+            a2[0] = 0
+        tot += (1.0 if c in (0, n // 2) else 2.0) * float(np.sum(a2))
+    return tot
 
 
 def peaks():
@@ -232,10 +302,15 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cfg = workload(args.workload)
-    n = cfg["nx"]
+    full = workload(args.workload)
+    # bounded sample of the workload: the oracle's setup alone (32-point ETD contour tables, numpy) takes minutes at
+    # 16384^2, so sizes above 4096^2 are sampled on a 4096^2 sub-problem of the same module, stepper and parameters
+    # scaled the same way; grid-point-steps/s is the metric, and the CPU path's rate only falls with size
+    n_full = full["nx"]
+    n = min(n_full, int(os.environ.get("GFB_REF_MAX_N", "4096")))
+    cfg = workload(args.workload.replace(str(n_full), str(n)))
     bh0 = initial_bh(n)
-    # bounded sample: one untimed step measures the cost, then as many of the K steps as fit ~150 s
+    # one untimed step measures the cost, then as many of the K steps as fit ~150 s
     t0 = time.perf_counter()
     gfo, po = oracle_problem(cfg)
     po.sol[...] = bh0
@@ -250,8 +325,11 @@ def run_reference(args):
     val = n * n / per
     cores = os.cpu_count() or 1
     sample = "%d of %d requested ETDRK4 steps at %d^2 timed after 1 warm-up step (bounded to ~%.0f s)" % (k, args.steps, n, budget)
+    if n != n_full:
+        sample += "; the %d^2 workload sampled on a %d^2 sub-problem (same module, stepper, scaled parameters)" % (n_full, n)
+    cfg = full
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": n_full * n_full / val * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(cfg),
                        "impl": "oracle port of the reference CPU path: numpy broadcast + scipy.fft(pocketfft) workers=%d; "
@@ -266,22 +344,27 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="sqg4096")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "cufft"])
+    ap.add_argument("--workload", default=None,
+                    help="sqgN | twodnsN; default: sqg4096 on one GPU (BASELINE configs[3]), twodns16384 on several (configs[4])")
+    ap.add_argument("--repeats", type=int, default=5, help="the K timed steps are repeated this often; the median is reported")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cufft", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: p2p = kernels store into peer memory over NVLink (fused exchange); nccl = all-to-all")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.workload is None:
+        args.workload = "sqg4096" if world == 1 else "twodns16384"
     if args.impl == "reference":
         return run_reference(args)
 
     import torch
     import gfb_loader
     pkg = gfb_loader.load()
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
@@ -295,10 +378,11 @@ def main():
     torch.cuda.set_device(local)
     cfg = workload(args.workload)
     n = cfg["nx"]
-    # N > 1: the SAME 4096^2 problem slab-sharded over the N GPUs (strong scaling): y-slabs in physical space,
-    # round-robin kr column pairs in spectral space, one NCCL all-to-all per 2-D transform direction and stage
+    # N > 1: ONE problem slab-sharded over the N GPUs (strong scaling): y-slabs in physical space, round-robin kr column
+    # pairs in spectral space, one exchange per 2-D transform direction and stage
     shard = (rank, world, None, args.transport) if world > 1 else None
     forced = cfg["module"] != "SurfaceQG"
+    t_setup = time.perf_counter()
     if not forced:
         prob = pkg.SurfaceQG.Problem(dev, nx=n, Lx=cfg["Lx"], nu=cfg["nu"], nnu=cfg["nnu"], H=cfg["H"], dt=cfg["dt"],
                                      stepper=cfg["stepper"], shard=shard)
@@ -310,42 +394,87 @@ def main():
             F.copy_(fh_dev[0], non_blocking=True)
         prob = pkg.TwoDNavierStokes.Problem(dev, nx=n, Lx=cfg["Lx"], nu=cfg["nu"], nnu=cfg["nnu"], mu=cfg["mu"], nmu=cfg["nmu"],
                                             dt=cfg["dt"], stepper=cfg["stepper"], calcF=calcF, stochastic=True, shard=shard)
-        fh = forcing_fh(cfg)
-        fh_dev.append(dev.array(prob.shard.spec_local(fh) if world > 1 else fh, torch.complex128))
         diag = pkg.TwoDNavierStokes.energy
-    bh0 = initial_bh(n)
-    bh0[0, 0] = 0
-    if world > 1:
-        bh0 = prob.shard.spec_local(bh0)
-    host_sol = torch.from_numpy(bh0).pin_memory()
+    cols = prob.shard.cols if world > 1 else np.arange(n // 2 + 1)
+    if forced:
+        # column-local generators: no rank ever forms a global 16384^2 array
+        fh_dev.append(dev.array(local_spectral_columns(cfg, cols, 1, "forcing"), torch.complex128))
+        bh0 = local_spectral_columns(cfg, cols, 0, "ic")
+        bh0 *= 0.1 * n * n / np.sqrt(ic_parseval_sumsq(n))  # rms 0.1 (exact Parseval sum of the amplitudes)
+    else:
+        bh0 = initial_bh(n)
+        bh0[0, 0] = 0
+        if world > 1:
+            bh0 = prob.shard.spec_local(bh0)
+    host_sol = torch.from_numpy(np.ascontiguousarray(bh0)).pin_memory()
     prob.sol.copy_(host_sol, non_blocking=True)
+    setup_s = time.perf_counter() - t_setup
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident throughput ---------------------------------------------------------
+    def allmax(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    if args.impl == "cufft":
+        if world != 1:
+            raise SystemExit("bench.py --impl cufft: one GPU only (the reference's device path is single-GPU)")
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        from cufft_arm import CufftArm
+        arm = CufftArm(prob, fh_dev[0] if forced else None)
+        ms = arm.time_steps(prob.sol, args.steps, args.warmup)
+        val = n * n / (ms * 1e-3)
+        print(json.dumps({"impl": "cufft", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "f64", "data": "synthetic",
+                          "config": {"workload": workload_name(cfg),
+                                     "impl": "the reference's GPU launch sequence restated with torch: cuFFT (torch.fft.rfft2/irfft2) + one "
+                                             "unfused elementwise kernel per broadcast statement (tools/cufft_arm.py)"}}))
+        return
+
+    # ---- device-resident throughput: W warm-up steps, then K steps timed `repeats` times; median, max over ranks -----
     pkg.stepforward_(prob, args.warmup)
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
-    prob.profile_begin()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    pkg.stepforward_(prob, args.steps)
-    e1.record()
-    barrier()
-    prof = prob.profile_end()
+    samples = []
+    for _ in range(max(1, args.repeats)):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        pkg.stepforward_(prob, args.steps)
+        e1.record()
+        barrier()
+        samples.append(allmax(e0.elapsed_time(e1)))
     sampler.stop_flag.set()
     sampler.join(timeout=2)
-    ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    ms = float(np.median(samples))
     ms_per_step = ms / args.steps
     value = n * n * args.steps / (ms * 1e-3)  # one problem, however many GPUs share it
+    # per-kernel device times (CUDA events around every launch) in a separate pass, so the events do not sit in the timed one
+    ksteps = min(args.steps, 20)
+    prob.profile_begin()
+    pkg.stepforward_(prob, ksteps)
+    barrier()
+    prof = prob.profile_end()
+    # the same K steps taken one stepforward! call at a time with a diagnostic after each (the reference's
+    # stepforward!(prob, diags, 1) loop): no step may skip the aliased band of N then
+    osteps = min(args.steps, 20)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(osteps):
+        pkg.stepforward_(prob, 1)
+        if not forced:
+            diag(prob)
+    e1.record()
+    barrier()
+    ms_observed = allmax(e0.elapsed_time(e1)) / osteps
     finite = bool(torch.isfinite(prob.sol.real).all().item())
 
     # ---- end to end through the public API with host buffers ----------------------------------
@@ -380,11 +509,25 @@ def main():
                                           "overlap stepforward!(prob, 1) + diagnostic of step i")
         except Exception as exc:  # noqa: BLE001
             sys.stderr.write("bench.py: pipelined end-to-end leg skipped: %r\n" % (exc,))
-    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s = float(te.item())
+    e2e_s = allmax(e2e_s)
     e2e_val = n * n / e2e_s
+
+    # ---- cuFFT comparison: the reference's GPU launch sequence (cuFFT + unfused broadcasts) on the same GPU, same problem
+    cufft = None
+    if world == 1 and not args.no_cufft and n <= 8192:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            from cufft_arm import CufftArm
+            arm = CufftArm(prob, fh_dev[0] if forced else None)
+            cms = arm.time_steps(host_sol.to(prob.sol.device), 10, 3)
+            cufft = {"ms_per_step": cms, "value": n * n / (cms * 1e-3), "unit": UNIT, "steps": 10, "warmup": 3,
+                     "speedup_of_this_library": cms / ms_per_step,
+                     "what": "torch.fft.rfft2/irfft2 (cuFFT) + one torch elementwise kernel per broadcast statement of the reference's "
+                             "calcN!/dealias!/ETDRK4 sequence (tools/cufft_arm.py), same GPU, same workload, CUDA events"}
+            del arm
+            torch.cuda.empty_cache()
+        except Exception as exc:  # noqa: BLE001
+            sys.stderr.write("bench.py: cuFFT comparison skipped: %r\n" % (exc,))
 
     if rank != 0:
         if dist is not None:
@@ -409,56 +552,75 @@ def main():
     if forced:                                          # + F_h in every stage, prevsol written in stage 1
         epi = [e + 16 for e in epi]
         epi[0] += 16
-    # one full (un-pruned) step per stepforward! call; the forced problem steps one call at a time (calcF! per step)
-    wfull = 1.0 if forced else 1.0 / float(args.steps)
-    kbytes = {                                          # the others skip the aliased band of N
+    # profiled pass: ksteps steps in one stepforward! call, the last one un-pruned; the forced problem steps one call at a
+    # time (calcF! per step) and only its last step computes the aliased band
+    wfull = 1.0 / float(ksteps)
+    kbytes = {                                          # the pruned launches skip the aliased band of N
         "k_col_inv": (16.0 + 8.0) * band + 3 * 16.0 * ny * kcut,
         "k_row": 3 * 16.0 * ny * kcut + 2 * 16.0 * ny * (wfull * nkr + (1 - wfull) * kcut),
         "k_col_fwd": wfull * k3_bytes(nkr, nkr * ny) + (1 - wfull) * k3_bytes(kcut, band),
     }
     kbytes = {k: v / world for k, v in kbytes.items()}  # each GPU launches the kernels on its 1/N share
+    info = prob.path_info()
+    kfun = kernel_functions(n, info)
     top = max(("k_col_inv", "k_row", "k_col_fwd"), key=lambda k: prof[k]["ms"])
     avg_ms = prof[top]["ms"] / max(prof[top]["launches"], 1)
     achieved = kbytes[top] / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else None
     step_gbs = ALGO_BYTES_PER_POINT_STEP * n * n / world / (ms_per_step * 1e-3) / 1e9  # per GPU
-    launches = sum(v["launches"] for v in prof.values())
+    moved = sum(kbytes.values()) * 4                    # bytes the kernels of one (pruned) step must move, per GPU
+    launches_per_step = sum(v["launches"] for v in prof.values()) / float(ksteps)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": workload_name(cfg),
                    "grid": [n, n], "stepper": cfg["stepper"], "dt": cfg["dt"],
-                   "initial_condition": "random-phase field_h ~ |k|(1+(|k|/6)^4)^-1/2, rms = 0.1, numpy default_rng(0)"
-                   + ("; ring forcing k_f = 14, one frozen realisation re-applied by calcF! every step" if forced else ""),
+                   "initial_condition": "random-phase field_h ~ |k|(1+(|k|/6)^4)^-1/2, rms = 0.1"
+                   + ("; ring forcing k_f = 14, one frozen realisation re-applied by calcF! every step" if forced else ", numpy default_rng(0)"),
                    "l2": "working set (>= 12 fields x %.0f MB) exceeds the 126 MB L2; no flush needed" % (16.0 * ny * nkr / 1e6),
+                   "timing": "%d warm-up steps, then %d steps per stepforward! call timed %d times with CUDA events (max over ranks); median "
+                             "reported, all samples in ms_samples" % (args.warmup, args.steps, len(samples)),
                    "parallelism": "1 GPU" if world == 1 else
                    "%d GPUs, one %d^2 problem: y-slabs / round-robin kr column pairs, 2 exchanges per stage via %s "
                    "(%.0f MB sent per GPU per step)" % (world, n, "P2P stores of K1/K2 into peer memory + flag barriers"
                                                         if prob.shard.transport == "p2p" else "NCCL all-to-all", a2a_bytes / 1e6),
-                   "state_finite": finite},
-        "roofline": {"bound": "hbm", "kernel": top, "kernel_function": KERNEL_FUNCTION[top].replace("4096", str(n)), "achieved": achieved, "peak": peak, "unit": "GB/s",
+                   "kernels": kfun, "setup_s": setup_s, "state_finite": finite},
+        "ms_samples": [x / args.steps for x in samples],
+        "ms_per_step_observed_every_step": ms_observed,
+        "roofline": {"bound": "hbm", "kernel": top, "kernel_function": kfun[top], "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None,
-                     "traffic": NCU_TRAFFIC.get(top) if (world == 1 and n == 4096 and not forced) else None, "peak_source": peak_src,
+                     "traffic": ncu_traffic(kfun[top]) if world == 1 else None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": kbytes[top], "avg_launch_ms": avg_ms,
-                     "all_kernels": {k: {"achieved_gbs": kbytes[k] / (prof[k]["ms"] / max(prof[k]["launches"], 1) * 1e-3) / 1e9
+                     "all_kernels": {k: {"function": kfun[k],
+                                         "achieved_gbs": kbytes[k] / (prof[k]["ms"] / max(prof[k]["launches"], 1) * 1e-3) / 1e9
                                          if prof[k]["ms"] > 0 else None,
-                                         "algorithmic_bytes_per_launch": kbytes[k]} for k in kbytes}},
+                                         "algorithmic_bytes_per_launch": kbytes[k], "traffic": ncu_traffic(kfun[k]) if world == 1 else None}
+                                     for k in kbytes}},
         "step_roofline": {"algorithmic_bytes_per_step": ALGO_BYTES_PER_POINT_STEP * n * n, "achieved_gbs_per_gpu": step_gbs,
-                          "frac_of_measured_peak": step_gbs / peak, "frac_of_8tbs_nominal": step_gbs / 8000.0},
-        "kernels": {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps} for k, v in prof.items()},
-        "gpu_launches": launches,
+                          "frac_of_measured_peak": step_gbs / peak, "frac_of_8tbs_nominal": step_gbs / 8000.0,
+                          "bytes_moved_per_pruned_step_per_gpu": moved,
+                          "frac_of_measured_peak_counting_only_moved_bytes": moved / (ms_per_step * 1e-3) / 1e9 / peak,
+                          "observed_every_step": {"ms_per_step": ms_observed,
+                                                  "frac_of_measured_peak": ALGO_BYTES_PER_POINT_STEP * n * n / world / (ms_observed * 1e-3) / 1e9 / peak,
+                                                  "what": "stepforward!(prob, 1) + diagnostic per step: every step computes the aliased band of N"}},
+        "kernels": {k: {"ms_per_step": v["ms"] / ksteps, "launches_per_step": v["launches"] / ksteps} for k, v in prof.items()},
+        "gpu_launches": int(round(launches_per_step * args.steps)),
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s * 1e3, "serial_ms_per_step": e2e_serial_s * 1e3,
                 "what": "per step: pinned-host sol -> device, stepforward!(prob, 1), sol + energy diagnostic -> host; " + e2e_how},
         "clocks": sampler.summary(),
     }
+    if cufft is not None:
+        line["cufft_baseline"] = cufft
     if world > 1:
         # NVLink roofline of the sharded step: bytes that must leave each GPU / measured peer bandwidth (770 GB/s/dir)
         line["nvlink"] = {"a2a_bytes_per_gpu_per_step": a2a_bytes, "floor_ms_at_770GBs": a2a_bytes / 770e9 * 1e3,
+                          "frac_of_nvlink_floor": (a2a_bytes / 770e9 * 1e3) / ms_per_step,
                           "exchanges_per_step": 8, "transport": prob.shard.transport}
     if world == 1 and not args.no_cpu_baseline:
         nsamp = 2 if n >= 4096 else 4
-        per = cpu_steps(cfg, bh0, nsamp, 1)
+        full0 = bh0 if not forced else None
+        per = cpu_steps(cfg, full0, nsamp, 1) if full0 is not None else cpu_steps(cfg, np.ascontiguousarray(bh0), nsamp, 1)
         line["cpu_baseline"] = {"value": n * n / per, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                                 "sample": "%d ETDRK4 steps at %d^2 after 1 warm-up step; numpy broadcast + scipy.fft workers=%d"
                                           % (nsamp, n, os.cpu_count() or 1), "ms_per_step": per * 1e3}

@@ -464,14 +464,16 @@ int gfb_create(gfb_ctx** out, const gfb_config* cfg) {
     }
     const char* off = getenv("GFB_NO_ROW_TMA");
     c->row_tma = !(off && off[0] == '1');
-    const char* offw = getenv("GFB_NO_ROW_WS");
-    c->row_ws = c->row_tma && g.nx == 4096 && !(offw && offw[0] == '1');
+    const char* onw = getenv("GFB_ROW_WS");
+    c->row_ws = c->row_tma && g.nx == 4096 && onw && onw[0] == '1';
   }
   {
     const char* off = getenv("GFB_NO_COL_WS");
     c->col_ws = c->kind == GFB_KIND_SINGLE && g.ny == 4096 && !(off && off[0] == '1');
-    const char* off3 = getenv("GFB_NO_COL_WS3");
-    c->col_ws3 = g.ny == 4096 && !(off3 && off3[0] == '1');
+    // the warp-specialised K3 / K2 are opt-in experiments (GFB_COL_WS3=1 / GFB_ROW_WS=1): correct on hardware, but so
+    // far slower than the kernels they would replace
+    const char* on3 = getenv("GFB_COL_WS3");
+    c->col_ws3 = g.ny == 4096 && on3 && on3[0] == '1';
   }
   int nstate = 0;
   switch (cfg->stepper) {
@@ -547,12 +549,15 @@ int gfb_profile_end(gfb_ctx* c, double* ms4, long long* launches4) {
   return GFB_OK;
 }
 
-int gfb_path_info(const gfb_ctx* c, long long* info4) {
-  if (!c || !info4) return GFB_ERR_INVALID;
-  info4[0] = c->row_tma ? 1 : 0;
-  info4[1] = c->row_tma_launches;
-  info4[2] = c->col_ws ? 1 : 0;
-  info4[3] = c->col_ws_launches;
+int gfb_path_info(const gfb_ctx* c, long long* info8) {
+  if (!c || !info8) return GFB_ERR_INVALID;
+  info8[0] = c->row_tma ? 1 : 0;
+  info8[1] = c->row_tma_launches;
+  info8[2] = c->col_ws ? 1 : 0;
+  info8[3] = c->col_ws_launches;
+  info8[4] = c->row_ws ? 1 : 0;
+  info8[5] = c->col_ws3 ? 1 : 0;
+  info8[6] = info8[7] = 0;
   return GFB_OK;
 }
 

@@ -35,7 +35,9 @@ __device__ __forceinline__ uint32_t ws_tmem_base(uint32_t base) {
   return base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(((warp >> 2) & 1) * 256);
 }
 
-template <int NY>
+// VAR: experiment switches (tools/, GFB_K1WS_VAR): bit 0 = twiddles in registers, bit 1 = L2 bulk prefetch of the next
+// unit, bit 2 = all 16 rows in one load batch (else two batches of 8), bit 3 = .x64 TMEM load of the input slot
+template <int NY, int VAR>
 __global__ void __launch_bounds__(WS_THREADS, 1)
     k_col_inv_ws(const __grid_constant__ GridDesc g, const __grid_constant__ PrepSingle prep, const __grid_constant__ PeerOut W,
                  const int ldw, const long long wfs, const int ncols, const int nfields, const int nunits,
@@ -67,7 +69,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
       const int off0 = toff(j, colA, prep.ld) + which;
       // the NEXT unit's column pair (state + G tiles of this thread's live rows) starts moving DRAM -> L2 now: one
       // thread in eight issues, for the 256-byte tile its row shares with its seven neighbours
-      if (which == 0 && (n >> 1) + 1 < nmine && (j & 7) == 0) {
+      if ((VAR & 2) && which == 0 && (n >> 1) + 1 < nmine && (j & 7) == 0) {
         const int un = unit + (int)gridDim.x, fn = un % nfields, cn = 2 * (un / nfields);
         const int pf0 = toff(j, cn, prep.ld);
 #pragma unroll
@@ -78,22 +80,45 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
           }
         }
       }
-      // all 16 rows in one batch: 16 x (16 + 8) bytes in flight per thread, one memory round trip per column
       cplx val[PT];
-      double gg[PT];
+      if (VAR & 4) {
+        // all 16 rows in one batch: 16 x (16 + 8) bytes in flight per thread, one memory round trip per column
+        double gg[PT];
 #pragma unroll
-      for (int r = 0; r < PT; ++r) {
-        const bool on = live_col && !l_aliased(g, j + r * T);
-        const int off = off0 + r * T * prep.ld;  // T % 8 == 0: the tiled layout is affine in r
-        val[r] = on ? prep.sol[off] : cmake(0.0, 0.0);
-        gg[r] = (on && field != 2) ? prep.G[off] : 0.0;
-      }
+        for (int r = 0; r < PT; ++r) {
+          const bool on = live_col && !l_aliased(g, j + r * T);
+          const int off = off0 + r * T * prep.ld;  // T % 8 == 0: the tiled layout is affine in r
+          val[r] = on ? prep.sol[off] : cmake(0.0, 0.0);
+          gg[r] = (on && field != 2) ? prep.G[off] : 0.0;
+        }
 #pragma unroll
-      for (int r = 0; r < PT; ++r) {
-        const int l = j + r * T;
-        const bool on = live_col && !l_aliased(g, l);
-        const cplx t = prep.apply(g, field, wav_l(g, l), kr, gg[r], val[r]);
-        val[r] = cmake(on ? t.x : 0.0, on ? t.y : 0.0);
+        for (int r = 0; r < PT; ++r) {
+          const int l = j + r * T;
+          const bool on = live_col && !l_aliased(g, l);
+          const cplx t = prep.apply(g, field, wav_l(g, l), kr, gg[r], val[r]);
+          val[r] = cmake(on ? t.x : 0.0, on ? t.y : 0.0);
+        }
+      } else {
+#pragma unroll
+        for (int h = 0; h < PT; h += 8) {  // two batches of eight rows: 8 x (16 + 8) bytes in flight per thread
+          cplx raw[8];
+          double gg[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int r = h + q, l = j + r * T;
+            const bool on = live_col && !l_aliased(g, l);
+            const int off = off0 + r * T * prep.ld;  // T % 8 == 0: the tiled layout is affine in r
+            raw[q] = on ? prep.sol[off] : cmake(0.0, 0.0);
+            gg[q] = (on && field != 2) ? prep.G[off] : 0.0;
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int r = h + q, l = j + r * T;
+            const bool on = live_col && !l_aliased(g, l);
+            const cplx t = prep.apply(g, field, wav_l(g, l), kr, gg[q], raw[q]);
+            val[r] = cmake(on ? t.x : 0.0, on ? t.y : 0.0);
+          }
+        }
       }
       if (n >= 2) {  // the FFT group has taken column n - 2 out of this slot
         bar_sync(WS_BAR_EMPTY + b, WS_THREADS);
@@ -114,13 +139,19 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
       const int unit = (int)blockIdx.x + (n >> 1) * (int)gridDim.x, which = n & 1, b = n & 1;
       bar_sync(WS_BAR_FULL + b, WS_THREADS);
       tmem_fence_after_sync();
-      tmem_load16(t_in[b], v);
+      if (VAR & 8) {
+        tmem_load16(t_in[b], v);
+      } else {
+#pragma unroll
+        for (int r = 0; r < PT; ++r) v[r] = tmem_load(t_in[b] + 4 * r);
+      }
       tmem_wait_ld();
       if (n + 2 < ncolumns) {  // hand the slot back (only if somebody will wait for it)
         tmem_fence_before_sync();
         bar_arrive(WS_BAR_EMPTY + b, WS_THREADS);
       }
-      block_fft4096<INV, WS_BAR_FFT>(v, j, xb, twr);
+      if (VAR & 1) block_fft4096<INV, WS_BAR_FFT>(v, j, xb, twr);
+      else block_fft<NY, INV, WS_BAR_FFT>(v, j, xb, tw);
       if (which == 0) {  // column A waits in TMEM for its partner
 #pragma unroll
         for (int r = 0; r < PT; ++r) tmem_store(t_park + 4 * r, v[r]);

@@ -157,6 +157,72 @@ __device__ __forceinline__ void epi_fetch(const GridDesc& g, const EpiArgs& e, i
   if (KIND == EPI_ETD_1 || KIND == EPI_ETD_2 || KIND == EPI_ETD_3 || KIND == EPI_ETD_4) in.c4.load(e.c4, layer, off);
 }
 
+// Start moving one 8-row tile (rows l .. l + 7 of the column pair at colA) of every array the epilogue of this kind READS
+// from DRAM into L2 (same selection as epi_fetch; the masks of masked_pair are honoured so nothing useless moves).
+template <int KIND, bool CL>
+__device__ __forceinline__ void epi_prefetch_tile(const GridDesc& g, const EpiArgs& e, const int layer, const int colA, const int off) {
+  auto pc = [&](const Spec& a) {
+    if (a.p) prefetch_l2_bulk(a.p + layer * a.ls + off, 256);
+  };
+  auto pk = [&](const Coef& t) {
+    if (CL) prefetch_l2_bulk(t.c + layer * t.ls + off, 256);
+    else prefetch_l2_bulk(t.r + layer * t.ls + off, 128);
+  };
+  const bool live_col = gcol(g, colA) < g.kcut;
+  if (KIND == EPI_RK_LAST || KIND == EPI_RK_ONLY || KIND == EPI_ETD_4 || KIND == EPI_AB3) {
+    if (e.filter.p) prefetch_l2_bulk(e.filter.p + off, 128);
+  }
+  if ((KIND == EPI_RK_FIRST || KIND == EPI_RK_MID || KIND == EPI_RK_ONLY || KIND == EPI_ETD_1 || KIND == EPI_ETD_2 || KIND == EPI_ETD_3 ||
+       KIND == EPI_AB3) && live_col)
+    pc(e.sol);
+  if ((KIND == EPI_RK_MID || KIND == EPI_RK_LAST) && live_col) pc(e.sin);
+  if (KIND == EPI_RK_FIRST || KIND == EPI_RK_MID || KIND == EPI_RK_LAST || KIND == EPI_RK_ONLY || KIND == EPI_AB3) pk(e.L);
+  if (KIND == EPI_RK_MID || KIND == EPI_RK_LAST || KIND == EPI_ETD_2 || KIND == EPI_ETD_3 || KIND == EPI_ETD_4) pc(e.acc);
+  if (KIND == EPI_AB3 && (e.b != 0.0 || e.d != 0.0)) {
+    pc(e.acc);
+    pc(e.n1);
+  }
+  if (KIND == EPI_ETD_3) pc(e.n1);
+  if (KIND == EPI_ETD_1 || KIND == EPI_ETD_2 || KIND == EPI_ETD_3) {
+    pk(e.c1);
+    pk(e.c2);
+  }
+  if (KIND == EPI_ETD_1) pk(e.c3);
+  if (KIND == EPI_ETD_1 || KIND == EPI_ETD_2 || KIND == EPI_ETD_3 || KIND == EPI_ETD_4) pk(e.c4);
+  pc(e.Nconst);
+  pc(e.F);
+}
+
+// prefetch (DRAM -> L2) of the epilogue's input tiles of rows [r_begin, r_end) of this thread -- issued by one thread in
+// eight (a tile = the rows of eight neighbouring threads), kind-dispatched like the epilogue itself
+template <int T, bool CL>
+__device__ __forceinline__ void epi_prefetch_rows(const GridDesc& g, const EpiArgs& e, const int layer, const int colA, const int j,
+                                                  const int r_begin, const int r_end) {
+  if ((j & 7) != 0) return;
+  const int poff = toff(j, colA, e.out.ld);
+#pragma unroll 1
+  for (int r = r_begin; r < r_end; ++r) {
+    const int l = j + r * T;
+    if (e.prune && l_aliased(g, l) && l_aliased(g, l + 7)) continue;
+    const int off = toff_row<T>(poff, j, r, colA, e.out.ld);
+    switch (e.kind) {
+#define GFB_EPI_CASE(K) case K: epi_prefetch_tile<K, CL>(g, e, layer, colA, off); break;
+      GFB_EPI_CASE(EPI_STORE)
+      GFB_EPI_CASE(EPI_RK_FIRST)
+      GFB_EPI_CASE(EPI_RK_MID)
+      GFB_EPI_CASE(EPI_RK_LAST)
+      GFB_EPI_CASE(EPI_RK_ONLY)
+      GFB_EPI_CASE(EPI_ETD_1)
+      GFB_EPI_CASE(EPI_ETD_2)
+      GFB_EPI_CASE(EPI_ETD_3)
+      GFB_EPI_CASE(EPI_ETD_4)
+      GFB_EPI_CASE(EPI_AB3)
+#undef GFB_EPI_CASE
+      default: break;
+    }
+  }
+}
+
 __device__ __forceinline__ cplx axpy(cplx y, double a, cplx x) { return cmake(y.x + a * x.x, y.y + a * x.y); }
 
 // ... then the arithmetic and all stores of that row
@@ -326,7 +392,7 @@ __device__ __forceinline__ void k3_issue(cplx* __restrict__ X, const cplx* __res
 template <int NY, bool TWO>
 __global__ void __launch_bounds__(GroupCfg<NY>::THREADS, GroupCfg<NY>::MINB)
     k_col_fwd(const __grid_constant__ GridDesc g, const cplx* __restrict__ P, const int ldp, const long long pfs,
-              const __grid_constant__ EpiArgs e, const int ncols, const cplx* __restrict__ tw) {
+              const __grid_constant__ EpiArgs e, const int ncols, const cplx* __restrict__ tw, const int l2pf) {
   using GC = GroupCfg<NY>;
   constexpr int T = GC::T, THREADS = GC::THREADS;
   GFB_DYN_SMEM(double, smd);
@@ -348,6 +414,13 @@ __global__ void __launch_bounds__(GroupCfg<NY>::THREADS, GroupCfg<NY>::MINB)
   }
   constexpr int NCI = TWO ? 4 : 2;
   if (liveA) k3_issue<NY>(X, TWO ? pv : pd, ldp, colA, 0, j, tid);
+  // The epilogue streams 5-6 arrays one or two rows at a time and used to wait a DRAM round trip per chunk (39 % of the
+  // warp samples).  Its input tiles of this thread's first eight rows start moving DRAM -> L2 NOW, four transforms before
+  // they are needed; the second eight follow when the epilogue starts (bounded L2 footprint: ~50 MB over all CTAs).
+  if (TWO && l2pf && liveA && T % 8 == 0) {
+    if (e.cplxL) epi_prefetch_rows<T, true>(g, e, layer, colA, j, 0, PT / 2);
+    else epi_prefetch_rows<T, false>(g, e, layer, colA, j, 0, PT / 2);
+  }
   cp_async_wait_all();
 #pragma unroll
   for (int r = 0; r < PT; ++r) v[r] = liveA ? X[r * THREADS + tid] : cmake(0.0, 0.0);
@@ -410,6 +483,10 @@ __global__ void __launch_bounds__(GroupCfg<NY>::THREADS, GroupCfg<NY>::MINB)
       for (int q = 0; q < 4; ++q) tmem_store(tA + 4 * (c0 + q), cadd(v[c0 + q], b[q]));
     }
     tmem_wait_st();
+    if (l2pf && liveA && T % 8 == 0) {
+      if (e.cplxL) epi_prefetch_rows<T, true>(g, e, layer, colA, j, PT / 2, PT);
+      else epi_prefetch_rows<T, false>(g, e, layer, colA, j, PT / 2, PT);
+    }
     if (e.cplxL) epilogue_dispatch<NY, true>(g, e, layer, colA, liveA, X, tA, j, tid);
     else epilogue_dispatch<NY, false>(g, e, layer, colA, liveA, X, tA, j, tid);
     tmem_release(tbase, TmemCfg<NY>::COLS);

@@ -32,42 +32,6 @@ namespace gfb {
 constexpr int WS_BAR_NFULL = 6;
 constexpr int WS_BAR_NEMPTY = 8;
 
-// Start moving one 8-row tile (rows l .. l + 7 of the column pair at colA) of every array the epilogue of this kind READS
-// from DRAM into L2 (same selection as epi_fetch; the masks of masked_pair are honoured so nothing useless moves).
-template <int KIND, bool CL>
-__device__ __forceinline__ void epi_prefetch_tile(const GridDesc& g, const EpiArgs& e, const int layer, const int colA, const int off) {
-  auto pc = [&](const Spec& a) {
-    if (a.p) prefetch_l2_bulk(a.p + layer * a.ls + off, 256);
-  };
-  auto pk = [&](const Coef& t) {
-    if (CL) prefetch_l2_bulk(t.c + layer * t.ls + off, 256);
-    else prefetch_l2_bulk(t.r + layer * t.ls + off, 128);
-  };
-  const bool live_col = gcol(g, colA) < g.kcut;
-  if (KIND == EPI_RK_LAST || KIND == EPI_RK_ONLY || KIND == EPI_ETD_4 || KIND == EPI_AB3) {
-    if (e.filter.p) prefetch_l2_bulk(e.filter.p + off, 128);
-  }
-  if ((KIND == EPI_RK_FIRST || KIND == EPI_RK_MID || KIND == EPI_RK_ONLY || KIND == EPI_ETD_1 || KIND == EPI_ETD_2 || KIND == EPI_ETD_3 ||
-       KIND == EPI_AB3) && live_col)
-    pc(e.sol);
-  if ((KIND == EPI_RK_MID || KIND == EPI_RK_LAST) && live_col) pc(e.sin);
-  if (KIND == EPI_RK_FIRST || KIND == EPI_RK_MID || KIND == EPI_RK_LAST || KIND == EPI_RK_ONLY || KIND == EPI_AB3) pk(e.L);
-  if (KIND == EPI_RK_MID || KIND == EPI_RK_LAST || KIND == EPI_ETD_2 || KIND == EPI_ETD_3 || KIND == EPI_ETD_4) pc(e.acc);
-  if (KIND == EPI_AB3 && (e.b != 0.0 || e.d != 0.0)) {
-    pc(e.acc);
-    pc(e.n1);
-  }
-  if (KIND == EPI_ETD_3) pc(e.n1);
-  if (KIND == EPI_ETD_1 || KIND == EPI_ETD_2 || KIND == EPI_ETD_3) {
-    pk(e.c1);
-    pk(e.c2);
-  }
-  if (KIND == EPI_ETD_1) pk(e.c3);
-  if (KIND == EPI_ETD_1 || KIND == EPI_ETD_2 || KIND == EPI_ETD_3 || KIND == EPI_ETD_4) pk(e.c4);
-  pc(e.Nconst);
-  pc(e.F);
-}
-
 // rows r_begin .. r_begin + 3 of this thread's 16 rows of the column pair, N of both columns in TMEM (ta, tb).
 // (nlayer, ncolA, nr_begin): the slice this thread works on NEXT (nr_begin < 0: none) -- its tiles are prefetched into
 // L2 first, by one thread in eight (a tile = the rows of eight neighbouring threads), so that the one-row-at-a-time loop

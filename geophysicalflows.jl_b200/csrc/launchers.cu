@@ -1,4 +1,6 @@
 // launchers.cu -- compiled once per FFT length: -DGFB_N=<16..8192>
+#include <cstdlib>
+
 #include "launch.h"
 
 #ifndef GFB_N
@@ -88,18 +90,33 @@ static int do_col_inv_single(const ColInvLaunch& L) {
 
 #if GFB_N == 4096
 // the warp-specialised pre-pass (k_col_inv_ws): one 512-thread CTA per SM
-static int do_col_inv_ws(const ColInvLaunch& L) {
+template <int VAR>
+static int do_col_inv_ws_var(const ColInvLaunch& L) {
   const size_t smem = (size_t)xbuf_elems(GFB_N) * sizeof(cplx) + 128;
   static AttrCache attr;
   if (!attr.done[cur_device()]) {
-    if (set_smem(k_col_inv_ws<GFB_N>, smem)) return -2;
+    if (set_smem(k_col_inv_ws<GFB_N, VAR>, smem)) return -2;
     attr.done[cur_device()] = true;
   }
   const int nunits = ((L.ncols + 1) / 2) * L.nfields;
   const int cap = sm_count();
   dim3 grid(nunits < cap ? nunits : cap);
-  GFB_LAUNCH((k_col_inv_ws<GFB_N>), grid, dim3(WS_THREADS), smem, L.st, L.g, L.ps, L.W, L.ldw, L.wfs, L.ncols, L.nfields, nunits, L.tw);
+  GFB_LAUNCH((k_col_inv_ws<GFB_N, VAR>), grid, dim3(WS_THREADS), smem, L.st, L.g, L.ps, L.W, L.ldw, L.wfs, L.ncols, L.nfields, nunits, L.tw);
   return 0;
+}
+static int do_col_inv_ws(const ColInvLaunch& L) {
+  static int var = -1;
+  if (var < 0) {
+    const char* e = getenv("GFB_K1WS_VAR");
+    var = e ? atoi(e) : 0;
+  }
+  switch (var) {
+    case 1: return do_col_inv_ws_var<1>(L);
+    case 2: return do_col_inv_ws_var<2>(L);
+    case 4: return do_col_inv_ws_var<4>(L);
+    case 8: return do_col_inv_ws_var<8>(L);
+    default: return do_col_inv_ws_var<0>(L);
+  }
 }
 #endif
 
@@ -313,7 +330,12 @@ static int do_col_fwd(const ColFwdLaunch& L) {
   }
   const int ntiles = ((L.ncols + 1) / 2 + GC::G - 1) / GC::G;
   dim3 grid(ntiles, L.nlayers);
-  GFB_LAUNCH((k_col_fwd<GFB_N, TWO>), grid, dim3(GC::THREADS), smem, L.st, L.g, L.P, L.ldp, L.pfs, L.e, L.ncols, L.tw);
+  static int l2pf = -1;
+  if (l2pf < 0) {
+    const char* e = getenv("GFB_NO_K3_L2PF");
+    l2pf = (e && e[0] == '1') ? 0 : 1;
+  }
+  GFB_LAUNCH((k_col_fwd<GFB_N, TWO>), grid, dim3(GC::THREADS), smem, L.st, L.g, L.P, L.ldp, L.pfs, L.e, L.ncols, L.tw, l2pf);
   return 0;
 }
 

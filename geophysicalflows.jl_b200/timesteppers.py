@@ -51,10 +51,41 @@ def getetdcoeffs(dt, L, ncirc=32, rcirc=1):
     return [o.reshape(L.shape) for o in out]
 
 
+def getetdcoeffs_torch(dt, L, device, ncirc=32, rcirc=1):
+    """Same contour means evaluated with torch complex128 on `device` (setup-time plumbing: at 16384^2 the numpy version
+    needs minutes per rank).  Returns numpy arrays (expLdt, exphalfLdt, zeta, alpha, beta, Gamma)."""
+    L = np.asarray(L)
+    real = not np.iscomplexobj(L)
+    pts = torch.as_tensor(rcirc * np.exp(2j * np.pi * (np.arange(ncirc) + 0.5) / ncirc), device=device)
+    flat = torch.as_tensor(np.ascontiguousarray(L).reshape(-1)).to(device).to(torch.complex128)
+    outs = [torch.empty_like(flat) for _ in range(6)]
+    step = 1 << 21
+    for i in range(0, flat.numel(), step):
+        Ldt = dt * flat[i:i + step]
+        z = Ldt[:, None] + pts
+        ez, ezh = torch.exp(z), torch.exp(z / 2)
+        z3 = z * z * z
+        vals = (torch.exp(Ldt), torch.exp(Ldt / 2),
+                dt * torch.mean((ezh - 1) / z, dim=-1),
+                dt * torch.mean((-4 - z + ez * (4 - 3 * z + z * z)) / z3, dim=-1),
+                dt * torch.mean((2 + z + ez * (z - 2)) / z3, dim=-1),
+                dt * torch.mean((-4 - 3 * z - z * z + ez * (4 - z)) / z3, dim=-1))
+        for o, val in zip(outs, vals):
+            o[i:i + step] = val
+    res = []
+    for o in outs:
+        a = o.cpu().numpy().reshape(L.shape)
+        res.append(np.ascontiguousarray(a.real) if real else a)
+    return res
+
+
+ETD_ON_DEVICE_ABOVE = 1 << 21  # table elements; below it the numpy evaluation takes a few seconds at most
+
+
 class TimeStepper:
     """Field names follow the reference's steppers where the library exposes them."""
 
-    def __init__(self, name, eqn, dt, shard=None):
+    def __init__(self, name, eqn, dt, shard=None, device=None):
         if name not in _lib.STEPPERS:
             raise ValueError("unknown stepper %r" % name)
         self.name = name
@@ -66,9 +97,13 @@ class TimeStepper:
         if self.etd:
             # on a sharded problem every rank evaluates the (32-point contour) coefficients of ITS kr columns only
             L = shard.cut("L", eqn.L) if self.local_tables else eqn.L
-            self.expLdt = np.exp(dt * L)
-            self.exphalfLdt = np.exp(dt * L / 2)
-            self.zeta, self.alpha, self.beta, self.Gamma = getetdcoeffs(dt, L)
+            tdev = getattr(device, "torch_device", None)
+            if np.size(L) > ETD_ON_DEVICE_ABOVE and tdev is not None and torch.device(tdev).type == "cuda":
+                self.expLdt, self.exphalfLdt, self.zeta, self.alpha, self.beta, self.Gamma = getetdcoeffs_torch(dt, L, tdev)
+            else:
+                self.expLdt = np.exp(dt * L)
+                self.exphalfLdt = np.exp(dt * L / 2)
+                self.zeta, self.alpha, self.beta, self.Gamma = getetdcoeffs(dt, L)
 
 
 def _ptr(a):
@@ -122,7 +157,7 @@ class Problem:
     def __init__(self, eqn, stepper, dt, grid, vars, params, kind, tables, shard=None):
         self.eqn, self.grid, self.vars, self.params = eqn, grid, vars, params
         self.clock = Clock(dt)
-        self.timestepper = TimeStepper(stepper, eqn, dt, shard)
+        self.timestepper = TimeStepper(stepper, eqn, dt, shard, device=grid.device)
         self.dev = grid.device
         self.lib = self.dev.lib
         self.nlayers = eqn.dims[0] if len(eqn.dims) == 3 else 1
@@ -325,10 +360,10 @@ class Problem:
         return vals
 
     def path_info(self):
-        info = (C.c_longlong * 4)()
+        info = (C.c_longlong * 8)()
         self._check(self.lib.gfb_path_info(self.ctx, info), "gfb_path_info")
         return {"row_tma": bool(info[0]), "row_tma_launches": int(info[1]), "col_ws": bool(info[2]),
-                "col_ws_launches": int(info[3])}
+                "col_ws_launches": int(info[3]), "row_ws": bool(info[4]), "col_ws3": bool(info[5])}
 
     def profile_begin(self):
         self._check(self.lib.gfb_profile_begin(self.ctx), "gfb_profile_begin")

@@ -213,10 +213,11 @@ int gfb_profile_begin(gfb_ctx* ctx);
 int gfb_profile_end(gfb_ctx* ctx, double* ms4, long long* launches4);
 
 /* Which kernel variants the context dispatches to (for tests and the bench line):
- *   info[0] = 1: the row pass of the stepping path is the TMA-staged kernel (k_row_product_tma)
- *   info[1] = launches of it so far
- *   info[2] = 1: the column pre-pass is the warp-specialised kernel (k_col_inv_ws), info[3] = its launches so far */
-int gfb_path_info(const gfb_ctx* ctx, long long* info4);
+ *   info[0] = 1: the row pass of the stepping path is TMA-staged (k_row_product_tma / k_row_product_ws); info[1] = launches
+ *   info[2] = 1: the column pre-pass is the warp-specialised kernel (k_col_inv_ws); info[3] = its launches so far
+ *   info[4] = 1: the row pass is the warp-specialised kernel (k_row_product_ws)
+ *   info[5] = 1: the forward column pass + epilogue is the warp-specialised kernel (k_col_fwd_ws); info[6..7] reserved */
+int gfb_path_info(const gfb_ctx* ctx, long long* info8);
 
 /* bytes of device memory owned by the context */
 long long gfb_device_bytes(const gfb_ctx* ctx);
