@@ -7,7 +7,7 @@ Julia `f!` is spelled `f_`; Julia arrays `(nkr, nl[, n])` are torch tensors `[n,
 (identical bytes).  There is no CPU path: importing works anywhere, creating a `Problem`
 needs the built library and a CUDA device.
 """
-from . import _lib, device, grid, timesteppers, twodnavierstokes, surfaceqg, singlelayerqg, multilayerqg, utils  # noqa: F401
+from . import _lib, device, grid, timesteppers, twodnavierstokes, surfaceqg, singlelayerqg, multilayerqg, barotropicqgql, utils  # noqa: F401
 from ._lib import GfbError  # noqa: F401
 from .device import GPU, CPU, Device  # noqa: F401
 from .grid import TwoDGrid  # noqa: F401
@@ -17,6 +17,7 @@ TwoDNavierStokes = twodnavierstokes
 SurfaceQG = surfaceqg
 SingleLayerQG = singlelayerqg
 MultiLayerQG = multilayerqg
+BarotropicQGQL = barotropicqgql
 
 
 def dealias_(sol, grid_or_prob):

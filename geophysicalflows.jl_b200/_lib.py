@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 DEFAULT_LIB = os.path.join(HERE, "libgfb.so")
 
-GFB_KIND_SINGLE, GFB_KIND_LAYERED = 0, 1
+GFB_KIND_SINGLE, GFB_KIND_LAYERED, GFB_KIND_QL = 0, 1, 2
 STEPPERS = {"ForwardEuler": 0, "FilteredForwardEuler": 1, "RK4": 2, "FilteredRK4": 3, "ETDRK4": 4,
             "FilteredETDRK4": 5, "AB3": 6, "FilteredAB3": 7}
 (DIAG_ABS2, DIAG_INVK_ABS2, DIAG_K_ABS2, DIAG_KP_ABS2, DIAG_G_ABS2, DIAG_G2_ABS2, DIAG_KG2_ABS2, DIAG_ABS2_PLUS,

@@ -24,6 +24,7 @@ struct gfb_ctx {
   gfb_config cfg;  // host pointers inside are NOT retained (nulled after create)
   GridDesc g;
   int nlayers = 1, kind = 0, stepper = 0;
+  bool ql = false;  // GFB_KIND_QL (kind is GFB_KIND_SINGLE then)
   bool filtered = false, cplxL = false;
   double dt = 0, t = 0;
   long long step = 0;
@@ -348,8 +349,11 @@ int gfb_create(gfb_ctx** out, const gfb_config* cfg) {
   if (!(pow2_ok(cfg->nx) || half_rows) || !(pow2_ok(cfg->ny) || quad_cols))
     return fail(nullptr, GFB_ERR_UNSUPPORTED, "nx=%d, ny=%d: sizes must be powers of two in [32, 16384]", cfg->nx, cfg->ny);
   if (cfg->nlayers < 1 || cfg->nlayers > MAX_LAYERS) return fail(nullptr, GFB_ERR_UNSUPPORTED, "nlayers=%d not in [1, %d]", cfg->nlayers, MAX_LAYERS);
-  if (cfg->kind == GFB_KIND_SINGLE && cfg->nlayers != 1) return fail(nullptr, GFB_ERR_INVALID, "GFB_KIND_SINGLE needs nlayers == 1");
-  if (cfg->kind != GFB_KIND_SINGLE && cfg->kind != GFB_KIND_LAYERED) return fail(nullptr, GFB_ERR_INVALID, "unknown kind %d", cfg->kind);
+  if ((cfg->kind == GFB_KIND_SINGLE || cfg->kind == GFB_KIND_QL) && cfg->nlayers != 1)
+    return fail(nullptr, GFB_ERR_INVALID, "GFB_KIND_SINGLE / GFB_KIND_QL need nlayers == 1");
+  if (cfg->kind != GFB_KIND_SINGLE && cfg->kind != GFB_KIND_LAYERED && cfg->kind != GFB_KIND_QL)
+    return fail(nullptr, GFB_ERR_INVALID, "unknown kind %d", cfg->kind);
+  if (cfg->kind == GFB_KIND_QL && (cfg->eta || cfg->Nconst)) return fail(nullptr, GFB_ERR_INVALID, "GFB_KIND_QL takes no eta / Nconst");
   if (cfg->stepper < GFB_FORWARD_EULER || cfg->stepper > GFB_FILTERED_AB3) return fail(nullptr, GFB_ERR_INVALID, "unknown stepper %d", cfg->stepper);
   if (cfg->no_dealias_in_calcN) return fail(nullptr, GFB_ERR_UNSUPPORTED, "calcNlinear! (no dealias) is not supported");
   if (!cfg->L) return fail(nullptr, GFB_ERR_INVALID, "config.L is null");
@@ -363,7 +367,9 @@ int gfb_create(gfb_ctx** out, const gfb_config* cfg) {
   gfb_ctx* c = new gfb_ctx();
   c->cfg = *cfg;
   c->nlayers = cfg->nlayers;
-  c->kind = cfg->kind;
+  // BarotropicQGQL is a single-layer kind whose row pass is k_row_ql; everything else treats it as GFB_KIND_SINGLE
+  c->ql = cfg->kind == GFB_KIND_QL;
+  c->kind = c->ql ? (int)GFB_KIND_SINGLE : cfg->kind;
   c->stepper = cfg->stepper;
   c->filtered = (cfg->stepper & 1) != 0;
   c->cplxL = cfg->L_is_complex != 0;
@@ -448,7 +454,7 @@ int gfb_create(gfb_ctx** out, const gfb_config* cfg) {
     TRY(dev_alloc(c, &c->W, (size_t)w_elems(c, 4 * n)));
     TRY(dev_alloc(c, &c->P, (size_t)w_elems(c, 2 * n)));
   }
-  if (nranks == 1 && c->kind == GFB_KIND_SINGLE && (g.nx == 4096 || g.nx == 8192) && (g.ny % 8) == 0) {
+  if (nranks == 1 && c->kind == GFB_KIND_SINGLE && !c->ql && (g.nx == 4096 || g.nx == 8192) && (g.ny % 8) == 0) {
     // TMA-staged row pass: tensor maps of W (3 fields) and P (2 fields); the output boxes come in two sizes
     int nbi, bpi, nbo, bpo;
     row_boxes(g.kcut, &nbi, &bpi);
@@ -655,6 +661,61 @@ static int run_col_inv_state(gfb_ctx* c, const Spec& sin, int nf, const PeerOut&
   return check_launch(c, launch_col_inv(c->g.ny, L), "k_col_inv");
 }
 
+// ---- BarotropicQGQL row pass (GFB_KIND_QL) -----------------------------------------------------------------------
+// calcN_advection! of /root/reference/src/barotropicqgql.jl:293-333 between the two column passes.  After K1 the work
+// array holds, per row y, the x-spectra W_f(kr, y) of u = i l G sol, v = -i kr G sol and q = sol.  The zonal parts are
+// the kr = 0 entries -- U(y) = Re W_u(0, y), Zeta(y) = Re W_q(0, y) -- and do not depend on x, so the reference's
+// eddy-mean products U zeta' + u' Zeta and v' Zeta are LINEAR in the eddy x-spectra: no x-transform is needed,
+//     P_d(kr, y) = -i kr nx (U W_q + Zeta W_u)(kr, y),   P_v(kr, y) = nx Zeta W_v(kr, y)        0 < kr < kcut,
+// and the only eddy-eddy term the quasi-linear closure keeps, the kr = 0 entry of (v' zeta')_h, is the x-sum of the
+// product, i.e. (Parseval) P_v(0, y) = nx sum_{kr != 0} W_v conj(W_q).  Columns >= kcut of both products are exactly
+// zero in the reference as well (the inputs are dealiased and a kr = 0 factor does not spread in kr).
+// One CTA per 8-row block of the tiled W/P (contiguous 256-byte tiles on one GPU); the row sums are reduced in a fixed
+// order (deterministic).
+static __global__ void __launch_bounds__(256) k_row_ql(const __grid_constant__ RowArgs a, const int nx) {
+  __shared__ double part[256];
+  __shared__ double UZ[16];
+  const int t = threadIdx.x, yy = (t & 15) >> 1, kk = t & 1;
+  const int y = (int)blockIdx.x * 8 + yy;
+  if (t < 16) {  // U and Zeta of the block's eight rows
+    const int r = (int)blockIdx.x * 8 + (t >> 1);
+    UZ[t] = a.W[a.wl.off((t & 1) ? 2 : 0, r, 0)].x;
+  }
+  __syncthreads();
+  const double U = UZ[2 * yy], Z = UZ[2 * yy + 1], sx = (double)nx;
+  const long long rd = a.pl.rowbase(0, y), rv = a.pl.rowbase(1, y);
+  double acc = 0.0;
+  const int npairs = (a.kout + 1) / 2;
+  for (int kp = t >> 4; kp < npairs; kp += 16) {
+    const int k = 2 * kp + kk;
+    if (k >= a.kout) continue;
+    cplx d = cmake(0.0, 0.0), v = cmake(0.0, 0.0);
+    if (k > 0 && k < a.kc) {
+      cplx wu = a.W[a.wl.off(0, y, k)], wv = a.W[a.wl.off(1, y, k)], wq = a.W[a.wl.off(2, y, k)];
+      const bool nyq = 2 * k == nx;  // c2r ignores the imaginary part of the Nyquist entry and counts it once
+      if (nyq) wu.y = wv.y = wq.y = 0.0;
+      const double kr = k * a.dkx;
+      const cplx s = cmake(sx * (U * wq.x + Z * wu.x), sx * (U * wq.y + Z * wu.y));
+      d = cmake(kr * s.y, -kr * s.x);
+      v = cmake(sx * Z * wv.x, sx * Z * wv.y);
+      acc += (nyq ? 1.0 : 2.0) * (wv.x * wq.x + wv.y * wq.y);
+    }
+    if (k > 0) {
+      *prow_ptr(a.pout, rd, k) = d;
+      *prow_ptr(a.pout, rv, k) = v;
+    }
+  }
+  part[t] = acc;
+  __syncthreads();
+  if (t < 8) {  // row t of the block: its 32 partial sums live at threads with ((tid & 15) >> 1) == t
+    double ssum = 0.0;
+    for (int i = 0; i < 16; ++i) ssum += part[i * 16 + 2 * t] + part[i * 16 + 2 * t + 1];
+    const int r = (int)blockIdx.x * 8 + t;
+    *prow_ptr(a.pout, a.pl.rowbase(0, r), 0) = cmake(0.0, 0.0);
+    *prow_ptr(a.pout, a.pl.rowbase(1, r), 0) = cmake(sx * ssum, 0.0);
+  }
+}
+
 static int run_row_product(gfb_ctx* c, const cplx* Wrecv, const PeerOut& Psend, bool prune, cudaStream_t st) {
   RowLaunch R;
   std::memset(&R, 0, sizeof R);
@@ -683,6 +744,10 @@ static int run_row_product(gfb_ctx* c, const cplx* Wrecv, const PeerOut& Psend, 
     c->row_tma_launches += 1;
   }
   ProfScope ps(c, 1, st);
+  if (c->ql) {
+    GFB_LAUNCH(k_row_ql, dim3(c->ny_loc / 8), dim3(256), 0, st, R.a, c->g.nx);
+    return check_launch(c, 0, "k_row_ql");
+  }
   return check_launch(c, launch_row(c->g.nx, R), "k_row");
 }
 

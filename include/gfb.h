@@ -51,8 +51,12 @@ enum gfb_status {
 /* which calcN! family */
 enum gfb_kind {
   GFB_KIND_SINGLE = 0, /* TwoDNavierStokes, SurfaceQG, SingleLayerQG with constant U:  psi_h = -G * sol */
-  GFB_KIND_LAYERED = 1 /* MultiLayerQG (any nlayers) and SingleLayerQG with U(y):       psi_h = S^-1 sol,
+  GFB_KIND_LAYERED = 1, /* MultiLayerQG (any nlayers) and SingleLayerQG with U(y):       psi_h = S^-1 sol,
                           extra (u+U) dQ/dx + v dQ/dy term, optional bottom drag */
+  GFB_KIND_QL = 2      /* BarotropicQGQL (src/barotropicqgql.jl:293-333): psi_h = -G * sol as GFB_KIND_SINGLE; calcN! keeps
+                          the eddy-mean products at kr != 0 and the eddy-eddy flux -d/dy <v'zeta'> at kr = 0 (zonal mean =
+                          the kr = 0 column).  Config fields as GFB_KIND_SINGLE (eta and Nconst are not used by the reference's
+                          calcN_advection! and must be NULL). */
 };
 
 enum gfb_stepper {

@@ -9,6 +9,6 @@ Parity status: pinned against every analytic known-answer test the reference hol
 vendored), so items only defined inside FourierFlows.jl -- filter constants, ETD contour parameters,
 the exact alias index formula and its aliased_fraction=0 behaviour -- are "parity unpinned".
 """
-from . import grid, timesteppers, twodnavierstokes, surfaceqg, singlelayerqg, multilayerqg, utils  # noqa: F401
+from . import grid, timesteppers, twodnavierstokes, surfaceqg, singlelayerqg, multilayerqg, barotropicqgql, utils  # noqa: F401
 from .grid import TwoDGrid, dealias_, parsevalsum, parsevalsum2, set_workers  # noqa: F401
 from .timesteppers import stepforward_, Diagnostic  # noqa: F401

@@ -25,7 +25,7 @@ pkg = gfb_loader.load()
 class ProductBackend:
     def __init__(self, dev, name):
         self.dev, self.name, self.pkg = dev, name, pkg
-        for mod in ("twodnavierstokes", "surfaceqg", "singlelayerqg"):
+        for mod in ("twodnavierstokes", "surfaceqg", "singlelayerqg", "barotropicqgql"):
             setattr(self, mod, self._proxy(getattr(pkg, mod), lambda f: functools.partial(f, dev)))
         self.multilayerqg = self._proxy(pkg.multilayerqg, lambda f: (lambda n, **kw: f(n, dev, **kw)))
         self.stepforward_ = pkg.stepforward_

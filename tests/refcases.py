@@ -24,6 +24,7 @@ class OracleBackend:
         self.surfaceqg = gfo.surfaceqg
         self.singlelayerqg = gfo.singlelayerqg
         self.multilayerqg = gfo.multilayerqg
+        self.barotropicqgql = gfo.barotropicqgql
         self.stepforward_ = gfo.stepforward_
 
     def dealias_(self, sol, grid):
@@ -276,6 +277,86 @@ def slqg_energyenstrophy(B, deformation_radius=np.inf, nx=64, ny=64):
     M.updatevars_(prob)
     ke, pe = 29 / 9, 5 / (8 * deformation_radius**2)
     return (M.kinetic_energy(prob) / ke - 1, M.potential_energy(prob) / pe - 1, M.energy(prob) / (ke + pe) - 1)
+
+
+# ------------------------------------------------------------------------------------------------
+# BarotropicQGQL
+# ------------------------------------------------------------------------------------------------
+def bqgql_rossbywave(B, stepper, dt, nsteps, nx=64):
+    """test/test_barotropicqgql.jl:6-42 (test_bqgql_rossbywave); returns (err, rtol)."""
+    Lx, beta = 2 * np.pi, 2.0
+    M = B.barotropicqgql
+    eta = np.zeros((nx, nx)) if stepper == "ForwardEuler" else (lambda x, y: 0 * x)
+    prob = M.Problem(nx=nx, Lx=Lx, eta=eta, beta=beta, mu=0.0, nu=0.0, stepper=stepper, dt=dt)
+    x, y = hostgrid(nx, Lx).gridpoints()
+    ampl = 1e-2
+    kw, lw = 3 * 2 * np.pi / Lx, 2 * 2 * np.pi / Lx
+    om = -beta * kw / (kw**2 + lw**2)
+    z0 = ampl * np.cos(kw * x) * np.cos(lw * y)
+    M.set_zeta_(prob, B.dev(z0))
+    B.stepforward_(prob, nsteps)
+    B.dealias_(prob.sol, prob.grid)
+    M.updatevars_(prob)
+    zt = ampl * np.cos(kw * (x - om / kw * prob.clock.t)) * np.cos(lw * y)
+    return relerr(zt, B.host(prob.vars.zeta)), nx * nx * nsteps * 1e-12
+
+
+def bqgql_advection(B, dt=0.0005, stepper="ForwardEuler", n=128, tf=1.0):
+    """test/test_barotropicqgql.jl:162-201 (test_bqgql_advection): zeta + Zeta stays on the forced solution."""
+    L, nu, nnu, mu = 2 * np.pi, 1e-2, 1, 0.0
+    nt = round(tf / dt)
+    x, y = hostgrid(n, L).gridpoints()
+    qf = -9 * np.cos(3 * y) - 8 * np.sin(2 * x) * np.cos(2 * y) - 20 * np.sin(x) * np.cos(3 * y)
+    Ff = (nu * (81 * np.cos(3 * y) + 200 * np.cos(3 * y) * np.sin(x) + 64 * np.cos(2 * y) * np.sin(2 * x))
+          - 3 * np.sin(3 * y) * (-16 * np.cos(2 * x) * np.cos(2 * y) - 20 * np.cos(x) * np.cos(3 * y))
+          - 27 * np.sin(3 * y) * (2 * np.cos(2 * x) * np.cos(2 * y) + 2 * np.cos(x) * np.cos(3 * y)))
+    M = B.barotropicqgql
+    prob = M.Problem(nx=n, Lx=L, nu=nu, nnu=nnu, mu=mu, dt=dt, stepper=stepper, calcF=const_forcing(B, -rfft2(Ff)))
+    M.set_zeta_(prob, B.dev(qf))
+    B.stepforward_(prob, nt)
+    M.updatevars_(prob)
+    return relerr(B.host(prob.vars.zeta) + B.host(prob.vars.Zeta), qf)
+
+
+def bqgql_energyenstrophy(B, nx=64, ny=64):
+    """test/test_barotropicqgql.jl:208-228: E = 29/9, Z = 2701/162."""
+    Lx, Ly = 2 * np.pi, 3 * np.pi
+    x, y = hostgrid(nx, Lx, ny, Ly).gridpoints()
+    k0, l0 = 2 * np.pi / Lx, 2 * np.pi / Ly
+    eta = np.cos(10 * k0 * x) * np.cos(10 * l0 * y)
+    z0 = (-((2 * k0) ** 2 + (2 * l0) ** 2) * np.sin(2 * k0 * x) * np.cos(2 * l0 * y)
+          - (k0**2 + (3 * l0) ** 2) * 2 * np.sin(k0 * x) * np.cos(3 * l0 * y))
+    M = B.barotropicqgql
+    prob = M.Problem(nx=nx, Lx=Lx, ny=ny, Ly=Ly, eta=eta, stepper="ForwardEuler")
+    M.set_zeta_(prob, B.dev(z0))
+    M.updatevars_(prob)
+    return M.energy(prob) / (29 / 9) - 1, M.enstrophy(prob) / (2701 / 162) - 1
+
+
+def bqgql_deterministicforcingbudgets(B, n=256, nt=None):
+    """test/test_barotropicqgql.jl:109-148: dE/dt = W - D - R to 1e-10 (atol) with centred differences."""
+    L, nu, nnu, mu, dt = 2 * np.pi, 1e-7, 2, 1e-1, 0.005
+    nt = round(0.1 / mu / dt) if nt is None else nt
+    x, y = hostgrid(n, L).gridpoints()
+    fh = B.dev(rfft2(0.01 * np.cos(4 * x) * np.cos(5 * y)))
+
+    def calcF(Fh, sol, t, clock, vars, params, grid):
+        B.assign(Fh, fh * np.cos(2 * t))
+    M = B.barotropicqgql
+    prob = M.Problem(nx=n, Lx=L, nu=nu, nnu=nnu, mu=mu, dt=dt, stepper="RK4", calcF=calcF, stochastic=False)
+    M.set_zeta_(prob, B.dev(np.zeros((n, n))))
+    E, D, Rr, W = [], [], [], []
+
+    def record():
+        E.append(M.energy(prob)); D.append(M.dissipation(prob)); Rr.append(M.drag(prob)); W.append(M.work(prob))
+    record()
+    for _ in range(nt):
+        B.stepforward_(prob, 1)
+        record()
+    E, D, Rr, W = map(np.array, (E, D, Rr, W))
+    dEdt_num = (E[2:] - E[:-2]) / (2 * dt)
+    dEdt_comp = W[1:-1] - D[1:-1] - Rr[1:-1]
+    return float(np.max(np.abs(dEdt_num - dEdt_comp)))
 
 
 # ------------------------------------------------------------------------------------------------

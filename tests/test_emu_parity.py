@@ -121,6 +121,52 @@ def test_reference_cases_slqg(emu):
             f(prob)
 
 
+def _bqgql_vs_oracle(B, O, nx, ny, stepper, nsteps, forced=False):
+    """random dealiased state with a strong zonal part: product vs oracle after nsteps, plus calcN! itself"""
+    kw = dict(nx=nx, ny=ny, Lx=2 * np.pi, Ly=3.0, beta=1.5, nu=1e-4, nnu=1, mu=0.02, dt=2e-3, stepper=stepper)
+    rng = np.random.default_rng(nx + ny)
+    s0 = np.fft.rfft2(rng.standard_normal((ny, nx))) * 30 / (nx * ny)
+    s0[:, 0] *= 20  # zonal jets
+    s0[0, 0] = 0
+    Fh = np.fft.rfft2(rng.standard_normal((ny, nx))) * 3 / (nx * ny)
+    kwo, kwb = dict(kw), dict(kw)
+    if forced:
+        kwo.update(calcF=R.const_forcing(O, Fh), stochastic=True)
+        kwb.update(calcF=R.const_forcing(B, Fh), stochastic=True)
+    po, pb = O.barotropicqgql.Problem(**kwo), B.barotropicqgql.Problem(**kwb)
+    po.sol[...] = s0
+    pb.sol.copy_(B.dev(s0))
+    No = np.zeros_like(po.sol)
+    O.barotropicqgql.calcN_(No, po.sol.copy(), 0.0, po.clock, po.vars, po.params, po.grid)
+    Nb = pb.sol.clone()
+    B.barotropicqgql.calcN_(Nb, pb.sol.clone(), 0.0, pb.clock, pb.vars, pb.params, pb.grid)
+    assert R.relerr(B.host(Nb), No) < 1e-12
+    O.stepforward_(po, nsteps)
+    B.stepforward_(pb, nsteps)
+    assert R.relerr(B.host(pb.sol), po.sol) < 1e-11
+    O.barotropicqgql.updatevars_(po)
+    B.barotropicqgql.updatevars_(pb)
+    for name in ("zeta", "Zeta", "psi", "Psi", "u", "v", "U"):
+        a, b = B.host(getattr(pb.vars, name)), getattr(po.vars, name)
+        assert np.linalg.norm(a - b) <= 1e-11 * max(np.linalg.norm(b), 1e-3), name
+    for f in ("energy", "enstrophy", "dissipation", "drag") + (("work",) if forced else ()):
+        a, b = getattr(B.barotropicqgql, f)(pb), getattr(O.barotropicqgql, f)(po)
+        assert abs(a - b) <= 1e-11 * max(abs(b), 1e-12), f
+
+
+def test_reference_cases_bqgql(emu, oracle_backend):
+    """test/runtests.jl:89-106 through the emulated kernels (reduced step counts), then product vs oracle on random states."""
+    for stepper, dt, ns in (("RK4", 1e-2, 20), ("FilteredETDRK4", 1e-2, 20), ("AB3", 1e-3, 200), ("ForwardEuler", 1e-4, 100)):
+        err, rtol = R.bqgql_rossbywave(emu, stepper, dt, ns)
+        assert err < rtol, stepper
+    assert R.bqgql_advection(emu, dt=0.005, stepper="RK4", n=64, tf=0.1) < RT
+    e, z = R.bqgql_energyenstrophy(emu)
+    assert abs(e) < RT and abs(z) < RT
+    assert R.bqgql_deterministicforcingbudgets(emu, n=64, nt=12) < 1e-10
+    _bqgql_vs_oracle(emu, oracle_backend, 64, 32, "FilteredRK4", 5)
+    _bqgql_vs_oracle(emu, oracle_backend, 32, 128, "ETDRK4", 4, forced=True)
+
+
 def test_reference_cases_mqg(emu):
     for n in (2, 3):
         assert R.mqg_pvtofromstreamfunction(emu, n, n=64) < 1e-13

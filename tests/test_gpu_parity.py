@@ -89,6 +89,25 @@ def test_ref_slqg(gpu):
     assert max(abs(e) for e in R.slqg_energyenstrophy(gpu, deformation_radius=1.23)) < RT
 
 
+@pytest.mark.parametrize("stepper,dt,nsteps", STEPPERS)
+def test_ref_bqgql_rossbywave(gpu, stepper, dt, nsteps):
+    """test/runtests.jl:92-99."""
+    err, rtol = R.bqgql_rossbywave(gpu, stepper, dt, nsteps)
+    assert err < rtol
+
+
+def test_ref_bqgql(gpu, O):
+    """test/runtests.jl:100-103 at the reference's own sizes, then product vs oracle on random states with strong jets."""
+    from test_emu_parity import _bqgql_vs_oracle
+    assert R.bqgql_advection(gpu) < RT
+    e, z = R.bqgql_energyenstrophy(gpu)
+    assert abs(e) < RT and abs(z) < RT
+    assert R.bqgql_deterministicforcingbudgets(gpu) < 1e-10
+    _bqgql_vs_oracle(gpu, O, 256, 128, "FilteredRK4", 10)
+    _bqgql_vs_oracle(gpu, O, 512, 1024, "ETDRK4", 5, forced=True)
+    _bqgql_vs_oracle(gpu, O, 4096, 64, "FilteredETDRK4", 3)
+
+
 def test_ref_mqg(gpu):
     for n in (2, 3):
         assert R.mqg_pvtofromstreamfunction(gpu, n) < 1e-13

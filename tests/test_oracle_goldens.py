@@ -170,3 +170,25 @@ def test_peakedisotropicspectrum():
     assert abs(E / E0 - 1) < 0.1  # src/utils.jl:49 sums the half-spectrum once: the kr=0 column gets double weight
     with pytest.raises(RuntimeError, match="the domain is not square"):
         peakedisotropicspectrum(TwoDGrid(32, 2 * np.pi, 34, 3 * np.pi), 6, 0.5, allones=True)
+
+
+# ---- BarotropicQGQL (test/runtests.jl:89-106) ------------------------------------------------------------------
+@pytest.mark.parametrize("stepper,dt,nsteps", STEPPERS)
+def test_bqgql_rossbywave(oracle_backend, stepper, dt, nsteps):
+    err, rtol = R.bqgql_rossbywave(oracle_backend, stepper, dt, nsteps)
+    assert err < rtol
+
+
+def test_bqgql_advection(oracle_backend):
+    """test/runtests.jl:102: test_bqgql_advection(0.0005, "ForwardEuler")."""
+    assert R.bqgql_advection(oracle_backend) < RT
+
+
+def test_bqgql_energyenstrophy(oracle_backend):
+    e, z = R.bqgql_energyenstrophy(oracle_backend)
+    assert abs(e) < RT and abs(z) < RT
+
+
+def test_bqgql_deterministicforcingbudgets(oracle_backend):
+    """test/runtests.jl:100 at a reduced size and step count (the closure is local in time)."""
+    assert R.bqgql_deterministicforcingbudgets(oracle_backend, n=128, nt=40) < 1e-10
