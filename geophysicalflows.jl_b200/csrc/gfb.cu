@@ -60,6 +60,10 @@ struct gfb_ctx {
   bool peer_ipc[MAX_RANKS] = {false, false, false, false, false, false, false, false};
   bool connected = false;
   unsigned long long epoch = 0;
+  // sticky barrier failure: a mapped pinned word a barrier that gave up writes its epoch into; every later barrier
+  // launch, gfb_step_p2p and the sharded transforms read it on the HOST (no synchronisation) and fail
+  unsigned long long* tmo_host = nullptr;
+  unsigned long long* tmo_dev = nullptr;
   bool defer_alias = false;  // gfb_set_defer_alias_band
   // TMA-staged row pass (single GPU, single-layer kinds, nx = 4096 / 8192): tensor maps of W and P
   bool row_tma = false;
@@ -333,6 +337,7 @@ int gfb_destroy(gfb_ctx* c) {
     if (c->peer_ipc[d] && c->peer[d]) cudaIpcCloseMemHandle(c->peer[d]);
 #endif
   for (void* p : c->allocs) cudaFree(p);
+  if (c->tmo_host) cudaFreeHost(c->tmo_host);
   for (auto& e : c->prof_ev) cudaEventDestroy(e);
   delete c;
   return GFB_OK;
@@ -910,7 +915,8 @@ __device__ __forceinline__ unsigned long long flag_load_acquire(const unsigned l
 #endif
 }
 
-static __global__ void k_peer_barrier(const PeerFlags f, const unsigned long long epoch, const long long max_spins) {
+static __global__ void k_peer_barrier(const PeerFlags f, const unsigned long long epoch, const long long max_spins,
+                                      unsigned long long* tmo) {
   const int d = threadIdx.x;
   if (d >= f.nranks) return;
 #ifdef GFB_EMULATE
@@ -929,6 +935,7 @@ static __global__ void k_peer_barrier(const PeerFlags f, const unsigned long lon
 #endif
     if (++spins > max_spins) {  // a peer died or never launched: give up instead of hanging the GPU
       flag_store_release(f.flags[f.rank] + FLAG_TIMEOUT_SLOT, epoch);
+      if (tmo) flag_store_release(tmo, epoch);
       break;
     }
   }
@@ -940,9 +947,17 @@ static int peer_barrier(gfb_ctx* c, cudaStream_t st) {
   f.rank = c->g.rank;
   f.nranks = c->g.nranks;
   for (int d = 0; d < f.nranks; ++d) f.flags[d] = reinterpret_cast<unsigned long long*>(c->peer[d]);
+  if (c->tmo_host && *(volatile unsigned long long*)c->tmo_host != 0)
+    return fail(c, GFB_ERR_CUDA, "peer barrier timed out at epoch %llu (a peer died or never launched); the state is invalid",
+                *(volatile unsigned long long*)c->tmo_host);
   c->epoch += 1;
   ProfScope ps(c, 3, st);
-  GFB_LAUNCH(k_peer_barrier, dim3(1), dim3(32), 0, st, f, c->epoch, (long long)40000000);
+  static long long spins = -1;
+  if (spins < 0) {
+    const char* e = getenv("GFB_BARRIER_SPINS");
+    spins = e ? atoll(e) : 40000000LL;
+  }
+  GFB_LAUNCH(k_peer_barrier, dim3(1), dim3(32), 0, st, f, c->epoch, spins, c->tmo_dev);
   return check_launch(c, 0, "k_peer_barrier");
 }
 
@@ -963,6 +978,11 @@ int gfb_comm_create(gfb_ctx* c, void* handle64_out, void** local_ptr_out) {
     if (rc) return rc;
     GFB_CUDA(c, cudaMemset(c->comm, 0, c->comm_bytes));
     GFB_CUDA(c, cudaDeviceSynchronize());
+    if (!c->tmo_host) {
+      GFB_CUDA(c, cudaHostAlloc((void**)&c->tmo_host, sizeof(unsigned long long), cudaHostAllocMapped));
+      *c->tmo_host = 0;
+      GFB_CUDA(c, cudaHostGetDevicePointer((void**)&c->tmo_dev, c->tmo_host, 0));
+    }
   }
   if (local_ptr_out) *local_ptr_out = c->comm;
   if (handle64_out) {
@@ -1053,7 +1073,12 @@ int gfb_step_p2p(gfb_ctx* c, void* sol_local, int nsteps, const void* Fh_local, 
     c->step += 1;
   }
   if (prevsol_local && (rc = export_spec(c, prevsol_local, c->PV, st))) return rc;
-  return export_spec(c, sol_local, c->S0, st);
+  if ((rc = export_spec(c, sol_local, c->S0, st))) return rc;
+  // asynchronous error model: a barrier of THIS call that gives up is reported by the next call that launches a barrier
+  // (or by gfb_comm_status, which synchronises); one that already gave up is reported here
+  if (c->tmo_host && *(volatile unsigned long long*)c->tmo_host != 0)
+    return fail(c, GFB_ERR_CUDA, "peer barrier timed out at epoch %llu; the state is invalid", *(volatile unsigned long long*)c->tmo_host);
+  return GFB_OK;
 }
 
 }  // extern "C"

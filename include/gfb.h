@@ -203,7 +203,10 @@ int gfb_set_defer_alias_band(gfb_ctx* ctx, int on);
  *   gfb_comm_connect  opens the other ranks' buffers: `handles` = nranks x 64 bytes, entry d from rank d
  *   gfb_comm_connect_ptrs  same for contexts living in ONE process (raw pointers from gfb_comm_create)
  *   gfb_step_p2p      the sharded stepforward! (same arguments as gfb_step, local arrays); every rank must call it
- *   gfb_comm_status   synchronises and reports a barrier that gave up on a missing peer */
+ *   gfb_comm_status   synchronises and reports a barrier that gave up on a missing peer
+ * Error model of the flag barriers (asynchronous, like CUDA's own): a barrier that gives up (GFB_BARRIER_SPINS polls,
+ * default 4e7) writes its epoch into a mapped host word.  Every later barrier launch and the end of gfb_step_p2p read
+ * that word on the host and return GFB_ERR_CUDA ("peer barrier timed out"); the failure is sticky for the context. */
 int gfb_comm_create(gfb_ctx* ctx, void* handle64_out, void** local_ptr_out);
 int gfb_comm_connect(gfb_ctx* ctx, const void* handles);
 int gfb_comm_connect_ptrs(gfb_ctx* ctx, void* const* ptrs);

@@ -73,6 +73,19 @@ static inline cudaError_t cudaMemset(void* d, int v, size_t n) {
   std::memset(d, v, n);
   return cudaSuccess;
 }
+enum { cudaHostAllocMapped = 2 };
+static inline cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) {
+  *p = std::malloc(n ? n : 1);
+  return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+}
+static inline cudaError_t cudaHostGetDevicePointer(void** d, void* h, unsigned) {
+  *d = h;
+  return cudaSuccess;
+}
+static inline cudaError_t cudaFreeHost(void* p) {
+  std::free(p);
+  return cudaSuccess;
+}
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }

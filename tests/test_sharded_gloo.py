@@ -216,3 +216,32 @@ def test_p2p_plain_transforms(nx, ny, monkeypatch):
         assert R.relerr(p.vars.u.numpy(), ref.vars.u[p.shard.rows]) < 1e-13
         assert R.relerr(p.vars.v.numpy(), ref.vars.v[p.shard.rows]) < 1e-13
         assert R.relerr(p.vars.uh.numpy(), ref.vars.uh[..., p.shard.cols]) < 1e-13
+
+
+def test_p2p_barrier_timeout_is_reported(monkeypatch):
+    """A peer that never launches: the flag barrier gives up and gfb_step_p2p must say so (no GFB_OK on a corrupt state),
+    and the failure is sticky for every later call on that context."""
+    import ctypes as C
+    sys.path.insert(0, HERE)
+    monkeypatch.setenv("GFB_EMU_THREADS", "1")
+    monkeypatch.setenv("GFB_BARRIER_SPINS", "2000")
+    import backends
+    B = backends.emu_backend()
+    gf = B.pkg
+    kw = dict(nx=32, ny=32, Lx=2 * np.pi, nu=1e-6, nnu=2, dt=2e-3, stepper="RK4")
+    probs = []
+    for r in range(2):
+        sh = gf.timesteppers.Shard(r, 2, gf.TwoDGrid(B.device, 32, 2 * np.pi), transport="p2p-manual")
+        probs.append(gf.surfaceqg.Problem(B.device, shard=sh, **kw))
+    ptrs = (C.c_void_p * 2)()
+    for r, p in enumerate(probs):
+        loc = C.c_void_p()
+        p._check(p.lib.gfb_comm_create(p.ctx, None, C.byref(loc)), "gfb_comm_create")
+        ptrs[r] = loc.value
+    for p in probs:
+        p._check(p.lib.gfb_comm_connect_ptrs(p.ctx, ptrs), "gfb_comm_connect_ptrs")
+    p = probs[0]  # rank 1 never steps
+    rc = p.lib.gfb_step_p2p(p.ctx, p._p(p.sol), 1, None, None, None)
+    assert rc != 0 and b"timed out" in p.lib.gfb_last_error(p.ctx)
+    assert p.lib.gfb_step_p2p(p.ctx, p._p(p.sol), 1, None, None, None) != 0  # sticky
+    assert p.lib.gfb_comm_status(p.ctx) != 0
