@@ -23,6 +23,8 @@ static thread_local std::string g_create_error;
 struct gfb_ctx {
   gfb_config cfg;  // host pointers inside are NOT retained (nulled after create)
   GridDesc g;
+  GridDesc gd;     // = g with the true alias ranges: what dealias! zeroes (differs from g only for calcNlinear!, which never dealiases)
+  bool linear = false;  // MultiLayerQG.calcNlinear! (config.no_dealias_in_calcN)
   int nlayers = 1, kind = 0, stepper = 0;
   bool ql = false;  // GFB_KIND_QL (kind is GFB_KIND_SINGLE then)
   bool filtered = false, cplxL = false;
@@ -360,7 +362,8 @@ int gfb_create(gfb_ctx** out, const gfb_config* cfg) {
     return fail(nullptr, GFB_ERR_INVALID, "unknown kind %d", cfg->kind);
   if (cfg->kind == GFB_KIND_QL && (cfg->eta || cfg->Nconst)) return fail(nullptr, GFB_ERR_INVALID, "GFB_KIND_QL takes no eta / Nconst");
   if (cfg->stepper < GFB_FORWARD_EULER || cfg->stepper > GFB_FILTERED_AB3) return fail(nullptr, GFB_ERR_INVALID, "unknown stepper %d", cfg->stepper);
-  if (cfg->no_dealias_in_calcN) return fail(nullptr, GFB_ERR_UNSUPPORTED, "calcNlinear! (no dealias) is not supported");
+  if (cfg->no_dealias_in_calcN && cfg->kind != GFB_KIND_LAYERED)
+    return fail(nullptr, GFB_ERR_INVALID, "no_dealias_in_calcN (MultiLayerQG.calcNlinear!) needs GFB_KIND_LAYERED");
   if (!cfg->L) return fail(nullptr, GFB_ERR_INVALID, "config.L is null");
   const int nkr = cfg->nx / 2 + 1;
   if (cfg->kr_alias0 < 1 || cfg->kr_alias0 > nkr || cfg->l_alias0 < 0 || cfg->l_alias1 > cfg->ny || cfg->l_alias0 > cfg->l_alias1)
@@ -397,6 +400,12 @@ int gfb_create(gfb_ctx** out, const gfb_config* cfg) {
   c->ldi = 2 * c->nkpl;
   c->ny_loc = cfg->ny / nranks;
   g.nkl = local_cols_below(c, nkr);
+  c->gd = g;
+  c->linear = cfg->no_dealias_in_calcN != 0;
+  if (c->linear) {  // calcNlinear! (src/multilayerqg.jl:675-683) does not call dealias!: the stepping kernels mask nothing
+    g.kcut = nkr;
+    g.la0 = g.la1 = 0;
+  }
   const int n = c->nlayers, nl = g.ny;
   c->ils = (long long)nl * c->ldi;
   int rc = 0;
@@ -736,6 +745,7 @@ static int run_row_product(gfb_ctx* c, const cplx* Wrecv, const PeerOut& Psend, 
   R.a.U = c->U;
   R.a.Qx = c->Qx;
   R.a.Qy = c->Qy;
+  R.a.linear = c->linear ? 1 : 0;
   R.a.dkx = c->g.dkx;
   R.a.ny = c->ny_loc;
   R.nlayers = c->nlayers;
@@ -1122,7 +1132,7 @@ extern "C" {
 
 int gfb_dealias(gfb_ctx* c, void* sol, void* stream) {
   if (!c || !sol) return fail(c, GFB_ERR_INVALID, "gfb_dealias: null argument");
-  GFB_LAUNCH(k_dealias, dim3(592), dim3(256), 0, (cudaStream_t)stream, c->g, (cplx*)sol, c->g.nkl,
+  GFB_LAUNCH(k_dealias, dim3(592), dim3(256), 0, (cudaStream_t)stream, c->gd, (cplx*)sol, c->g.nkl,
              (long long)c->g.ny * c->g.nkl, c->nlayers);
   return check_launch(c, 0, "k_dealias");
 }
@@ -1131,7 +1141,7 @@ int gfb_calcN(gfb_ctx* c, void* N, void* sol, const void* Fh, void* stream) {
   if (!c || !N || !sol) return fail(c, GFB_ERR_INVALID, "gfb_calcN: null argument");
   NEED_SINGLE_GPU(c, "gfb_calcN");
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = gfb_dealias(c, sol, stream);
+  int rc = c->linear ? 0 : gfb_dealias(c, sol, stream);  // calcNlinear! leaves sol alone
   if (rc) return rc;
   if ((rc = import_spec(c, c->Cin, sol, st))) return rc;
   if (Fh && (rc = import_spec(c, c->Fint, Fh, st))) return rc;

@@ -116,6 +116,7 @@ struct RowArgs {
   int ny;       // LOCAL rows handled by this launch
   int wstride;  // fields per layer in W (3, or 4 when updatevars! also wants psi; 1 for plain transforms)
   int fsel;     // ROW_C2R: which of the wstride fields of each layer to transform
+  int linear;   // ROW_PRODUCT_Q: MultiLayerQG.calcNlinear! -- the self-advection (u q, v q) is dropped, U q stays
 };
 
 template <int NX, int MODE>
@@ -349,6 +350,10 @@ __global__ void __launch_bounds__(GroupCfg<NX>::THREADS, GroupCfg<NX>::MINB)
           for (int q = 0; q < 4; ++q) tmem_store(tg + 4 * (c0 + q), gs[q]);
         }
         tmem_wait_st();
+        if (a.linear) {  // calcN_linearadvection! (src/multilayerqg.jl:744-779): only -d/dx (U q) of the q-advection remains
+#pragma unroll
+          for (int r = 0; r < PT; ++r) v[r] = cmake(Uy, 0.0);
+        }
       }
 #pragma unroll
       for (int c0 = 0; c0 < PT; c0 += 4) {

@@ -139,6 +139,10 @@ __global__ void __launch_bounds__(GroupCfg<NH>::THREADS, GroupCfg<NH>::MINB)
           for (int q = 0; q < 4; ++q) tmem_store(tg + 4 * (c0 + q), gs[q]);
         }
         tmem_wait_st();
+        if (a.linear) {  // calcN_linearadvection!: U q in the u phase, nothing in the v phase
+#pragma unroll
+          for (int r = 0; r < PT; ++r) v[r] = cmake(Uy, Uy);
+        }
       }
 #pragma unroll
       for (int c0 = 0; c0 < PT; c0 += 4) {

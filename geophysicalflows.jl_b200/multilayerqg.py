@@ -33,8 +33,6 @@ def Problem(nlayers, dev=None, nx=128, ny=None, Lx=2 * np.pi, Ly=None, f0=1.0, b
             eta=None, topographic_pv_gradient=(0.0, 0.0), mu=0.0, nu=0.0, nnu=1, dt=0.01, stepper="RK4",
             calcFq=None, stochastic=False, linear=False, aliased_fraction=1 / 3, shard=None):
     """src/multilayerqg.jl:87-135."""
-    if linear:
-        raise _lib.GfbError("MultiLayerQG linear=true (calcNlinear!) is not on the accelerated path yet")
     dev = GPU() if dev is None else dev
     U = np.zeros(nlayers) if U is None else U
     H = np.ones(nlayers) / nlayers if H is None else H
@@ -58,13 +56,16 @@ def Problem(nlayers, dev=None, nx=128, ny=None, Lx=2 * np.pi, Ly=None, f0=1.0, b
     params.calcF = calcFq
     L = np.ones((n, 1, 1)) * (-params.nu * grid.Krsq ** params.nnu)  # hyperviscosity, :338-347
     L[:, 0, 0] = 0
-    eqn = Equation(L, calcN_, grid, (n, grid.nl, grid.nkr))
+    eqn = Equation(L, calcNlinear_ if linear else calcN_, grid, (n, grid.nl, grid.nkr))
     sp, ph = (grid.nl, grid.nkr), (grid.ny, grid.nx)
     tables = {"Sinv": (params.Sinv, np.float64, sp + (n, n)), "S": (params.S, np.float64, sp + (n, n)),
               "U": (params.U[:, :, 0], np.float64, (n, grid.ny)),
               "Qx": (params.Qx, np.float64, (n,) + ph), "Qy": (params.Qy, np.float64, (n,) + ph),
               "mu": (params.mu, None, None)}
+    if linear:  # calcNlinear! (src/multilayerqg.jl:675-683): no dealias!, no self-advection of q
+        tables["no_dealias_in_calcN"] = (1, None, None)
     prob = _Problem(eqn, stepper, dt, grid, v, params, _lib.GFB_KIND_LAYERED, tables, shard=shard)
+    prob.linear = bool(linear)
     return prob
 
 
@@ -118,6 +119,19 @@ def calcN_(N, sol, t, clock, vars, params, grid):
         if not vars.stochastic or t == clock.t:
             if vars.stochastic:
                 prob.dealias_lib(sol)
+                vars.prevsol.copy_(sol)
+            params.calcFq(vars.Fqh, sol, t, clock, vars, params, grid)
+        Fh = vars.Fqh
+    prob.calcN_lib(N, sol, Fh)
+
+
+def calcNlinear_(N, sol, t, clock, vars, params, grid):
+    """src/multilayerqg.jl:675-683 (the context was created with no_dealias_in_calcN: `sol` is left untouched)."""
+    prob = params._prob
+    Fh = None
+    if vars.forced:
+        if not vars.stochastic or t == clock.t:
+            if vars.stochastic:
                 vars.prevsol.copy_(sol)
             params.calcFq(vars.Fqh, sol, t, clock, vars, params, grid)
         Fh = vars.Fqh

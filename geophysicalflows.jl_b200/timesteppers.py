@@ -201,6 +201,8 @@ class Problem:
         for key, (arr, dtype, shape) in tables.items():
             if key == "mu":
                 cfg.mu = float(arr)
+            elif key == "no_dealias_in_calcN":
+                cfg.no_dealias_in_calcN = int(arr)
             else:
                 setattr(cfg, key, _ptr(table(key, arr, dtype, shape)))
         ctx = C.c_void_p()
@@ -410,7 +412,8 @@ def stepforward_(prob, nsteps=1, diags=()):
         # The aliased band of the state is only computed when somebody can look at it: after the last step of this
         # call, or when a diagnostic fires (they read the raw sol); otherwise the next dealias! wipes it unseen.
         for i in range(nsteps):
-            prob.dealias_lib(prob.sol)
+            if not getattr(prob, "linear", False):  # calcNlinear! never dealiases
+                prob.dealias_lib(prob.sol)
             calcF(Fh, prob.sol, c.t, c, v, p, prob.grid)
             observed = i == nsteps - 1 or any((c.step + 1) % d.freq == 0 for d in diags)
             prob.set_defer_alias_band(not observed)

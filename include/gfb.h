@@ -103,7 +103,7 @@ typedef struct gfb_config {
   const double* Qx;       /* [nlayers][ny][nx] */
   const double* Qy;       /* [nlayers][ny][nx] */
   double mu;              /* bottom-layer linear drag (MultiLayerQG calcN!), 0 if none */
-  int no_dealias_in_calcN; /* 1 for MultiLayerQG.calcNlinear! (src/multilayerqg.jl:675-683); not supported yet */
+  int no_dealias_in_calcN; /* 1: MultiLayerQG.calcNlinear! (src/multilayerqg.jl:675-683, 744-779): calcN! never dealiases and drops the self-advection (u q, v q); GFB_KIND_LAYERED only */
   /* Multi-GPU slab decomposition (the reference is single-device).  nranks = 0 or 1: one GPU.
    * nranks = P > 1 (power of two, ny % (8P) == 0): this context owns
    *   - spectral side: column PAIRS dealt round-robin -- local pair p is global pair p*P + rank; every

@@ -181,25 +181,38 @@ def test_reference_cases_mqg(emu):
     assert max(R.mqg_topographicPV_gradient(emu, nx=32, ny=32)) < RT
     err, rtol = R.mqg_rossbywave(emu)
     assert err < rtol
+    eq, epsi = R.mqg_nonlinearadvection(emu, 2, nx=64, ny=64, nsteps=20, linear=True)  # test_mqg_linearadvection
+    assert eq < RT and epsi < RT
 
 
-@pytest.mark.parametrize("nlayers", [2, 5])
-def test_mqg_steps_vs_oracle(emu, oracle_backend, nlayers):
-    """Random multi-layer state with U(y), topography, beta, drag: full-state parity incl. alias band."""
-    nx, ny = 32, 64
+@pytest.mark.parametrize("nlayers,linear", [(2, False), (5, False), (2, True), (3, True)])
+def test_mqg_steps_vs_oracle(emu, oracle_backend, nlayers, linear):
+    """Random multi-layer state with U(y), topography, beta, drag: full-state parity incl. alias band.  linear = True:
+    calcNlinear! (src/multilayerqg.jl:675-683) -- no dealias!, so the un-dealiased random state stays un-dealiased."""
+    _mqg_steps_vs_oracle(emu, oracle_backend, nlayers, linear, 32, 64, 4)
+
+
+def _mqg_steps_vs_oracle(emu, oracle_backend, nlayers, linear, nx, ny, nsteps):
     rng = np.random.default_rng(11)
     y = np.linspace(-np.pi, np.pi, ny, endpoint=False)
     U = np.stack([0.1 * (j + 1) * np.cos(y) for j in range(nlayers)], axis=1)
     eta = 0.3 * rng.standard_normal((ny, nx))
     kw = dict(nx=nx, ny=ny, Lx=2 * np.pi, Ly=2 * np.pi, f0=1.0, beta=0.5, U=U, eta=eta, mu=0.05, nu=1e-4,
-              topographic_pv_gradient=(0.01, 0.02), dt=2e-3, stepper="FilteredRK4")
+              topographic_pv_gradient=(0.01, 0.02), dt=2e-3, stepper="FilteredRK4", linear=linear)
     po = oracle_backend.multilayerqg.Problem(nlayers, **kw)
     pb = emu.multilayerqg.Problem(nlayers, **kw)
     s0 = np.fft.rfft2(rng.standard_normal((nlayers, ny, nx))) * 5 / (nx * ny)
     po.sol[...] = s0
     pb.sol.copy_(emu.dev(s0))
-    oracle_backend.stepforward_(po, 4)
-    emu.stepforward_(pb, 4)
+    if linear:  # calcNlinear! itself, on the raw state
+        No = np.zeros_like(po.sol)
+        oracle_backend.multilayerqg.calcNlinear_(No, po.sol, 0.0, po.clock, po.vars, po.params, po.grid)
+        Nb = pb.sol.clone()
+        emu.multilayerqg.calcNlinear_(Nb, pb.sol, 0.0, pb.clock, pb.vars, pb.params, pb.grid)
+        assert R.relerr(emu.host(Nb), No) < 1e-13
+        assert R.relerr(emu.host(pb.sol), s0) == 0  # untouched
+    oracle_backend.stepforward_(po, nsteps)
+    emu.stepforward_(pb, nsteps)
     assert R.relerr(emu.host(pb.sol), po.sol) < 1e-13
     KEo, PEo = oracle_backend.multilayerqg.energies(po)
     KEb, PEb = emu.multilayerqg.energies(pb)

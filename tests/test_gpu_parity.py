@@ -113,6 +113,8 @@ def test_ref_mqg(gpu):
         assert R.mqg_pvtofromstreamfunction(gpu, n) < 1e-13
         eq, epsi = R.mqg_nonlinearadvection(gpu, n, nx=64, ny=64)
         assert eq < RT and epsi < RT
+    eq, epsi = R.mqg_nonlinearadvection(gpu, 2, nx=64, ny=64, nsteps=100, linear=True)  # test/runtests.jl:130 (test_mqg_linearadvection)
+    assert eq < RT and epsi < RT
     assert max(abs(e) for e in R.mqg_energies(gpu, nx=64, ny=64)) < RT
     assert abs(R.mqg_energysinglelayer(gpu)) < RT
     for n in (2, 3):
@@ -334,3 +336,10 @@ def test_4096_step_conserves_and_matches_stagewise(gpu, big):
             prob.stage_lib(i)
     assert float(torch.linalg.norm(prob.sol - fused)) == 0.0  # same kernels, same order: bit-identical
     assert abs(bv1 / bv0 - 1) < 1e-4  # white-noise state: hyperviscosity removes a little variance in 3 steps
+
+
+@pytest.mark.parametrize("nlayers,nx,ny", [(2, 256, 128), (3, 64, 512)])
+def test_mqg_calcNlinear_vs_oracle(gpu, O, nlayers, nx, ny):
+    """MultiLayerQG linear = true (calcNlinear!, src/multilayerqg.jl:675-683, 744-779): calcN on the raw state and 6 steps."""
+    from test_emu_parity import _mqg_steps_vs_oracle
+    _mqg_steps_vs_oracle(gpu, O, nlayers, True, nx, ny, 6)

@@ -6,8 +6,8 @@ T=r2i
 true
 
 
-for wl in twodns16384 sqg4096 twodns8192; do
-  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 \
+for wl in ${WLS:-twodns16384 sqg4096 twodns8192}; do
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 \
     bench.py --gpus $N --workload $wl --steps 8 --warmup 3 --repeats 3 --e2e-steps 1 > gpurun_out/${T}_${wl}_${N}gpu.json 2> gpurun_out/${T}_${wl}_${N}gpu.err
   cat gpurun_out/${T}_${wl}_${N}gpu.err | tail -5 | cut -c1-300
   python - <<PY
