@@ -11,7 +11,7 @@ DEFAULT_LIB = os.path.join(HERE, "libgfb.so")
 
 GFB_KIND_SINGLE, GFB_KIND_LAYERED, GFB_KIND_QL = 0, 1, 2
 STEPPERS = {"ForwardEuler": 0, "FilteredForwardEuler": 1, "RK4": 2, "FilteredRK4": 3, "ETDRK4": 4,
-            "FilteredETDRK4": 5, "AB3": 6, "FilteredAB3": 7}
+            "FilteredETDRK4": 5, "AB3": 6, "FilteredAB3": 7, "LSRK54": 8, "FilteredLSRK54": 9}
 (DIAG_ABS2, DIAG_INVK_ABS2, DIAG_K_ABS2, DIAG_KP_ABS2, DIAG_G_ABS2, DIAG_G2_ABS2, DIAG_KG2_ABS2, DIAG_ABS2_PLUS,
  DIAG_WORK, DIAG_WORK_INVK, DIAG_LAYERED_ENERGIES) = range(11)
 

@@ -361,7 +361,7 @@ int gfb_create(gfb_ctx** out, const gfb_config* cfg) {
   if (cfg->kind != GFB_KIND_SINGLE && cfg->kind != GFB_KIND_LAYERED && cfg->kind != GFB_KIND_QL)
     return fail(nullptr, GFB_ERR_INVALID, "unknown kind %d", cfg->kind);
   if (cfg->kind == GFB_KIND_QL && (cfg->eta || cfg->Nconst)) return fail(nullptr, GFB_ERR_INVALID, "GFB_KIND_QL takes no eta / Nconst");
-  if (cfg->stepper < GFB_FORWARD_EULER || cfg->stepper > GFB_FILTERED_AB3) return fail(nullptr, GFB_ERR_INVALID, "unknown stepper %d", cfg->stepper);
+  if (cfg->stepper < GFB_FORWARD_EULER || cfg->stepper > GFB_FILTERED_LSRK54) return fail(nullptr, GFB_ERR_INVALID, "unknown stepper %d", cfg->stepper);
   if (cfg->no_dealias_in_calcN && cfg->kind != GFB_KIND_LAYERED)
     return fail(nullptr, GFB_ERR_INVALID, "no_dealias_in_calcN (MultiLayerQG.calcNlinear!) needs GFB_KIND_LAYERED");
   if (!cfg->L) return fail(nullptr, GFB_ERR_INVALID, "config.L is null");
@@ -500,6 +500,7 @@ int gfb_create(gfb_ctx** out, const gfb_config* cfg) {
     case GFB_FORWARD_EULER: case GFB_FILTERED_FORWARD_EULER: nstate = 0; break;
     case GFB_RK4: case GFB_FILTERED_RK4: nstate = 3; break;        // s1, s2 (ping-pong), acc
     case GFB_ETDRK4: case GFB_FILTERED_ETDRK4: nstate = 5; break;  // s1, s2, acc, N1, s3
+    case GFB_LSRK54: case GFB_FILTERED_LSRK54: nstate = (cfg->kind == GFB_KIND_LAYERED) ? 3 : 1; break;  // S2 (+ two stage states)
     default: nstate = 3; break;                                    // AB3: rhs, rhs-1, rhs-2
   }
   for (int i = 0; i < nstate; ++i) {
@@ -805,6 +806,7 @@ static EpiArgs base_epi(const gfb_ctx* c, bool forced) {
 static int nstages_of(const gfb_ctx* c) {
   switch (c->stepper) {
     case GFB_RK4: case GFB_FILTERED_RK4: case GFB_ETDRK4: case GFB_FILTERED_ETDRK4: return 4;
+    case GFB_LSRK54: case GFB_FILTERED_LSRK54: return 5;
     default: return 1;
   }
 }
@@ -863,6 +865,31 @@ static int plan_stage(gfb_ctx* c, int istage, bool forced, bool want_prevsol, in
       } else {
         e.kind = EPI_ETD_4; sin = s3; e.out = S0; e.c4 = coef(c, c->Gamma);
       }
+    } break;
+    case GFB_LSRK54: case GFB_FILTERED_LSRK54: {
+      // [FF] LSRK54TimeStepper (Carpenter & Kennedy 1994, 2N-storage RK4(5)): per stage S2 = A_i S2 + dt (N + L sol),
+      // sol += B_i S2 -- the state is updated IN PLACE (every element is read and written by the same thread)
+      static const double A[5] = {0.0, -567301805773.0 / 1357537059087.0, -2404267990393.0 / 2016746695238.0,
+                                  -3550918686646.0 / 2091501179385.0, -1275806237668.0 / 842570457699.0};
+      static const double B[5] = {1432997174477.0 / 9575080441755.0, 5161836677717.0 / 13612068292357.0,
+                                  1720146321549.0 / 2090206949498.0, 3134564353537.0 / 4481467310338.0,
+                                  2277821191437.0 / 14882151754819.0};
+      e.kind = EPI_LSRK;
+      e.a = A[istage];
+      e.b = B[istage];
+      e.d = dt;
+      e.acc = int_spec(c, c->st[0]);
+      e.out = S0;
+      if (c->kind == GFB_KIND_LAYERED) {
+        // the bottom-drag term of a layer reads the stage input of ALL layers, which other CTAs would be overwriting:
+        // the layered kind steps out of place, S0 -> A -> B -> A -> B -> S0
+        const Spec A2 = int_spec(c, c->st[1]), B2 = int_spec(c, c->st[2]);
+        sin = (istage == 0) ? S0 : ((istage & 1) ? A2 : B2);
+        e.out = (istage == ns - 1) ? S0 : ((istage & 1) ? B2 : A2);
+        e.sol = sin;
+      }
+      if (istage == 0) e.prevsol = pv;
+      if (istage != ns - 1) e.filter.p = nullptr;  // the filter closes the step
     } break;
     default: {  // AB3
       const long long k = c->step;

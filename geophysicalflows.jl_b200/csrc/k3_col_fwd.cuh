@@ -19,6 +19,7 @@ enum EpiKind {
   EPI_ETD_3,
   EPI_ETD_4,
   EPI_AB3,
+  EPI_LSRK,        // one stage of the low-storage RK (LSRK54): S2 = a S2 + d (N + L sol); sol += b S2 (in place)
   EPI_PLAIN        // plain forward transform: single field, store
 };
 
@@ -65,7 +66,7 @@ struct EpiArgs {
   Coef L;          // linear operator
   Coef c1, c2, c3, c4;  // ETD: exp(L dt/2), zeta, exp(L dt) / alpha, beta or Gamma  (see gfb.cu)
   SpecR filter;    // null p -> no filter (layer stride 0: shared by layers)
-  double a, b, d;  // RK: a = c_i*dt (sub-step), b = weight*dt ; AB3: a, b, d = dt*(23/12, -16/12, 5/12)
+  double a, b, d;  // RK: a = c_i*dt (sub-step), b = weight*dt ; AB3: a, b, d = dt*(23/12, -16/12, 5/12) ; LSRK: A_i, B_i, dt
   // MultiLayerQG bottom drag: N[nlayers-1] += mu * Krsq * psi_h[nlayers-1], psi = S^-1 q recomputed
   double mu;
   const double* Sinv;
@@ -148,6 +149,12 @@ __device__ __forceinline__ void epi_fetch(const GridDesc& g, const EpiArgs& e, i
     in.acc = ldpair(e.acc.p + layer * e.acc.ls + off);
     in.n1 = ldpair(e.n1.p + layer * e.n1.ls + off);
   }
+  if (KIND == EPI_LSRK) {
+    in.filt = e.filter.p ? ldpair_d(e.filter.p + off) : make_double2(1.0, 1.0);  // filter set on the last stage only
+    in.s0 = masked_pair(g, e.sol, layer, l, colA, off);
+    in.L.load(e.L, layer, off);
+    in.acc = (e.a != 0.0) ? ldpair(e.acc.p + layer * e.acc.ls + off) : zero_pair();
+  }
   if (KIND == EPI_ETD_3) in.n1 = ldpair(e.n1.p + layer * e.n1.ls + off);
   if (KIND == EPI_ETD_1 || KIND == EPI_ETD_2 || KIND == EPI_ETD_3) {
     in.c1.load(e.c1, layer, off);
@@ -183,6 +190,12 @@ __device__ __forceinline__ void epi_prefetch_tile(const GridDesc& g, const EpiAr
     pc(e.n1);
   }
   if (KIND == EPI_ETD_3) pc(e.n1);
+  if (KIND == EPI_LSRK) {
+    if (e.filter.p) prefetch_l2_bulk(e.filter.p + off, 128);
+    if (live_col) pc(e.sol);
+    pk(e.L);
+    if (e.a != 0.0) pc(e.acc);
+  }
   if (KIND == EPI_ETD_1 || KIND == EPI_ETD_2 || KIND == EPI_ETD_3) {
     pk(e.c1);
     pk(e.c2);
@@ -217,6 +230,7 @@ __device__ __forceinline__ void epi_prefetch_rows(const GridDesc& g, const EpiAr
       GFB_EPI_CASE(EPI_ETD_3)
       GFB_EPI_CASE(EPI_ETD_4)
       GFB_EPI_CASE(EPI_AB3)
+      GFB_EPI_CASE(EPI_LSRK)
 #undef GFB_EPI_CASE
       default: break;
     }
@@ -280,6 +294,12 @@ __device__ __forceinline__ void epi_finish(const GridDesc& g, const EpiArgs& e, 
     if (e.prevsol.p) stpair(e.prevsol.p + layer * e.prevsol.ls + off, in.s0.a, in.s0.b);
     stpair(e.rhs.p + layer * e.rhs.ls + off, ra, rb);
     stpair(out, cscale(cadd(in.s0.a, ua), in.filt.x), cscale(cadd(in.s0.b, ub), in.filt.y));
+  } else if (KIND == EPI_LSRK) {  // a = A_i, b = B_i, d = dt
+    const cplx ra = cadd(NA, in.L.mulA(in.s0.a)), rb = cadd(NB, in.L.mulB(in.s0.b));
+    const cplx sa = axpy(cscale(in.acc.a, e.a), e.d, ra), sb = axpy(cscale(in.acc.b, e.a), e.d, rb);
+    if (e.prevsol.p) stpair(e.prevsol.p + layer * e.prevsol.ls + off, in.s0.a, in.s0.b);
+    stpair(e.acc.p + layer * e.acc.ls + off, sa, sb);
+    stpair(out, cscale(axpy(in.s0.a, e.b, sa), in.filt.x), cscale(axpy(in.s0.b, e.b, sb), in.filt.y));
   }
 }
 
@@ -358,6 +378,7 @@ __device__ __forceinline__ void epilogue_dispatch(const GridDesc& g, const EpiAr
     GFB_EPI_CASE(EPI_ETD_3)
     GFB_EPI_CASE(EPI_ETD_4)
     GFB_EPI_CASE(EPI_AB3)
+    GFB_EPI_CASE(EPI_LSRK)
 #undef GFB_EPI_CASE
     default: break;
   }

@@ -98,6 +98,7 @@ __device__ __forceinline__ void epilogue_rows_ws_dispatch(const GridDesc& g, con
     GFB_EPI_CASE(EPI_ETD_3)
     GFB_EPI_CASE(EPI_ETD_4)
     GFB_EPI_CASE(EPI_AB3)
+    GFB_EPI_CASE(EPI_LSRK)
 #undef GFB_EPI_CASE
     default: break;
   }

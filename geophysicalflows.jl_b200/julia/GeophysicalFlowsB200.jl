@@ -16,9 +16,9 @@ import FourierFlows: stepforward!, dealias!
 
 const libgfb = get(ENV, "LIBGFB", "libgfb.so")
 
-const KIND_SINGLE, KIND_LAYERED = Cint(0), Cint(1)
+const KIND_SINGLE, KIND_LAYERED, KIND_QL = Cint(0), Cint(1), Cint(2)   # KIND_QL: BarotropicQGQL
 const STEPPERS = Dict("ForwardEuler" => 0, "FilteredForwardEuler" => 1, "RK4" => 2, "FilteredRK4" => 3,
-                      "ETDRK4" => 4, "FilteredETDRK4" => 5, "AB3" => 6, "FilteredAB3" => 7)
+                      "ETDRK4" => 4, "FilteredETDRK4" => 5, "AB3" => 6, "FilteredAB3" => 7, "LSRK54" => 8, "FilteredLSRK54" => 9)
 
 # mirrors `struct gfb_config` field for field (include/gfb.h)
 Base.@kwdef mutable struct GfbConfig

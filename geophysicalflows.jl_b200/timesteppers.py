@@ -382,7 +382,9 @@ class Problem:
         return g.Lx * g.Ly / (g.nx**2 * g.ny**2)
 
 
-_STAGE_C = {4: (0.0, 0.5, 0.5, 1.0), 1: (0.0,)}
+_STAGE_C = {4: (0.0, 0.5, 0.5, 1.0), 1: (0.0,),
+            5: (0.0, 1432997174477 / 9575080441755, 2526269341429 / 6820363962896, 2006345519317 / 3224310063776,
+                2802321613138 / 2924317926251)}  # LSRK54 stage times C_i
 
 
 def stepforward_(prob, nsteps=1, diags=()):

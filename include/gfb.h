@@ -67,7 +67,9 @@ enum gfb_stepper {
   GFB_ETDRK4 = 4,
   GFB_FILTERED_ETDRK4 = 5,
   GFB_AB3 = 6,
-  GFB_FILTERED_AB3 = 7
+  GFB_FILTERED_AB3 = 7,
+  GFB_LSRK54 = 8,          /* [FF] LSRK54TimeStepper: Carpenter-Kennedy five-stage fourth-order 2N-storage Runge-Kutta */
+  GFB_FILTERED_LSRK54 = 9  /* the same with timestepper.filter applied at the end of the step */
 };
 
 /* All pointers in the config are HOST pointers, read (copied to the device) during gfb_create. */

@@ -165,7 +165,43 @@ class FilteredAB3TimeStepper(AB3TimeStepper):
     filtered = True
 
 
+class LSRK54TimeStepper(TimeStepper):
+    """[FF-upstream] LSRK54TimeStepper: the Carpenter-Kennedy (1994) five-stage fourth-order 2N-storage Runge-Kutta scheme,
+        S2 = 0 ; for i = 1..5:  RHS = calcN!(sol, t + C_i dt) + L sol ;  S2 = A_i S2 + dt RHS ;  sol += B_i S2 .
+    No test, example or source file of the reference uses it (test/runtests.jl lists the eight steppers above), so there
+    is nothing in /root/reference to pin it on: "parity unpinned".  tests/test_oracle_goldens.py pins what can be pinned
+    without FourierFlows -- the published coefficients satisfy the order conditions (fourth-order convergence on a
+    problem with a closed-form solution).  FilteredLSRK54 (the filter closing the step) is this package's own extension."""
+    A = (0.0, -567301805773 / 1357537059087, -2404267990393 / 2016746695238, -3550918686646 / 2091501179385,
+         -1275806237668 / 842570457699)
+    B = (1432997174477 / 9575080441755, 5161836677717 / 13612068292357, 1720146321549 / 2090206949498,
+         3134564353537 / 4481467310338, 2277821191437 / 14882151754819)
+    C = (0.0, 1432997174477 / 9575080441755, 2526269341429 / 6820363962896, 2006345519317 / 3224310063776,
+         2802321613138 / 2924317926251)
+
+    def __init__(self, eqn, dt):
+        super().__init__(eqn, dt)
+        self.S2, self.RHS = self._z(), self._z()
+
+    def step(self, prob):
+        sol, c, e = prob.sol, prob.clock, prob.eqn
+        self.S2[...] = 0
+        for i in range(5):
+            e.calcN(self.RHS, sol, c.t + self.C[i] * c.dt, c, prob.vars, prob.params, prob.grid)
+            self.RHS += e.L * sol
+            self.S2[...] = self.A[i] * self.S2 + c.dt * self.RHS
+            sol += self.B[i] * self.S2
+        if self.filtered:
+            sol *= self.filter
+
+
+class FilteredLSRK54TimeStepper(LSRK54TimeStepper):
+    filtered = True
+
+
 _STEPPERS = {
+    "LSRK54": LSRK54TimeStepper,
+    "FilteredLSRK54": FilteredLSRK54TimeStepper,
     "ForwardEuler": ForwardEulerTimeStepper,
     "FilteredForwardEuler": FilteredForwardEulerTimeStepper,
     "RK4": RK4TimeStepper,

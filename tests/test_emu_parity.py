@@ -443,3 +443,41 @@ def test_mqg_16384(emu, oracle_backend, nx, ny):
     KEo, PEo = oracle_backend.multilayerqg.energies(po)
     KEb, PEb = emu.multilayerqg.energies(pb)
     assert np.allclose(KEb, KEo, rtol=1e-12) and np.allclose(PEb, PEo, rtol=1e-12)
+
+
+@pytest.mark.parametrize("stepper", ["LSRK54", "FilteredLSRK54"])
+def test_lsrk54_vs_oracle(emu, oracle_backend, stepper):
+    """[FF] LSRK54 (five in-place low-storage stages) on the emulated kernels: forced TwoDNavierStokes with time-dependent
+    deterministic forcing (stage times C_i), the stochastic one-call-per-step path with prevsol, and a layered problem."""
+    n = 64
+    rng = np.random.default_rng(21)
+    fh = np.fft.rfft2(rng.standard_normal((n, n))) * 1e-2
+
+    def mk(B):
+        f = B.dev(fh)
+
+        def calcF(Fh, sol, t, clock, vars, params, grid):
+            B.assign(Fh, f * np.cos(3 * t))
+        return calcF
+    s0 = np.fft.rfft2(rng.standard_normal((n, n))) / n
+    for stochastic in (False, True):
+        kw = dict(nx=n, Lx=2 * np.pi, nu=1e-3, mu=0.05, dt=5e-3, stepper=stepper, stochastic=stochastic)
+        po = oracle_backend.twodnavierstokes.Problem(calcF=mk(oracle_backend), **kw)
+        pb = emu.twodnavierstokes.Problem(calcF=mk(emu), **kw)
+        po.sol[...] = s0
+        pb.sol.copy_(emu.dev(s0))
+        oracle_backend.stepforward_(po, 3)
+        emu.stepforward_(pb, 3)
+        assert R.relerr(emu.host(pb.sol), po.sol) < 1e-13
+        if stochastic:
+            assert R.relerr(emu.host(pb.vars.prevsol), po.vars.prevsol) < 1e-13
+    kw = dict(nx=32, ny=64, Lx=2 * np.pi, f0=1.0, beta=0.5, U=[0.3, 0.1], mu=0.05, nu=1e-4, dt=2e-3, stepper=stepper)
+    po, pb = oracle_backend.multilayerqg.Problem(2, **kw), emu.multilayerqg.Problem(2, **kw)
+    q0 = np.fft.rfft2(rng.standard_normal((2, 64, 32))) * 5 / 2048
+    po.sol[...] = q0
+    pb.sol.copy_(emu.dev(q0))
+    oracle_backend.stepforward_(po, 3)
+    emu.stepforward_(pb, 3)
+    assert R.relerr(emu.host(pb.sol), po.sol) < 1e-13
+    err, rtol = R.slqg_rossbywave(emu, stepper, 1e-2, 20)
+    assert err < rtol

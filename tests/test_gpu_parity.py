@@ -157,9 +157,14 @@ def test_config1_twodns_decaying_128(gpu, O):
 
 
 def test_config2_slqg_stochastic_betaplane(gpu, O):
-    """configs[1] scaled to 256^2: SingleLayerQG beta-plane, finite deformation radius, stochastic forcing,
-    FilteredRK4 (examples/singlelayerqg_betaforced.jl); forcing realisations pre-generated and shared."""
-    n, L = 256, 2 * np.pi
+    """configs[1] scaled to 256^2 (full size: tests/test_zy_gpu_fullsize.py)."""
+    config2_slqg(gpu, O, 256, 100, 10)
+
+
+def config2_slqg(gpu, O, n, nsteps, every):
+    """configs[1]: SingleLayerQG beta-plane, finite deformation radius, stochastic forcing, FilteredRK4
+    (examples/singlelayerqg_betaforced.jl); forcing realisations pre-generated and shared."""
+    L = 2 * np.pi
     beta, mu, ell = 10.0, 0.01, 0.35
     dt, kf, dkf, eps = 0.05 * 128 / n, 14.0 * 2 * np.pi / L, 1.5 * 2 * np.pi / L, 1e-3
     g = R.hostgrid(n, L)
@@ -172,7 +177,7 @@ def test_config2_slqg_stochastic_betaplane(gpu, O):
     spec = spec * eps / max(eps0, 1e-300) * 1e-6
     rng = np.random.default_rng(1234)
     draws = [(rng.standard_normal(spec.shape) + 1j * rng.standard_normal(spec.shape)) / np.sqrt(2) * np.sqrt(spec / dt) * n * n
-             for _ in range(100)]
+             for _ in range(nsteps)]
 
     def mk(B):
         it = iter(draws)
@@ -183,8 +188,8 @@ def test_config2_slqg_stochastic_betaplane(gpu, O):
     kw = dict(nx=n, Lx=L, beta=beta, deformation_radius=ell, mu=mu, dt=dt, stepper="FilteredRK4", stochastic=True)
     po = O.singlelayerqg.Problem(calcF=mk(O), **kw)
     pg = gpu.singlelayerqg.Problem(calcF=mk(gpu), **kw)
-    so = _series(O, po, (O.singlelayerqg.energy, O.singlelayerqg.enstrophy), 100, 10)
-    sg = _series(gpu, pg, (gpu.singlelayerqg.energy, gpu.singlelayerqg.enstrophy), 100, 10)
+    so = _series(O, po, (O.singlelayerqg.energy, O.singlelayerqg.enstrophy), nsteps, every)
+    sg = _series(gpu, pg, (gpu.singlelayerqg.energy, gpu.singlelayerqg.enstrophy), nsteps, every)
     assert np.linalg.norm(po.sol) > 0
     assert R.relerr(gpu.host(pg.sol), po.sol) < TOL
     assert R.relerr(gpu.host(pg.vars.prevsol), po.vars.prevsol) < TOL
@@ -193,7 +198,12 @@ def test_config2_slqg_stochastic_betaplane(gpu, O):
 
 @pytest.mark.parametrize("nlayers,n", [(2, 256), (5, 128)])
 def test_config3_mqg(gpu, O, nlayers, n):
-    """configs[2] scaled: MultiLayerQG baroclinic, imposed zonal flow, aliased_fraction = 0, FilteredRK4
+    """configs[2] scaled (full size: tests/test_zy_gpu_fullsize.py)."""
+    config3_mqg(gpu, O, nlayers, n, 100, 20)
+
+
+def config3_mqg(gpu, O, nlayers, n, nsteps, every):
+    """configs[2]: MultiLayerQG baroclinic, imposed zonal flow, aliased_fraction = 0, FilteredRK4
     (examples/multilayerqg_2layer.jl); the 5-layer variant uses a linear shear."""
     from oracle.gfo.timesteppers import makefilter
     L = 2 * np.pi
@@ -211,7 +221,7 @@ def test_config3_mqg(gpu, O, nlayers, n):
     gpu.multilayerqg.set_q_(pg, gpu.dev(q0))
     fo = lambda p: np.concatenate(O.multilayerqg.energies(p))
     fg = lambda p: np.concatenate(gpu.multilayerqg.energies(p))
-    so, sg = _series(O, po, (fo,), 100, 20), _series(gpu, pg, (fg,), 100, 20)
+    so, sg = _series(O, po, (fo,), nsteps, every), _series(gpu, pg, (fg,), nsteps, every)
     assert R.relerr(gpu.host(pg.sol), po.sol) < TOL
     assert np.max(np.abs(sg / so - 1)) < TOL
     O.multilayerqg.updatevars_(po)
@@ -222,16 +232,21 @@ def test_config3_mqg(gpu, O, nlayers, n):
 
 @pytest.mark.parametrize("stepper", ["ETDRK4", "FilteredETDRK4"])
 def test_config4_sqg_etdrk4(gpu, O, stepper):
-    """configs[3] scaled to 512^2: SurfaceQG decaying, elliptical vortex (examples/surfaceqg_decaying.jl:35-74)."""
-    n, L = 512, 2 * np.pi
+    """configs[3] scaled to 512^2 (full size: tests/test_zy_gpu_fullsize.py)."""
+    config4_sqg(gpu, O, stepper, 512, 100, 20)
+
+
+def config4_sqg(gpu, O, stepper, n, nsteps, every):
+    """configs[3]: SurfaceQG decaying, elliptical vortex (examples/surfaceqg_decaying.jl:35-74)."""
+    L = 2 * np.pi
     kw = dict(nx=n, Lx=L, nu=1e-19 * (256 / n) ** 8, nnu=4, dt=0.03 * 256 / n, stepper=stepper)
     po, pg = O.surfaceqg.Problem(**kw), gpu.surfaceqg.Problem(**kw)
     x, y = po.grid.gridpoints()
     b0 = np.exp(-(x**2 + 4 * y**2))
     O.surfaceqg.set_b_(po, b0)
     gpu.surfaceqg.set_b_(pg, gpu.dev(b0))
-    so = _series(O, po, (O.surfaceqg.kinetic_energy, O.surfaceqg.buoyancy_variance), 100, 20)
-    sg = _series(gpu, pg, (gpu.surfaceqg.kinetic_energy, gpu.surfaceqg.buoyancy_variance), 100, 20)
+    so = _series(O, po, (O.surfaceqg.kinetic_energy, O.surfaceqg.buoyancy_variance), nsteps, every)
+    sg = _series(gpu, pg, (gpu.surfaceqg.kinetic_energy, gpu.surfaceqg.buoyancy_variance), nsteps, every)
     assert R.relerr(gpu.host(pg.sol), po.sol) < TOL
     assert np.max(np.abs(sg / so - 1)) < TOL
     O.surfaceqg.updatevars_(po)
@@ -343,3 +358,10 @@ def test_mqg_calcNlinear_vs_oracle(gpu, O, nlayers, nx, ny):
     """MultiLayerQG linear = true (calcNlinear!, src/multilayerqg.jl:675-683, 744-779): calcN on the raw state and 6 steps."""
     from test_emu_parity import _mqg_steps_vs_oracle
     _mqg_steps_vs_oracle(gpu, O, nlayers, True, nx, ny, 6)
+
+
+@pytest.mark.parametrize("stepper", ["LSRK54", "FilteredLSRK54"])
+def test_lsrk54_vs_oracle(gpu, O, stepper):
+    """[FF] LSRK54: the five in-place low-storage stages on the GPU vs the oracle (same cases as the emulation test)."""
+    import test_emu_parity
+    test_emu_parity.test_lsrk54_vs_oracle(gpu, O, stepper)

@@ -192,3 +192,19 @@ def test_bqgql_energyenstrophy(oracle_backend):
 def test_bqgql_deterministicforcingbudgets(oracle_backend):
     """test/runtests.jl:100 at a reduced size and step count (the closure is local in time)."""
     assert R.bqgql_deterministicforcingbudgets(oracle_backend, n=128, nt=40) < 1e-10
+
+
+# ---- LSRK54 ([FF-upstream], not used anywhere in the reference: "parity unpinned") ------------------------------
+def test_lsrk54_is_fourth_order(oracle_backend):
+    """The coefficient set is pinned on the order conditions: errors on the Rossby-wave problem (closed-form solution)
+    fall 16x per halving of dt, and on a purely linear problem (N = 0) one step equals the degree-4 Taylor polynomial
+    of exp(L dt) that every fourth-order five-stage explicit scheme with b.c^k = 1/(k+1)! ... reproduces to O(dt^5)."""
+    errs = []
+    for dt, ns in ((0.2, 10), (0.1, 20), (0.05, 40)):
+        err, _ = R.slqg_rossbywave(oracle_backend, "LSRK54", dt, ns)
+        errs.append(err)
+    assert 12 < errs[0] / errs[1] < 20 and 12 < errs[1] / errs[2] < 20, errs
+    err_rk4, _ = R.slqg_rossbywave(oracle_backend, "RK4", 0.1, 20)
+    assert errs[1] < err_rk4  # Carpenter-Kennedy's scheme has the smaller error constant
+    err, rtol = R.slqg_rossbywave(oracle_backend, "FilteredLSRK54", 1e-2, 20)
+    assert err < rtol
