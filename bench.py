@@ -339,6 +339,89 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_other_config(args):
+    """Device-resident lines for BASELINE.json configs[1] (slqg1024: SingleLayerQG beta-plane, finite deformation radius,
+    stochastic forcing, FilteredRK4) and configs[2] (mqg2_1024 / mqg5_2048: MultiLayerQG, imposed shear, aliased_fraction 0,
+    FilteredRK4): same timing protocol and per-kernel CUDA-event breakdown as the headline line, algorithmic bytes from
+    SURVEY.md 8(d) (62 F; (19 + n/2) n F per stage x 4).  One GPU."""
+    import torch
+    import gfb_loader
+    pkg = gfb_loader.load()
+    dev = pkg.GPU()
+    name = args.workload
+    L = 2 * np.pi
+    rng = np.random.default_rng(7)
+    if name.startswith("slqg"):
+        n = int(name[4:])
+        nlay, fields_per_step = 1, 62.0
+        dt = 0.05 * 128 / n
+        K = np.sqrt(np.arange(n // 2 + 1)[None, :] ** 2 + np.fft.fftfreq(n, 1 / n)[:, None] ** 2)
+        spec = np.exp(-(K - 14.0) ** 2 / (2 * 1.5**2))
+        spec[(K < 2) | (K > 20)] = 0
+        Fh = dev.array((rng.standard_normal(spec.shape) + 1j * rng.standard_normal(spec.shape)) * np.sqrt(spec * 1e-9 / dt) * n * n,
+                       torch.complex128)
+
+        def calcF(F, sol, t, clock, vars, params, grid):
+            F.copy_(Fh, non_blocking=True)
+        prob = pkg.SingleLayerQG.Problem(dev, nx=n, Lx=L, beta=10.0, deformation_radius=0.35, mu=0.01, dt=dt, stepper="FilteredRK4",
+                                         calcF=calcF, stochastic=True)
+        label = "SingleLayerQG beta-plane stochastic %d^2 FilteredRK4 Float64 (BASELINE.json configs[1])" % n
+        kfun = {"k_col_inv": "k_col_inv_single<%d>" % n, "k_row": "k_row_product<%d,0>" % n, "k_col_fwd": "k_col_fwd<%d,1>" % n}
+    else:
+        nlay, n = int(name[3]), int(name.split("_")[1])
+        fields_per_step = 4 * (19 + nlay / 2.0) * nlay
+        if nlay == 2:
+            H, b, U = [0.2, 0.8], [-1.0, -1.2], [1.0, 0.0]
+        else:
+            H, b, U = [1.0 / nlay] * nlay, None, list(np.linspace(1.0, 0.0, nlay))
+        prob = pkg.MultiLayerQG.Problem(nlay, dev, nx=n, Lx=L, f0=1.0, beta=5.0, mu=5e-2, H=H, b=b, U=U, dt=2.5e-3 * 128 / n,
+                                        stepper="FilteredRK4", aliased_fraction=0)
+        q0 = 1e-2 * rng.standard_normal((nlay, n, n))
+        pkg.MultiLayerQG.set_q_(prob, dev.array(q0))
+        label = "MultiLayerQG %d-layer %d^2 FilteredRK4 Float64 (BASELINE.json configs[2])" % (nlay, n)
+        kfun = {"k_col_inv": "k_col_inv<%d,PrepMulti>" % n, "k_row": "k_row_product<%d,1>" % n, "k_col_fwd": "k_col_fwd<%d,1>" % n}
+    pkg.stepforward_(prob, args.warmup)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    samples = []
+    for _ in range(max(1, args.repeats)):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        pkg.stepforward_(prob, args.steps)
+        e1.record()
+        torch.cuda.synchronize()
+        samples.append(e0.elapsed_time(e1))
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+    ms_per_step = float(np.median(samples)) / args.steps
+    ksteps = min(args.steps, 20)
+    prob.profile_begin()
+    pkg.stepforward_(prob, ksteps)
+    torch.cuda.synchronize()
+    prof = prob.profile_end()
+    peak, peak_src = peaks()
+    algo = fields_per_step * 8.0 * n * n
+    gbs = algo / (ms_per_step * 1e-3) / 1e9
+    top = max(("k_col_inv", "k_row", "k_col_fwd"), key=lambda k: prof[k]["ms"])
+    print(json.dumps({
+        "metric": METRIC, "value": n * n / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": label, "grid": [n, n], "layers": nlay, "kernels": kfun,
+                   "l2": "per-stage working set %.0f MB vs 126 MB of L2: at 1024^2 much of a stage stays L2-resident, so the 'HBM fraction' "
+                         "below can exceed what DRAM counters would show (SURVEY.md 8d)" % (fields_per_step / 4 * 8.0 * n * n / 1e6),
+                   "state_finite": bool(torch.isfinite(prob.sol.real).all().item())},
+        "ms_samples": [x / args.steps for x in samples],
+        "step_roofline": {"algorithmic_fields_per_step": fields_per_step, "algorithmic_bytes_per_step": algo, "achieved_gbs": gbs,
+                          "frac_of_measured_peak": gbs / peak, "peak": peak, "peak_source": peak_src},
+        "roofline": {"bound": "hbm", "kernel": top, "kernel_function": kfun[top], "peak": peak, "unit": "GB/s",
+                     "avg_launch_ms": prof[top]["ms"] / max(prof[top]["launches"], 1), "achieved": None, "frac": None, "traffic": None},
+        "kernels": {k: {"ms_per_step": v["ms"] / ksteps, "launches_per_step": v["launches"] / ksteps} for k, v in prof.items()},
+        "gpu_launches": int(round(sum(v["launches"] for v in prof.values()) / float(ksteps) * args.steps)),
+        "clocks": sampler.summary()}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -346,7 +429,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "cufft"])
     ap.add_argument("--workload", default=None,
-                    help="sqgN | twodnsN; default: sqg4096 on one GPU (BASELINE configs[3]), twodns16384 on several (configs[4])")
+                    help="sqgN | twodnsN | slqgN | mqg<layers>_N; default: sqg4096 on one GPU (BASELINE configs[3]), twodns16384 on several (configs[4])")
     ap.add_argument("--repeats", type=int, default=5, help="the K timed steps are repeated this often; the median is reported")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cufft", action="store_true")
@@ -361,6 +444,8 @@ def main():
         args.workload = "sqg4096" if world == 1 else "twodns16384"
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload.startswith("slqg") or args.workload.startswith("mqg"):
+        return run_other_config(args)
 
     import torch
     import gfb_loader

@@ -47,10 +47,13 @@ def build(force=False, verbose=False, nvcc="nvcc"):
     obj = os.path.join(OBJ, "gfb.o")
     if force or _stale(obj, deps):
         jobs.append(([nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, "gfb.cu"), "-o", obj], obj[:-2] + ".log"))
+    obj = os.path.join(OBJ, "cols_dft.o")
+    if force or _stale(obj, deps):
+        jobs.append(([nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, "cols_dft.cu"), "-o", obj], obj[:-2] + ".log"))
     if jobs:
         with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
             list(ex.map(lambda j: _run(*j), jobs))
-    objs = [os.path.join(OBJ, "launchers_%d.o" % n) for n in SIZES] + [os.path.join(OBJ, "gfb.o")]
+    objs = [os.path.join(OBJ, "launchers_%d.o" % n) for n in SIZES] + [os.path.join(OBJ, "gfb.o"), os.path.join(OBJ, "cols_dft.o")]
     if force or jobs or _stale(LIB, objs):
         _run([nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"], os.path.join(OBJ, "link.log"))
     if verbose:

@@ -35,6 +35,7 @@ struct gfb_ctx {
   std::vector<void*> allocs;
   // sharding (single GPU: rank 0 of 1, ny_loc = ny)
   int ny_loc = 0;   // physical rows owned by this rank (row pass)
+  int nyp = 0;      // ny rounded up to the 8-row tiles of the ctx-owned layouts (= ny unless ny is not a power of two)
   int nkpl = 0;     // column pairs per rank (ldi = 2 * nkpl)
   // tables
   cplx *tw_x = nullptr, *tw_y = nullptr;
@@ -148,11 +149,12 @@ static int dev_upload(gfb_ctx* c, T** p, const void* host, size_t n) {
 static int upload_padded(gfb_ctx* c, void** out, const void* host, int nlay, bool is_cplx) {
   const int nl = c->g.ny, nkr = c->g.nkl, ldi = c->ldi;
   const size_t es = is_cplx ? sizeof(cplx) : sizeof(double);
-  std::vector<char> tmp((size_t)nlay * nl * ldi * es, 0);
+  const size_t nlp = (size_t)c->nyp;  // tiled: whole 8-row blocks
+  std::vector<char> tmp((size_t)nlay * nlp * ldi * es, 0);
   for (int a = 0; a < nlay; ++a)
     for (int l = 0; l < nl; ++l)
       for (int k = 0; k < nkr; ++k)
-        std::memcpy(&tmp[((size_t)a * nl * ldi + (size_t)toff(l, k, ldi)) * es],
+        std::memcpy(&tmp[((size_t)a * nlp * ldi + (size_t)toff(l, k, ldi)) * es],
                     (const char*)host + ((size_t)(a * nl + l) * nkr + k) * es, es);
   char* d = nullptr;
   int rc = dev_alloc(c, &d, tmp.size());
@@ -244,6 +246,7 @@ int launch_col_inv(int NY, const ColInvLaunch& L) {
     GFB_CASE(32) GFB_CASE(64) GFB_CASE(128) GFB_CASE(256) GFB_CASE(512) GFB_CASE(1024) GFB_CASE(2048) GFB_CASE(4096) GFB_CASE(8192)
 #undef GFB_CASE
   }
+  if (NY >= 4 && NY <= DFT_MAX_NY && NY % 2 == 0) return launch_col_inv_dft(L);
   return -1;
 }
 int launch_row(int NX, const RowLaunch& L) {
@@ -262,6 +265,7 @@ int launch_col_fwd(int NY, const ColFwdLaunch& L) {
     GFB_CASE(32) GFB_CASE(64) GFB_CASE(128) GFB_CASE(256) GFB_CASE(512) GFB_CASE(1024) GFB_CASE(2048) GFB_CASE(4096) GFB_CASE(8192)
 #undef GFB_CASE
   }
+  if (NY >= 4 && NY <= DFT_MAX_NY && NY % 2 == 0) return launch_col_fwd_dft(L);
   return -1;
 }
 }  // namespace gfb
@@ -278,7 +282,7 @@ static int local_cols_below(const gfb_ctx* c, int gbound) {  // local columns wh
   }
   return n;
 }
-static long long w_elems(const gfb_ctx* c, int nf) { return (long long)c->g.ny * nf * c->ldi; }
+static long long w_elems(const gfb_ctx* c, int nf) { return (long long)c->nyp * nf * c->ldi; }
 static RowLayout row_layout(const gfb_ctx* c, int nf) {
   RowLayout r;
   r.nranks = c->g.nranks;
@@ -353,8 +357,11 @@ int gfb_create(gfb_ctx** out, const gfb_config* cfg) {
                 cfg->struct_size, (int)sizeof(gfb_config));
   // 16384-point lines: rows as 8192-point half-length transforms, columns as 4 x 4096 
   const bool half_rows = cfg->nx == 16384, quad_cols = cfg->ny == 16384;
-  if (!(pow2_ok(cfg->nx) || half_rows) || !(pow2_ok(cfg->ny) || quad_cols))
-    return fail(nullptr, GFB_ERR_UNSUPPORTED, "nx=%d, ny=%d: sizes must be powers of two in [32, 16384]", cfg->nx, cfg->ny);
+  // any other even ny <= DFT_MAX_NY: direct column transforms (cols_dft.cu; the reference's tests use ny = 126, 66, 34), one GPU
+  const bool dft_cols = !pow2_ok(cfg->ny) && !quad_cols && cfg->ny >= 8 && cfg->ny <= DFT_MAX_NY && cfg->ny % 2 == 0 && cfg->nranks <= 1;
+  if (!(pow2_ok(cfg->nx) || half_rows) || !(pow2_ok(cfg->ny) || quad_cols || dft_cols))
+    return fail(nullptr, GFB_ERR_UNSUPPORTED, "nx=%d, ny=%d: nx must be a power of two in [32, 16384]; ny a power of two in [32, 16384] or any "
+                "even number in [8, %d] (one GPU)", cfg->nx, cfg->ny, DFT_MAX_NY);
   if (cfg->nlayers < 1 || cfg->nlayers > MAX_LAYERS) return fail(nullptr, GFB_ERR_UNSUPPORTED, "nlayers=%d not in [1, %d]", cfg->nlayers, MAX_LAYERS);
   if ((cfg->kind == GFB_KIND_SINGLE || cfg->kind == GFB_KIND_QL) && cfg->nlayers != 1)
     return fail(nullptr, GFB_ERR_INVALID, "GFB_KIND_SINGLE / GFB_KIND_QL need nlayers == 1");
@@ -370,7 +377,7 @@ int gfb_create(gfb_ctx** out, const gfb_config* cfg) {
     return fail(nullptr, GFB_ERR_INVALID, "bad alias ranges");
   const int nranks = cfg->nranks > 0 ? cfg->nranks : 1;
   const int rank = cfg->nranks > 0 ? cfg->rank : 0;
-  if (rank < 0 || rank >= nranks || nranks > MAX_RANKS || (nranks & (nranks - 1)) != 0 || cfg->ny % (8 * nranks) != 0)
+  if (rank < 0 || rank >= nranks || nranks > MAX_RANKS || (nranks & (nranks - 1)) != 0 || (cfg->ny % (8 * nranks) != 0 && !dft_cols))
     return fail(nullptr, GFB_ERR_INVALID, "bad sharding: rank %d of %d (power of two, ny divisible by 8*nranks)", rank, nranks);
   gfb_ctx* c = new gfb_ctx();
   c->cfg = *cfg;
@@ -407,7 +414,8 @@ int gfb_create(gfb_ctx** out, const gfb_config* cfg) {
     g.la0 = g.la1 = 0;
   }
   const int n = c->nlayers, nl = g.ny;
-  c->ils = (long long)nl * c->ldi;
+  c->nyp = (g.ny + 7) & ~7;
+  c->ils = (long long)c->nyp * c->ldi;
   int rc = 0;
 #define TRY(x)             \
   do {                     \
@@ -694,14 +702,14 @@ static __global__ void __launch_bounds__(256) k_row_ql(const __grid_constant__ R
   const int y = (int)blockIdx.x * 8 + yy;
   if (t < 16) {  // U and Zeta of the block's eight rows
     const int r = (int)blockIdx.x * 8 + (t >> 1);
-    UZ[t] = a.W[a.wl.off((t & 1) ? 2 : 0, r, 0)].x;
+    UZ[t] = r < a.ny ? a.W[a.wl.off((t & 1) ? 2 : 0, r, 0)].x : 0.0;
   }
   __syncthreads();
   const double U = UZ[2 * yy], Z = UZ[2 * yy + 1], sx = (double)nx;
   const long long rd = a.pl.rowbase(0, y), rv = a.pl.rowbase(1, y);
   double acc = 0.0;
   const int npairs = (a.kout + 1) / 2;
-  for (int kp = t >> 4; kp < npairs; kp += 16) {
+  for (int kp = t >> 4; kp < npairs && y < a.ny; kp += 16) {
     const int k = 2 * kp + kk;
     if (k >= a.kout) continue;
     cplx d = cmake(0.0, 0.0), v = cmake(0.0, 0.0);
@@ -722,7 +730,7 @@ static __global__ void __launch_bounds__(256) k_row_ql(const __grid_constant__ R
   }
   part[t] = acc;
   __syncthreads();
-  if (t < 8) {  // row t of the block: its 32 partial sums live at threads with ((tid & 15) >> 1) == t
+  if (t < 8 && (int)blockIdx.x * 8 + t < a.ny) {  // row t of the block: its 32 partial sums live at threads with ((tid & 15) >> 1) == t
     double ssum = 0.0;
     for (int i = 0; i < 16; ++i) ssum += part[i * 16 + 2 * t] + part[i * 16 + 2 * t + 1];
     const int r = (int)blockIdx.x * 8 + t;
@@ -761,7 +769,7 @@ static int run_row_product(gfb_ctx* c, const cplx* Wrecv, const PeerOut& Psend, 
   }
   ProfScope ps(c, 1, st);
   if (c->ql) {
-    GFB_LAUNCH(k_row_ql, dim3(c->ny_loc / 8), dim3(256), 0, st, R.a, c->g.nx);
+    GFB_LAUNCH(k_row_ql, dim3((c->ny_loc + 7) / 8), dim3(256), 0, st, R.a, c->g.nx);
     return check_launch(c, 0, "k_row_ql");
   }
   return check_launch(c, launch_row(c->g.nx, R), "k_row");

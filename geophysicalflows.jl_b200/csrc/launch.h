@@ -73,6 +73,10 @@ int launch_row_half_8192(const RowLaunch& L);
 int launch_col_inv_16384(const ColInvLaunch& L);  // columns of 16384 points as 4 x 4096 (radix-4 DIF while loading)
 int launch_col_fwd_16384(const ColFwdLaunch& L);  // rows of 16384 points as 8192-point half-length transforms
 
+int launch_col_inv_dft(const ColInvLaunch& L);    // any even ny <= DFT_MAX_NY: direct transforms (cols_dft.cu)
+int launch_col_fwd_dft(const ColFwdLaunch& L);
+constexpr int DFT_MAX_NY = 1024;
+
 int launch_col_inv(int NY, const ColInvLaunch& L);
 int launch_row(int NX, const RowLaunch& L);
 int launch_col_fwd(int NY, const ColFwdLaunch& L);

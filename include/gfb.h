@@ -45,7 +45,7 @@ enum gfb_status {
   GFB_ERR_INVALID = -1,     /* bad argument / unsupported configuration */
   GFB_ERR_CUDA = -2,        /* CUDA runtime error (message has the CUDA string) */
   GFB_ERR_ALLOC = -3,
-  GFB_ERR_UNSUPPORTED = -4  /* e.g. grid size that is not a power of two in [32, 16384] */
+  GFB_ERR_UNSUPPORTED = -4  /* e.g. nx that is not a power of two in [32, 16384] */
 };
 
 /* which calcN! family */
@@ -77,7 +77,8 @@ typedef struct gfb_config {
   int struct_size;        /* = sizeof(gfb_config) of the header the CALLER was built against; gfb_create rejects a
                              mismatch (a binding whose struct mirror has drifted) instead of reading past the struct */
   int kind;               /* gfb_kind */
-  int nx, ny, nlayers;    /* nx, ny powers of two in [32, 16384] */
+  int nx, ny, nlayers;    /* nx: power of two in [32, 16384]; ny: power of two in [32, 16384], or (one GPU) any even number in
+                             [8, 1024] -- those columns run as direct transforms (csrc/cols_dft.cu; the reference's tests use 126, 66, 34) */
   double Lx, Ly;
   /* dealias! index ranges, 0-based half-open ([FF] getaliasedwavenumbers): columns [kr_alias0, nkr) and
    * rows [l_alias0, l_alias1) are zeroed.  kr_alias0 = nkr and l_alias0 = l_alias1 disables. */

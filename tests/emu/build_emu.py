@@ -39,10 +39,13 @@ def build(force=False):
     obj = os.path.join(OBJ, "gfb.o")
     if force or _stale(obj, deps):
         jobs.append(["g++"] + FLAGS + ["-DGFB_EMU_IMPLEMENTATION", "-c", os.path.join(CSRC, "gfb.cu"), "-o", obj])
+    obj = os.path.join(OBJ, "cols_dft.o")
+    if force or _stale(obj, deps):
+        jobs.append(["g++"] + FLAGS + ["-c", os.path.join(CSRC, "cols_dft.cu"), "-o", obj])
     if jobs:
         with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
             list(ex.map(_run, jobs))
-    objs = [os.path.join(OBJ, "launchers_%d.o" % n) for n in SIZES] + [os.path.join(OBJ, "gfb.o")]
+    objs = [os.path.join(OBJ, "launchers_%d.o" % n) for n in SIZES] + [os.path.join(OBJ, "gfb.o"), os.path.join(OBJ, "cols_dft.o")]
     if force or jobs or _stale(LIB, objs):
         _run(["g++", "-shared", "-o", LIB] + objs + ["-lpthread"])
     return LIB

@@ -481,3 +481,42 @@ def test_lsrk54_vs_oracle(emu, oracle_backend, stepper):
     assert R.relerr(emu.host(pb.sol), po.sol) < 1e-13
     err, rtol = R.slqg_rossbywave(emu, stepper, 1e-2, 20)
     assert err < rtol
+
+
+def nonpow2_case(B, O, nx, ny, stepper):
+    rng = np.random.default_rng(nx * ny)
+    kw = dict(nx=nx, ny=ny, Lx=2 * np.pi, Ly=3.0, beta=1.0, deformation_radius=1.3, eta=0.2 * rng.standard_normal((ny, nx)), mu=0.01,
+              nu=1e-4, nnu=1, dt=2e-3, stepper=stepper)
+    po, pb = O.singlelayerqg.Problem(**kw), B.singlelayerqg.Problem(**kw)
+    q0 = rng.standard_normal((ny, nx))
+    O.singlelayerqg.set_q_(po, q0)
+    B.singlelayerqg.set_q_(pb, B.dev(q0))
+    assert R.relerr(B.host(pb.sol), po.sol) < 1e-13              # mul!
+    assert R.relerr(B.host(pb.vars.u), po.vars.u) < 1e-13        # ldiv! through updatevars!
+    O.stepforward_(po, 4)
+    B.stepforward_(pb, 4)
+    assert R.relerr(B.host(pb.sol), po.sol) < 1e-12
+    assert abs(B.singlelayerqg.energy(pb) / O.singlelayerqg.energy(po) - 1) < 1e-12
+    y = np.linspace(-1.5, 1.5, ny, endpoint=False)
+    U = np.stack([0.2 * np.cos(2 * np.pi * y / 3.0), 0.05 * np.ones(ny)], axis=1)
+    kw = dict(nx=nx, ny=ny, Lx=2 * np.pi, Ly=3.0, f0=1.0, beta=0.5, U=U, mu=0.05, nu=1e-4, dt=2e-3, stepper=stepper)
+    po, pb = O.multilayerqg.Problem(2, **kw), B.multilayerqg.Problem(2, **kw)
+    q0 = 0.1 * rng.standard_normal((2, ny, nx))
+    O.multilayerqg.set_q_(po, q0)
+    B.multilayerqg.set_q_(pb, B.dev(q0))
+    O.stepforward_(po, 3)
+    B.stepforward_(pb, 3)
+    assert R.relerr(B.host(pb.sol), po.sol) < 1e-12
+    O.multilayerqg.updatevars_(po)
+    B.multilayerqg.updatevars_(pb)
+    assert R.relerr(B.host(pb.vars.psi), po.vars.psi) < 1e-12
+
+
+def test_nonpow2_ny(emu, oracle_backend):
+    """the reference's own test grids (ny = 126, 66, 34) through the emulated kernels"""
+    assert max(abs(e) for e in R.twodns_energyenstrophypalinstrophy(emu, nx=128, ny=126)) < RT
+    eq, epsi = R.mqg_nonlinearadvection(emu, 2, nx=64, ny=66, nsteps=20)
+    assert eq < RT and epsi < RT
+    assert max(R.mqg_setqsetpsi(emu, nx=32, ny=34)) < RT
+    nonpow2_case(emu, oracle_backend, 32, 66, "FilteredETDRK4")
+    nonpow2_case(emu, oracle_backend, 64, 24, "LSRK54")

@@ -55,7 +55,7 @@ def test_ref_twodns(gpu):
     assert R.twodns_advection(gpu) < RT                                   # 128^2, ForwardEuler, 2000 steps
     for stepper, dt in (("FilteredRK4", 0.005), ("ETDRK4", 0.005), ("FilteredETDRK4", 0.005), ("AB3", 0.0005)):
         assert R.twodns_advection(gpu, dt=dt, stepper=stepper, tf=0.5) < RT
-    assert max(abs(e) for e in R.twodns_energyenstrophypalinstrophy(gpu, nx=128, ny=128)) < RT
+    assert max(abs(e) for e in R.twodns_energyenstrophypalinstrophy(gpu, nx=128, ny=126)) < RT
     assert R.twodns_lambdipole(gpu) < 1e-2                                # 256^2 FilteredRK4
 
 
@@ -111,18 +111,18 @@ def test_ref_bqgql(gpu, O):
 def test_ref_mqg(gpu):
     for n in (2, 3):
         assert R.mqg_pvtofromstreamfunction(gpu, n) < 1e-13
-        eq, epsi = R.mqg_nonlinearadvection(gpu, n, nx=64, ny=64)
+        eq, epsi = R.mqg_nonlinearadvection(gpu, n, nx=64, ny=66)  # the reference's own grid (ny = 66: direct column transforms)
         assert eq < RT and epsi < RT
-    eq, epsi = R.mqg_nonlinearadvection(gpu, 2, nx=64, ny=64, nsteps=100, linear=True)  # test/runtests.jl:130 (test_mqg_linearadvection)
+    eq, epsi = R.mqg_nonlinearadvection(gpu, 2, nx=64, ny=66, nsteps=100, linear=True)  # test/runtests.jl:130 (test_mqg_linearadvection)
     assert eq < RT and epsi < RT
-    assert max(abs(e) for e in R.mqg_energies(gpu, nx=64, ny=64)) < RT
+    assert max(abs(e) for e in R.mqg_energies(gpu, nx=64, ny=66)) < RT
     assert abs(R.mqg_energysinglelayer(gpu)) < RT
     for n in (2, 3):
-        lat, ver = R.mqg_fluxes(gpu, n, nx=128, ny=128)
+        lat, ver = R.mqg_fluxes(gpu, n, nx=128, ny=126)
         assert abs(lat[0] / 0.00626267 - 1) < 1e-6 and abs(lat[1]) < 1e-12 and abs(ver[0] / -0.196539 - 1) < 1e-6
-    assert abs(R.mqg_fluxessinglelayer(gpu, nx=128, ny=128) - 0.0313134) < 1e-7
-    assert max(R.mqg_setqsetpsi(gpu, nx=32, ny=32)) < RT
-    assert max(R.mqg_topographicPV_gradient(gpu, nx=32, ny=32)) < RT
+    assert abs(R.mqg_fluxessinglelayer(gpu, nx=128, ny=126) - 0.0313134) < 1e-7
+    assert max(R.mqg_setqsetpsi(gpu, nx=32, ny=34)) < RT
+    assert max(R.mqg_topographicPV_gradient(gpu, nx=32, ny=34)) < RT
     err, rtol = R.mqg_rossbywave(gpu)
     assert err < rtol
 
@@ -365,3 +365,11 @@ def test_lsrk54_vs_oracle(gpu, O, stepper):
     """[FF] LSRK54: the five in-place low-storage stages on the GPU vs the oracle (same cases as the emulation test)."""
     import test_emu_parity
     test_emu_parity.test_lsrk54_vs_oracle(gpu, O, stepper)
+
+
+@pytest.mark.parametrize("nx,ny,stepper", [(64, 66, "FilteredETDRK4"), (128, 126, "RK4"), (32, 250, "FilteredAB3"), (256, 24, "LSRK54")])
+def test_nonpow2_ny_vs_oracle(gpu, O, nx, ny, stepper):
+    """ny that is not a power of two (the reference's tests use 126, 66, 34): direct column transforms (cols_dft.cu) under the
+    same row pass and epilogues -- single-layer and layered problems, plain transforms, diagnostics, vs the oracle."""
+    import test_emu_parity
+    test_emu_parity.nonpow2_case(gpu, O, nx, ny, stepper)
