@@ -520,3 +520,25 @@ def test_nonpow2_ny(emu, oracle_backend):
     assert max(R.mqg_setqsetpsi(emu, nx=32, ny=34)) < RT
     nonpow2_case(emu, oracle_backend, 32, 66, "FilteredETDRK4")
     nonpow2_case(emu, oracle_backend, 64, 24, "LSRK54")
+
+
+def ic_generators_case(B, O):
+    """src/utils.jl on the device: same fields as the oracle's host generators (same host-drawn phases)."""
+    from oracle.gfo.utils import peakedisotropicspectrum, lambdipole
+    from oracle.gfo.timesteppers import makefilter
+    n = 64
+    po = O.twodnavierstokes.Problem(nx=n, Lx=2 * np.pi, stepper="FilteredRK4")
+    pb = B.twodnavierstokes.Problem(nx=n, Lx=2 * np.pi, stepper="FilteredRK4")
+    mask = makefilter(po.grid, (n, n // 2 + 1))
+    want = peakedisotropicspectrum(po.grid, 6, 0.5, mask=mask, rng=np.random.default_rng(5))
+    got = B.pkg.utils.peakedisotropicspectrum_device(pb, 6, 0.5, mask=mask, rng=np.random.default_rng(5))
+    assert got.device == pb.sol.device and R.relerr(B.host(got), want) < 1e-13
+    with pytest.raises(RuntimeError, match="the domain is not square"):   # test/test_utils.jl:18-24
+        B.pkg.utils.peakedisotropicspectrum_device(B.twodnavierstokes.Problem(nx=32, ny=64, Lx=2 * np.pi, Ly=3 * np.pi), 6, 0.5, allones=True)
+    want = lambdipole(1.0, 0.7, po.grid)
+    got = B.pkg.utils.lambdipole_device(pb, 1.0, 0.7)
+    assert np.max(np.abs(B.host(got) - want)) < 1e-12 * np.max(np.abs(want))
+
+
+def test_ic_generators_on_device(emu, oracle_backend):
+    ic_generators_case(emu, oracle_backend)

@@ -373,3 +373,9 @@ def test_nonpow2_ny_vs_oracle(gpu, O, nx, ny, stepper):
     same row pass and epilogues -- single-layer and layered problems, plain transforms, diagnostics, vs the oracle."""
     import test_emu_parity
     test_emu_parity.nonpow2_case(gpu, O, nx, ny, stepper)
+
+
+def test_ic_generators_on_device(gpu, O):
+    """peakedisotropicspectrum / lambdipole built on the GPU (src/utils.jl:8-54), vs the oracle's host generators."""
+    import test_emu_parity
+    test_emu_parity.ic_generators_case(gpu, O)
