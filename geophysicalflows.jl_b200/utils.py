@@ -67,12 +67,16 @@ def peakedisotropicspectrum_device(prob, kpeak, E0, mask=None, allones=False, rn
 
 def lambdipole_device(prob, U, R, center=None):
     """src/utils.jl:8-20 on the device of `prob`."""
-    from scipy.special import j0
+    from scipy.special import j0, j1
     grid, dev = prob.grid, prob.dev
     k = 3.8317059702075123156 / R
     q0 = -2 * U * k / j0(k * R)
     x, y = (dev.array(a, torch.float64) for a in grid.gridpoints())
     xc, yc = (float(np.mean(grid.x)), float(np.mean(grid.y))) if center is None else center
     r = torch.hypot(x - xc, y - yc)
-    q = q0 * torch.special.bessel_j1(k * r) * (y - yc) / torch.where(r > 0, r, torch.ones_like(r))
+    # the Bessel function is evaluated on the host, as the reference does (src/utils.jl:16 builds besselj1 element by
+    # element under CUDA.@allowscalar); torch.special.bessel_j1 is only good to ~1e-10
+    xh, yh = grid.gridpoints()
+    bj1 = dev.array(j1(k * np.hypot(xh - xc, yh - yc)), torch.float64)
+    q = q0 * bj1 * (y - yc) / torch.where(r > 0, r, torch.ones_like(r))
     return torch.where((r >= R) | (r == 0), torch.zeros_like(q), q).contiguous()
