@@ -7,11 +7,12 @@ Julia `f!` is spelled `f_`; Julia arrays `(nkr, nl[, n])` are torch tensors `[n,
 (identical bytes).  There is no CPU path: importing works anywhere, creating a `Problem`
 needs the built library and a CUDA device.
 """
-from . import _lib, device, grid, timesteppers, twodnavierstokes, surfaceqg, singlelayerqg, multilayerqg, barotropicqgql, utils  # noqa: F401
+from . import _lib, device, grid, timesteppers, twodnavierstokes, surfaceqg, singlelayerqg, multilayerqg, barotropicqgql, utils, output  # noqa: F401
 from ._lib import GfbError  # noqa: F401
 from .device import GPU, CPU, Device  # noqa: F401
 from .grid import TwoDGrid  # noqa: F401
 from .timesteppers import stepforward_, Diagnostic, Shard  # noqa: F401
+from .output import Output, saveproblem, saveoutput, savecheckpoint, loadcheckpoint  # noqa: F401
 
 TwoDNavierStokes = twodnavierstokes
 SurfaceQG = surfaceqg

@@ -542,3 +542,58 @@ def ic_generators_case(B, O):
 
 def test_ic_generators_on_device(emu, oracle_backend):
     ic_generators_case(emu, oracle_backend)
+
+
+def test_output_and_checkpoint_resharded(emu, tmp_path, monkeypatch):
+    """Output/saveoutput pieces and a checkpoint written by a 2-rank sharded run, restored into an unsharded problem:
+    the continued run equals the uninterrupted one bit for bit (the state of RK4 is sol + clock)."""
+    import ctypes as C
+    import threading
+    monkeypatch.setenv("GFB_EMU_THREADS", "1")
+    gf = emu.pkg
+    n = 32
+    kw = dict(nx=n, Lx=2 * np.pi, nu=1e-3, dt=5e-3, stepper="FilteredRK4")
+    s0 = np.fft.rfft2(np.random.default_rng(2).standard_normal((n, n))) / n
+    ref = gf.twodnavierstokes.Problem(emu.device, **kw)
+    ref.sol.copy_(emu.dev(s0))
+    gf.stepforward_(ref, 5)
+    probs = []
+    for r in range(2):
+        sh = gf.timesteppers.Shard(r, 2, gf.TwoDGrid(emu.device, n, 2 * np.pi), transport="p2p-manual")
+        probs.append(gf.twodnavierstokes.Problem(emu.device, shard=sh, **kw))
+    ptrs = (C.c_void_p * 2)()
+    for r, p in enumerate(probs):
+        loc = C.c_void_p()
+        p._check(p.lib.gfb_comm_create(p.ctx, None, C.byref(loc)), "gfb_comm_create")
+        ptrs[r] = loc.value
+    for p in probs:
+        p._check(p.lib.gfb_comm_connect_ptrs(p.ctx, ptrs), "gfb_comm_connect_ptrs")
+        p.sol.copy_(torch.from_numpy(p.shard.spec_local(s0)))
+    fn = str(tmp_path / "run" / "twodns")
+    errs = []
+
+    def run(p):
+        try:
+            out = gf.Output(p, fn, ("zetah", lambda q: q.sol))
+            gf.saveproblem(out)
+            gf.saveoutput(out)
+            gf.stepforward_(p, 3)
+            gf.saveoutput(out)
+            gf.savecheckpoint(p, fn + ".chk")
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+    th = [threading.Thread(target=run, args=(p,)) for p in probs]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=600)
+    assert not errs, errs
+    z = np.load(fn + ".rank1of2.npz")
+    assert "snapshots/zetah/0" in z.files and "snapshots/zetah/3" in z.files and float(z["snapshots/t/3"]) == probs[1].clock.t
+    assert np.array_equal(z["cols"], probs[1].shard.cols)
+    again = gf.twodnavierstokes.Problem(emu.device, **kw)
+    gf.loadcheckpoint(again, fn + ".chk", 2)
+    assert again.clock.step == 3
+    gf.stepforward_(again, 2)
+    assert again.clock.t == ref.clock.t
+    assert R.relerr(again.sol.numpy(), ref.sol.numpy()) < 1e-14
