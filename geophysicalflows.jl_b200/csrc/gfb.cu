@@ -54,6 +54,10 @@ struct gfb_ctx {
   cplx* st[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // stage states / accumulators / histories
   cplx *S0 = nullptr, *Fint = nullptr, *PV = nullptr, *Cin = nullptr, *Nint = nullptr;  // tiled copies of user arrays
   double *dpart = nullptr, *dout = nullptr;
+  // diagnostics come back through a mapped pinned buffer the final reduction kernel writes itself: no copy engine is
+  // involved (a cudaMemcpy to the caller's pageable memory serialised against in-flight PCIe transfers of other streams,
+  // profiles/r2l_e2e_probe_modes.txt)
+  double *dres_host = nullptr, *dres_dev = nullptr;
   int dblocks = 0;
   // "p2p" transport: one IPC-shareable buffer per rank = [flags | W receive | P receive]; peer[d] is rank d's
   // buffer mapped into this process (peer[rank] = comm)
@@ -344,6 +348,7 @@ int gfb_destroy(gfb_ctx* c) {
 #endif
   for (void* p : c->allocs) cudaFree(p);
   if (c->tmo_host) cudaFreeHost(c->tmo_host);
+  if (c->dres_host) cudaFreeHost(c->dres_host);
   for (auto& e : c->prof_ev) cudaEventDestroy(e);
   delete c;
   return GFB_OK;
@@ -525,6 +530,11 @@ int gfb_create(gfb_ctx** out, const gfb_config* cfg) {
   c->dblocks = 592;
   TRY(dev_alloc(c, &c->dpart, (size_t)c->dblocks * DIAG_MAXOUT));
   TRY(dev_alloc(c, &c->dout, (size_t)DIAG_MAXOUT));
+  if (cudaHostAlloc((void**)&c->dres_host, DIAG_MAXOUT * sizeof(double), cudaHostAllocMapped) != cudaSuccess ||
+      cudaHostGetDevicePointer((void**)&c->dres_dev, c->dres_host, 0) != cudaSuccess) {
+    fail(c, GFB_ERR_ALLOC, "cudaHostAlloc of the diagnostics buffer failed");
+    TRY(GFB_ERR_ALLOC);
+  }
 #undef TRY
   c->cfg.L = c->cfg.filter = nullptr;  // host pointers are not retained
   *out = c;
@@ -1468,11 +1478,11 @@ int gfb_diag(gfb_ctx* c, int kind, const void* sol, const void* aux, const void*
   }
   int rc = check_launch(c, 0, "k_diag_partial");
   if (rc) return rc;
-  GFB_LAUNCH(k_diag_final, dim3(1), dim3(256), 0, st, (const double*)c->dpart, c->dblocks, need, c->dout);
+  GFB_LAUNCH(k_diag_final, dim3(1), dim3(256), 0, st, (const double*)c->dpart, c->dblocks, need, c->dres_dev);
   rc = check_launch(c, 0, "k_diag_final");
   if (rc) return rc;
-  GFB_CUDA(c, cudaMemcpyAsync(out_host, c->dout, need * sizeof(double), cudaMemcpyDeviceToHost, st));
-  GFB_CUDA(c, cudaStreamSynchronize(st));
+  GFB_CUDA(c, cudaStreamSynchronize(st));  // kernel completion makes its stores to the mapped buffer visible to the host
+  std::memcpy(out_host, c->dres_host, need * sizeof(double));
   return GFB_OK;
 }
 
