@@ -313,7 +313,7 @@ __device__ __forceinline__ void epi_finish(const GridDesc& g, const EpiArgs& e, 
 template <int NY, int KIND, bool CL, int S = GroupCfg<NY>::T>
 __device__ __forceinline__ void epilogue_tile(const GridDesc& g, const EpiArgs& e, const int layer, const int colA,
                                               const bool liveA, cplx* __restrict__ X, const uint32_t tb, const int l0,
-                                              const int tid) {
+                                              const int tid, const int pf = 0) {
   using GC = GroupCfg<NY>;
   constexpr int T = S, THREADS = GC::THREADS;
   const int j = l0;
@@ -342,8 +342,28 @@ __device__ __forceinline__ void epilogue_tile(const GridDesc& g, const EpiArgs& 
     }
     tmem_wait_st();
   }
+  // pf == 2: rolling L2 prefetch -- the input tiles of the chunk two iterations ahead start moving DRAM -> L2 while this
+  // chunk is fetched and finished (one thread in eight issues: a tile = the rows of eight neighbouring threads); nothing
+  // is prefetched that is not consumed a few microseconds later, so no extra DRAM traffic (unlike the bulk variant, pf == 1)
+  constexpr int PFD = 2 * CH;
+  auto pf_rows = [&](const int rb) {
+    if (T % 8 != 0 || (j & 7) != 0 || !liveA) return;
+#pragma unroll
+    for (int q = 0; q < CH; ++q) {
+      const int r = rb + q;
+      if (r < PT) {
+        const int l = j + r * T;
+        if (!(e.prune && l_aliased(g, l) && l_aliased(g, l + 7))) epi_prefetch_tile<KIND, CL>(g, e, layer, colA, toff_row<T>(off0, j, r, colA, e.out.ld));
+      }
+    }
+  };
+  if (pf == 2) {
+    pf_rows(0);
+    pf_rows(CH);
+  }
 #pragma unroll 1
   for (int r0 = 0; r0 < PT; r0 += CH) {
+    if (pf == 2) pf_rows(r0 + PFD);
     EpiIn<KIND, CL> in[CH];
     bool act[CH];
     int off[CH];
@@ -365,9 +385,9 @@ __device__ __forceinline__ void epilogue_tile(const GridDesc& g, const EpiArgs& 
 
 template <int NY, bool CL, int S = GroupCfg<NY>::T>
 __device__ __forceinline__ void epilogue_dispatch(const GridDesc& g, const EpiArgs& e, int layer, int colA, bool liveA, cplx* X,
-                                                  uint32_t tb, int l0, int tid) {
+                                                  uint32_t tb, int l0, int tid, int pf = 0) {
   switch (e.kind) {
-#define GFB_EPI_CASE(K) case K: epilogue_tile<NY, K, CL, S>(g, e, layer, colA, liveA, X, tb, l0, tid); break;
+#define GFB_EPI_CASE(K) case K: epilogue_tile<NY, K, CL, S>(g, e, layer, colA, liveA, X, tb, l0, tid, pf); break;
     GFB_EPI_CASE(EPI_STORE)
     GFB_EPI_CASE(EPI_RK_FIRST)
     GFB_EPI_CASE(EPI_RK_MID)
@@ -438,7 +458,7 @@ __global__ void __launch_bounds__(GroupCfg<NY>::THREADS, GroupCfg<NY>::MINB)
   // The epilogue streams 5-6 arrays one or two rows at a time and used to wait a DRAM round trip per chunk (39 % of the
   // warp samples).  Its input tiles of this thread's first eight rows start moving DRAM -> L2 NOW, four transforms before
   // they are needed; the second eight follow when the epilogue starts (bounded L2 footprint: ~50 MB over all CTAs).
-  if (TWO && l2pf && liveA && T % 8 == 0) {
+  if (TWO && l2pf == 1 && liveA && T % 8 == 0) {
     if (e.cplxL) epi_prefetch_rows<T, true>(g, e, layer, colA, j, 0, PT / 2);
     else epi_prefetch_rows<T, false>(g, e, layer, colA, j, 0, PT / 2);
   }
@@ -504,12 +524,12 @@ __global__ void __launch_bounds__(GroupCfg<NY>::THREADS, GroupCfg<NY>::MINB)
       for (int q = 0; q < 4; ++q) tmem_store(tA + 4 * (c0 + q), cadd(v[c0 + q], b[q]));
     }
     tmem_wait_st();
-    if (l2pf && liveA && T % 8 == 0) {
+    if (l2pf == 1 && liveA && T % 8 == 0) {
       if (e.cplxL) epi_prefetch_rows<T, true>(g, e, layer, colA, j, PT / 2, PT);
       else epi_prefetch_rows<T, false>(g, e, layer, colA, j, PT / 2, PT);
     }
-    if (e.cplxL) epilogue_dispatch<NY, true>(g, e, layer, colA, liveA, X, tA, j, tid);
-    else epilogue_dispatch<NY, false>(g, e, layer, colA, liveA, X, tA, j, tid);
+    if (e.cplxL) epilogue_dispatch<NY, true>(g, e, layer, colA, liveA, X, tA, j, tid, l2pf);
+    else epilogue_dispatch<NY, false>(g, e, layer, colA, liveA, X, tA, j, tid, l2pf);
     tmem_release(tbase, TmemCfg<NY>::COLS);
   }
 }

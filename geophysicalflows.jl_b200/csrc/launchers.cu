@@ -333,8 +333,9 @@ static int do_col_fwd(const ColFwdLaunch& L) {
   static int l2pf = -1;
   if (l2pf < 0) {
     // opt-in experiment (GFB_K3_L2PF=1): measured slower on B200 (K3 0.645 vs 0.576 ms/step, DRAM reads 491 vs 359 MB/launch)
+    // GFB_K3_L2PF=1: bulk prefetch of half a unit (slower), =2: rolling prefetch two chunks ahead inside the epilogue loop
     const char* e = getenv("GFB_K3_L2PF");
-    l2pf = (e && e[0] == '1') ? 1 : 0;
+    l2pf = e ? atoi(e) : 0;
   }
   GFB_LAUNCH((k_col_fwd<GFB_N, TWO>), grid, dim3(GC::THREADS), smem, L.st, L.g, L.P, L.ldp, L.pfs, L.e, L.ncols, L.tw, l2pf);
   return 0;

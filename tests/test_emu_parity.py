@@ -398,7 +398,7 @@ def test_columns_of_16384_points(emu, oracle_backend, nx, stepper):
 
 def test_16384_is_limited_to_what_is_built(emu):
     """Loud, specific failures for what the 16384-point support does not cover yet."""
-    with pytest.raises(emu.pkg.GfbError, match="powers of two"):
+    with pytest.raises(emu.pkg.GfbError, match="power of two"):
         emu.twodnavierstokes.Problem(nx=64, ny=32768, Lx=2 * np.pi, stepper="RK4")
 
 
