@@ -438,7 +438,7 @@ def main():
     ap.add_argument("--repeats", type=int, default=5, help="the K timed steps are repeated this often; the median is reported")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cufft", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--e2e-steps", type=int, default=30)
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: p2p = kernels store into peer memory over NVLink (fused exchange); nccl = all-to-all")
     args = ap.parse_args()
@@ -704,11 +704,22 @@ def main():
     if cufft is not None:
         line["cufft_baseline"] = cufft
     if world > 1:
+        # strong-scaling reference: the SAME workload measured on one GPU of this pool (committed bench line; the 16384^2
+        # problem needs 46 GB and fits one B200), so that N-GPU lines can be read as t1 / (N tN) without re-running it
+        refs = {"twodns16384": "r2j_twodns16384_1gpu.json", "sqg4096": "r2k_bench.json"}
+        try:
+            ref = json.loads(open(os.path.join(ROOT, "profiles", refs[args.workload])).read().strip().splitlines()[-1])
+            if ref["n_gpus"] == 1 and ref["config"]["workload"] == workload_name(cfg):
+                line["strong_scaling"] = {"one_gpu_ms_per_step": ref["ms_per_step"], "source": "profiles/" + refs[args.workload],
+                                          "speedup": ref["ms_per_step"] / ms_per_step,
+                                          "efficiency": ref["ms_per_step"] / (world * ms_per_step)}
+        except Exception:  # noqa: BLE001
+            pass
         # NVLink roofline of the sharded step: bytes that must leave each GPU / measured peer bandwidth (770 GB/s/dir)
         line["nvlink"] = {"a2a_bytes_per_gpu_per_step": a2a_bytes, "floor_ms_at_770GBs": a2a_bytes / 770e9 * 1e3,
                           "frac_of_nvlink_floor": (a2a_bytes / 770e9 * 1e3) / ms_per_step,
                           "exchanges_per_step": 8, "transport": prob.shard.transport}
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and n <= 4096:  # larger grids: `--impl reference` samples them at 4096^2
         nsamp = 2 if n >= 4096 else 4
         full0 = bh0 if not forced else None
         per = cpu_steps(cfg, full0, nsamp, 1) if full0 is not None else cpu_steps(cfg, np.ascontiguousarray(bh0), nsamp, 1)
