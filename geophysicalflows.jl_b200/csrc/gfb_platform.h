@@ -80,6 +80,26 @@ __device__ __forceinline__ double2 ldpair_d(const double* p) {  // two adjacent 
   return r;
 #endif
 }
+// one complex value / one double, L2 only (no L1 allocation): the lane-paired column kernels read a 32-byte sector as two
+// adjacent lanes' halves, merged by the LSU
+__device__ __forceinline__ double2 ldcplx(const double2* p) {
+#ifdef GFB_EMULATE
+  return *p;
+#else
+  double2 r;
+  asm volatile("ld.global.cg.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+#endif
+}
+__device__ __forceinline__ double lddouble(const double* p) {
+#ifdef GFB_EMULATE
+  return *p;
+#else
+  double r;
+  asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(r) : "l"(p));
+  return r;
+#endif
+}
 __device__ __forceinline__ void compiler_fence() { asm volatile("" ::: "memory"); }
 
 // ---- Tensor Memory (TMEM) as thread-private parking space ------------------------------------------------

@@ -20,6 +20,12 @@ struct PrepPlain {  // irfft of arbitrary (user, dense) spectra: field = batch i
     a = cscale(p[0], scale);
     b = liveB ? cscale(p[1], scale) : cmake(0.0, 0.0);
   }
+  // one column (the lane-paired kernels: adjacent lanes hold the two columns of a pair, the LSU merges their halves)
+  __device__ __forceinline__ cplx load_one(const GridDesc&, int field, int l, int col, int) const {
+    return cscale(in[field * ls + (long long)l * ld + col], scale);
+  }
+  __device__ __forceinline__ int off_one(int, int) const { return 0; }
+  __device__ __forceinline__ void prefetch_pair(const GridDesc&, int, int, int, int) const {}
 };
 
 struct PrepSingle {  // single-layer modules: psi_h = -G*sol ; uh = i l G sol ; vh = -i kr G sol ; qh = sol
@@ -45,6 +51,22 @@ struct PrepSingle {  // single-layer modules: psi_h = -G*sol ; uh = i l G sol ; 
     const double ll = wav_l(g, l);
     a = apply(g, field, ll, wav_kr(g, colA), gg.x, p.a);
     b = apply(g, field, ll, wav_kr(g, colA + 1), gg.y, p.b);
+  }
+  __device__ __forceinline__ cplx load_one(const GridDesc& g, int field, int l, int col, int off) const {
+    if (l_aliased(g, l)) return cmake(0.0, 0.0);
+    const cplx raw = ldcplx(sol + off);
+    const double gg = (field != 2) ? lddouble(G + off) : 0.0;
+    return apply(g, field, wav_l(g, l), wav_kr(g, col), gg, raw);
+  }
+  __device__ __forceinline__ int off_one(int l, int col) const { return toff(l, col, ld); }
+  // pull the live 8-row tile lines of a column pair (256 bytes of the state, 128 bytes of G each) into L2
+  __device__ __forceinline__ void prefetch_pair(const GridDesc& g, int field, int colA, int tid, int nthreads) const {
+    for (int t = tid; t < g.ny / 8; t += nthreads) {
+      if (8 * t >= g.la0 && 8 * t + 8 <= g.la1) continue;  // the whole tile is zeroed by dealias!
+      const int off = toff(8 * t, colA, ld);
+      prefetch_l2_bulk(sol + off, 256);
+      if (field != 2) prefetch_l2_bulk(G + off, 128);
+    }
   }
 };
 
@@ -94,6 +116,25 @@ struct PrepMulti {  // MultiLayerQG: psi_h = S^-1 q_h ; uh = -i l psi_h ; vh = i
       b = pb;
     }
   }
+  __device__ __forceinline__ cplx load_one(const GridDesc& g, int field, int l, int col, int off) const {
+    if (l_aliased(g, l)) return cmake(0.0, 0.0);
+    const int layer = field / nf, what = field - nf * layer;
+    if (what == 2) return cscale(ldcplx(sol + layer * ls + off), g.invN);
+    const double* M = Sinv + ((long long)l * ldS + col) * (nl * nl) + layer * nl;
+    cplx p = cmake(0.0, 0.0);
+    for (int m = 0; m < nl; ++m) {
+      const cplx q = ldcplx(sol + m * ls + off);
+      const double cm = __ldg(&M[m]);
+      p.x += cm * q.x;
+      p.y += cm * q.y;
+    }
+    p = cscale(p, g.invN);
+    if (what == 0) return cscale(cmul_mi(p), wav_l(g, l));
+    if (what == 1) return cscale(cmul_i(p), wav_kr(g, col));
+    return p;
+  }
+  __device__ __forceinline__ int off_one(int l, int col) const { return toff(l, col, ld); }
+  __device__ __forceinline__ void prefetch_pair(const GridDesc&, int, int, int, int) const {}
 };
 
 // K1 (generic: MultiLayerQG pre-pass and plain transforms; the single-layer hot path is k_col_inv_single below).

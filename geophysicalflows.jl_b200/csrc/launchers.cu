@@ -235,6 +235,28 @@ static int do_col_inv_16384(const ColInvLaunch& L, const Prep& prep) {
     attr.done[cur_device()] = true;
   }
   const int npairs = (L.ncols + 1) / 2;
+  // default: the lane-paired decimation-in-time kernel (one CTA per SM, every row read once, natural-order stores);
+  // GFB_K1_16K_DIT=0 selects the four independent q units per pair (kept for comparison)
+  static int dit = -1, l2pf = 0;
+  if (dit < 0) {
+    const char* e = getenv("GFB_K1_16K_DIT");
+    dit = (e && e[0] == '0') ? 0 : 1;
+    const char* f = getenv("GFB_K1_16K_PF");
+    if (f) l2pf = atoi(f);
+  }
+  if (dit) {
+    using PC = Pair16kCfg<4096>;
+    static AttrCache attr2;
+    if (!attr2.done[cur_device()]) {
+      if (set_smem(k_col_inv16k_dit<4096, Prep>, PC::SMEM)) return -2;
+      attr2.done[cur_device()] = true;
+    }
+    const int nunits = npairs * L.nfields;
+    const int nsm = sm_count();
+    GFB_LAUNCH((k_col_inv16k_dit<4096, Prep>), dim3(nunits < nsm ? nunits : nsm), dim3(PC::THREADS), PC::SMEM, L.st, L.g, prep, L.W, L.ldw,
+               L.wfs, L.ncols, L.nfields, nunits, l2pf, L.tw, L.tw2);
+    return 0;
+  }
   dim3 grid(npairs * L.nfields * 4);
   GFB_LAUNCH((k_col_inv16k<4096, Prep>), grid, dim3(GC::THREADS), smem, L.st, L.g, prep, L.W, L.ldw, L.wfs, L.ncols, L.nfields, L.tw,
              L.tw2);
@@ -262,6 +284,25 @@ int launch_col_fwd_16384(const ColFwdLaunch& L) {
     }
     GFB_LAUNCH((k_col_fwd16k_plain<4096>), grid, dim3(GC::THREADS), smem, L.st, L.g, L.P, L.ldp, L.pfs, L.e.out.p, L.e.out.ld, L.e.out.ls,
                L.ncols, L.tw, L.tw2);
+    return 0;
+  }
+  // default: the lane-paired kernel (one 512-thread CTA per column pair, rows pulled through L2 twice instead of four
+  // times); GFB_K3_16K_LP=0 selects the four independent q units per pair (kept for comparison)
+  static int lp = -1;
+  if (lp < 0) {
+    const char* e = getenv("GFB_K3_16K_LP");
+    lp = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (lp) {
+    using PC = Pair16kCfg<4096>;
+    static AttrCache attr3;
+    if (!attr3.done[cur_device()]) {
+      if (set_smem(k_col_fwd16k_lp<4096>, PC::SMEM)) return -2;
+      attr3.done[cur_device()] = true;
+    }
+    const int npairs = (L.ncols + 1) / 2;
+    GFB_LAUNCH((k_col_fwd16k_lp<4096>), dim3(2 * npairs, L.nlayers), dim3(PC::THREADS), PC::SMEM, L.st, L.g,
+               L.P, L.ldp, L.pfs, L.e, L.ncols, npairs, L.tw, L.tw2);
     return 0;
   }
   const size_t smem = (size_t)GC::XB_DOUBLES * sizeof(double) + (size_t)GC::STASH * sizeof(cplx) + 16;
