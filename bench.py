@@ -218,6 +218,24 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
+def nvlink_kib(index):
+    """NVLink data bytes of GPU `index` since boot, summed over its links, in KiB: (tx, rx) from NVML's
+    NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX / _RX field values (payload only, no protocol overhead); None if unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        out = []
+        for fid in (pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX):
+            v = pynvml.nvmlDeviceGetFieldValues(h, [(fid, 0xFFFFFFFF)])[0]  # scope UINT_MAX: all links
+            if v.nvmlReturn != 0:
+                return None
+            out.append(int(v.value.ullVal))
+        return tuple(out)
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def e2e_pipelined(prob, pkg, diag, host_sol, steps):
     """steps x (pinned host -> device state, stepforward!(prob, 1), one diagnostic to the host, device -> pinned host state),
     triple-buffered: stepforward! runs IN PLACE on the buffer the state was uploaded into (the C ABI takes the state
@@ -390,6 +408,7 @@ def run_other_config(args):
     sampler = ClockSampler(0)
     sampler.start()
     samples = []
+    nvl0 = nvlink_kib(local) if world > 1 else None
     for _ in range(max(1, args.repeats)):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
@@ -533,6 +552,7 @@ def main():
     barrier()
     sampler.start()
     samples = []
+    nvl0 = nvlink_kib(local) if world > 1 else None
     for _ in range(max(1, args.repeats)):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
@@ -541,6 +561,7 @@ def main():
         e1.record()
         barrier()
         samples.append(allmax(e0.elapsed_time(e1)))
+    nvl1 = nvlink_kib(local) if world > 1 else None
     sampler.stop_flag.set()
     sampler.join(timeout=2)
     ms = float(np.median(samples))
@@ -719,6 +740,14 @@ def main():
         line["nvlink"] = {"a2a_bytes_per_gpu_per_step": a2a_bytes, "floor_ms_at_770GBs": a2a_bytes / 770e9 * 1e3,
                           "frac_of_nvlink_floor": (a2a_bytes / 770e9 * 1e3) / ms_per_step,
                           "exchanges_per_step": 8, "transport": prob.shard.transport}
+        if nvl0 is not None and nvl1 is not None:
+            # measured on rank 0's GPU over the timed repeats (NVML link counters, payload bytes)
+            nst = args.steps * max(1, args.repeats)
+            tx, rx = (nvl1[0] - nvl0[0]) * 1024.0 / nst, (nvl1[1] - nvl0[1]) * 1024.0 / nst
+            line["nvlink"].update({"measured_tx_bytes_per_step": tx, "measured_rx_bytes_per_step": rx,
+                                   "measured_tx_gbs": tx / (ms_per_step * 1e-3) / 1e9,
+                                   "measured_vs_model": tx / a2a_bytes if a2a_bytes else None,
+                                   "measured_how": "NVML NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX/RX deltas of this rank's GPU over the timed repeats"})
     if world == 1 and not args.no_cpu_baseline and n <= 4096:  # larger grids: `--impl reference` samples them at 4096^2
         nsamp = 2 if n >= 4096 else 4
         full0 = bh0 if not forced else None

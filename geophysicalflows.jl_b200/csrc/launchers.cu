@@ -286,12 +286,14 @@ int launch_col_fwd_16384(const ColFwdLaunch& L) {
                L.ncols, L.tw, L.tw2);
     return 0;
   }
-  // default: the lane-paired kernel (one 512-thread CTA per column pair, rows pulled through L2 twice instead of four
-  // times); GFB_K3_16K_LP=0 selects the four independent q units per pair (kept for comparison)
+  // GFB_K3_16K_LP=1 selects the lane-paired kernel (one 512-thread CTA per column pair and half, rows pulled through L2
+  // twice instead of four times).  Measured on B200 (profiles/r2q_*): correct, but slower than the four independent q
+  // units per pair (20.6 vs 17.7 ms/step at 16384^2) -- one CTA per SM in lock step exposes every load phase (65 % of the
+  // warp samples on long-scoreboard stalls) -- so it stays opt-in
   static int lp = -1;
   if (lp < 0) {
     const char* e = getenv("GFB_K3_16K_LP");
-    lp = (e && e[0] == '0') ? 0 : 1;
+    lp = (e && e[0] == '1') ? 1 : 0;
   }
   if (lp) {
     using PC = Pair16kCfg<4096>;
