@@ -100,7 +100,43 @@ __device__ __forceinline__ double lddouble(const double* p) {
   return r;
 #endif
 }
+// predicated forms: zero when `on` is false, WITHOUT a branch (a branch per row puts every row's loads in their own basic
+// block and the rows are then fetched one round trip after the other)
+__device__ __forceinline__ double2 ldcplx_if(const double2* p, const bool on) {
+#ifdef GFB_EMULATE
+  return on ? *p : make_double2(0.0, 0.0);
+#else
+  double2 r;
+  asm volatile(
+      "{\n.reg .pred q;\nsetp.ne.s32 q, %3, 0;\nmov.f64 %0, 0d0000000000000000;\nmov.f64 %1, 0d0000000000000000;\n"
+      "@q ld.global.cg.v2.f64 {%0,%1}, [%2];\n}\n"
+      : "=d"(r.x), "=d"(r.y)
+      : "l"(p), "r"((int)on));
+  return r;
+#endif
+}
+__device__ __forceinline__ double lddouble_if(const double* p, const bool on) {
+#ifdef GFB_EMULATE
+  return on ? *p : 0.0;
+#else
+  double r;
+  asm volatile("{\n.reg .pred q;\nsetp.ne.s32 q, %2, 0;\nmov.f64 %0, 0d0000000000000000;\n@q ld.global.cg.f64 %0, [%1];\n}\n"
+               : "=d"(r)
+               : "l"(p), "r"((int)on));
+  return r;
+#endif
+}
 __device__ __forceinline__ void compiler_fence() { asm volatile("" ::: "memory"); }
+// Persistent kernels start all their CTAs at once on identical work: without help the whole chip loads, transforms and
+// stores in lock step (HBM bursts above the peak, then silence).  A pseudo-random per-CTA start delay in [0, ns) keeps the
+// phases of different SMs interleaved for the rest of the launch.
+__device__ __forceinline__ void cta_stagger(const int ns) {
+#ifndef GFB_EMULATE
+  if (ns > 0) __nanosleep((unsigned)(((blockIdx.x * 2654435761u) >> 16) % (unsigned)ns));
+#else
+  (void)ns;
+#endif
+}
 
 // ---- Tensor Memory (TMEM) as thread-private parking space ------------------------------------------------
 // 256 KB per SM, 512 columns x 128 lanes x 32 bit, reachable only through tcgen05.st / tcgen05.ld.  With the

@@ -41,9 +41,10 @@ template <int NY, int VAR>
 __global__ void __launch_bounds__(WS_THREADS, 1)
     k_col_inv_ws(const __grid_constant__ GridDesc g, const __grid_constant__ PrepSingle prep, const __grid_constant__ PeerOut W,
                  const int ldw, const long long wfs, const int ncols, const int nfields, const int nunits,
-                 const cplx* __restrict__ tw) {
+                 const cplx* __restrict__ tw, const int stagger_ns) {
   constexpr int T = NY / PT;
   static_assert(T == WS_FFT_THREADS, "one 256-thread FFT group: ny = 4096");
+  cta_stagger(stagger_ns);
   GFB_DYN_SMEM(double, smd);
   cplx* xb = reinterpret_cast<cplx*>(smd);  // un-split exchange buffer of the FFT group
   uint32_t* tmem_word = reinterpret_cast<uint32_t*>(xb + xbuf_elems(NY));

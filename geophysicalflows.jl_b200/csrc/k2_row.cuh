@@ -437,7 +437,9 @@ struct RowTma {
 
 template <int NX>
 __global__ void __launch_bounds__(GroupCfg<NX>::THREADS, GroupCfg<NX>::MINB)
-    k_row_product_tma(const __grid_constant__ RowArgs a, const __grid_constant__ RowTma tm, const cplx* __restrict__ tw, const int nunits) {
+    k_row_product_tma(const __grid_constant__ RowArgs a, const __grid_constant__ RowTma tm, const cplx* __restrict__ tw, const int nunits,
+                      const int stagger_ns) {
+  cta_stagger(stagger_ns);
   using RC = GroupCfg<NX>;
   constexpr int T = RC::T;
   static_assert(RC::G == 1, "one FFT group per CTA");

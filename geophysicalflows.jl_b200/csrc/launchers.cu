@@ -50,6 +50,12 @@ static int do_col_inv(const ColInvLaunch& L, const Prep& prep) {
   return 0;
 }
 
+// GFB_STAGGER_K1 / GFB_STAGGER_K2: start stagger (ns) of the persistent 4096 kernels (cta_stagger), 0 = off
+static int env_ns(const char* name) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : 0;
+}
+
 static int sm_count() {
   static int n[MAX_DEVICES] = {};
   const int dev = cur_device();
@@ -101,7 +107,9 @@ static int do_col_inv_ws_var(const ColInvLaunch& L) {
   const int nunits = ((L.ncols + 1) / 2) * L.nfields;
   const int cap = sm_count();
   dim3 grid(nunits < cap ? nunits : cap);
-  GFB_LAUNCH((k_col_inv_ws<GFB_N, VAR>), grid, dim3(WS_THREADS), smem, L.st, L.g, L.ps, L.W, L.ldw, L.wfs, L.ncols, L.nfields, nunits, L.tw);
+  static const int stagger = env_ns("GFB_STAGGER_K1");
+  GFB_LAUNCH((k_col_inv_ws<GFB_N, VAR>), grid, dim3(WS_THREADS), smem, L.st, L.g, L.ps, L.W, L.ldw, L.wfs, L.ncols, L.nfields, nunits, L.tw,
+             stagger);
   return 0;
 }
 static int do_col_inv_ws(const ColInvLaunch& L) {
@@ -182,7 +190,8 @@ static int do_row_product_tma(const RowLaunch& L) {
   const int nunits = (L.a.ny / 2) * L.nlayers;
   const int cap = sm_count() * RC::MINB;
   dim3 grid(nunits < cap ? nunits : cap);
-  GFB_LAUNCH((k_row_product_tma<GFB_N>), grid, dim3(RC::THREADS), smem, L.st, L.a, t, L.tw, nunits);
+  static const int stagger = env_ns("GFB_STAGGER_K2");
+  GFB_LAUNCH((k_row_product_tma<GFB_N>), grid, dim3(RC::THREADS), smem, L.st, L.a, t, L.tw, nunits, stagger);
   return 0;
 }
 #endif
