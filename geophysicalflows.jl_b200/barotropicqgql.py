@@ -7,18 +7,18 @@ import numpy as np
 import torch
 
 from . import _lib
-from .device import GPU
-from .grid import TwoDGrid
+from .device import GPU, typed
+from .grid import TwoDGrid, _np_float
 from .timesteppers import Equation, Problem as _Problem
 from .twodnavierstokes import _make_shard, _ps, _sharded, _vars
 from .twodnavierstokes import calcN_  # noqa: F401  (calcN! + addforcing!, src/barotropicqgql.jl:345-377: same seam)
 
 
 def Problem(dev=None, nx=256, ny=None, Lx=2 * np.pi, Ly=None, beta=0.0, eta=None, nu=0.0, nnu=1, mu=0.0, dt=0.01,
-            stepper="RK4", calcF=None, stochastic=False, aliased_fraction=1 / 3, shard=None):
+            stepper="RK4", calcF=None, stochastic=False, aliased_fraction=1 / 3, shard=None, T=np.float64):
     """src/barotropicqgql.jl:62-99.  `eta` is stored in params like the reference does; its calcN_advection! never reads it."""
-    dev = GPU() if dev is None else dev
-    grid = TwoDGrid(dev, nx, Lx, ny, Ly, aliased_fraction=aliased_fraction)
+    dev = typed(GPU() if dev is None else dev, T)
+    grid = TwoDGrid(dev, nx, Lx, ny, Ly, aliased_fraction=aliased_fraction, T=_np_float(T))
     x, y = grid.gridpoints()
     if eta is None:
         eta_on_grid = np.zeros((grid.ny, grid.nx))

@@ -35,8 +35,15 @@ __device__ __forceinline__ uint32_t ws_tmem_base(uint32_t base) {
   return base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(((warp >> 2) & 1) * 256);
 }
 
+__device__ __forceinline__ cpair zero_pair_k1() {
+  cpair z;
+  z.a = z.b = cmake(0.0, 0.0);
+  return z;
+}
+
 // VAR: experiment switches (tools/, GFB_K1WS_VAR): bit 0 = twiddles in registers, bit 1 = L2 bulk prefetch of the next
-// unit, bit 2 = all 16 rows in one load batch (else two batches of 8), bit 3 = .x64 TMEM load of the input slot
+// unit, bit 2 = all 16 rows in one load batch (else two batches of 8), bit 3 = .x64 TMEM load of the input slot,
+// bit 4 = the helper group reads whole sectors and prepares both columns of a unit in one pass
 template <int NY, int VAR>
 __global__ void __launch_bounds__(WS_THREADS, 1)
     k_col_inv_ws(const __grid_constant__ GridDesc g, const __grid_constant__ PrepSingle prep, const __grid_constant__ PeerOut W,
@@ -59,7 +66,54 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
   const int nmine = (nunits - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int ncolumns = 2 * nmine;
 
-  if (!is_fft) {
+  if (!is_fft && (VAR & 16)) {
+    // ---------------- helper group, pair form: BOTH columns of a unit from one pass over the rows -----------------------
+    // The per-column form below reads every 32-byte sector twice (once per column, 16 bytes each time) and spends two
+    // memory round trips per column; ncu showed the FFT group waiting on the helper more than half of the time.  Here a
+    // thread reads whole sectors (state pair + G pair, eight rows = 96 registers in flight per batch), prepares the values
+    // of both columns and streams them straight into the two input slots: half the load instructions, two round trips per
+    // UNIT.  Same barrier protocol: one EMPTY wait and one FULL arrive per column.
+#pragma unroll 1
+    for (int u = 0; u < nmine; ++u) {
+      const int unit = (int)blockIdx.x + u * (int)gridDim.x;
+      const int field = unit % nfields, colA = 2 * (unit / nfields);
+      const bool liveA = colA < ncols, liveB = colA + 1 < ncols;
+      const double krA = wav_kr(g, colA), krB = wav_kr(g, colA + 1);
+      const int off0 = toff(j, colA, prep.ld);
+#pragma unroll
+      for (int h = 0; h < PT; h += 8) {
+        cpair raw[8];
+        double2 gg[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int r = h + q;
+          const bool on = liveA && !l_aliased(g, j + r * T);
+          const int off = off0 + r * T * prep.ld;  // T % 8 == 0: the tiled layout is affine in r
+          raw[q] = on ? ldpair(prep.sol + off) : zero_pair_k1();
+          gg[q] = (on && field != 2) ? ldpair_d(prep.G + off) : make_double2(0.0, 0.0);
+        }
+        if (h == 0 && u >= 1) {  // the FFT group has taken both columns of the previous unit out of the slots
+          bar_sync(WS_BAR_EMPTY + 0, WS_THREADS);
+          bar_sync(WS_BAR_EMPTY + 1, WS_THREADS);
+          tmem_fence_after_sync();
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int r = h + q, l = j + r * T;
+          const bool on = liveA && !l_aliased(g, l);
+          const double ll = wav_l(g, l);
+          const cplx ta = prep.apply(g, field, ll, krA, gg[q].x, raw[q].a);
+          const cplx tb = prep.apply(g, field, ll, krB, gg[q].y, raw[q].b);
+          tmem_store(t_in[0] + 4 * r, cmake(on ? ta.x : 0.0, on ? ta.y : 0.0));
+          tmem_store(t_in[1] + 4 * r, cmake(on && liveB ? tb.x : 0.0, on && liveB ? tb.y : 0.0));
+        }
+      }
+      tmem_wait_st();
+      tmem_fence_before_sync();
+      bar_arrive(WS_BAR_FULL + 0, WS_THREADS);
+      bar_arrive(WS_BAR_FULL + 1, WS_THREADS);
+    }
+  } else if (!is_fft) {
     // ---------------- helper group: raw state + G -> masked, inverted, differentiated column -> TMEM slot -------------
 #pragma unroll 1
     for (int n = 0; n < ncolumns; ++n) {

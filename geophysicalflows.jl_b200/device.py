@@ -32,6 +32,33 @@ class Device:
         return t.to(self.torch_device).contiguous()
 
 
+class TypedDevice(Device):
+    """`Problem(dev; T = Float32)` (/root/reference/src/twodnavierstokes.jl:89): the same device, but every array the
+    problem owns (sol, vars, transform outputs) is allocated in `T` / `Complex{T}`.  The library computes in Float64: the
+    Float32 arrays are widened on the way in and rounded on the way out of every C-ABI call (timesteppers.Problem._p)."""
+    _MAP = {torch.float64: torch.float32, torch.complex128: torch.complex64}
+
+    def __init__(self, dev):
+        super().__init__(dev.torch_device, dev.lib)
+
+    def zeros(self, shape, dtype):
+        return super().zeros(shape, self._MAP.get(dtype, dtype))
+
+    def array(self, a, dtype=None):
+        t = super().array(a, dtype)
+        return t.to(self._MAP.get(t.dtype, t.dtype))
+
+
+def typed(dev, T):
+    """dev for T = Float64 (numpy float64 / torch.float64 / "Float64"), a TypedDevice for Float32"""
+    name = str(T).split(".")[-1].lower().replace("'>", "")
+    if name in ("float64", "double"):
+        return dev
+    if name in ("float32", "single"):
+        return dev if isinstance(dev, TypedDevice) else TypedDevice(dev)
+    raise _lib.GfbError("T must be Float32 or Float64, got %r" % (T,))
+
+
 _gpu = {}
 
 

@@ -20,9 +20,16 @@ def getaliasedwavenumbers(nk, nkr, aliased_fraction):
     return (nk // 2 + 1, nk // 2 + 1), (nkr, nkr)
 
 
+def _np_float(T):
+    """numpy float type of a `T` given as numpy / torch dtype or name"""
+    name = str(T).split(".")[-1].lower().replace("'>", "")
+    return np.float32 if name in ("float32", "single") else np.float64
+
+
 class TwoDGrid:
-    def __init__(self, dev, nx, Lx, ny=None, Ly=None, x0=None, y0=None, aliased_fraction=1 / 3):
+    def __init__(self, dev, nx, Lx, ny=None, Ly=None, x0=None, y0=None, aliased_fraction=1 / 3, T=np.float64):
         self.device = dev
+        self.T = np.dtype(T).type
         self.nx, self.ny = int(nx), int(nx if ny is None else ny)
         self.Lx, self.Ly = float(Lx), float(Lx if Ly is None else Ly)
         self.nk, self.nl, self.nkr = self.nx, self.ny, self.nx // 2 + 1
@@ -41,6 +48,11 @@ class TwoDGrid:
         self.invKrsq = np.zeros_like(self.Krsq)
         nz = self.Krsq != 0
         self.invKrsq[nz] = 1 / self.Krsq[nz]
+        if self.T is not np.float64:  # TwoDGrid{T}: coordinates, wavenumbers and lengths carry the problem's float type
+            for name in ("x", "y", "kr", "l", "Krsq", "invKrsq"):
+                setattr(self, name, getattr(self, name).astype(self.T))
+            for name in ("Lx", "Ly", "dx", "dy"):
+                setattr(self, name, self.T(getattr(self, name)))
         self.kalias, self.kralias = getaliasedwavenumbers(self.nk, self.nkr, aliased_fraction)
         self.lalias, _ = getaliasedwavenumbers(self.nl, self.nl // 2 + 1, aliased_fraction)
 

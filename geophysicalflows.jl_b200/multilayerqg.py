@@ -7,8 +7,8 @@ import numpy as np
 import torch
 
 from . import _lib
-from .device import GPU
-from .grid import TwoDGrid
+from .device import GPU, typed
+from .grid import TwoDGrid, _np_float
 from .timesteppers import Equation, Problem as _Problem
 from .twodnavierstokes import _make_shard
 
@@ -31,13 +31,13 @@ def convert_U_to_U3D(nlayers, grid, U):
 
 def Problem(nlayers, dev=None, nx=128, ny=None, Lx=2 * np.pi, Ly=None, f0=1.0, beta=0.0, U=None, H=None, b=None,
             eta=None, topographic_pv_gradient=(0.0, 0.0), mu=0.0, nu=0.0, nnu=1, dt=0.01, stepper="RK4",
-            calcFq=None, stochastic=False, linear=False, aliased_fraction=1 / 3, shard=None):
+            calcFq=None, stochastic=False, linear=False, aliased_fraction=1 / 3, shard=None, T=np.float64):
     """src/multilayerqg.jl:87-135."""
-    dev = GPU() if dev is None else dev
+    dev = typed(GPU() if dev is None else dev, T)
     U = np.zeros(nlayers) if U is None else U
     H = np.ones(nlayers) / nlayers if H is None else H
     b = -(1 + np.arange(nlayers) / nlayers) if b is None else b
-    grid = TwoDGrid(dev, nx, Lx, ny, Ly, aliased_fraction=aliased_fraction)
+    grid = TwoDGrid(dev, nx, Lx, ny, Ly, aliased_fraction=aliased_fraction, T=_np_float(T))
     params = Params(nlayers, f0, beta, b, H, U, eta, topographic_pv_gradient, mu, nu, nnu, grid, calcFq)
     n = nlayers
     shard = _make_shard(shard, grid)

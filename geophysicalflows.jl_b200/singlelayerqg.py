@@ -9,18 +9,18 @@ import numpy as np
 import torch
 
 from . import _lib
-from .device import GPU
-from .grid import TwoDGrid
+from .device import GPU, typed
+from .grid import TwoDGrid, _np_float
 from .timesteppers import Equation, Problem as _Problem
 from .twodnavierstokes import _vars, _ps, _spectral_vars, _make_shard, _sharded, calcN_ as _calcN_common
 
 
 def Problem(dev=None, nx=256, ny=None, Lx=2 * np.pi, Ly=None, beta=0.0, deformation_radius=np.inf, U=0.0,
             eta=None, nu=0.0, nnu=1, mu=0.0, dt=0.01, stepper="RK4", calcF=None, stochastic=False,
-            aliased_fraction=1 / 3, shard=None):
+            aliased_fraction=1 / 3, shard=None, T=np.float64):
     """src/singlelayerqg.jl:80-121."""
-    dev = GPU() if dev is None else dev
-    grid = TwoDGrid(dev, nx, Lx, ny, Ly, aliased_fraction=aliased_fraction)
+    dev = typed(GPU() if dev is None else dev, T)
+    grid = TwoDGrid(dev, nx, Lx, ny, Ly, aliased_fraction=aliased_fraction, T=_np_float(T))
     params = Params(grid, deformation_radius, beta, U, eta, mu, nu, nnu, calcF)
     shard = _make_shard(shard, grid)
     vars = _vars(dev, grid, calcF is not None, stochastic, phys=("q", "psi", "u", "v"),

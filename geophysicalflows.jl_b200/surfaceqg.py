@@ -5,8 +5,8 @@ import numpy as np
 import torch
 
 from . import _lib
-from .device import GPU
-from .grid import TwoDGrid
+from .device import GPU, typed
+from .grid import TwoDGrid, _np_float
 from .timesteppers import Equation, Problem as _Problem
 from .twodnavierstokes import _vars, _ps, _make_shard, _sharded
 
@@ -21,10 +21,10 @@ def psihfrombh(H, grid):
 
 
 def Problem(dev=None, nx=256, ny=None, Lx=2 * np.pi, Ly=None, H=np.inf, nu=0.0, nnu=1, dt=0.01,
-            stepper="RK4", calcF=None, stochastic=False, aliased_fraction=1 / 3, shard=None):
+            stepper="RK4", calcF=None, stochastic=False, aliased_fraction=1 / 3, shard=None, T=np.float64):
     """src/surfaceqg.jl:65-93."""
-    dev = GPU() if dev is None else dev
-    grid = TwoDGrid(dev, nx, Lx, ny, Ly, aliased_fraction=aliased_fraction)
+    dev = typed(GPU() if dev is None else dev, T)
+    grid = TwoDGrid(dev, nx, Lx, ny, Ly, aliased_fraction=aliased_fraction, T=_np_float(T))
     params = SimpleNamespace(H=float(H), nu=float(nu), nnu=nnu, calcF=calcF, psihfrombh=psihfrombh(H, grid))
     shard = _make_shard(shard, grid)
     vars = _vars(dev, grid, calcF is not None, stochastic, phys=("b", "u", "v"), spec=("bh", "uh", "vh"), shard=shard)

@@ -163,7 +163,10 @@ class Problem:
         self.nlayers = eqn.dims[0] if len(eqn.dims) == 3 else 1
         self.shard = shard
         nkl = grid.nkr if shard is None else shard.nkl
-        self.sol = self.dev.zeros(tuple(eqn.dims[:-1]) + (nkl,), torch.complex128)
+        self.sol = self.dev.zeros(tuple(eqn.dims[:-1]) + (nkl,), torch.complex128)  # Complex{T} on a TypedDevice
+        if self.sol.dtype != torch.complex128 and shard is not None and shard.nranks > 1:
+            raise _lib.GfbError("T = Float32 problems are single-GPU (the sharded transports exchange Float64 buffers)")
+        self._pending = []
         self._keep = []  # host arrays referenced by the config during gfb_create
         cfg = _lib.new_config()
         cfg.kind = kind
@@ -236,13 +239,22 @@ class Problem:
 
     # -- thin checked wrappers over the C ABI ------------------------------------------------
     def _check(self, rc, what):
+        pending, self._pending = getattr(self, "_pending", []), []
         if rc != 0:
             raise _lib.GfbError("%s failed (%d): %s" % (what, rc, self.lib.gfb_last_error(self.ctx).decode()))
+        for t, wide in pending:  # Float32 problems: round the library's Float64 results back into the caller's arrays
+            t.copy_(wide)
 
     def _p(self, t):
+        """device pointer of a Float64 / ComplexF64 tensor.  Float32 / ComplexF32 tensors (T = Float32 problems) are
+        widened into a temporary for the call; _check copies the temporary back afterwards"""
         if t is None:
             return None
         assert t.is_contiguous() and t.device == self.sol.device
+        if t.dtype in (torch.float32, torch.complex64):
+            wide = t.to(torch.float64 if t.dtype == torch.float32 else torch.complex128)
+            self._pending = getattr(self, "_pending", []) + [(t, wide)]
+            return wide.data_ptr()
         return t.data_ptr()
 
     def _connect_p2p(self):

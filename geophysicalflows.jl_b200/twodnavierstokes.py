@@ -6,16 +6,16 @@ import numpy as np
 import torch
 
 from . import _lib
-from .device import GPU
-from .grid import TwoDGrid
+from .device import GPU, typed
+from .grid import TwoDGrid, _np_float
 from .timesteppers import Equation, Problem as _Problem, Shard
 
 
 def Problem(dev=None, nx=256, ny=None, Lx=2 * np.pi, Ly=None, nu=0.0, nnu=1, mu=0.0, nmu=0, dt=0.01,
-            stepper="RK4", calcF=None, stochastic=False, aliased_fraction=1 / 3, shard=None):
+            stepper="RK4", calcF=None, stochastic=False, aliased_fraction=1 / 3, shard=None, T=np.float64):
     """src/twodnavierstokes.jl:71-100."""
-    dev = GPU() if dev is None else dev
-    grid = TwoDGrid(dev, nx, Lx, ny, Ly, aliased_fraction=aliased_fraction)
+    dev = typed(GPU() if dev is None else dev, T)
+    grid = TwoDGrid(dev, nx, Lx, ny, Ly, aliased_fraction=aliased_fraction, T=_np_float(T))
     params = SimpleNamespace(nu=float(nu), nnu=nnu, mu=float(mu), nmu=nmu, calcF=calcF)
     shard = _make_shard(shard, grid)
     vars = _vars(dev, grid, calcF is not None, stochastic, shard=shard)

@@ -1,0 +1,67 @@
+"""`Problem(dev; T = Float32)`: the reference's `problemtype` tests (/root/reference/test/test_twodnavierstokes.jl:319-325,
+test_singlelayerqg.jl, test_multilayerqg.jl, test_surfaceqg.jl, test_barotropicqgql.jl, called with Float32 from
+test/runtests.jl) plus what they leave open: such a problem steps, and its Float32 state tracks the Float64 one.
+
+A Float32 problem here keeps `sol`, `vars` and the grid in Float32 / ComplexF32 exactly as the reference does; the
+library computes in Float64 (the arrays are widened on the way into every C-ABI call and rounded on the way out), so
+the result differs from a Float64 run by Float32 rounding of the state only."""
+import numpy as np
+import pytest
+import torch
+
+import refcases as R
+
+
+def _backend(kind):
+    import backends
+    return backends.emu_backend() if kind == "emu" else backends.gpu_backend()
+
+
+KINDS = [pytest.param("emu", id="emulated"), pytest.param("gpu", marks=pytest.mark.gpu, id="gpu")]
+
+
+def _problems(B, T):
+    yield "twodnavierstokes", B.twodnavierstokes.Problem(nx=32, T=T), "u"
+    yield "surfaceqg", B.surfaceqg.Problem(nx=32, T=T), "u"
+    yield "singlelayerqg", B.singlelayerqg.Problem(nx=32, deformation_radius=1.23, U=0.3, T=T), "u"
+    yield "barotropicqgql", B.barotropicqgql.Problem(nx=32, T=T), "u"
+    yield "multilayerqg", B.multilayerqg.Problem(2, nx=32, T=T), "u"
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("T", [np.float32, np.float64])
+def test_problemtype(kind, T):
+    B = _backend(kind)
+    real, cplx = (torch.float32, torch.complex64) if T is np.float32 else (torch.float64, torch.complex128)
+    for name, prob, field in _problems(B, T):
+        assert prob.sol.dtype == cplx, name
+        assert (type(prob.grid.Lx) is np.float32 if T is np.float32 else isinstance(prob.grid.Lx, float)), name
+        assert prob.grid.x.dtype == T, name
+        assert getattr(prob.vars, field).dtype == real, name
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_float32_problem_steps_like_the_float64_one(kind):
+    B = _backend(kind)
+    kw = dict(nx=64, ny=32, Lx=2 * np.pi, Ly=3.0, nu=1e-3, nnu=1, dt=5e-3, stepper="FilteredRK4")
+    p64 = B.twodnavierstokes.Problem(**kw)
+    p32 = B.twodnavierstokes.Problem(T="Float32", **kw)
+    rng = np.random.default_rng(32)
+    s0 = (np.fft.rfft2(rng.standard_normal((32, 64))) / 40).astype(np.complex64)  # representable in both
+    p64.sol.copy_(B.dev(s0.astype(np.complex128)))
+    p32.sol.copy_(B.dev(s0))
+    B.stepforward_(p64, 10)
+    B.stepforward_(p32, 10)
+    assert p32.sol.dtype == torch.complex64
+    err = R.relerr(B.host(p32.sol).astype(np.complex128), B.host(p64.sol))
+    assert 0 < err < 5e-6, err  # Float32 rounding of the state once per stepforward! call, nothing more
+    e64, e32 = B.twodnavierstokes.energy(p64), B.twodnavierstokes.energy(p32)
+    assert abs(e32 / e64 - 1) < 1e-5
+    B.twodnavierstokes.updatevars_(p32)
+    assert p32.vars.u.dtype == torch.float32 and bool(torch.isfinite(p32.vars.u).all())
+
+
+def test_float32_refuses_unknown_types():
+    B = _backend("emu")
+    with pytest.raises(Exception, match="Float32 or Float64"):
+        B.twodnavierstokes.Problem(nx=32, T="Float16")
