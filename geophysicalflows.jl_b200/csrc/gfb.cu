@@ -53,6 +53,7 @@ struct gfb_ctx {
   long long ils = 0;  // layer stride of ctx-owned spectral arrays
   cplx* st[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // stage states / accumulators / histories
   cplx *S0 = nullptr, *Fint = nullptr, *PV = nullptr, *Cin = nullptr, *Nint = nullptr;  // tiled copies of user arrays
+  cplx* ALT = nullptr;  // layered kind with a one-stage stepper (ForwardEuler, AB3): the state ping-pongs S0 <-> ALT (plan_stage)
   double *dpart = nullptr, *dout = nullptr;
   // diagnostics come back through a mapped pinned buffer the final reduction kernel writes itself: no copy engine is
   // involved (a cudaMemcpy to the caller's pageable memory serialised against in-flight PCIe transfers of other streams,
@@ -129,6 +130,16 @@ static int check_launch(gfb_ctx* c, int rc, const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(c, GFB_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
   return 0;
+}
+
+template <class T>
+static int dev_alloc(gfb_ctx* c, T** p, size_t n);
+static int nstages_of_stepper(int stepper) {
+  switch (stepper) {
+    case GFB_RK4: case GFB_FILTERED_RK4: case GFB_ETDRK4: case GFB_FILTERED_ETDRK4: return 4;
+    case GFB_LSRK54: case GFB_FILTERED_LSRK54: return 5;
+    default: return 1;
+  }
 }
 
 template <class T>
@@ -520,6 +531,10 @@ int gfb_create(gfb_ctx** out, const gfb_config* cfg) {
     TRY(dev_alloc(c, &c->st[i], (size_t)n * c->ils));
     GFB_CUDA(c, cudaMemset(c->st[i], 0, (size_t)n * c->ils * sizeof(cplx)));
   }
+  if (cfg->kind == GFB_KIND_LAYERED && nstages_of_stepper(cfg->stepper) == 1) {
+    TRY(dev_alloc(c, &c->ALT, (size_t)n * c->ils));
+    GFB_CUDA(c, cudaMemset(c->ALT, 0, (size_t)n * c->ils * sizeof(cplx)));
+  }
   {
     cplx** arrs[5] = {&c->S0, &c->Fint, &c->PV, &c->Cin, &c->Nint};
     for (auto a : arrs) {
@@ -821,13 +836,7 @@ static EpiArgs base_epi(const gfb_ctx* c, bool forced) {
   return e;
 }
 
-static int nstages_of(const gfb_ctx* c) {
-  switch (c->stepper) {
-    case GFB_RK4: case GFB_FILTERED_RK4: case GFB_ETDRK4: case GFB_FILTERED_ETDRK4: return 4;
-    case GFB_LSRK54: case GFB_FILTERED_LSRK54: return 5;
-    default: return 1;
-  }
-}
+static int nstages_of(const gfb_ctx* c) { return nstages_of_stepper(c->stepper); }
 
 // Which array feeds stage `istage` and what its epilogue does.
 // prune = 1 ("lazy alias band"): the aliased band of N -- which only ever lands in the aliased band of the next
@@ -921,8 +930,16 @@ static int plan_stage(gfb_ctx* c, int istage, bool forced, bool want_prevsol, in
       e.prevsol = pv;
     } break;
   }
+  // Layered kind: the bottom-drag term of a layer reads the stage input of ALL layers (epi_addends), which the CTAs of the
+  // other layers would be overwriting if a one-stage stepper updated S0 in place (seen on hardware as a run-to-run
+  // varying 1e-9 error of the bottom layer under AB3).  ForwardEuler / AB3 therefore write the new state to ALT and
+  // commit_stage swaps the two pointers once the stage is enqueued.
+  if (c->ALT && e.out.p == S0.p) e.out = int_spec(c, c->ALT);
   e.sin = sin;
   return 0;
+}
+static void commit_stage(gfb_ctx* c, const EpiArgs& e) {
+  if (c->ALT && e.out.p == c->ALT) std::swap(c->S0, c->ALT);
 }
 
 static bool is_ab3(const gfb_ctx* c) { return c->stepper == GFB_AB3 || c->stepper == GFB_FILTERED_AB3; }
@@ -936,6 +953,7 @@ static int do_stage(gfb_ctx* c, int istage, bool forced, bool want_prevsol, int 
   if ((rc = run_col_inv_state(c, sin, 3, out_local(c->W), st))) return rc;
   if ((rc = run_row_product(c, c->W, out_local(c->P), e.prune != 0, st))) return rc;
   if ((rc = run_col_fwd(c, e, c->P, st))) return rc;
+  commit_stage(c, e);
   if (istage == nstages_of(c) - 1) {
     c->t += c->dt;
     c->step += 1;
@@ -1123,6 +1141,7 @@ int gfb_step_p2p(gfb_ctx* c, void* sol_local, int nsteps, const void* Fh_local, 
       if ((rc = run_row_product(c, wrecv, pout, e.prune != 0, st))) return rc;
       if ((rc = peer_barrier(c, st))) return rc;
       if ((rc = run_col_fwd(c, e, precv, st))) return rc;
+      commit_stage(c, e);
     }
     c->t += c->dt;
     c->step += 1;
@@ -1272,6 +1291,7 @@ int gfb_stage_post(gfb_ctx* c, int istage, const void* precv, const void* Fh_loc
   EpiArgs e;
   if ((rc = plan_stage(c, istage, Fh_local != nullptr, prevsol_local != nullptr, prune, sin, e))) return rc;
   if ((rc = run_col_fwd(c, e, (const cplx*)precv, st))) return rc;
+  commit_stage(c, e);
   if (istage == 0 && prevsol_local && (rc = export_spec(c, prevsol_local, c->PV, st))) return rc;
   if (istage == nstages_of(c) - 1) {
     c->t += c->dt;

@@ -85,6 +85,12 @@ CASES = {
     "sqg_etdrk4_512": ("surfaceqg", dict(nx=512, ny=512, Lx=2 * np.pi, nu=1e-8, nnu=2, dt=1e-3, stepper="FilteredETDRK4"), 5, 0),
     "twodns_rk4_rect": ("twodnavierstokes", dict(nx=1024, ny=256, Lx=2 * np.pi, Ly=3.0, nu=1e-5, nnu=1, mu=0.01, nmu=0,
                                                  dt=5e-4, stepper="RK4"), 4, 0),
+    # 16384-point lines on the sharded path (rows as half-length transforms; columns by the lane-paired kernel whose
+    # natural-order stores go straight into the peers' buffers), the hardware twins of the gloo emulation cases
+    "twodns_16384_rows": ("twodnavierstokes", dict(nx=16384, ny=32, Lx=2 * np.pi, Ly=3.0, nu=1e-4, nnu=1, mu=0.01, nmu=0,
+                                                   dt=1e-3, stepper="ETDRK4"), 2, 0),
+    "twodns_16384_cols": ("twodnavierstokes", dict(nx=32, ny=16384, Lx=2 * np.pi, Ly=3.0, nu=1e-4, nnu=1, mu=0.01, nmu=0,
+                                                   dt=1e-3, stepper="FilteredRK4"), 2, 0),
     "mqg3_frk4": ("multilayerqg", dict(nx=128, ny=256, Lx=2 * np.pi, f0=1.0, beta=0.5, mu=0.05, nu=1e-5,
                                         H=[0.25, 0.25, 0.5], b=[-1.0, -1.2, -1.4], U=[0.3, 0.1, 0.0], dt=1e-3,
                                         stepper="FilteredRK4"), 3, 3),

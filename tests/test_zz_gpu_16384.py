@@ -39,3 +39,42 @@ def test_16384_plain_transforms(gpu, nx, ny):
     ah = prob.rfft(gpu.dev(a))
     assert R.relerr(gpu.host(ah), np.fft.rfft2(a)) < 1e-14
     assert R.relerr(gpu.host(prob.irfft(ah)), a) < 1e-14
+
+
+@pytest.mark.timeout(600)
+def test_16384_squared_invariants(gpu):
+    """BASELINE configs[4]'s grid at FULL size on one GPU (the oracle cannot finish a 16384^2 step in test time): the
+    size-independent properties of the path.  (1) ldiv!(mul!(a)) = a and Parseval's identity through the half-length row
+    kernels and the 4 x 4096 column kernels; (2) inviscid, unforced TwoDNavierStokes conserves energy and enstrophy: two RK4
+    steps from a smooth random vorticity field move neither by more than 1e-10 (any indexing fault of the 64-bit tiled
+    offsets, the pruned band or the lane-paired stores breaks this at the 1e-2 level)."""
+    import torch
+    n = 16384
+    M = gpu.twodnavierstokes
+    prob = M.Problem(nx=n, Lx=2 * np.pi, nu=0.0, nnu=1, dt=1e-4, stepper="RK4")
+    g = torch.Generator(device=prob.sol.device).manual_seed(16384)
+    a = torch.randn((n, n), dtype=torch.float64, device=prob.sol.device, generator=g)
+    ah = prob.rfft(a)
+    w = torch.full((n // 2 + 1,), 2.0, dtype=torch.float64, device=a.device)
+    w[0] = w[-1] = 1.0
+    pars = float(((ah.real**2 + ah.imag**2) * w).sum()) / (float(n) ** 2)
+    assert abs(pars / float((a * a).sum()) - 1) < 1e-12
+    back = prob.irfft(ah)
+    assert float((back - a).abs().max()) < 1e-11
+    del back, ah, a
+    # smooth random vorticity: modes |kr|, |l| <= 24, Hermitian on the kr = 0 column through an rfft of a real field
+    small = np.random.default_rng(5).standard_normal((64, 64))
+    sh = np.fft.rfft2(small)[:, :25]
+    prob.sol.zero_()
+    blk = gpu.dev(sh * (n * n) / (64 * 64) * 0.5)
+    prob.sol[:25, :25] = blk[:25]
+    prob.sol[-24:, :25] = blk[-24:]
+    e0, z0 = M.energy(prob), M.enstrophy(prob)
+    assert e0 > 0 and z0 > 0
+    gpu.stepforward_(prob, 2)
+    e1, z1 = M.energy(prob), M.enstrophy(prob)
+    assert abs(e1 / e0 - 1) < 1e-10, (e0, e1)
+    assert abs(z1 / z0 - 1) < 1e-10, (z0, z1)
+    assert bool(torch.isfinite(prob.sol.real).all())
+    moved = float((prob.sol[:25, :25] - blk[:25]).abs().max() / blk.abs().max())
+    assert moved > 1e-6  # the field did advect
