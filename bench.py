@@ -305,8 +305,8 @@ def oracle_problem(cfg):
 def workload_name(cfg):
     n = cfg["nx"]
     if cfg["module"] == "SurfaceQG":
-        return "SurfaceQG decaying %d^2 ETDRK4 Float64 (BASELINE.json configs[3])" % n
-    return "TwoDNavierStokes stochastically forced %d^2 ETDRK4 Float64 (BASELINE.json configs[4] at the largest supported size)" % n
+        return "SurfaceQG decaying %d^2 %s Float64 (BASELINE.json configs[3])" % (n, cfg["stepper"])
+    return "TwoDNavierStokes stochastically forced %d^2 %s Float64 (BASELINE.json configs[4] at the largest supported size)" % (n, cfg["stepper"])
 
 
 def cpu_steps(cfg, bh0, nsteps, warmup):
@@ -454,6 +454,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "cufft"])
     ap.add_argument("--workload", default=None,
                     help="sqgN | twodnsN | slqgN | mqg<layers>_N; default: sqg4096 on one GPU (BASELINE configs[3]), twodns16384 on several (configs[4])")
+    ap.add_argument("--stepper", default=None, help="override the workload's stepper (e.g. FilteredRK4: the RK4 form of north_star's 60 %% target)")
     ap.add_argument("--repeats", type=int, default=5, help="the K timed steps are repeated this often; the median is reported")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cufft", action="store_true")
@@ -486,6 +487,9 @@ def main():
     dev = pkg.GPU(local)
     torch.cuda.set_device(local)
     cfg = workload(args.workload)
+    if args.stepper:  # side line: the cuFFT arm and the CPU sample restate the ETDRK4 sequence, so they are skipped
+        cfg["stepper"] = args.stepper
+        args.no_cufft = args.no_cpu_baseline = True
     n = cfg["nx"]
     # N > 1: ONE problem slab-sharded over the N GPUs (strong scaling): y-slabs in physical space, round-robin kr column
     # pairs in spectral space, one exchange per 2-D transform direction and stage
@@ -727,7 +731,7 @@ def main():
     if world > 1:
         # strong-scaling reference: the SAME workload measured on one GPU of this pool (committed bench line; the 16384^2
         # problem needs 46 GB and fits one B200), so that N-GPU lines can be read as t1 / (N tN) without re-running it
-        refs = {"twodns16384": "r2j_twodns16384_1gpu.json", "sqg4096": "r2k_bench.json"}
+        refs = {"twodns16384": "r2x_twodns16384_1gpu.json", "sqg4096": "r2x_bench100.json"}
         try:
             ref = json.loads(open(os.path.join(ROOT, "profiles", refs[args.workload])).read().strip().splitlines()[-1])
             if ref["n_gpus"] == 1 and ref["config"]["workload"] == workload_name(cfg):

@@ -2,7 +2,6 @@
 GPU over NCCL, the CUDA library through the C ABI, gathered state and all-reduced diagnostics against the
 oracle on the same seeded input (north_star tolerance 1e-10; measured ~1e-14)."""
 import os
-import socket
 import sys
 
 import numpy as np
@@ -15,20 +14,26 @@ ROOT = os.path.dirname(HERE)
 
 
 def _free_port():
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    p = s.getsockname()[1]
-    s.close()
-    return p
+    """a rendezvous FILE, not a port: a port probed here and re-bound by rank 0 a moment later collided once with a socket of
+    the previous test's NCCL bootstrap (EADDRINUSE on the GPU box, r2aa), and the other rank then hung until the timeout"""
+    import tempfile
+    fd, path = tempfile.mkstemp(prefix="gfb_rdzv_")
+    os.close(fd)
+    os.unlink(path)
+    return path
+
+
+def _init(rank, world, rdzv):
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method="file://" + rdzv, rank=rank, world_size=world, device_id=torch.device("cuda", rank))
 
 
 def _worker(rank, world, port, case, transport, out_q):
     import torch.distributed as dist
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     sys.path.insert(0, ROOT)
     sys.path.insert(0, HERE)
-    torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    _init(rank, world, port)
     try:
         import gfb_loader
         import refcases as R
@@ -125,11 +130,9 @@ def test_sharded_gpus_match_oracle(case, transport):
 
 def _transform_worker(rank, world, port, out_q):
     import torch.distributed as dist
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     sys.path.insert(0, ROOT)
     sys.path.insert(0, HERE)
-    torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    _init(rank, world, port)
     try:
         import gfb_loader
         import refcases as R
