@@ -12,6 +12,7 @@ Prints ONE JSON line (rank 0).
 """
 import argparse
 import json
+import re
 import os
 import subprocess
 import sys
@@ -36,7 +37,12 @@ def kernel_functions(n, info):
     """which kernel serves each class for this context (gfb_path_info); spelled as ncu prints the instantiation, which is
     the key of profiles/ncu_traffic.json"""
     ws_r, ws_c = info.get("row_ws"), info.get("col_ws")
-    return {"k_col_inv": ("k_col_inv_ws<%d,%d>" % (n, int(os.environ.get("GFB_K1WS_VAR", "0")))) if ws_c else "k_col_inv_single<%d>" % n,
+    if n == 16384:  # 16384-point lines: rows at half length, columns as 4 x 4096 (lane-paired K1 unless GFB_K1_16K_DIT=0)
+        dit = os.environ.get("GFB_K1_16K_DIT", "1") != "0"
+        lp = os.environ.get("GFB_K3_16K_LP", "0") == "1"
+        return {"k_col_inv": "k_col_inv16k_dit<4096,PrepSingle>" if dit else "k_col_inv16k<4096,PrepSingle>",
+                "k_row": "k_row_product_half<8192,0>", "k_col_fwd": "k_col_fwd16k_lp<4096>" if lp else "k_col_fwd16k<4096>"}
+    return {"k_col_inv": ("k_col_inv_ws<%d,%d>" % (n, int(os.environ.get("GFB_K1WS_VAR", "16")))) if ws_c else "k_col_inv_single<%d>" % n,
             "k_row": ("k_row_product_ws<%d>" % n) if ws_r else (("k_row_product_tma<%d>" % n) if info.get("row_tma") else "k_row_product<%d,0>" % n),
             "k_col_fwd": ("k_col_fwd_ws<%d>" if info.get("col_ws3") else "k_col_fwd<%d,1>") % n}
 
@@ -218,22 +224,53 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
-def nvlink_kib(index):
-    """NVLink data bytes of GPU `index` since boot, summed over its links, in KiB: (tx, rx) from NVML's
-    NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX / _RX field values (payload only, no protocol overhead); None if unavailable."""
+def nvlink_kib(index, why=None):
+    """NVLink data bytes of GPU `index` since boot, summed over its links, in KiB: (tx, rx).  NVML's
+    NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX / _RX field values (payload only, no protocol overhead), all links at once (scope
+    UINT_MAX) or link by link; `nvidia-smi nvlink -gt d` as the fallback.  None if nothing works (`why` collects the reasons)."""
+    why = [] if why is None else why
     try:
         import pynvml
         pynvml.nvmlInit()
         h = pynvml.nvmlDeviceGetHandleByIndex(index)
-        out = []
-        for fid in (pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX):
-            v = pynvml.nvmlDeviceGetFieldValues(h, [(fid, 0xFFFFFFFF)])[0]  # scope UINT_MAX: all links
-            if v.nvmlReturn != 0:
-                return None
-            out.append(int(v.value.ullVal))
-        return tuple(out)
-    except Exception:  # noqa: BLE001
-        return None
+        fids = (pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX)
+
+        def read(scope):
+            out = []
+            for fid in fids:
+                v = pynvml.nvmlDeviceGetFieldValues(h, [(fid, scope)])[0]
+                if v.nvmlReturn != 0:
+                    raise RuntimeError("field %d scope %d: nvmlReturn %d" % (fid, scope, v.nvmlReturn))
+                out.append(int(v.value.ullVal))
+            return out
+        try:
+            return tuple(read(0xFFFFFFFF))
+        except Exception as e:  # noqa: BLE001
+            why.append("all-links scope: %s" % e)
+        tot, nlinks = [0, 0], 0
+        for link in range(18):
+            try:
+                a = read(link)
+                tot[0] += a[0]
+                tot[1] += a[1]
+                nlinks += 1
+            except Exception as e:  # noqa: BLE001
+                if link == 0:
+                    why.append("per-link scope: %s" % e)
+        if nlinks:
+            return tuple(tot)
+    except Exception as e:  # noqa: BLE001
+        why.append("nvml: %s" % e)
+    try:
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(index)], capture_output=True, text=True, timeout=10).stdout
+        tx = sum(int(x) for x in re.findall(r"Data Tx:\s*(\d+)\s*KiB", out))
+        rx = sum(int(x) for x in re.findall(r"Data Rx:\s*(\d+)\s*KiB", out))
+        if tx or rx:
+            return tx, rx
+        why.append("nvidia-smi nvlink -gt d: no counters in %r" % out[:200])
+    except Exception as e:  # noqa: BLE001
+        why.append("nvidia-smi: %s" % e)
+    return None
 
 
 def e2e_pipelined(prob, pkg, diag, host_sol, steps):
@@ -408,7 +445,9 @@ def run_other_config(args):
     sampler = ClockSampler(0)
     sampler.start()
     samples = []
-    nvl0 = nvlink_kib(local) if world > 1 else None
+    nvl_why = []
+    nvl0 = nvlink_kib(local, nvl_why) if world > 1 else None
+    barrier()
     for _ in range(max(1, args.repeats)):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
@@ -556,7 +595,9 @@ def main():
     barrier()
     sampler.start()
     samples = []
-    nvl0 = nvlink_kib(local) if world > 1 else None
+    nvl_why = []
+    nvl0 = nvlink_kib(local, nvl_why) if world > 1 else None
+    barrier()
     for _ in range(max(1, args.repeats)):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
@@ -566,6 +607,7 @@ def main():
         barrier()
         samples.append(allmax(e0.elapsed_time(e1)))
     nvl1 = nvlink_kib(local) if world > 1 else None
+    barrier()  # the counter read (an nvidia-smi subprocess where NVML has no counters) takes a different time on every rank
     sampler.stop_flag.set()
     sampler.join(timeout=2)
     ms = float(np.median(samples))
@@ -752,6 +794,8 @@ def main():
                                    "measured_tx_gbs": tx / (ms_per_step * 1e-3) / 1e9,
                                    "measured_vs_model": tx / a2a_bytes if a2a_bytes else None,
                                    "measured_how": "NVML NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX/RX deltas of this rank's GPU over the timed repeats"})
+        elif nvl_why:
+            line["nvlink"]["measured_unavailable"] = "; ".join(nvl_why)[:400]
     if world == 1 and not args.no_cpu_baseline and n <= 4096:  # larger grids: `--impl reference` samples them at 4096^2
         nsamp = 2 if n >= 4096 else 4
         full0 = bh0 if not forced else None
