@@ -82,6 +82,10 @@ CASES = {
     "mqg3_frk4": ("multilayerqg", dict(nx=32, ny=64, Lx=2 * np.pi, f0=1.0, beta=0.5, mu=0.05, nu=1e-4,
                                         H=[0.25, 0.25, 0.5], b=[-1.0, -1.2, -1.4], U=[0.3, 0.1, 0.0], dt=2e-3,
                                         stepper="FilteredRK4"), 3, 3),
+    # one-stage stepper on the layered kind: the state ping-pongs S0 <-> ALT (bottom drag reads every layer's stage input)
+    "mqg3_fab3": ("multilayerqg", dict(nx=32, ny=64, Lx=2 * np.pi, f0=1.0, beta=0.5, mu=0.05, nu=1e-4,
+                                        H=[0.25, 0.25, 0.5], b=[-1.0, -1.2, -1.4], U=[0.3, 0.1, 0.0], dt=2e-3,
+                                        stepper="FilteredAB3"), 5, 3),
 }
 
 
