@@ -47,9 +47,9 @@ def kernel_functions(n, info):
             "k_col_fwd": ("k_col_fwd_ws<%d>" if info.get("col_ws3") else "k_col_fwd<%d,1>") % n}
 
 
-def ncu_traffic(function):
+def ncu_traffic(function, key="dram_bytes_per_launch"):
     try:
-        return json.load(open(NCU_TRAFFIC_FILE)).get(function, {}).get("dram_bytes_per_launch")
+        return json.load(open(NCU_TRAFFIC_FILE)).get(function, {}).get(key)
     except Exception:
         return None
 
@@ -749,6 +749,9 @@ def main():
                      "frac": (achieved / peak) if achieved else None,
                      "traffic": ncu_traffic(kfun[top]) if world == 1 else None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": kbytes[top], "avg_launch_ms": avg_ms,
+                     # the dominant kernel is bound by the FP64 pipe, not by HBM (five transforms per 131 KB in): its share of
+                     # FP64-pipe-active cycles from the same ncu capture as `traffic` (sm__inst_executed_pipe_fp64, % of peak)
+                     "fp64_pipe_frac_ncu": (ncu_traffic(kfun[top], "fp64_pipe_pct") or 0) / 100.0 or None if world == 1 else None,
                      "all_kernels": {k: {"function": kfun[k],
                                          "achieved_gbs": kbytes[k] / (prof[k]["ms"] / max(prof[k]["launches"], 1) * 1e-3) / 1e9
                                          if prof[k]["ms"] > 0 else None,

@@ -57,7 +57,7 @@ def main():
         n = a["n"]
         rd, wr, us = a.get(METRICS[0], 0) / n, a.get(METRICS[1], 0) / n, a.get(METRICS[2], 0) / n
         res[name] = {"dram_bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr, "ncu_duration_us": us, "launches_captured": n,
-                     "report": tag}
+                     "fp64_pipe_pct": a.get(METRICS[5], 0) / n, "warps_active_pct": a.get(METRICS[6], 0) / n, "report": tag}
         lines.append("%-34s grid %-14s block %-12s n=%d  %8.1f us  DRAM read %7.1f MB  write %7.1f MB  (%.0f GB/s)  regs %3.0f  "
                      "SM%% %4.1f  DRAM%% %4.1f  fp64 pipe%% %4.1f  warps active%% %4.1f  smem wavefronts %.1f M"
                      % (name, a["grid"], a["block"], n, us, rd / 1e6, wr / 1e6, (rd + wr) / us / 1e3 if us else 0,
