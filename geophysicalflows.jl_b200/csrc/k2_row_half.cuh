@@ -59,6 +59,41 @@ __device__ __forceinline__ void assemble_half(cplx (&v)[PT], const int j, const 
   }
 }
 
+// The twiddles W_{2NH}^k, k = j + r*T, a thread needs in assemble_half and again when it separates the output spectra are the
+// same for every row it ever processes.  Without the Q-gradient term a thread owns 64 spare TMEM columns: they are parked
+// there once per kernel (HTW = true) instead of being fetched from L2 twice per phase, a round trip that nothing hides in a
+// one-CTA-per-SM kernel.  ttw: TMEM address of the thread's 16 values (forward sign).
+template <int NH, bool HTW>
+__device__ __forceinline__ void assemble_half_tw(cplx (&v)[PT], const int j, const cplx* __restrict__ lb, const int kc,
+                                                 const cplx* __restrict__ tw2, const uint32_t ttw) {
+  if (!HTW) {
+    assemble_half<NH>(v, j, lb, kc, tw2);
+    return;
+  }
+  constexpr int T = NH / PT;
+#pragma unroll
+  for (int r0 = 0; r0 < PT; r0 += 2) {
+    cplx w4[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) w4[i] = tmem_load(ttw + 4 * (r0 + i));
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int r = r0 + i, k = j + r * T, km = NH - k;
+      cplx a = cmake(0.0, 0.0), b = cmake(0.0, 0.0);
+      if (k < kc) a = lb[k];
+      if (km < kc) b = lb[km];
+      if (k == 0) {
+        a.y = 0.0;
+        b.y = 0.0;
+      }
+      const cplx s = cmake(a.x + b.x, a.y - b.y), d = cmake(a.x - b.x, a.y + b.y);
+      const cplx t = cmul(cconj(w4[i]), d);
+      v[r] = cmake(s.x - t.y, s.y + t.x);
+    }
+  }
+}
+
 template <int NH, bool WITHQ>
 __global__ void __launch_bounds__(GroupCfg<NH>::THREADS, GroupCfg<NH>::MINB)
     k_row_product_half(const __grid_constant__ RowArgs a, const cplx* __restrict__ tw, const cplx* __restrict__ tw2, const int nunits,
@@ -70,10 +105,16 @@ __global__ void __launch_bounds__(GroupCfg<NH>::THREADS, GroupCfg<NH>::MINB)
   const int gi = tid / T, j = tid % T;
   double* xb = smd + gi * RC::GSD;
   cplx* lb = reinterpret_cast<cplx*>(smd + RC::XB_DOUBLES) + 1 + (size_t)gi * kcp;  // [0] holds the TMEM base word
-  constexpr int tmcols = (RC::THREADS / 128) * (WITHQ ? 128 : 64);
+  constexpr bool HTW = !WITHQ;  // the second 64-column slot holds the row twiddles when the Q-gradient term does not need it
+  constexpr int tmcols = (RC::THREADS / 128) * 128;
   const uint32_t tbase = tmem_setup(reinterpret_cast<uint32_t*>(smd + RC::XB_DOUBLES), tmcols);
-  const uint32_t tq = tmem_thread_base(tbase, WITHQ ? 128 : 64);
-  const uint32_t tg = tq + 64;  // WITHQ: (u + U) Qx + v Qy of this row at the thread's even / odd points
+  const uint32_t tq = tmem_thread_base(tbase, 128);
+  const uint32_t tg = tq + 64;  // WITHQ: (u + U) Qx + v Qy of this row at the thread's even / odd points ; else: twiddles
+  if (HTW) {
+#pragma unroll
+    for (int r = 0; r < PT; ++r) tmem_store(tg + 4 * r, __ldg(&tw2[j + r * T]));
+    tmem_wait_st();
+  }
   const int stride = (int)gridDim.x * G, unit0 = (int)blockIdx.x * G + gi;
   const int niter = (nunits - (int)blockIdx.x * G + stride - 1) / stride;  // same for every group of the CTA
   cplx v[PT];
@@ -89,7 +130,7 @@ __global__ void __launch_bounds__(GroupCfg<NH>::THREADS, GroupCfg<NH>::MINB)
     for (int ph = 0; ph < 3; ++ph) {
       cp_async_wait_all();
       __syncthreads();  // the line buffer is complete and visible
-      if (live) assemble_half<NH>(v, j, lb, a.kc, tw2);
+      if (live) assemble_half_tw<NH, HTW>(v, j, lb, a.kc, tw2, tg);
       else {
 #pragma unroll
         for (int r = 0; r < PT; ++r) v[r] = cmake(0.0, 0.0);
@@ -158,13 +199,18 @@ __global__ void __launch_bounds__(GroupCfg<NH>::THREADS, GroupCfg<NH>::MINB)
       }
       block_fft_split<NH, FWD>(v, j, xb, tw);
       unpack_pair<NH>(v, j, xb, A, B);  // A = E, B = O for k = j + r*T <= NH/2
-      if (live) {
+      if (live) {  // `live` is uniform over the CTA (one group per CTA): the TMEM reads below are warp-uniform
         const long long rb = a.pl.rowbase(2 * layer + (ph - 1), y);
 #pragma unroll
         for (int r = 0; r < 9; ++r) {
           const int k = j + r * T, km = NH - k;
+          cplx wk;
+          if (HTW) {
+            wk = tmem_load(tg + 4 * r);
+            tmem_wait_ld();
+          }
           if (r < 8 || j == 0) {
-            const cplx t = cmul(__ldg(&tw2[k]), B[r]);
+            const cplx t = cmul(HTW ? wk : __ldg(&tw2[k]), B[r]);
             cplx X = cadd(A[r], t), Xm = cconj(csub(A[r], t));  // X[k], X[NH - k]
             if (ph == 1) {  // the d field carries -i kr (uq)_h
               const double kr = k * a.dkx, krm = km * a.dkx;
