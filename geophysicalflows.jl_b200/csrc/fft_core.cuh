@@ -356,6 +356,50 @@ __device__ __forceinline__ void fft_pass_split(cplx (&v)[PT], const int j, doubl
   }
 }
 
+// fft_pass_split with the butterfly twiddle handed in by a functor, w1(i) = W_N^{k (N / (Ns R))} of butterfly i (forward
+// sign): kernels that run ONE CTA per SM cannot hide the L2 round trip of the table load at the head of every pass behind
+// another CTA, so they keep these per-thread constants on chip (shared-memory tables, TMEM) and pass them in.
+template <int N, int DIR, int R, int Ns, bool LAST, class W1>
+__device__ __forceinline__ void fft_pass_split_w1(cplx (&v)[PT], const int j, double* __restrict__ xb, const W1& w1of) {
+  constexpr int T = N / PT;
+  constexpr int M = PT / R;
+  int base[M];
+#pragma unroll
+  for (int i = 0; i < M; ++i) {
+    const int b = j + i * T;
+    cplx x[R];
+#pragma unroll
+    for (int s = 0; s < R; ++s) x[s] = v[i + s * M];
+    cplx w1 = w1of(i);
+    if (DIR == INV) w1.y = -w1.y;
+    twiddle_apply<R>(x, w1);
+    Dft<DIR, R>::run(x);
+#pragma unroll
+    for (int s = 0; s < R; ++s) v[i + s * M] = x[s];
+    const int k = b & (Ns - 1);
+    base[i] = (b - k) * R + k;
+  }
+  if (!LAST) {
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+#pragma unroll
+      for (int s = 0; s < R; ++s) xb[xpad(base[i] + s * Ns)] = v[i + s * M].x;
+    __syncthreads();
+    double re[PT];
+#pragma unroll
+    for (int r = 0; r < PT; ++r) re[r] = xb[xpad(j + r * T)];
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+#pragma unroll
+      for (int s = 0; s < R; ++s) xb[xpad(base[i] + s * Ns)] = v[i + s * M].y;
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < PT; ++r) v[r] = cmake(re[r], xb[xpad(j + r * T)]);
+    __syncthreads();
+  }
+}
+
 template <int N, int DIR>
 __device__ __forceinline__ void block_fft_split(cplx (&v)[PT], const int j, double* __restrict__ xb,
                                                 const cplx* __restrict__ tw) {

@@ -94,6 +94,22 @@ __device__ __forceinline__ void assemble_half_tw(cplx (&v)[PT], const int j, con
   }
 }
 
+// 8192-point transform of the group's registers with every pass twiddle taken from on-chip copies: pass 2 (16 distinct
+// values per CTA) and pass 3 (256) from the shared-memory tables t2 / t3, the radix-2 pass 4 from the thread's row twiddles
+// in TMEM -- W_8192^{j + 512 i} is the square of W_16384^{j + 512 i}.
+template <int DIR>
+__device__ __forceinline__ void block_fft_split_8192_onchip(cplx (&v)[PT], const int j, double* __restrict__ xb, const cplx* __restrict__ tw,
+                                                            const cplx* __restrict__ t2, const cplx* __restrict__ t3, const uint32_t ttw) {
+  fft_pass_split<8192, DIR, 16, 1, false>(v, j, xb, tw);
+  fft_pass_split_w1<8192, DIR, 16, 16, false>(v, j, xb, [&](int) { return t2[j & 15]; });
+  fft_pass_split_w1<8192, DIR, 16, 256, false>(v, j, xb, [&](int) { return t3[j & 255]; });
+  cplx w[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) w[i] = tmem_load(ttw + 4 * i);
+  tmem_wait_ld();
+  fft_pass_split_w1<8192, DIR, 2, 4096, true>(v, j, xb, [&](int i) { return cmake(w[i].x * w[i].x - w[i].y * w[i].y, 2.0 * w[i].x * w[i].y); });
+}
+
 template <int NH, bool WITHQ>
 __global__ void __launch_bounds__(GroupCfg<NH>::THREADS, GroupCfg<NH>::MINB)
     k_row_product_half(const __grid_constant__ RowArgs a, const cplx* __restrict__ tw, const cplx* __restrict__ tw2, const int nunits,
@@ -110,10 +126,16 @@ __global__ void __launch_bounds__(GroupCfg<NH>::THREADS, GroupCfg<NH>::MINB)
   const uint32_t tbase = tmem_setup(reinterpret_cast<uint32_t*>(smd + RC::XB_DOUBLES), tmcols);
   const uint32_t tq = tmem_thread_base(tbase, 128);
   const uint32_t tg = tq + 64;  // WITHQ: (u + U) Qx + v Qy of this row at the thread's even / odd points ; else: twiddles
+  cplx* t2 = reinterpret_cast<cplx*>(smd + RC::XB_DOUBLES) + 1 + (size_t)G * kcp;  // pass-2 / pass-3 twiddle tables (HTW)
+  cplx* t3 = t2 + 16;
   if (HTW) {
+    static_assert(!HTW || NH == 8192, "on-chip twiddles: 8192-point half-length rows");
 #pragma unroll
     for (int r = 0; r < PT; ++r) tmem_store(tg + 4 * r, __ldg(&tw2[j + r * T]));
     tmem_wait_st();
+    if (tid < 16) t2[tid] = tw[tid * 32];
+    if (tid < 256) t3[tid] = tw[tid * 2];
+    __syncthreads();
   }
   const int stride = (int)gridDim.x * G, unit0 = (int)blockIdx.x * G + gi;
   const int niter = (nunits - (int)blockIdx.x * G + stride - 1) / stride;  // same for every group of the CTA
@@ -139,7 +161,8 @@ __global__ void __launch_bounds__(GroupCfg<NH>::THREADS, GroupCfg<NH>::MINB)
       if (live && ph < 2) row_prefetch1<T>(lb, a.W, a.wl, a.wstride * layer + (ph == 0 ? 0 : 1), y, a.kc, j);
       else if (ph == 2 && unit + stride < nunits)
         row_prefetch1<T>(lb, a.W, a.wl, a.wstride * ((unit + stride) / a.ny) + 2, (unit + stride) % a.ny, a.kc, j);
-      block_fft_split<NH, INV>(v, j, xb, tw);  // v[r] = (x[2n], x[2n+1]), n = j + r*T
+      if constexpr (HTW) block_fft_split_8192_onchip<INV>(v, j, xb, tw, t2, t3, tg);
+      else block_fft_split<NH, INV>(v, j, xb, tw);  // v[r] = (x[2n], x[2n+1]), n = j + r*T
       if (ph == 0) {  // q (+ eta) of this row -> TMEM
         if (a.eta != nullptr && live) {
           const double* ea = a.eta + (long long)y * (2 * NH);
@@ -197,7 +220,8 @@ __global__ void __launch_bounds__(GroupCfg<NH>::THREADS, GroupCfg<NH>::MINB)
           v[c0 + q].y *= q2[q].y;
         }
       }
-      block_fft_split<NH, FWD>(v, j, xb, tw);
+      if constexpr (HTW) block_fft_split_8192_onchip<FWD>(v, j, xb, tw, t2, t3, tg);
+      else block_fft_split<NH, FWD>(v, j, xb, tw);
       unpack_pair<NH>(v, j, xb, A, B);  // A = E, B = O for k = j + r*T <= NH/2
       if (live) {  // `live` is uniform over the CTA (one group per CTA): the TMEM reads below are warp-uniform
         const long long rb = a.pl.rowbase(2 * layer + (ph - 1), y);

@@ -348,7 +348,7 @@ template <bool WITHQ>
 static int do_row_half_product(const RowLaunch& L) {
   using RC = GroupCfg<8192>;
   const int kcp = (L.a.kc + 1) & ~1;
-  const size_t smem = (size_t)RC::XB_DOUBLES * sizeof(double) + 16 + (size_t)RC::G * kcp * sizeof(cplx);
+  const size_t smem = (size_t)RC::XB_DOUBLES * sizeof(double) + 16 + (size_t)RC::G * kcp * sizeof(cplx) + (16 + 256) * sizeof(cplx);  // + twiddle tables
   static AttrCache attr;
   if (smem > attr.bytes[cur_device()]) {
     if (set_smem(k_row_product_half<8192, WITHQ>, smem)) return -2;
