@@ -776,7 +776,7 @@ def main():
     if world > 1:
         # strong-scaling reference: the SAME workload measured on one GPU of this pool (committed bench line; the 16384^2
         # problem needs 46 GB and fits one B200), so that N-GPU lines can be read as t1 / (N tN) without re-running it
-        refs = {"twodns16384": "r2x_twodns16384_1gpu.json", "sqg4096": "r2x_bench100.json"}
+        refs = {"twodns16384": "r2am_twodns16384_1gpu.json", "sqg4096": "r2x_bench100.json"}
         try:
             ref = json.loads(open(os.path.join(ROOT, "profiles", refs[args.workload])).read().strip().splitlines()[-1])
             if ref["n_gpus"] == 1 and ref["config"]["workload"] == workload_name(cfg):

@@ -2,7 +2,7 @@
 # r2aa (N GPUs): sharded GPU tests (incl. the 16384-line cases), then the north_star multi-GPU workload and the strong-scaled 4096^2 headline problem
 N=${1:-2}
 mkdir -p gpurun_out
-T=r2aa
+T=${TAG:-r2aa}
 if [ "$N" = "2" ]; then
   timeout 900 python -m pytest tests/test_gpu_sharded.py -m gpu -q -p no:cacheprovider --durations=5 > gpurun_out/${T}_pytest_sharded_${N}.log 2>&1
   echo "pytest rc=$?" >> gpurun_out/${T}_pytest_sharded_${N}.log
