@@ -597,3 +597,17 @@ def test_output_and_checkpoint_resharded(emu, tmp_path, monkeypatch):
     gf.stepforward_(again, 2)
     assert again.clock.t == ref.clock.t
     assert R.relerr(again.sol.numpy(), ref.sol.numpy()) < 1e-14
+
+
+def test_columns_of_16384_points_without_dealiasing(emu, oracle_backend):
+    """ny = 16384 with aliased_fraction = 0 (only the Nyquist row is masked) and an odd number of kr columns: the
+    lane-paired K1 (k_col_inv16k_dit) with every row live and a dead partner column in the last pair."""
+    kw = dict(nx=32, ny=16384, Lx=2 * np.pi, Ly=3.0, nu=1e-4, nnu=1, mu=0.02, nmu=0, dt=1e-3, stepper="RK4", aliased_fraction=0.0)
+    po = oracle_backend.twodnavierstokes.Problem(**kw)
+    pb = emu.twodnavierstokes.Problem(**kw)
+    s0 = np.fft.rfft2(np.random.default_rng(1).standard_normal((16384, 32))) * 300 / (32 * 16384)
+    po.sol[...] = s0
+    pb.sol.copy_(emu.dev(s0))
+    oracle_backend.stepforward_(po, 2)
+    emu.stepforward_(pb, 2)
+    assert R.relerr(emu.host(pb.sol), po.sol) < 1e-13
