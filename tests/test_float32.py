@@ -65,3 +65,32 @@ def test_float32_refuses_unknown_types():
     B = _backend("emu")
     with pytest.raises(Exception, match="Float32 or Float64"):
         B.twodnavierstokes.Problem(nx=32, T="Float16")
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_every_module_steps_in_float32(kind):
+    """set an initial condition, step, update the physical variables and take a diagnostic on a Float32 problem of every
+    module: all C-ABI entry points reached through the widening / rounding layer (several arrays per call)"""
+    B = _backend(kind)
+    rng = np.random.default_rng(5)
+    q0 = (0.1 * rng.standard_normal((32, 32))).astype(np.float32)
+    cases = [
+        ("twodnavierstokes", B.twodnavierstokes.Problem(nx=32, dt=1e-3, nu=1e-3, stepper="ETDRK4", T=np.float32), "set_zeta_", "energy"),
+        ("surfaceqg", B.surfaceqg.Problem(nx=32, dt=1e-3, stepper="FilteredRK4", T=np.float32), "set_b_", "kinetic_energy"),
+        ("singlelayerqg", B.singlelayerqg.Problem(nx=32, dt=1e-3, beta=1.0, deformation_radius=1.2, stepper="FilteredAB3", T=np.float32), "set_q_", "energy"),
+        ("barotropicqgql", B.barotropicqgql.Problem(nx=32, dt=1e-3, beta=1.0, stepper="RK4", T=np.float32), "set_zeta_", "energy"),
+    ]
+    for name, prob, setter, diag in cases:
+        M = getattr(B, name)
+        getattr(M, setter)(prob, B.dev(q0))
+        assert prob.sol.dtype == torch.complex64, name
+        B.stepforward_(prob, 2)
+        M.updatevars_(prob)
+        e = getattr(M, diag)(prob)
+        assert np.isfinite(e) and e > 0, (name, e)
+        assert bool(torch.isfinite(prob.sol.real).all()) and prob.vars.u.dtype == torch.float32, name
+    pm = B.multilayerqg.Problem(2, nx=32, dt=1e-3, U=[0.3, 0.0], mu=0.05, stepper="FilteredRK4", T=np.float32)
+    B.multilayerqg.set_q_(pm, B.dev(np.stack([q0, -q0])))
+    B.stepforward_(pm, 2)
+    KE, PE = B.multilayerqg.energies(pm)
+    assert pm.sol.dtype == torch.complex64 and np.all(np.isfinite(KE)) and np.all(np.isfinite(PE))
